@@ -1,0 +1,323 @@
+"""ctypes wrapper around oracle/liboracle.so (the CPU oracle).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  Never import this from
+spl_slam_b200/ (the product path has no CPU fallback).
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                           ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"),
+                          ("pt_x", "<f4"), ("pt_y", "<f4"), ("response", "<f4"), ("size", "<f4"),
+                          ("startPointX", "<f4"), ("startPointY", "<f4"),
+                          ("endPointX", "<f4"), ("endPointY", "<f4"),
+                          ("sPointInOctaveX", "<f4"), ("sPointInOctaveY", "<f4"),
+                          ("ePointInOctaveX", "<f4"), ("ePointInOctaveY", "<f4"),
+                          ("lineLength", "<f4"), ("numOfPixels", "<i4")])
+assert KEYPOINT_DTYPE.itemsize == 28 and KEYLINE_DTYPE.itemsize == 68
+
+
+class LineParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("nlevels", C.c_int), ("refine", C.c_int),
+                ("scale", C.c_double), ("sigma_scale", C.c_double), ("quant", C.c_double),
+                ("ang_th", C.c_double), ("log_eps", C.c_double), ("density_th", C.c_double),
+                ("n_bins", C.c_int), ("min_line_length", C.c_double)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("orc_prims.c", "orc_orb.c", "orc_lsd.c", "orc_lbd.c", "plf_oracle.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "liboracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        u8p, i32p, f32p, vp = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+        L.orc_orb_create.restype = vp
+        L.orc_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_orb_destroy.argtypes = [vp]
+        L.orc_orb_features_per_level.argtypes = [vp, C.c_int]
+        L.orc_orb_scale_factor.argtypes = [vp, C.c_int]
+        L.orc_orb_scale_factor.restype = C.c_float
+        L.orc_orb_umax.argtypes = [vp, C.c_int]
+        L.orc_orb_extract.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_size_t, vp, u8p, C.c_int]
+        L.orc_orb_level_size.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_orb_level_image.restype = vp
+        L.orc_orb_level_image.argtypes = [vp, C.c_int, C.POINTER(C.c_size_t)]
+        L.orc_orb_level_blurred.restype = vp
+        L.orc_orb_level_blurred.argtypes = [vp, C.c_int, C.POINTER(C.c_size_t)]
+        L.orc_orb_level_raw_count.argtypes = [vp, C.c_int]
+        L.orc_orb_level_raw.argtypes = [vp, C.c_int, i32p, i32p, i32p]
+        L.orc_orb_level_kept_count.argtypes = [vp, C.c_int]
+        L.orc_distribute_octree.argtypes = [i32p, i32p, i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, i32p, C.c_int]
+        L.orc_resize_linear_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, u8p, C.c_int, C.c_int, C.c_size_t]
+        L.orc_resize_linear_exact_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, u8p, C.c_int, C.c_int,
+                                                 C.c_size_t, C.c_double, C.c_double]
+        L.orc_border_reflect101_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, u8p, C.c_int, C.c_size_t]
+        L.orc_gauss_kernel_q8.argtypes = [C.c_int, C.c_double, i32p]
+        L.orc_gauss_blur_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, u8p, C.c_size_t, C.c_int, C.c_double]
+        L.orc_pyrdown_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, u8p, C.c_size_t]
+        L.orc_sobel3_s16.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, vp, vp]
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_fast9.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, i32p, i32p, i32p, C.c_int]
+        L.orc_lsd_detect.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_double, C.c_double, C.c_double,
+                                     C.c_double, C.c_int, f32p, C.c_int]
+        L.orc_line_features_per_level.argtypes = [C.POINTER(LineParams), C.c_int]
+        L.orc_lsd_detect_keylines.argtypes = [C.POINTER(LineParams), u8p, C.c_int, C.c_int, C.c_size_t, vp, C.c_int]
+        L.orc_lbd_compute.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, u8p, f32p]
+        L.orc_line_extract.argtypes = [C.POINTER(LineParams), u8p, C.c_int, C.c_int, C.c_size_t, vp, vp, u8p, C.c_int]
+        L.orc_descriptor_distance.argtypes = [u8p, u8p]
+        L.orc_knn2.argtypes = [u8p, C.c_int, u8p, C.c_long, i32p, i32p]
+        L.orc_match_nnr.argtypes = [u8p, C.c_int, u8p, C.c_long, C.c_float, i32p]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _img(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    assert a.ndim == 2
+    return a
+
+
+# ---------------- primitives ----------------
+def resize_linear(img, dw, dh):
+    img = _img(img)
+    out = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), dw, dh, dw)
+    return out
+
+
+def resize_linear_exact(img, fx, fy=None):
+    img = _img(img)
+    fy = fx if fy is None else fy
+    dw, dh = int(np.rint(img.shape[1] * fx)), int(np.rint(img.shape[0] * fy))
+    out = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_exact_u8(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), dw, dh, dw, fx, fy)
+    return out
+
+
+def border_reflect101(img, b):
+    img = _img(img)
+    h, w = img.shape
+    out = np.empty((h + 2 * b, w + 2 * b), np.uint8)
+    lib().orc_border_reflect101_u8(_p(img), w, h, img.strides[0], _p(out), b, w + 2 * b)
+    return out
+
+
+def gauss_kernel_q8(ksize, sigma):
+    q = np.zeros(ksize, np.int32)
+    rc = lib().orc_gauss_kernel_q8(ksize, sigma, _p(q))
+    assert rc == 0
+    return q
+
+
+def gauss_blur(img, ksize, sigma):
+    img = _img(img)
+    out = np.empty_like(img)
+    lib().orc_gauss_blur_u8(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), out.strides[0], ksize, sigma)
+    return out
+
+
+def pyrdown(img):
+    img = _img(img)
+    h, w = img.shape
+    out = np.empty((h // 2, w // 2), np.uint8)
+    lib().orc_pyrdown_u8(_p(img), w, h, img.strides[0], _p(out), out.strides[0])
+    return out
+
+
+def sobel3(img):
+    img = _img(img)
+    h, w = img.shape
+    dx = np.empty((h, w), np.int16)
+    dy = np.empty((h, w), np.int16)
+    lib().orc_sobel3_s16(_p(img), w, h, img.strides[0], _p(dx), _p(dy))
+    return dx, dy
+
+
+def fast_atan2(y, x):
+    return float(lib().orc_fast_atan2(float(y), float(x)))
+
+
+def fast9(img, th):
+    img = _img(img)
+    h, w = img.shape
+    cap = max(1, w * h)
+    xs = np.empty(cap, np.int32); ys = np.empty(cap, np.int32); sc = np.empty(cap, np.int32)
+    n = lib().orc_fast9(_p(img), w, h, img.strides[0], th, _p(xs), _p(ys), _p(sc), cap)
+    return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def distribute_octree(xs, ys, resp, minX, maxX, minY, maxY, N):
+    xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32)
+    resp = np.ascontiguousarray(resp, np.int32)
+    out = np.empty(max(1, len(xs)), np.int32)
+    n = lib().orc_distribute_octree(_p(xs), _p(ys), _p(resp), len(xs), minX, maxX, minY, maxY, N, _p(out), len(out))
+    return out[:n].copy()
+
+
+# ---------------- ORB extractor ----------------
+class ORBextractor:
+    """Oracle mirror of PL_SLAM::ORBextractor (include/ORBextractor.h:45-113)."""
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST):
+        self._h = lib().orc_orb_create(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_orb_destroy(self._h)
+            self._h = None
+
+    def features_per_level(self):
+        return [lib().orc_orb_features_per_level(self._h, l) for l in range(self.nlevels)]
+
+    def scale_factors(self):
+        return [lib().orc_orb_scale_factor(self._h, l) for l in range(self.nlevels)]
+
+    def umax(self):
+        return [lib().orc_orb_umax(self._h, v) for v in range(16)]
+
+    def __call__(self, image):
+        img = _img(image)
+        cap = self.nfeatures * 2 + 64 * self.nlevels
+        kps = np.zeros(cap, KEYPOINT_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = lib().orc_orb_extract(self._h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(desc), cap)
+        assert n >= 0, "oracle keypoint capacity too small"
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level_image(self, level):
+        w, h = C.c_int(), C.c_int()
+        assert lib().orc_orb_level_size(self._h, level, C.byref(w), C.byref(h)) == 0
+        st = C.c_size_t()
+        p = lib().orc_orb_level_image(self._h, level, C.byref(st))
+        buf = (C.c_uint8 * (st.value * h.value)).from_address(p)
+        return np.frombuffer(buf, np.uint8).reshape(h.value, st.value)[:, :w.value].copy()
+
+    def level_blurred(self, level):
+        w, h = C.c_int(), C.c_int()
+        assert lib().orc_orb_level_size(self._h, level, C.byref(w), C.byref(h)) == 0
+        st = C.c_size_t()
+        p = lib().orc_orb_level_blurred(self._h, level, C.byref(st))
+        if not p:
+            return None
+        buf = (C.c_uint8 * (w.value * h.value)).from_address(p)
+        return np.frombuffer(buf, np.uint8).reshape(h.value, w.value).copy()
+
+    def level_raw(self, level):
+        n = lib().orc_orb_level_raw_count(self._h, level)
+        xs = np.empty(max(n, 1), np.int32); ys = np.empty(max(n, 1), np.int32); rr = np.empty(max(n, 1), np.int32)
+        if n:
+            lib().orc_orb_level_raw(self._h, level, _p(xs), _p(ys), _p(rr))
+        return xs[:n], ys[:n], rr[:n]
+
+    def level_kept_count(self, level):
+        return lib().orc_orb_level_kept_count(self._h, level)
+
+
+# ---------------- lines ----------------
+def line_params(nfeatures=600, nlevels=2, refine=0, scale=1.1, sigma_scale=0.6, quant=2.2, ang_th=12.5,
+                log_eps=1.0, density_th=0.6, n_bins=1024, min_line_length=0.0):
+    return LineParams(nfeatures, nlevels, refine, scale, sigma_scale, quant, ang_th, log_eps, density_th,
+                      n_bins, min_line_length)
+
+
+def lsd_detect(img, scale=1.1, sigma_scale=0.6, quant=2.2, ang_th=12.5, n_bins=1024):
+    img = _img(img)
+    cap = 1 << 16
+    lines = np.empty((cap, 4), np.float32)
+    n = lib().orc_lsd_detect(_p(img), img.shape[1], img.shape[0], img.strides[0], scale, sigma_scale, quant,
+                             ang_th, n_bins, _p(lines), cap)
+    return lines[:n].copy()
+
+
+def lsd_detect_keylines(params, img):
+    img = _img(img)
+    cap = 1 << 16
+    kl = np.zeros(cap, KEYLINE_DTYPE)
+    n = lib().orc_lsd_detect_keylines(C.byref(params), _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kl), cap)
+    return kl[:n].copy()
+
+
+def lbd_compute(img, keylines, want_float=False):
+    img = _img(img)
+    kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+    n = len(kl)
+    desc = np.zeros((n, 32), np.uint8)
+    fdesc = np.zeros((n, 72), np.float32)
+    lib().orc_lbd_compute(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(kl), n, _p(desc), _p(fdesc))
+    return (desc, fdesc) if want_float else desc
+
+
+def line_extract(params, img):
+    """Oracle mirror of Lineextractor::ComputeLsdWithLbd (src/Lineextractor.cc:112-212)."""
+    img = _img(img)
+    cap = max(16, params.nfeatures * 2 + 16)
+    kl = np.zeros(cap, KEYLINE_DTYPE)
+    mid = np.zeros(cap, KEYPOINT_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    n = lib().orc_line_extract(C.byref(params), _p(img), img.shape[1], img.shape[0], img.strides[0],
+                               _p(kl), _p(mid), _p(desc), cap)
+    assert n >= 0
+    return kl[:n].copy(), mid[:n].copy(), desc[:n].copy()
+
+
+def features_per_level_lines(params):
+    return [lib().orc_line_features_per_level(C.byref(params), l) for l in range(params.nlevels)]
+
+
+# ---------------- matching ----------------
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_descriptor_distance(_p(a), _p(b))
+
+
+def knn2(q, t):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    idx = np.empty((len(q), 2), np.int32); dist = np.empty((len(q), 2), np.int32)
+    lib().orc_knn2(_p(q), len(q), _p(t), len(t), _p(idx), _p(dist))
+    return idx, dist
+
+
+def match_nnr(q, t, nnr):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    m = np.empty(len(q), np.int32)
+    n = lib().orc_match_nnr(_p(q), len(q), _p(t), len(t), nnr, _p(m))
+    return m, n
+
+
+# ---------------- synthetic images ----------------
+def synth_image(w, h, seed):
+    """uniform u8 noise -> Gaussian s=2 -> K filled rectangles -> 3x3 s=0.8 blur (pure numpy + oracle blur)."""
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+    img = gauss_blur(img, 13, 2.0)
+    K = int(round(60.0 * (w * h) / (640.0 * 480.0)))
+    for _ in range(K):
+        x0 = int(rng.integers(0, w - 8)); y0 = int(rng.integers(0, h - 8))
+        rw = int(rng.integers(8, max(9, w // 4))); rh = int(rng.integers(8, max(9, h // 4)))
+        g = int(rng.integers(0, 256))
+        img[y0:min(h, y0 + rh), x0:min(w, x0 + rw)] = g
+    img = gauss_blur(img, 3, 0.8)
+    return img
