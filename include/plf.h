@@ -1,0 +1,194 @@
+/*
+ * plf.h -- C ABI of the B200-native point-line feature front-end (libplf.so).
+ *
+ * Drop-in boundary for the hot path of Hero941215/spl-slam (reference paths are
+ * relative to the reference root).  Every entry point names the reference interface
+ * it replaces.  Plain pointers and sizes only; no exceptions cross this boundary;
+ * every function returns a plf_status and plf_last_error() explains failures.
+ * There is NO CPU fallback behind this ABI: without a usable CUDA device every call
+ * fails with PLF_ERR_CUDA.
+ *
+ * Buffers named host_* are host memory (pageable or pinned); buffers named dev_* are
+ * device pointers on the context's device.  All images are 8-bit single channel
+ * (CV_8UC1) with a row stride in bytes.
+ */
+#ifndef PLF_H
+#define PLF_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PLF_OK = 0,
+    PLF_ERR_INVALID = 1,  /* bad argument */
+    PLF_ERR_CUDA = 2,     /* CUDA runtime error / no device */
+    PLF_ERR_CAPACITY = 3, /* an output or internal buffer was too small */
+    PLF_ERR_STATE = 4     /* call order error (e.g. pyramid requested before extract) */
+} plf_status;
+
+/* cv::KeyPoint memory layout (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} plf_keypoint;
+
+/* cv::line_descriptor::KeyLine memory layout (68 bytes),
+ * Thirdparty/line_descriptor/include/line_descriptor/descriptor_custom.hpp:105-174 */
+typedef struct {
+    float angle;
+    int32_t class_id;
+    int32_t octave;
+    float pt_x, pt_y;
+    float response;
+    float size;
+    float startPointX, startPointY, endPointX, endPointY;
+    float sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY;
+    float lineLength;
+    int32_t numOfPixels;
+} plf_keyline;
+
+typedef struct plf_ctx plf_ctx;
+typedef struct plf_orb plf_orb;
+typedef struct plf_line plf_line;
+
+/* ---- context: one per host thread / GPU stream.  The reference calls its extractors and
+ * matchNNR from concurrent std::threads (src/Frame.cc:116-119, :301-304;
+ * src/Linematcher.cc:454-457); give each such thread its own context. ---- */
+plf_status plf_ctx_create(int device, plf_ctx** out);
+void plf_ctx_destroy(plf_ctx* ctx);
+const char* plf_last_error(const plf_ctx* ctx);
+plf_status plf_ctx_synchronize(plf_ctx* ctx);
+/* cudaStream_t of the context (as void*) so callers can order their own work / events on it */
+void* plf_ctx_stream(plf_ctx* ctx);
+/* device-side stopwatch on the context's stream (CUDA events) */
+plf_status plf_timer_start(plf_ctx* ctx);
+plf_status plf_timer_stop(plf_ctx* ctx, float* elapsed_ms);
+/* number of kernels this context has launched since creation (bench "gpu_launches") */
+uint64_t plf_ctx_launch_count(const plf_ctx* ctx);
+
+/* ---- ORB extractor: replaces PL_SLAM::ORBextractor
+ * (include/ORBextractor.h:45-113, src/ORBextractor.cc:410-470, :1043-1132) ---- */
+typedef struct {
+    int nfeatures;      /* ORBextractor.nFeatures */
+    float scale_factor; /* ORBextractor.scaleFactor */
+    int nlevels;        /* ORBextractor.nLevels */
+    int ini_th_fast;    /* ORBextractor.iniThFAST */
+    int min_th_fast;    /* ORBextractor.minThFAST */
+} plf_orb_params;
+
+plf_status plf_orb_create(plf_ctx* ctx, const plf_orb_params* p, plf_orb** out);
+void plf_orb_destroy(plf_orb* orb);
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (include/ORBextractor.h:63-83) and mnFeaturesPerLevel; each array has nlevels entries, any may be NULL */
+plf_status plf_orb_tables(const plf_orb* orb, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                          int32_t* features_per_level);
+/* upper bound on keypoints one frame can return (the reference may exceed nfeatures by a few per level) */
+int plf_orb_max_keypoints(const plf_orb* orb);
+/* ORBextractor::operator()(image, mask, keypoints, descriptors) -- src/ORBextractor.cc:1043-1105.
+ * host_kps/host_desc (cap x 28 B, cap x 32 B) receive *n_out entries.  An empty image
+ * (w<=0 || h<=0 || !host_img) returns PLF_OK with *n_out = 0, like the reference's silent return. */
+plf_status plf_orb_extract(plf_orb* orb, const uint8_t* host_img, int w, int h, size_t stride,
+                           plf_keypoint* host_kps, uint8_t* host_desc, int cap, int* n_out);
+/* Batched form: nframes images of identical size, frame f at host_imgs + f*frame_stride.
+ * Outputs for frame f start at host_kps + f*cap and host_desc + f*cap*32; n_out[f] entries valid.
+ * Host<->device copies are part of the call. */
+plf_status plf_orb_extract_batch(plf_orb* orb, const uint8_t* host_imgs, int nframes, int w, int h, size_t stride,
+                                 size_t frame_stride, plf_keypoint* host_kps, uint8_t* host_desc, int cap,
+                                 int32_t* n_out);
+/* Same, inputs and outputs resident in device memory (no copies; asynchronous on the context stream;
+ * dev_n_out is an int32[nframes] device array). */
+plf_status plf_orb_extract_batch_device(plf_orb* orb, const uint8_t* dev_imgs, int nframes, int w, int h,
+                                        size_t stride, size_t frame_stride, plf_keypoint* dev_kps,
+                                        uint8_t* dev_desc, int cap, int32_t* dev_n_out);
+/* mvImagePyramid[level] of frame `frame` of the last extract call (include/ORBextractor.h:85; read by
+ * Frame::ComputeStereoMatches, src/Frame.cc:967-1007).  Copies the level image (without the 19-px
+ * border, which nothing on the hot path reads) to host_dst; host_dst may be NULL to query the size. */
+plf_status plf_orb_pyramid_level(plf_orb* orb, int frame, int level, uint8_t* host_dst, size_t dst_stride,
+                                 int* w, int* h);
+/* stage-level access for parity tests: blurred level and raw FAST keys (x, y relative to the 16-px
+ * border origin, response, order key) of one frame/level of the last call */
+plf_status plf_orb_debug_blurred(plf_orb* orb, int frame, int level, uint8_t* host_dst, size_t dst_stride);
+plf_status plf_orb_debug_raw_keys(plf_orb* orb, int frame, int level, int32_t* xs, int32_t* ys, int32_t* resp,
+                                  int cap, int* n_out);
+/* ORBextractor::DistributeOctTree alone (src/ORBextractor.cc:539-763) on host-provided keys of one level:
+ * out_idx receives indices into xs/ys/resp in final list order */
+plf_status plf_orb_distribute_octree(plf_ctx* ctx, const int32_t* xs, const int32_t* ys, const int32_t* resp, int n,
+                                     int minX, int maxX, int minY, int maxY, int N, int32_t* out_idx, int cap,
+                                     int* n_out);
+
+/* ---- line extractor: replaces PL_SLAM::Lineextractor (LSD branch) with the vendored
+ * LSDDetectorC::detect + BinaryDescriptor::compute beneath it
+ * (include/Lineextractor.h:49-61, src/Lineextractor.cc:32-67, :112-212;
+ * Thirdparty/line_descriptor/src/LSDDetector_custom.cpp:218-324;
+ * Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp:524-687, :1026-1372) ---- */
+typedef struct {
+    int nfeatures;          /* Lineextractor.nFeatures */
+    int nlevels;            /* Lineextractor.nLevels (octaves, ratio 2) */
+    int refine;             /* must be 0 (LSD_REFINE_NONE): the only mode the shipped configs use */
+    double scale;           /* LSD scale (also the feature-split factor, Lineextractor.cc:56) */
+    double sigma_scale;
+    double quant;
+    double ang_th;
+    double log_eps;         /* unused with refine = 0 */
+    double density_th;      /* unused with refine = 0 */
+    int n_bins;
+    double min_line_length; /* LSDOptions.min_length */
+} plf_line_params;
+
+plf_status plf_line_create(plf_ctx* ctx, const plf_line_params* p, plf_line** out);
+void plf_line_destroy(plf_line* le);
+plf_status plf_line_tables(const plf_line* le, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                           int32_t* features_per_level);
+int plf_line_max_keylines(const plf_line* le);
+/* Lineextractor::ComputeLsdWithLbd(image, keyLines, keypoints, descriptors) -- src/Lineextractor.cc:112-212.
+ * host_mid receives the mid-point KeyPoints (pt, octave; other fields cv::KeyPoint() defaults). */
+plf_status plf_line_extract(plf_line* le, const uint8_t* host_img, int w, int h, size_t stride,
+                            plf_keyline* host_kl, plf_keypoint* host_mid, uint8_t* host_desc, int cap, int* n_out);
+plf_status plf_line_extract_batch(plf_line* le, const uint8_t* host_imgs, int nframes, int w, int h, size_t stride,
+                                  size_t frame_stride, plf_keyline* host_kl, plf_keypoint* host_mid,
+                                  uint8_t* host_desc, int cap, int32_t* n_out);
+plf_status plf_line_extract_batch_device(plf_line* le, const uint8_t* dev_imgs, int nframes, int w, int h,
+                                         size_t stride, size_t frame_stride, plf_keyline* dev_kl,
+                                         plf_keypoint* dev_mid, uint8_t* dev_desc, int cap, int32_t* dev_n_out);
+/* LSDDetectorC::detect(image, keylines, 2, nlevels, opts) alone (LSDDetector_custom.cpp:218-324) */
+plf_status plf_lsd_detect(plf_line* le, const uint8_t* host_img, int w, int h, size_t stride,
+                          plf_keyline* host_kl, int cap, int* n_out);
+/* BinaryDescriptor::compute(image, keylines, descriptors, returnFloatDescr) alone
+ * (binary_descriptor_custom.cpp:524-687); host_fdesc (n x 72 float) may be NULL */
+plf_status plf_lbd_compute(plf_line* le, const uint8_t* host_img, int w, int h, size_t stride,
+                           const plf_keyline* host_kl, int n, uint8_t* host_desc, float* host_fdesc);
+
+/* ---- matching: replaces ORBmatcher::DescriptorDistance / Linematcher::DescriptorDistance
+ * (src/ORBmatcher.cc:1656-1672, src/Linematcher.cc:50-66), cv::BFMatcher(NORM_HAMMING).knnMatch(k=2)
+ * as used by Linematcher::matchNNR (src/Linematcher.cc:520-541) and the mutual-consistency step of
+ * Linematcher::SearchByKNN / SearchForTriangulation (:454-471, :825-839).  Descriptors are n x 32 bytes. ---- */
+/* pairwise distances dist[i] = Hamming(a[i], b[i]) */
+plf_status plf_descriptor_distance(plf_ctx* ctx, const uint8_t* host_a, const uint8_t* host_b, int n, int32_t* host_dist);
+/* knnMatch(k=2): idx/dist are nq x 2; ascending distance, ties -> lowest train index; -1 where the
+ * train set has fewer than 2 rows.  train_index_base is added to every returned index (shards). */
+plf_status plf_hamming_knn2(plf_ctx* ctx, const uint8_t* host_q, int nq, const uint8_t* host_t, int64_t nt,
+                            int32_t* host_idx, int32_t* host_dist);
+plf_status plf_hamming_knn2_device(plf_ctx* ctx, const uint8_t* dev_q, int nq, const uint8_t* dev_t, int64_t nt,
+                                   int64_t train_index_base, int32_t* dev_idx, int32_t* dev_dist);
+/* merge nshards partial top-2 tables (each nq x 2, global indices) into one; exact same ordering rule.
+ * dev_idx_parts/dev_dist_parts are [nshards][nq][2] contiguous (e.g. an NCCL all-gather result). */
+plf_status plf_knn2_merge_device(plf_ctx* ctx, const int32_t* dev_idx_parts, const int32_t* dev_dist_parts,
+                                 int nshards, int nq, int32_t* dev_idx, int32_t* dev_dist);
+/* Linematcher::matchNNR: matches12[q] = train index if d0 < d1 * nnr (float compare) else -1.
+ * Fewer than 2 train rows is undefined behaviour in the reference; here: no match. */
+plf_status plf_match_nnr(plf_ctx* ctx, const uint8_t* host_q, int nq, const uint8_t* host_t, int64_t nt, float nnr,
+                         int32_t* host_matches12, int* nmatches);
+plf_status plf_nnr_from_knn2_device(plf_ctx* ctx, const int32_t* dev_idx, const int32_t* dev_dist, int nq, float nnr,
+                                    int32_t* dev_matches12, int32_t* dev_nmatches);
+/* both directions + mutual-consistency filter of SearchByKNN (:454-471): matches12[i1] = i2 kept only if
+ * matches21[i2] == i1.  (The reference indexes matches_21[-1] when i2 == -1; defined here as "no match".) */
+plf_status plf_match_nnr_mutual(plf_ctx* ctx, const uint8_t* host_d1, int n1, const uint8_t* host_d2, int n2,
+                                float nnr, int32_t* host_matches12, int* nmatches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLF_H */
