@@ -1,0 +1,585 @@
+// plf_orb_kernels.cuh -- device kernels of the ORB path.
+// Integer work is bit-exact by construction; the float pieces (fastAtan2, rBRIEF rotation) use IEEE
+// single ops without FMA (-fmad=false) and round-half-even conversions, like the oracle.
+#pragma once
+#include "plf_orb.cuh"
+
+__device__ const signed char d_orb_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+
+// ------------------------------------------------------------------------------------------------
+// ComputePyramid: cv::resize INTER_LINEAR 8U, level l from level l-1 (src/ORBextractor.cc:1120).
+// tab entries: .x = source offset, .y = coef0 | coef1 << 16 (11-bit fixed point).
+// block = (32, 8): each thread produces 4 adjacent pixels of one row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_resize_linear(const uint8_t* __restrict__ src, size_t srcFrameStride, int spitch, int sw, int sh,
+                uint8_t* __restrict__ dst, size_t dstFrameStride, int dpitch, int dw, int dh,
+                const int2* __restrict__ xtab, const int2* __restrict__ ytab)
+{
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x0 >= dw || y >= dh) return;
+    const uint8_t* s = src + (size_t)blockIdx.z * srcFrameStride;
+    uint8_t* d = dst + (size_t)blockIdx.z * dstFrameStride + (size_t)y * dpitch;
+    const int2 ty = ytab[y];
+    const int sy0 = ty.x, sy1 = min(sy0 + 1, sh - 1);
+    const int b0 = (short)(ty.y & 0xffff), b1 = (short)(ty.y >> 16);
+    const uint8_t* r0 = s + (size_t)sy0 * spitch;
+    const uint8_t* r1 = s + (size_t)sy1 * spitch;
+    unsigned out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int x = x0 + k;
+        if (x < dw) {
+            const int2 tx = xtab[x];
+            const int sx = tx.x, sx1 = min(sx + 1, sw - 1);
+            const int a0 = (short)(tx.y & 0xffff), a1 = (short)(tx.y >> 16);
+            int h0 = r0[sx] * a0 + r0[sx1] * a1;
+            int h1 = r1[sx] * a0 + r1[sx1] * a1;
+            int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            out |= (unsigned)(v & 0xff) << (8 * k);
+        }
+    }
+    if (x0 + 3 < dw) {
+        *(unsigned*)(d + x0) = out;  // dpitch and x0 are multiples of 4
+    } else {
+        for (int k = 0; k < 4 && x0 + k < dw; k++) d[x0 + k] = (uint8_t)(out >> (8 * k));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GaussianBlur 7x7 sigma 2, BORDER_REFLECT_101, Q8 kernel [18 34 48 56 48 34 18]
+// (src/ORBextractor.cc:1086).  One CTA = 128 x 32 output tile of one level of one frame.
+// ------------------------------------------------------------------------------------------------
+#define BLUR_TW 128
+#define BLUR_TH 32
+__global__ void __launch_bounds__(256)
+k_blur7(OrbGeom g, OrbPtrs p)
+{
+    __shared__ uint8_t tile[(BLUR_TH + 6) * (BLUR_TW + 8)];
+    __shared__ unsigned short hbuf[(BLUR_TH + 6) * BLUR_TW];
+    int tileId = blockIdx.x, l = 0;
+    while (l + 1 < g.nlevels && tileId >= g.lv[l + 1].blurTileBase) l++;
+    tileId -= g.lv[l].blurTileBase;
+    const OrbLevelGeom& L = g.lv[l];
+    const int tx0 = (tileId % L.blurTilesX) * BLUR_TW, ty0 = (tileId / L.blurTilesX) * BLUR_TH;
+    const uint8_t* src = p.lvl[l] + (size_t)blockIdx.y * p.frameStride[l];
+    const int spitch = p.pitch[l];
+    uint8_t* dst = p.blr[l] + (size_t)blockIdx.y * L.frameBytes;
+    const int tid = threadIdx.x;
+    const int TWP = BLUR_TW + 8;
+    for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
+        int ry = i / (BLUR_TW + 6), rx = i - ry * (BLUR_TW + 6);
+        int sy = plf_reflect101(ty0 + ry - 3, L.h), sx = plf_reflect101(tx0 + rx - 3, L.w);
+        tile[ry * TWP + rx] = src[(size_t)sy * spitch + sx];
+    }
+    __syncthreads();
+    for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
+        int ry = i / BLUR_TW, rx = i - ry * BLUR_TW;
+        const uint8_t* t = &tile[ry * TWP + rx];
+        unsigned v = 18u * (t[0] + t[6]) + 34u * (t[1] + t[5]) + 48u * (t[2] + t[4]) + 56u * t[3];
+        hbuf[i] = (unsigned short)v;
+    }
+    __syncthreads();
+    for (int i = tid; i < BLUR_TH * BLUR_TW; i += 256) {
+        int ry = i / BLUR_TW, rx = i - ry * BLUR_TW;
+        int x = tx0 + rx, y = ty0 + ry;
+        if (x < L.w && y < L.h) {
+            const unsigned short* hcol = &hbuf[ry * BLUR_TW + rx];
+            unsigned v = 18u * (hcol[0] + hcol[6 * BLUR_TW]) + 34u * (hcol[BLUR_TW] + hcol[5 * BLUR_TW]) +
+                         48u * (hcol[2 * BLUR_TW] + hcol[4 * BLUR_TW]) + 56u * hcol[3 * BLUR_TW] + 32768u;
+            dst[(size_t)y * L.pitch + x] = (uint8_t)(v >> 16);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-cell FAST-9/16 with threshold retry and per-cell NMS (src/ORBextractor.cc:789-829 over cv::FAST).
+// One CTA per 30-px cell.  Keys are appended to the (frame, level) list with one atomic per cell; their
+// order in the list is irrelevant because the octree breaks response ties with an explicit order key
+// (cell row, cell column, y, x) that restates the reference's push_back order.
+// ------------------------------------------------------------------------------------------------
+#define FAST_MAXC 72          // max cell window edge (wCell + 6); geometry setup checks this
+#define FAST_MAXKEYS 1024     // per cell after NMS (<= interior / 4)
+
+__device__ __forceinline__ int fast_best(const uint8_t* c, int pitch, int th)
+{
+    // returns max(A, B) if the pixel is a FAST-9 corner at threshold th, else 0
+    const int v = c[0];
+    int d[16];
+    d[0] = v - c[3 * pitch];      d[1] = v - c[3 * pitch + 1];  d[2] = v - c[2 * pitch + 2];  d[3] = v - c[pitch + 3];
+    d[4] = v - c[3];              d[5] = v - c[-pitch + 3];     d[6] = v - c[-2 * pitch + 2]; d[7] = v - c[-3 * pitch + 1];
+    d[8] = v - c[-3 * pitch];     d[9] = v - c[-3 * pitch - 1]; d[10] = v - c[-2 * pitch - 2]; d[11] = v - c[-pitch - 3];
+    d[12] = v - c[-3];            d[13] = v - c[pitch - 3];     d[14] = v - c[2 * pitch - 2]; d[15] = v - c[3 * pitch - 1];
+    unsigned hi = 0, lo = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        hi |= (unsigned)(d[k] > th) << k;
+        lo |= (unsigned)(d[k] < -th) << k;
+    }
+    hi |= hi << 16; lo |= lo << 16;
+    unsigned h = hi & (hi >> 1); h &= h >> 2; h &= h >> 4; h &= hi >> 8;  // runs of 9
+    unsigned w = lo & (lo >> 1); w &= w >> 2; w &= w >> 4; w &= lo >> 8;
+    if (!(h | w)) return 0;
+    int A = -1000, B = -1000;
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        int mn = d[s], mx = d[s];
+#pragma unroll
+        for (int k = 1; k < 9; k++) {
+            int t = d[(s + k) & 15];
+            mn = min(mn, t);
+            mx = max(mx, t);
+        }
+        A = max(A, mn);
+        B = max(B, -mx);
+    }
+    return max(A, B);
+}
+
+__global__ void __launch_bounds__(256)
+k_fast_cells(OrbGeom g, OrbPtrs p)
+{
+    __shared__ uint8_t tile[FAST_MAXC * FAST_MAXC];
+    __shared__ uint8_t best[FAST_MAXC * FAST_MAXC];
+    __shared__ unsigned keys[FAST_MAXKEYS];
+    __shared__ int s_count, s_base;
+    int cell = blockIdx.x, l = 0;
+    while (l + 1 < g.nlevels && cell >= g.lv[l + 1].cellBase) l++;
+    cell -= g.lv[l].cellBase;
+    const OrbLevelGeom& L = g.lv[l];
+    const int ci = cell / L.nCols, cj = cell - ci * L.nCols;
+    const int maxBorderX = L.w - ORB_MINB, maxBorderY = L.h - ORB_MINB;
+    const int iniY = ORB_MINB + ci * L.hCell, iniX = ORB_MINB + cj * L.wCell;
+    if (iniY >= maxBorderY - 3 || iniX >= maxBorderX - 6) return;   // skip rules, :794, :803
+    const int maxY = min(iniY + L.hCell + 6, maxBorderY), maxX = min(iniX + L.wCell + 6, maxBorderX);
+    const int cw = maxX - iniX, ch = maxY - iniY;
+    if (cw < 7 || ch < 7) return;
+    const int tid = threadIdx.x;
+    const uint8_t* src = p.lvl[l] + (size_t)blockIdx.y * p.frameStride[l] + (size_t)iniY * p.pitch[l] + iniX;
+    const int spitch = p.pitch[l];
+    for (int i = tid; i < cw * ch; i += 256) {
+        int ry = i / cw, rx = i - ry * cw;
+        tile[ry * FAST_MAXC + rx] = src[(size_t)ry * spitch + rx];
+        best[ry * FAST_MAXC + rx] = 0;
+    }
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    const int iw = cw - 6, ih = ch - 6;
+    for (int i = tid; i < iw * ih; i += 256) {
+        int ry = i / iw + 3, rx = i - (ry - 3) * iw + 3;
+        int b = fast_best(&tile[ry * FAST_MAXC + rx], FAST_MAXC, g.minTh);
+        best[ry * FAST_MAXC + rx] = (uint8_t)b;   // b <= 255
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 2; pass++) {
+        const int th = pass == 0 ? g.iniTh : g.minTh;
+        for (int i = tid; i < iw * ih; i += 256) {
+            int ry = i / iw + 3, rx = i - (ry - 3) * iw + 3;
+            const uint8_t* b = &best[ry * FAST_MAXC + rx];
+            int s = b[0];
+            if (s <= th) continue;
+            // strict maximum over the 8 neighbours; scores below the threshold (and the non-interior ring,
+            // which stays 0) count as 0, and score = best - 1 is monotone so best values compare the same
+#define NB(o) ((int)b[o] > th ? (int)b[o] : 0)
+            if (s > NB(-1) && s > NB(1) && s > NB(-FAST_MAXC - 1) && s > NB(-FAST_MAXC) && s > NB(-FAST_MAXC + 1) &&
+                s > NB(FAST_MAXC - 1) && s > NB(FAST_MAXC) && s > NB(FAST_MAXC + 1)) {
+                int slot = atomicAdd(&s_count, 1);
+                int kx = rx + cj * L.wCell, ky = ry + ci * L.hCell;   // relative to minBorder, :822-823
+                if (slot < FAST_MAXKEYS) keys[slot] = (unsigned)kx | ((unsigned)ky << 12) | ((unsigned)(s - 1) << 24);
+            }
+#undef NB
+        }
+        __syncthreads();
+        const int found = s_count;
+        __syncthreads();          // every thread has read the count before the retry pass can change it
+        if (found > 0) break;
+    }
+    const int n = min(s_count, FAST_MAXKEYS);
+    if (n == 0) return;
+    int* cnt = p.rawcount + (size_t)blockIdx.y * g.nlevels + l;
+    if (tid == 0) s_base = atomicAdd(cnt, n);
+    __syncthreads();
+    unsigned* out = p.rawkeys + (size_t)blockIdx.y * g.rawPerFrame + L.rawOff;
+    for (int i = tid; i < n; i += 256) {
+        int o = s_base + i;
+        if (o < L.rawcap) out[o] = keys[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DistributeOctTree (src/ORBextractor.cc:539-763), one CTA per (level, frame).
+//
+// The reference walks a std::list; this kernel keeps the list as an array and rebuilds it once per pass.
+// A pass (full or "refinement") is: pick the nodes to divide and their processing order, count the keys
+// of every child, find where the pass stops (refinement breaks as soon as size >= N), then emit
+// [children of the last processed parent n4..n1, ..., children of the first processed parent n4..n1,
+//  old list without the divided parents] -- exactly the push_front / erase result.
+// Equal-size ties in the refinement sort are broken by creation order, later-created first (the oracle's
+// documented stand-in for the reference's heap-address order).
+// ------------------------------------------------------------------------------------------------
+#define OCT_T 256
+struct OctSmem {
+    int cap;
+    short* nb[2];      // bounds: 4 shorts per node (ulx, uly, brx, bry)
+    int* ncount[2];
+    int* ncid[2];
+    int* ord;          // list pos -> processing order o (or -1)
+    int* proc;         // o -> list pos
+    int* cc;           // 4 per candidate: child key counts
+    int* cpos;         // 4 per candidate: child new position (or -1)
+    int* spos;         // list pos -> survivor new position
+    int* tmp;          // scan buffer, 4*cap
+    unsigned long long* best;
+    int* partial;      // OCT_T + 1
+};
+
+__device__ __forceinline__ void oct_carve(unsigned char* base, int cap, OctSmem& s)
+{
+    size_t o = 0;
+    s.cap = cap;
+    s.best = (unsigned long long*)(base + o); o += sizeof(unsigned long long) * cap;
+    for (int b = 0; b < 2; b++) { s.ncount[b] = (int*)(base + o); o += sizeof(int) * cap; }
+    for (int b = 0; b < 2; b++) { s.ncid[b] = (int*)(base + o); o += sizeof(int) * cap; }
+    s.ord = (int*)(base + o); o += sizeof(int) * cap;
+    s.proc = (int*)(base + o); o += sizeof(int) * cap;
+    s.spos = (int*)(base + o); o += sizeof(int) * cap;
+    s.cc = (int*)(base + o); o += sizeof(int) * 4 * cap;
+    s.cpos = (int*)(base + o); o += sizeof(int) * 4 * cap;
+    s.tmp = (int*)(base + o); o += sizeof(int) * 4 * cap;
+    s.partial = (int*)(base + o); o += sizeof(int) * (OCT_T + 1);
+    for (int b = 0; b < 2; b++) { s.nb[b] = (short*)(base + o); o += sizeof(short) * 4 * cap; }
+}
+static inline size_t oct_smem_bytes(int cap)
+{
+    return sizeof(unsigned long long) * cap + sizeof(int) * cap * (2 + 2 + 3 + 12) + sizeof(int) * (OCT_T + 1) +
+           sizeof(short) * 8 * cap + 16;
+}
+
+// exclusive scan of data[0..n) in place; returns the total. All threads must call.
+__device__ __forceinline__ int oct_exscan(int* data, int n, int* partial)
+{
+    const int tid = threadIdx.x;
+    const int per = (n + OCT_T - 1) / OCT_T;
+    const int b = tid * per, e = min(b + per, n);
+    int sum = 0;
+    for (int i = b; i < e; i++) sum += data[i];
+    partial[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int i = 0; i < OCT_T; i++) { int v = partial[i]; partial[i] = acc; acc += v; }
+        partial[OCT_T] = acc;
+    }
+    __syncthreads();
+    int acc = partial[tid];
+    for (int i = b; i < e; i++) { int v = data[i]; data[i] = acc; acc += v; }
+    int total = partial[OCT_T];
+    __syncthreads();
+    return total;
+}
+
+__device__ __forceinline__ int oct_quadrant(unsigned key, const short* nb)
+{
+    const int x = key & 0xfff, y = (key >> 12) & 0xfff;
+    const int mx = nb[0] + ((nb[2] - nb[0] + 1) >> 1);   // UL.x + ceil((UR.x-UL.x)/2)
+    const int my = nb[1] + ((nb[3] - nb[1] + 1) >> 1);
+    return (x < mx ? 0 : 1) + (y < my ? 0 : 2);
+}
+
+__device__ void oct_distribute(const unsigned* __restrict__ keys, int K, unsigned short* __restrict__ knode,
+                               int W, int H, int N, int wCell, int hCell, int* __restrict__ out, int outcap,
+                               int* __restrict__ outcount, unsigned char* smem, int cap)
+{
+    __shared__ int s_n, s_mode, s_finish, s_ostar, s_cidbase;
+    OctSmem S;
+    oct_carve(smem, cap, S);
+    const int tid = threadIdx.x;
+    if (K <= 0) {
+        if (tid == 0) *outcount = 0;
+        return;
+    }
+    int nIni = (int)roundf((float)W / (float)H);
+    if (nIni < 1) nIni = 1;
+    if (nIni > cap) nIni = cap;
+    const float hX = (float)W / (float)nIni;
+    int cur = 0;
+    for (int i = tid; i < nIni; i += OCT_T) {
+        S.nb[0][4 * i + 0] = (short)(int)(hX * (float)i);
+        S.nb[0][4 * i + 1] = 0;
+        S.nb[0][4 * i + 2] = (short)(int)(hX * (float)(i + 1));
+        S.nb[0][4 * i + 3] = (short)H;
+        S.ncount[0][i] = 0;
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += OCT_T) {
+        int i = (int)((float)(keys[k] & 0xfff) / hX);
+        if (i >= nIni) i = nIni - 1;
+        atomicAdd(&S.ncount[0][i], 1);
+        knode[k] = (unsigned short)i;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int m = 0;
+        for (int i = 0; i < nIni; i++) {
+            if (S.ncount[0][i] > 0) {
+                S.spos[i] = m;
+                for (int c = 0; c < 4; c++) S.nb[0][4 * m + c] = S.nb[0][4 * i + c];
+                S.ncount[0][m] = S.ncount[0][i];
+                S.ncid[0][m] = i;
+                m++;
+            } else S.spos[i] = -1;
+        }
+        s_n = m; s_mode = 0; s_finish = 0; s_cidbase = nIni;
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += OCT_T) knode[k] = (unsigned short)S.spos[knode[k]];
+    __syncthreads();
+
+    while (true) {
+        const int n = s_n, mode = s_mode;
+        const int* cnt = S.ncount[cur];
+        const int* cid = S.ncid[cur];
+        const short* nb = S.nb[cur];
+        // 1. candidates and processing order
+        for (int p = tid; p < n; p += OCT_T) S.tmp[p] = cnt[p] > 1 ? 1 : 0;
+        __syncthreads();
+        int E;
+        if (mode == 0) {
+            E = oct_exscan(S.tmp, n, S.partial);
+            for (int p = tid; p < n; p += OCT_T) S.ord[p] = cnt[p] > 1 ? S.tmp[p] : -1;
+        } else {
+            for (int p = tid; p < n; p += OCT_T) {
+                int o = -1;
+                if (cnt[p] > 1) {
+                    o = 0;
+                    const int c0 = cnt[p], i0 = cid[p];
+                    for (int r = 0; r < n; r++) {
+                        int c1 = cnt[r];
+                        if (c1 > 1 && (c1 > c0 || (c1 == c0 && cid[r] > i0))) o++;
+                    }
+                }
+                S.ord[p] = o;
+            }
+            __syncthreads();
+            E = oct_exscan(S.tmp, n, S.partial);
+        }
+        __syncthreads();
+        if (E == 0) break;   // nothing to divide: size == prevSize -> finish (uniform)
+        for (int p = tid; p < n; p += OCT_T) if (S.ord[p] >= 0) S.proc[S.ord[p]] = p;
+        for (int j = tid; j < 4 * E; j += OCT_T) S.cc[j] = 0;
+        __syncthreads();
+        // 2. child key counts
+        for (int k = tid; k < K; k += OCT_T) {
+            int p = knode[k], o = S.ord[p];
+            if (o >= 0) atomicAdd(&S.cc[4 * o + oct_quadrant(keys[k], &nb[4 * p])], 1);
+        }
+        __syncthreads();
+        // 3. where the pass stops
+        if (mode == 0) {
+            if (tid == 0) s_ostar = E - 1;
+        } else {
+            if (tid == 0) {
+                int sz = n, os = E - 1;
+                for (int o = 0; o < E; o++) {
+                    int nc = (S.cc[4 * o] > 0) + (S.cc[4 * o + 1] > 0) + (S.cc[4 * o + 2] > 0) + (S.cc[4 * o + 3] > 0);
+                    sz += nc - 1;
+                    if (sz >= N) { os = o; break; }
+                }
+                s_ostar = os;
+            }
+        }
+        __syncthreads();
+        const int ostar = s_ostar, J = 4 * (ostar + 1);
+        // 4. child positions (o descending, q descending)
+        for (int j = tid; j < J; j += OCT_T) S.tmp[j] = S.cc[j] > 0 ? 1 : 0;
+        __syncthreads();
+        const int C = oct_exscan(S.tmp, J, S.partial);
+        for (int j = tid; j < J; j += OCT_T) S.cpos[j] = S.cc[j] > 0 ? C - 1 - S.tmp[j] : -1;
+        __syncthreads();
+        // 5. survivors keep their relative order behind the new children
+        for (int p = tid; p < n; p += OCT_T) S.tmp[p] = (S.ord[p] >= 0 && S.ord[p] <= ostar) ? 0 : 1;
+        __syncthreads();
+        const int NS = oct_exscan(S.tmp, n, S.partial);
+        for (int p = tid; p < n; p += OCT_T) S.spos[p] = (S.ord[p] >= 0 && S.ord[p] <= ostar) ? -1 : C + S.tmp[p];
+        __syncthreads();
+        const int nn = C + NS;
+        if (nn > cap) {   // cannot happen for a consistent geometry; fail loudly through the count
+            if (tid == 0) *outcount = -1;
+            return;
+        }
+        // 6. build the new list
+        const int nxt = cur ^ 1;
+        const int cidbase = s_cidbase;
+        for (int j = tid; j < J; j += OCT_T) {
+            int np = S.cpos[j];
+            if (np < 0) continue;
+            const int pp = S.proc[j >> 2], q = j & 3;
+            const short* b = &nb[4 * pp];
+            const short mx = (short)(b[0] + ((b[2] - b[0] + 1) >> 1)), my = (short)(b[1] + ((b[3] - b[1] + 1) >> 1));
+            short* d = &S.nb[nxt][4 * np];
+            d[0] = (q & 1) ? mx : b[0];
+            d[1] = (q & 2) ? my : b[1];
+            d[2] = (q & 1) ? b[2] : mx;
+            d[3] = (q & 2) ? b[3] : my;
+            S.ncount[nxt][np] = S.cc[j];
+            S.ncid[nxt][np] = cidbase + j;
+        }
+        for (int p = tid; p < n; p += OCT_T) {
+            int np = S.spos[p];
+            if (np < 0) continue;
+            for (int c = 0; c < 4; c++) S.nb[nxt][4 * np + c] = nb[4 * p + c];
+            S.ncount[nxt][np] = cnt[p];
+            S.ncid[nxt][np] = cid[p];
+        }
+        // 7. move the keys
+        for (int k = tid; k < K; k += OCT_T) {
+            int p = knode[k], o = S.ord[p];
+            int np = (o >= 0 && o <= ostar) ? S.cpos[4 * o + oct_quadrant(keys[k], &nb[4 * p])] : S.spos[p];
+            knode[k] = (unsigned short)np;
+        }
+        __syncthreads();
+        // 8. loop control (:669-673, :734-735)
+        if (tid == 0) {
+            int nexp = 0;
+            for (int i = 0; i < nn; i++) nexp += S.ncount[nxt][i] > 1;
+            s_cidbase = cidbase + J;
+            s_n = nn;
+            if (nn >= N || nn == n) s_finish = 1;
+            else if (mode == 0 && nn + nexp * 3 > N) s_mode = 1;
+        }
+        cur = nxt;
+        __syncthreads();
+        if (s_finish) break;
+    }
+    // best key per node: maximal response, first in the reference's push_back order
+    const int n = s_n;
+    for (int p = tid; p < n; p += OCT_T) S.best[p] = 0ull;
+    __syncthreads();
+    for (int k = tid; k < K; k += OCT_T) {
+        unsigned key = keys[k];
+        int x = key & 0xfff, y = (key >> 12) & 0xfff, r = key >> 24;
+        unsigned long long prio = ((unsigned long long)r << 44) | ((unsigned long long)(1023 - (y - 3) / hCell) << 34) |
+                                  ((unsigned long long)(1023 - (x - 3) / wCell) << 24) |
+                                  ((unsigned long long)(4095 - y) << 12) | (unsigned long long)(4095 - x);
+        atomicMax(&S.best[knode[k]], prio);
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += OCT_T) {
+        unsigned key = keys[k];
+        int x = key & 0xfff, y = (key >> 12) & 0xfff, r = key >> 24;
+        unsigned long long prio = ((unsigned long long)r << 44) | ((unsigned long long)(1023 - (y - 3) / hCell) << 34) |
+                                  ((unsigned long long)(1023 - (x - 3) / wCell) << 24) |
+                                  ((unsigned long long)(4095 - y) << 12) | (unsigned long long)(4095 - x);
+        int p = knode[k];
+        if (S.best[p] == prio && p < outcap) out[p] = k;
+    }
+    if (tid == 0) *outcount = n <= outcap ? n : -1;
+}
+
+__global__ void __launch_bounds__(OCT_T)
+k_octree(OrbGeom g, OrbPtrs p, int maxcap)
+{
+    PLF_DYN_SMEM(smem);
+    const int l = blockIdx.x, f = blockIdx.y;
+    const OrbLevelGeom& L = g.lv[l];
+    int K = p.rawcount[(size_t)f * g.nlevels + l];
+    int* outcount = p.keptcount + (size_t)f * g.nlevels + l;
+    if (K > L.rawcap) {   // raw key list overflowed: report instead of truncating silently
+        if (threadIdx.x == 0) { *outcount = -1; }
+        return;
+    }
+    oct_distribute(p.rawkeys + (size_t)f * g.rawPerFrame + L.rawOff, K, p.knode + (size_t)f * g.rawPerFrame + L.rawOff,
+                   L.w - 2 * ORB_MINB, L.h - 2 * ORB_MINB, L.nfeat, L.wCell, L.hCell,
+                   p.kept + (size_t)f * g.keptPerFrame + L.keptOff, L.keptcap, outcount, smem, L.nodecap < maxcap ? L.nodecap : maxcap);
+}
+
+// standalone entry (plf_orb_distribute_octree): keys given explicitly
+__global__ void __launch_bounds__(OCT_T)
+k_octree_single(const unsigned* keys, int K, unsigned short* knode, int W, int H, int N, int wCell, int hCell,
+                int* out, int outcap, int* outcount, int cap)
+{
+    PLF_DYN_SMEM(smem);
+    oct_distribute(keys, K, knode, W, H, N, wCell, hCell, out, outcap, outcount, smem, cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// IC_Angle (:77-104) + computeOrbDescriptor (:107-147) + keypoint assembly (:837-847, :1095-1101).
+// One warp per retained keypoint; output position = level offset + list position (levels concatenated).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_describe(OrbGeom g, OrbPtrs p, plf_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int cap,
+           int* __restrict__ n_out)
+{
+    const int f = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int* kc = p.keptcount + (size_t)f * g.nlevels;
+    int total = 0, l = -1, pos = 0;
+    bool bad = false;
+    for (int i = 0; i < g.nlevels; i++) {
+        int c = kc[i];
+        if (c < 0) { bad = true; c = 0; }
+        if (l < 0 && wid < total + c) { l = i; pos = wid - total; }
+        total += c;
+    }
+    if (wid == 0 && lane == 0) n_out[f] = bad ? -1 : (total <= cap ? total : -2);
+    if (bad || l < 0 || wid >= cap) return;
+    const OrbLevelGeom& L = g.lv[l];
+    const int kidx = p.kept[(size_t)f * g.keptPerFrame + L.keptOff + pos];
+    const unsigned key = p.rawkeys[(size_t)f * g.rawPerFrame + L.rawOff + kidx];
+    const int X = (int)(key & 0xfff) + ORB_MINB, Y = (int)((key >> 12) & 0xfff) + ORB_MINB;
+    const int resp = key >> 24;
+    // orientation on the un-blurred level
+    const uint8_t* img = p.lvl[l] + (size_t)f * p.frameStride[l];
+    const int pitch = p.pitch[l];
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int v = lane - ORB_HALF_PATCH;
+        const int d = g.umax[v < 0 ? -v : v];
+        const uint8_t* row = img + (size_t)(Y + v) * pitch + X;
+        int s = 0;
+        for (int u = -d; u <= d; u++) {
+            int val = row[u];
+            s += val;
+            m10 += u * val;
+        }
+        m01 = v * s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = plf_fast_atan2((float)m01, (float)m10);
+    // steered BRIEF on the blurred level; lane i produces descriptor byte i
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    const float ang = angle * factorPI;
+    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+    const uint8_t* center = p.blr[l] + (size_t)f * L.frameBytes + (size_t)Y * L.pitch + X;
+    const signed char* pat = d_orb_pattern + lane * 32;
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1], x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
+        float r0 = x0 * b, r1 = y0 * a, r2 = x0 * a, r3 = y0 * b;
+        int t0 = center[__float2int_rn(r0 + r1) * L.pitch + __float2int_rn(r2 - r3)];
+        r0 = x1 * b; r1 = y1 * a; r2 = x1 * a; r3 = y1 * b;
+        int t1 = center[__float2int_rn(r0 + r1) * L.pitch + __float2int_rn(r2 - r3)];
+        val |= (t0 < t1) << k;
+    }
+    desc[((size_t)f * cap + wid) * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+        plf_keypoint kp;
+        kp.x = (float)X; kp.y = (float)Y;
+        if (l != 0) { kp.x = kp.x * L.scale; kp.y = kp.y * L.scale; }
+        kp.size = (float)L.sizeval;
+        kp.angle = angle;
+        kp.response = (float)resp;
+        kp.octave = l;
+        kp.class_id = -1;
+        kps[(size_t)f * cap + wid] = kp;
+    }
+}

@@ -1,0 +1,54 @@
+"""CPU: the C-ABI library loads and exports every symbol include/plf.h declares (no compute calls)."""
+import os
+import re
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "plf.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(plf_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported():
+    import ctypes
+    import __graft_entry__ as g
+    lib = g.build()
+    L = ctypes.CDLL(lib)
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_python_mirror_declares_all_symbols():
+    import spl_slam_b200 as S
+    L = S.load()
+    assert not L._plf_missing
+    assert set(declared_symbols()) == set(L._plf_symbols)
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device the product path must fail loudly, not fall back."""
+    import spl_slam_b200 as S
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(S.PlfError):
+        S.Context(0)
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "spl_slam_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle", "").replace("oracle's", "").replace("like the oracle", "") \
+                    or f.endswith((".cu", ".cuh")), f
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f

@@ -1,0 +1,93 @@
+"""CPU: the product kernels, compiled for the CPU with the TEST-ONLY CUDA emulation (tests/emu), against the
+oracle on small inputs.  This exercises the same kernel and host-driver source the GPU runs (logic, not speed)."""
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def S():
+    import spl_slam_b200 as S
+    return S
+
+
+def test_emu_matching(S, oracle, emu_lib):
+    ctx = S.Context(0, emu_lib)
+    m = S.Linematcher(0.75, ctx=ctx)
+    rng = np.random.default_rng(1)
+    for (nq, nt, hi) in [(300, 500, 256), (260, 1025, 3), (5, 1, 256), (3, 0, 256)]:
+        q = rng.integers(0, hi, (nq, 32), dtype=np.uint8)
+        t = rng.integers(0, hi, (nt, 32), dtype=np.uint8)
+        i, d = m.knnMatch2(q, t)
+        oi, od = oracle.knn2(q, t)
+        assert np.array_equal(i, oi) and np.array_equal(d, od)
+        mm, n = m.matchNNR(q, t)
+        om, on = oracle.match_nnr(q, t, 0.75)
+        assert np.array_equal(mm, om) and n == on
+        mu, nu = m.matchNNRMutual(q, t)
+        om21, _ = oracle.match_nnr(t, q, 0.75) if nt else (np.zeros(0, np.int32), 0)
+        ref = om.copy()
+        for a in range(nq):
+            if ref[a] >= 0 and om21[ref[a]] != a:
+                ref[a] = -1
+        assert np.array_equal(mu, ref) and nu == int((ref >= 0).sum())
+    assert m.DescriptorDistance(q[0], q[1]) == oracle.descriptor_distance(q[0], q[1])
+
+
+@pytest.mark.parametrize("w,h,nf,nl,seed", [(160, 120, 100, 3, 0), (320, 240, 300, 5, 1)])
+def test_emu_orb(S, oracle, emu_lib, w, h, nf, nl, seed):
+    ctx = S.Context(0, emu_lib)
+    ex = S.ORBextractor(nf, 1.2, nl, 20, 7, ctx=ctx)
+    ox = oracle.ORBextractor(nf, 1.2, nl, 20, 7)
+    assert list(ex.features_per_level()) == ox.features_per_level()
+    assert np.array_equal(ex.GetScaleFactors(), np.array(ox.scale_factors(), np.float32))
+    img = oracle.synth_image(w, h, seed)
+    k, d = ex(img)
+    ok, od = ox(img)
+    for l in range(nl):
+        assert np.array_equal(ex.pyramid_level(l), ox.level_image(l))
+        if ox.level_blurred(l) is not None:
+            assert np.array_equal(ex.debug_blurred(l), ox.level_blurred(l))
+        xs, ys, rr = ex.debug_raw_keys(l)
+        oxs, oys, orr = ox.level_raw(l)
+        assert sorted(zip(xs.tolist(), ys.tolist(), rr.tolist())) == sorted(zip(oxs.tolist(), oys.tolist(), orr.tolist()))
+    assert len(k) == len(ok) and np.array_equal(k.view(np.uint8), ok.view(np.uint8))
+    assert np.array_equal(d, od)
+
+
+def test_emu_orb_batch_and_empty(S, oracle, emu_lib):
+    ctx = S.Context(0, emu_lib)
+    ex = S.ORBextractor(100, 1.2, 3, 20, 7, ctx=ctx)
+    ox = oracle.ORBextractor(100, 1.2, 3, 20, 7)
+    imgs = np.stack([oracle.synth_image(160, 120, s) for s in (3, 4)])
+    ks, ds = ex.extract_batch(imgs)
+    for b in range(2):
+        ok, od = ox(imgs[b])
+        assert np.array_equal(ks[b].view(np.uint8), ok.view(np.uint8)) and np.array_equal(ds[b], od)
+    k, d = ex(np.zeros((0, 0), np.uint8))       # empty image: silent return
+    assert len(k) == 0 and d.shape == (0, 32)
+    flat = np.full((120, 160), 128, np.uint8)   # no corners at all
+    k, d = ex(flat)
+    assert len(k) == 0
+    with pytest.raises(AssertionError):
+        ex(np.zeros((10, 10, 3), np.uint8))      # the reference asserts CV_8UC1
+
+
+def test_emu_octree_standalone(S, oracle, emu_lib):
+    ctx = S.Context(0, emu_lib)
+    rng = np.random.default_rng(9)
+    for (W, H, n, N) in [(608, 448, 900, 217), (1209, 344, 1500, 434), (300, 200, 50, 60), (300, 200, 5, 0)]:
+        pts = set()
+        while len(pts) < n:
+            pts.add((int(rng.integers(3, W - 3)), int(rng.integers(3, H - 3))))
+        pts = sorted(pts, key=lambda p: (p[1], p[0]))
+        xs = np.array([p[0] for p in pts], np.int32)
+        ys = np.array([p[1] for p in pts], np.int32)
+        rr = rng.integers(7, 40, n).astype(np.int32)   # many response ties
+        # the oracle takes keys in the reference's push_back order (cell-major); reorder accordingly
+        nC, nR = int(np.float32(W) / np.float32(30)), int(np.float32(H) / np.float32(30))
+        wC, hC = int(np.ceil(np.float32(W) / nC)), int(np.ceil(np.float32(H) / nR))
+        order = sorted(range(n), key=lambda i: ((ys[i] - 3) // hC, (xs[i] - 3) // wC, ys[i], xs[i]))
+        xo, yo, ro = xs[order], ys[order], rr[order]
+        ref = oracle.distribute_octree(xo, yo, ro, 16, 16 + W, 16, 16 + H, N)
+        got = S.distribute_octree(ctx, xo, yo, ro, 16, 16 + W, 16, 16 + H, N)
+        assert np.array_equal(ref, got), (W, H, n, N)
