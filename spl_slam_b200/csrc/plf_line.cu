@@ -1,22 +1,99 @@
-// plf_line.cu -- host driver of the line path (LSD + LBD). (skeleton; kernels follow)
-#include "plf_common.cuh"
+// plf_line.cu -- host driver of the line path: replaces PL_SLAM::Lineextractor (LSD branch,
+// src/Lineextractor.cc:32-67, :112-212) with LSDDetectorC::detect (LSDDetector_custom.cpp:56-73, :218-324)
+// and BinaryDescriptor::compute (binary_descriptor_custom.cpp:350-398, :524-687, :1026-1372) beneath it.
+#include "plf_line_kernels.cuh"
 #include <math.h>
+#include <vector>
+#include <algorithm>
+#ifndef PLF_EMU
+#include <cub/device/device_radix_sort.cuh>   // library radix sort (a plain sort, like cuBLAS for a plain GEMM)
+#endif
+
+#define LINE_MAX_OCT 2
+#define LINE_DETCAP 8192       // detected lines per (frame, octave) before the response quota
+#define LINE_REGCAP_PER_FRAME 16384
 
 struct plf_line {
     plf_ctx* ctx;
     plf_line_params prm;
     float scale[16], inv_scale[16], sigma2[16], inv_sigma2[16];
     int per_level[16];
+    // LSD constants
+    double prec, rho;
+    GaussQ8 lsd_gauss;      // pre-blur of cv::LineSegmentDetector when SCALE != 1
+    GaussQ8 lbd_gauss;      // 5x5 sigma 1 (binary_descriptor_custom.cpp:358)
+    LbdCoefs lbd_coefs;
+    // workspace
+    int ws_w, ws_h, ws_frames;
+    int ow[LINE_MAX_OCT], oh[LINE_MAX_OCT], sw[LINE_MAX_OCT], sh[LINE_MAX_OCT], min_reg[LINE_MAX_OCT];
+    uint8_t* d_base;
+    uint8_t *d_oct[LINE_MAX_OCT], *d_tmp, *d_scaled;       // images (pitch == width)
+    uint8_t *d_lbdimg[LINE_MAX_OCT];
+    short *d_dx[LINE_MAX_OCT], *d_dy[LINE_MAX_OCT];
+    int *d_q, *d_label, *d_regpts, *d_comp, *d_lineidx, *d_lineidx2, *d_cnt, *d_detcount;
+    float* d_fa;
+    float2* d_cs;
+    unsigned long long *d_keys, *d_keys2, *d_linekey, *d_linekey2;
+    LsdRegion* d_regions;
+    float4* d_lines;
+    plf_keyline* d_det;
+    int2* d_tabs;
+    const int2 *xtab[LINE_MAX_OCT], *ytab[LINE_MAX_OCT];
+    void* d_cubtmp;
+    size_t cubtmp_bytes;
+    size_t keycap;
+    int regcap;
+    // output staging for host entry points
+    plf_keyline* d_okl;
+    plf_keypoint* d_omid;
+    uint8_t* d_odesc;
+    float* d_ofdesc;
+    int* d_onout;
+    int out_frames, out_cap;
 };
+
+// d_cnt layout (ints): [0]=nkeys [1]=ncomp [2]=next [3]=nregions [4]=sticky overflow flag [8..8+frames) = maxq
+enum { CNT_NKEYS = 0, CNT_NCOMP = 1, CNT_NEXT = 2, CNT_NREG = 3, CNT_ERR = 4, CNT_MAXQ = 8 };
+
+static int gauss_kernel_q8(int ksize, double sigma, int* q)
+{
+    if (ksize < 1 || !(ksize & 1) || ksize > 15) return -1;
+    int n2 = ksize / 2;
+    double w[16];
+    if (sigma <= 0) sigma = ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8;
+    double scale2x = -0.125 / (sigma * sigma);
+    double sum = 0;
+    for (int i = 0, x = 1 - ksize; i < n2; i++, x += 2) {
+        double t = exp((double)(x * x) * scale2x);
+        w[i] = t;
+        sum += t;
+    }
+    sum = sum * 2 + 1;
+    sum = 1.0 / sum;
+    double err = 0;
+    long tot = 0;
+    for (int i = 0; i < n2; i++) {
+        double v = w[i] * sum * 256.0 + err;
+        long v0 = lrint(v);
+        err = v - (double)v0;
+        q[i] = (int)v0;
+        q[ksize - 1 - i] = (int)v0;
+        tot += v0;
+    }
+    q[n2] = (int)(256 - 2 * tot);
+    return 0;
+}
 
 extern "C" plf_status plf_line_create(plf_ctx* ctx, const plf_line_params* p, plf_line** out)
 {
     if (!ctx || !p || !out) return PLF_ERR_INVALID;
-    if (p->nlevels < 1 || p->nlevels > 2 || p->nfeatures < 1 || p->refine != 0 || !(p->scale > 0) || p->n_bins < 2 || p->n_bins > 65536)
-        return plf_fail(ctx, PLF_ERR_INVALID, "plf_line_create: unsupported parameters (refine must be 0, nlevels 1..2)");
+    if (p->nlevels < 1 || p->nlevels > LINE_MAX_OCT || p->nfeatures < 1 || p->refine != 0 || !(p->scale > 0) ||
+        p->n_bins < 2 || p->n_bins > 4096 || !(p->ang_th > 0) || !(p->ang_th < 180) || !(p->quant >= 0))
+        return plf_fail(ctx, PLF_ERR_INVALID, "plf_line_create: unsupported parameters (refine must be 0, nlevels 1..2, n_bins <= 4096)");
     plf_line* o = (plf_line*)calloc(1, sizeof(plf_line));
     o->ctx = ctx; o->prm = *p;
     const int n = p->nlevels;
+    // Lineextractor::Lineextractor scale tables and feature split, src/Lineextractor.cc:36-66
     o->scale[0] = 1.0f; o->sigma2[0] = 1.0f;
     for (int i = 1; i < n; i++) { o->scale[i] = (float)((double)o->scale[i - 1] * p->scale); o->sigma2[i] = o->scale[i] * o->scale[i]; }
     for (int i = 0; i < n; i++) { o->inv_scale[i] = 1.0f / o->scale[i]; o->inv_sigma2[i] = 1.0f / o->sigma2[i]; }
@@ -25,10 +102,57 @@ extern "C" plf_status plf_line_create(plf_ctx* ctx, const plf_line_params* p, pl
     int sum = 0;
     for (int l = 0; l < n - 1; l++) { o->per_level[l] = (int)lrintf(nDesired); sum += o->per_level[l]; nDesired *= factor; }
     o->per_level[n - 1] = p->nfeatures - sum > 0 ? p->nfeatures - sum : 0;
+    // LSD constants (OpenCV lsd.cpp flsd)
+    o->prec = LSD_PI * p->ang_th / 180;
+    o->rho = p->quant / sin(o->prec);
+    if (p->scale != 1) {
+        const double sigma = (p->scale < 1) ? (p->sigma_scale / p->scale) : p->sigma_scale;
+        const unsigned hh = (unsigned)(ceil(sigma * sqrt(2 * 3.0 * log(10.0))));
+        o->lsd_gauss.ksize = 1 + 2 * (int)hh;
+        if (gauss_kernel_q8(o->lsd_gauss.ksize, sigma, o->lsd_gauss.q)) {
+            free(o);
+            return plf_fail(ctx, PLF_ERR_INVALID, "LSD pre-blur kernel larger than 15 taps (sigma_scale too large)");
+        }
+    }
+    o->lbd_gauss.ksize = 5;
+    gauss_kernel_q8(5, 1.0, o->lbd_gauss.q);
+    {   // BinaryDescriptor ctor weights (binary_descriptor_custom.cpp:217-259), integer-division quirks kept
+        double u = (7 * 3 - 1) / 2;
+        double sigma = (7 * 2 + 1) / 2;
+        double inv = -1 / (2 * sigma * sigma);
+        for (int i = 0; i < 21; i++) { double d = i - u; o->lbd_coefs.l[i] = (float)exp(d * d * inv); }
+        u = (9 * 7 - 1) / 2;
+        sigma = u;
+        inv = -1 / (2 * sigma * sigma);
+        for (int i = 0; i < 63; i++) { double d = i - u; o->lbd_coefs.g[i] = (float)exp(d * d * inv); }
+    }
     *out = o;
     return PLF_OK;
 }
-extern "C" void plf_line_destroy(plf_line* o) { free(o); }
+
+static void line_free_ws(plf_line* o)
+{
+    if (o->d_base) cudaFree(o->d_base);
+    if (o->d_tabs) cudaFree(o->d_tabs);
+    if (o->d_cubtmp) cudaFree(o->d_cubtmp);
+    o->d_base = nullptr; o->d_tabs = nullptr; o->d_cubtmp = nullptr;
+    o->ws_w = o->ws_h = o->ws_frames = 0;
+}
+
+extern "C" void plf_line_destroy(plf_line* o)
+{
+    if (!o) return;
+    cudaSetDevice(o->ctx->device);
+    cudaStreamSynchronize(o->ctx->stream);
+    line_free_ws(o);
+    if (o->d_okl) cudaFree(o->d_okl);
+    if (o->d_omid) cudaFree(o->d_omid);
+    if (o->d_odesc) cudaFree(o->d_odesc);
+    if (o->d_ofdesc) cudaFree(o->d_ofdesc);
+    if (o->d_onout) cudaFree(o->d_onout);
+    free(o);
+}
+
 extern "C" plf_status plf_line_tables(const plf_line* o, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int32_t* per_level)
 {
     if (!o) return PLF_ERR_INVALID;
@@ -41,10 +165,431 @@ extern "C" plf_status plf_line_tables(const plf_line* o, float* scale, float* in
     }
     return PLF_OK;
 }
+
 extern "C" int plf_line_max_keylines(const plf_line* o) { return o ? o->prm.nfeatures + 16 : 0; }
-#define NOTYET(ctx) return plf_fail((ctx), PLF_ERR_STATE, "line path not built yet")
-extern "C" plf_status plf_line_extract(plf_line* le, const uint8_t*, int, int, size_t, plf_keyline*, plf_keypoint*, uint8_t*, int, int*) { NOTYET(le->ctx); }
-extern "C" plf_status plf_line_extract_batch(plf_line* le, const uint8_t*, int, int, int, size_t, size_t, plf_keyline*, plf_keypoint*, uint8_t*, int, int32_t*) { NOTYET(le->ctx); }
-extern "C" plf_status plf_line_extract_batch_device(plf_line* le, const uint8_t*, int, int, int, size_t, size_t, plf_keyline*, plf_keypoint*, uint8_t*, int, int32_t*) { NOTYET(le->ctx); }
-extern "C" plf_status plf_lsd_detect(plf_line* le, const uint8_t*, int, int, size_t, plf_keyline*, int, int*) { NOTYET(le->ctx); }
-extern "C" plf_status plf_lbd_compute(plf_line* le, const uint8_t*, int, int, size_t, const plf_keyline*, int, uint8_t*, float*) { NOTYET(le->ctx); }
+
+static void exact_table(int ssize, int dsize, double inv_scale, int2* tab)
+{
+    double scale = 1.0 / inv_scale;
+    for (int d = 0; d < dsize; d++) {
+        double f = (d + 0.5) * scale - 0.5;
+        int s = (int)floor(f);
+        f -= s;
+        if (s < 0) { s = 0; f = 0; }
+        if (s >= ssize - 1) { s = ssize - 1; f = 0; }
+        tab[d].x = s;
+        tab[d].y = (int)floor(f * 256.0 + 0.5);
+    }
+}
+
+template <class T> static T* carve(uint8_t*& p, size_t count)
+{
+    T* r = (T*)p;
+    p += plf_align_up(count * sizeof(T), 256);
+    return r;
+}
+
+static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
+{
+    plf_ctx* ctx = o->ctx;
+    if (o->ws_w == w && o->ws_h == h && o->ws_frames >= nframes) return PLF_OK;
+    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    line_free_ws(o);
+    if (nframes > 255) return plf_fail(ctx, PLF_ERR_INVALID, "at most 255 frames per line batch");
+    const int noct = o->prm.nlevels;
+    const double S = o->prm.scale;
+    size_t maxpx = 0, tabCount = 0;
+    for (int k = 0; k < noct; k++) {
+        o->ow[k] = w >> k; o->oh[k] = h >> k;
+        if (o->ow[k] < 8 || o->oh[k] < 8) return plf_fail(ctx, PLF_ERR_INVALID, "image too small for %d octaves", noct);
+        o->sw[k] = S != 1 ? (int)lrint(o->ow[k] * S) : o->ow[k];
+        o->sh[k] = S != 1 ? (int)lrint(o->oh[k] * S) : o->oh[k];
+        if ((size_t)o->sw[k] * o->sh[k] > maxpx) maxpx = (size_t)o->sw[k] * o->sh[k];
+        if ((size_t)o->sw[k] * o->sh[k] >= (1u << 22)) return plf_fail(ctx, PLF_ERR_INVALID, "scaled octave larger than 4M pixels");
+        const double LOG_NT = 5 * (log10((double)o->sw[k]) + log10((double)o->sh[k])) / 2 + log10(11.0);
+        o->min_reg[k] = (int)(size_t)(-LOG_NT / log10(o->prm.ang_th / 180));
+        tabCount += (size_t)o->sw[k] + o->sh[k];
+    }
+    const size_t F = (size_t)nframes;
+    o->keycap = F * maxpx;
+    o->regcap = nframes * LINE_REGCAP_PER_FRAME;
+    size_t bytes = 0;
+    auto need = [&](size_t count, size_t elt) { bytes += plf_align_up(count * elt, 256); };
+    for (int k = 0; k < noct; k++) {
+        size_t px = (size_t)o->ow[k] * o->oh[k];
+        need(F * px, 1); need(F * px, 1); need(F * px, 2); need(F * px, 2);
+    }
+    need(F * (size_t)w * h, 1); need(F * maxpx, 1);
+    need(F * maxpx, 4); need(F * maxpx, 4); need(F * maxpx, 4); need(F * maxpx, 8);   // q, label, fa, cs
+    need(o->keycap, 8); need(o->keycap, 8); need(o->keycap, 4); need(o->keycap, 4);    // keys, keys2, regpts, comp
+    need(o->regcap, sizeof(LsdRegion)); need(o->regcap, sizeof(float4));
+    need(o->regcap, 8); need(o->regcap, 8); need(o->regcap, 4); need(o->regcap, 4);
+    need(F * noct * LINE_DETCAP, sizeof(plf_keyline));
+    need(CNT_MAXQ + F, 4); need(F * noct, 4);
+    PLF_CUDA(ctx, cudaMalloc((void**)&o->d_base, bytes + 4096));
+    uint8_t* p = o->d_base;
+    for (int k = 0; k < noct; k++) {
+        size_t px = (size_t)o->ow[k] * o->oh[k];
+        o->d_oct[k] = carve<uint8_t>(p, F * px);
+        o->d_lbdimg[k] = carve<uint8_t>(p, F * px);
+        o->d_dx[k] = carve<short>(p, F * px);
+        o->d_dy[k] = carve<short>(p, F * px);
+    }
+    o->d_tmp = carve<uint8_t>(p, F * (size_t)w * h);
+    o->d_scaled = carve<uint8_t>(p, F * maxpx);
+    o->d_q = carve<int>(p, F * maxpx);
+    o->d_label = carve<int>(p, F * maxpx);
+    o->d_fa = carve<float>(p, F * maxpx);
+    o->d_cs = carve<float2>(p, F * maxpx);
+    o->d_keys = carve<unsigned long long>(p, o->keycap);
+    o->d_keys2 = carve<unsigned long long>(p, o->keycap);
+    o->d_regpts = carve<int>(p, o->keycap);
+    o->d_comp = carve<int>(p, o->keycap);
+    o->d_regions = carve<LsdRegion>(p, o->regcap);
+    o->d_lines = carve<float4>(p, o->regcap);
+    o->d_linekey = carve<unsigned long long>(p, o->regcap);
+    o->d_linekey2 = carve<unsigned long long>(p, o->regcap);
+    o->d_lineidx = carve<int>(p, o->regcap);
+    o->d_lineidx2 = carve<int>(p, o->regcap);
+    o->d_det = carve<plf_keyline>(p, F * noct * LINE_DETCAP);
+    o->d_cnt = carve<int>(p, CNT_MAXQ + F);
+    o->d_detcount = carve<int>(p, F * noct);
+    // INTER_LINEAR_EXACT tables
+    PLF_CUDA(ctx, cudaMalloc((void**)&o->d_tabs, (tabCount + 1) * sizeof(int2)));
+    if (S != 1) {
+        std::vector<int2> tabs(tabCount + 1);
+        size_t to = 0;
+        for (int k = 0; k < noct; k++) {
+            exact_table(o->ow[k], o->sw[k], S, &tabs[to]); o->xtab[k] = o->d_tabs + to; to += o->sw[k];
+            exact_table(o->oh[k], o->sh[k], S, &tabs[to]); o->ytab[k] = o->d_tabs + to; to += o->sh[k];
+        }
+        PLF_CUDA(ctx, cudaMemcpy(o->d_tabs, tabs.data(), tabCount * sizeof(int2), cudaMemcpyHostToDevice));
+    }
+#ifndef PLF_EMU
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, t1, o->d_keys, o->d_keys2, (int)o->keycap, 0, 64, ctx->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, o->d_linekey, o->d_linekey2, o->d_lineidx, o->d_lineidx2, o->regcap, 0, 48, ctx->stream);
+    o->cubtmp_bytes = t1 > t2 ? t1 : t2;
+    PLF_CUDA(ctx, cudaMalloc(&o->d_cubtmp, o->cubtmp_bytes + 256));
+#endif
+    o->ws_w = w; o->ws_h = h; o->ws_frames = nframes;
+    return PLF_OK;
+}
+
+static plf_status sort_keys(plf_line* o, int n)
+{
+    plf_ctx* ctx = o->ctx;
+#ifdef PLF_EMU
+    std::sort(o->d_keys, o->d_keys + n);
+    memcpy(o->d_keys2, o->d_keys, (size_t)n * 8);
+#else
+    size_t tb = o->cubtmp_bytes;
+    PLF_CUDA(ctx, cub::DeviceRadixSort::SortKeys(o->d_cubtmp, tb, o->d_keys, o->d_keys2, n, 0, 64, ctx->stream));
+    ctx->launches += 8;
+#endif
+    return PLF_OK;
+}
+
+static plf_status sort_lines(plf_line* o)
+{
+    plf_ctx* ctx = o->ctx;
+#ifdef PLF_EMU
+    std::vector<std::pair<unsigned long long, int>> v(o->regcap);
+    for (int i = 0; i < o->regcap; i++) v[i] = std::make_pair(o->d_linekey[i], o->d_lineidx[i]);
+    std::stable_sort(v.begin(), v.end(), [](const std::pair<unsigned long long, int>& a, const std::pair<unsigned long long, int>& b) { return a.first < b.first; });
+    for (int i = 0; i < o->regcap; i++) { o->d_linekey2[i] = v[i].first; o->d_lineidx2[i] = v[i].second; }
+#else
+    size_t tb = o->cubtmp_bytes;
+    // padding keys are ~0: sort all 64 bits so they land at the end
+    PLF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(o->d_cubtmp, tb, o->d_linekey, o->d_linekey2, o->d_lineidx, o->d_lineidx2, o->regcap, 0, 64, ctx->stream));
+    ctx->launches += 8;
+#endif
+    return PLF_OK;
+}
+
+// LSDDetectorC::detect for a batch resident in d_oct[0]: fills d_det / d_detcount
+static plf_status lsd_detect_batch(plf_line* o, int nframes)
+{
+    plf_ctx* ctx = o->ctx;
+    cudaStream_t st = ctx->stream;
+    const int noct = o->prm.nlevels;
+    const double S = o->prm.scale;
+    PLF_CUDA(ctx, cudaMemsetAsync(o->d_detcount, 0, (size_t)nframes * noct * sizeof(int), st));
+    PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt + CNT_ERR, 0, sizeof(int), st));
+    for (int k = 0; k < noct; k++) {
+        const int ow = o->ow[k], oh = o->oh[k], sw = o->sw[k], sh = o->sh[k];
+        if (k > 0) {   // computeGaussianPyramid: pyrDown, no pre-blur (LSDDetector_custom.cpp:56-73)
+            PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(ow, 32), plf_div_up(oh, 8), nframes), dim3(32, 8), 0, st, (const uint8_t*)o->d_oct[k - 1],
+                       (size_t)o->ow[k - 1] * o->oh[k - 1], o->ow[k - 1], o->ow[k - 1], o->oh[k - 1], o->d_oct[k], (size_t)ow * oh, ow);
+            PLF_CHECK_LAUNCH(ctx);
+        }
+        const uint8_t* scaled = o->d_oct[k];
+        if (S != 1) {
+            PLF_LAUNCH(k_gauss_q8, dim3(plf_div_up(ow, GB_TW), plf_div_up(oh, GB_TH), nframes), dim3(256), 0, st, (const uint8_t*)o->d_oct[k],
+                       (size_t)ow * oh, ow, o->d_tmp, (size_t)ow * oh, ow, ow, oh, o->lsd_gauss);
+            PLF_CHECK_LAUNCH(ctx);
+            PLF_LAUNCH(k_resize_exact, dim3(plf_div_up(sw, 32), plf_div_up(sh, 8), nframes), dim3(32, 8), 0, st, (const uint8_t*)o->d_tmp,
+                       (size_t)ow * oh, ow, ow, oh, o->d_scaled, (size_t)sw * sh, sw, sw, sh, o->xtab[k], o->ytab[k]);
+            PLF_CHECK_LAUNCH(ctx);
+            scaled = o->d_scaled;
+        }
+        PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt, 0, 4 * sizeof(int), st));
+        PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt + CNT_MAXQ, 0xff, (size_t)nframes * sizeof(int), st));   // maxq = -1
+        dim3 g2(plf_div_up(sw, 32), plf_div_up(sh, 8), nframes), b2(32, 8);
+        PLF_LAUNCH(k_lsd_grad, g2, b2, 0, st, scaled, (size_t)sw * sh, sw, sw, sh, o->rho, o->d_q, o->d_fa, o->d_cs, o->d_label,
+                   o->d_cnt + CNT_MAXQ);
+        PLF_CHECK_LAUNCH(ctx);
+        PLF_LAUNCH(k_ccl_merge, g2, b2, 0, st, o->d_label, sw, sh);
+        PLF_CHECK_LAUNCH(ctx);
+        PLF_LAUNCH(k_lsd_keys, g2, b2, 0, st, (const int*)o->d_label, (const int*)o->d_q, (const int*)(o->d_cnt + CNT_MAXQ), sw, sh,
+                   o->prm.n_bins, o->d_keys, o->d_cnt + CNT_NKEYS, (int)o->keycap);
+        PLF_CHECK_LAUNCH(ctx);
+        int nkeys = 0;
+        PLF_CUDA(ctx, cudaMemcpyAsync(&nkeys, o->d_cnt + CNT_NKEYS, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PLF_CUDA(ctx, cudaStreamSynchronize(st));
+        if (nkeys > (int)o->keycap) return plf_fail(ctx, PLF_ERR_CAPACITY, "LSD key buffer overflow");
+        if (nkeys > 0) {
+            plf_status s = sort_keys(o, nkeys);
+            if (s) return s;
+            PLF_LAUNCH(k_lsd_heads, dim3(plf_div_up(nkeys, 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2, nkeys, o->d_comp,
+                       o->d_cnt + CNT_NCOMP);
+            PLF_CHECK_LAUNCH(ctx);
+            PLF_LAUNCH(k_lsd_grow, dim3(148 * 4), dim3(128), 0, st, (const unsigned long long*)o->d_keys2, nkeys, (const int*)o->d_comp,
+                       (const int*)(o->d_cnt + CNT_NCOMP), o->d_cnt + CNT_NEXT, o->d_fa, (const float2*)o->d_cs, sw, sh, o->prec,
+                       o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap);
+            PLF_CHECK_LAUNCH(ctx);
+        }
+        PLF_LAUNCH(k_lsd_rect, dim3(plf_div_up(o->regcap, 128)), dim3(128), 0, st, (const LsdRegion*)o->d_regions,
+                   (const int*)(o->d_cnt + CNT_NREG), o->regcap, (const int*)o->d_regpts, (const int*)o->d_q, sw, sh, o->prec, S, o->d_lines,
+                   o->d_linekey, o->d_lineidx, o->d_cnt + CNT_ERR);
+        PLF_CHECK_LAUNCH(ctx);
+        plf_status s = sort_lines(o);
+        if (s) return s;
+        PLF_LAUNCH(k_lsd_keylines, dim3(plf_div_up(o->regcap, 128)), dim3(128), 0, st, (const unsigned long long*)o->d_linekey2,
+                   (const int*)o->d_lineidx2, o->regcap, (const float4*)o->d_lines, nframes, k, noct, ow, oh, o->prm.min_line_length,
+                   o->d_det, o->d_detcount, LINE_DETCAP);
+        PLF_CHECK_LAUNCH(ctx);
+    }
+    return PLF_OK;
+}
+
+// selection (or plain min_length filter) into out_kl / out_mid / n_out (device)
+static plf_status line_select(plf_line* o, int nframes, bool select, plf_keyline* d_kl, plf_keypoint* d_mid, int cap, int* d_nout)
+{
+    plf_ctx* ctx = o->ctx;
+    const int noct = o->prm.nlevels;
+    PLF_LAUNCH(k_line_select, dim3(nframes), dim3(SEL_T), LINE_DETCAP * sizeof(int), ctx->stream, (const plf_keyline*)o->d_det,
+               (const int*)o->d_detcount, LINE_DETCAP, noct, select ? 1 : 0, o->per_level[0], noct > 1 ? o->per_level[1] : 0, d_kl, d_mid,
+               cap, d_nout);
+    PLF_CHECK_LAUNCH(ctx);
+    return PLF_OK;
+}
+
+// BinaryDescriptor::compute for keylines resident on the device; image batch in d_oct[0]
+static plf_status lbd_batch(plf_line* o, int nframes, const plf_keyline* d_kl, const int* d_nlines, int cap, int maxlines,
+                            uint8_t* d_desc, float* d_fdesc)
+{
+    plf_ctx* ctx = o->ctx;
+    cudaStream_t st = ctx->stream;
+    const int noct = o->prm.nlevels;
+    LbdImages im;
+    memset(&im, 0, sizeof(im));
+    for (int k = 0; k < noct; k++) {
+        const int ow = o->ow[k], oh = o->oh[k];
+        if (k == 0) {   // computeGaussianPyramid (binary_descriptor_custom.cpp:350-370): blur 5x5 sigma 1, then pyrDown
+            PLF_LAUNCH(k_gauss_q8, dim3(plf_div_up(ow, GB_TW), plf_div_up(oh, GB_TH), nframes), dim3(256), 0, st, (const uint8_t*)o->d_oct[0],
+                       (size_t)ow * oh, ow, o->d_lbdimg[0], (size_t)ow * oh, ow, ow, oh, o->lbd_gauss);
+        } else {
+            PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(ow, 32), plf_div_up(oh, 8), nframes), dim3(32, 8), 0, st, (const uint8_t*)o->d_lbdimg[k - 1],
+                       (size_t)o->ow[k - 1] * o->oh[k - 1], o->ow[k - 1], o->ow[k - 1], o->oh[k - 1], o->d_lbdimg[k], (size_t)ow * oh, ow);
+        }
+        PLF_CHECK_LAUNCH(ctx);
+        PLF_LAUNCH(k_sobel3, dim3(plf_div_up(ow, 32), plf_div_up(oh, 8), nframes), dim3(32, 8), 0, st, (const uint8_t*)o->d_lbdimg[k],
+                   (size_t)ow * oh, ow, ow, oh, o->d_dx[k], o->d_dy[k], (size_t)ow * oh);
+        PLF_CHECK_LAUNCH(ctx);
+        im.dx[k] = o->d_dx[k]; im.dy[k] = o->d_dy[k]; im.frame[k] = (size_t)ow * oh; im.w[k] = ow; im.h[k] = oh;
+    }
+    if (maxlines > 0) {
+        PLF_LAUNCH(k_lbd, dim3(maxlines, nframes), dim3(64), 0, st, d_kl, d_nlines, cap, im, o->lbd_coefs, d_desc, d_fdesc);
+        PLF_CHECK_LAUNCH(ctx);
+    }
+    return PLF_OK;
+}
+
+static plf_status line_out_staging(plf_line* o, int nframes, int cap)
+{
+    plf_ctx* ctx = o->ctx;
+    if (o->out_frames >= nframes && o->out_cap == cap) return PLF_OK;
+    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (o->d_okl) cudaFree(o->d_okl);
+    if (o->d_omid) cudaFree(o->d_omid);
+    if (o->d_odesc) cudaFree(o->d_odesc);
+    if (o->d_ofdesc) cudaFree(o->d_ofdesc);
+    if (o->d_onout) cudaFree(o->d_onout);
+    o->d_okl = nullptr; o->d_omid = nullptr; o->d_odesc = nullptr; o->d_ofdesc = nullptr; o->d_onout = nullptr; o->out_frames = 0;
+    PLF_CUDA(ctx, cudaMalloc((void**)&o->d_okl, (size_t)nframes * cap * sizeof(plf_keyline)));
+    PLF_CUDA(ctx, cudaMalloc((void**)&o->d_omid, (size_t)nframes * cap * sizeof(plf_keypoint)));
+    PLF_CUDA(ctx, cudaMalloc((void**)&o->d_odesc, (size_t)nframes * cap * 32));
+    PLF_CUDA(ctx, cudaMalloc((void**)&o->d_ofdesc, (size_t)nframes * cap * 72 * sizeof(float)));
+    PLF_CUDA(ctx, cudaMalloc((void**)&o->d_onout, (size_t)nframes * sizeof(int)));
+    o->out_frames = nframes; o->out_cap = cap;
+    return PLF_OK;
+}
+
+static plf_status upload_images(plf_line* o, const uint8_t* host_imgs, int nframes, int w, int h, size_t stride, size_t frame_stride, bool device_src)
+{
+    plf_ctx* ctx = o->ctx;
+    const cudaMemcpyKind kind = device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (stride == (size_t)w && frame_stride == (size_t)w * h) {
+        PLF_CUDA(ctx, cudaMemcpyAsync(o->d_oct[0], host_imgs, (size_t)nframes * frame_stride, kind, ctx->stream));
+    } else {
+        for (int f = 0; f < nframes; f++)
+            PLF_CUDA(ctx, cudaMemcpy2DAsync(o->d_oct[0] + (size_t)f * w * h, w, host_imgs + (size_t)f * frame_stride, stride, w, h, kind, ctx->stream));
+    }
+    return PLF_OK;
+}
+
+static plf_status line_extract_device_impl(plf_line* o, int nframes, plf_keyline* d_kl, plf_keypoint* d_mid, uint8_t* d_desc, int cap, int* d_nout)
+{
+    plf_status st = lsd_detect_batch(o, nframes);
+    if (st) return st;
+    st = line_select(o, nframes, true, d_kl, d_mid, cap, d_nout);
+    if (st) return st;
+    int maxlines = o->prm.nfeatures < cap ? o->prm.nfeatures : cap;
+    return lbd_batch(o, nframes, d_kl, d_nout, cap, maxlines, d_desc, nullptr);
+}
+
+extern "C" plf_status plf_line_extract_batch_device(plf_line* o, const uint8_t* dev_imgs, int nframes, int w, int h, size_t stride,
+                                                    size_t frame_stride, plf_keyline* dev_kl, plf_keypoint* dev_mid, uint8_t* dev_desc,
+                                                    int cap, int32_t* dev_n_out)
+{
+    if (!o) return PLF_ERR_INVALID;
+    plf_ctx* ctx = o->ctx;
+    if (!dev_imgs || nframes < 1 || w <= 0 || h <= 0 || stride < (size_t)w || !dev_kl || !dev_desc || !dev_n_out || cap < 1)
+        return plf_fail(ctx, PLF_ERR_INVALID, "plf_line_extract_batch_device: bad arguments");
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    plf_status st = line_prepare(o, w, h, nframes);
+    if (st) return st;
+    st = upload_images(o, dev_imgs, nframes, w, h, stride, frame_stride, true);
+    if (st) return st;
+    return line_extract_device_impl(o, nframes, dev_kl, dev_mid, dev_desc, cap, dev_n_out);
+}
+
+static plf_status check_counts(plf_ctx* ctx, const int32_t* n_out, int nframes)
+{
+    for (int f = 0; f < nframes; f++) {
+        if (n_out[f] == -1) return plf_fail(ctx, PLF_ERR_CAPACITY, "frame %d: more than %d lines detected in one octave", f, LINE_DETCAP);
+        if (n_out[f] == -2) return plf_fail(ctx, PLF_ERR_CAPACITY, "frame %d: keyline output capacity too small", f);
+    }
+    return PLF_OK;
+}
+
+static plf_status check_regions(plf_line* o)
+{
+    plf_ctx* ctx = o->ctx;
+    int err = 0;
+    PLF_CUDA(ctx, cudaMemcpyAsync(&err, o->d_cnt + CNT_ERR, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (err) return plf_fail(ctx, PLF_ERR_CAPACITY, "LSD region buffer overflow (more than %d regions in the batch)", o->regcap);
+    return PLF_OK;
+}
+
+extern "C" plf_status plf_line_extract_batch(plf_line* o, const uint8_t* host_imgs, int nframes, int w, int h, size_t stride,
+                                             size_t frame_stride, plf_keyline* host_kl, plf_keypoint* host_mid, uint8_t* host_desc,
+                                             int cap, int32_t* n_out)
+{
+    if (!o) return PLF_ERR_INVALID;
+    plf_ctx* ctx = o->ctx;
+    if (nframes < 1 || !n_out) return plf_fail(ctx, PLF_ERR_INVALID, "plf_line_extract_batch: bad arguments");
+    if (!host_imgs || w <= 0 || h <= 0) {   // empty image: silent return (src/Lineextractor.cc:115-116)
+        for (int f = 0; f < nframes; f++) n_out[f] = 0;
+        return PLF_OK;
+    }
+    if (stride < (size_t)w || !host_kl || !host_desc || cap < 1) return plf_fail(ctx, PLF_ERR_INVALID, "plf_line_extract_batch: bad arguments");
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    plf_status st = line_prepare(o, w, h, nframes);
+    if (st) return st;
+    st = line_out_staging(o, nframes, cap);
+    if (st) return st;
+    st = upload_images(o, host_imgs, nframes, w, h, stride, frame_stride, false);
+    if (st) return st;
+    st = line_extract_device_impl(o, nframes, o->d_okl, o->d_omid, o->d_odesc, cap, o->d_onout);
+    if (st) return st;
+    cudaStream_t s = ctx->stream;
+    PLF_CUDA(ctx, cudaMemcpyAsync(n_out, o->d_onout, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, s));
+    PLF_CUDA(ctx, cudaMemcpyAsync(host_kl, o->d_okl, (size_t)nframes * cap * sizeof(plf_keyline), cudaMemcpyDeviceToHost, s));
+    if (host_mid) PLF_CUDA(ctx, cudaMemcpyAsync(host_mid, o->d_omid, (size_t)nframes * cap * sizeof(plf_keypoint), cudaMemcpyDeviceToHost, s));
+    PLF_CUDA(ctx, cudaMemcpyAsync(host_desc, o->d_odesc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, s));
+    st = check_regions(o);
+    if (st) return st;
+    return check_counts(ctx, n_out, nframes);
+}
+
+extern "C" plf_status plf_line_extract(plf_line* o, const uint8_t* host_img, int w, int h, size_t stride, plf_keyline* host_kl,
+                                       plf_keypoint* host_mid, uint8_t* host_desc, int cap, int* n_out)
+{
+    if (!o || !n_out) return PLF_ERR_INVALID;
+    int32_t n = 0;
+    plf_status st = plf_line_extract_batch(o, host_img, 1, w, h, stride, stride * (size_t)(h > 0 ? h : 0), host_kl, host_mid, host_desc, cap, &n);
+    *n_out = n;
+    return st;
+}
+
+extern "C" plf_status plf_lsd_detect(plf_line* o, const uint8_t* host_img, int w, int h, size_t stride, plf_keyline* host_kl, int cap, int* n_out)
+{
+    if (!o || !n_out) return PLF_ERR_INVALID;
+    plf_ctx* ctx = o->ctx;
+    *n_out = 0;
+    if (!host_img || w <= 0 || h <= 0) return PLF_OK;
+    if (stride < (size_t)w || !host_kl || cap < 1) return plf_fail(ctx, PLF_ERR_INVALID, "plf_lsd_detect: bad arguments");
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    plf_status st = line_prepare(o, w, h, 1);
+    if (st) return st;
+    st = line_out_staging(o, 1, cap);
+    if (st) return st;
+    st = upload_images(o, host_img, 1, w, h, stride, stride * (size_t)h, false);
+    if (st) return st;
+    st = lsd_detect_batch(o, 1);
+    if (st) return st;
+    st = line_select(o, 1, false, o->d_okl, nullptr, cap, o->d_onout);
+    if (st) return st;
+    int32_t n = 0;
+    PLF_CUDA(ctx, cudaMemcpyAsync(&n, o->d_onout, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    st = check_regions(o);
+    if (st) return st;
+    st = check_counts(ctx, &n, 1);
+    if (st) return st;
+    PLF_CUDA(ctx, cudaMemcpyAsync(host_kl, o->d_okl, (size_t)n * sizeof(plf_keyline), cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = n;
+    return PLF_OK;
+}
+
+extern "C" plf_status plf_lbd_compute(plf_line* o, const uint8_t* host_img, int w, int h, size_t stride, const plf_keyline* host_kl, int n,
+                                      uint8_t* host_desc, float* host_fdesc)
+{
+    if (!o) return PLF_ERR_INVALID;
+    plf_ctx* ctx = o->ctx;
+    if (n <= 0) return PLF_OK;   // the reference prints an error and returns (binary_descriptor_custom.cpp:556-560)
+    if (!host_img || w <= 0 || h <= 0 || stride < (size_t)w || !host_kl || (!host_desc && !host_fdesc))
+        return plf_fail(ctx, PLF_ERR_INVALID, "plf_lbd_compute: bad arguments");
+    for (int i = 0; i < n; i++)
+        if (host_kl[i].octave < 0 || host_kl[i].octave >= o->prm.nlevels || host_kl[i].numOfPixels < 0 || host_kl[i].numOfPixels > 32767)
+            return plf_fail(ctx, PLF_ERR_INVALID, "keyline %d: octave/numOfPixels out of range", i);
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    plf_status st = line_prepare(o, w, h, 1);
+    if (st) return st;
+    st = line_out_staging(o, 1, n > o->out_cap ? n : (o->out_cap > 0 ? o->out_cap : n));
+    if (st) return st;
+    const int cap = o->out_cap;
+    st = upload_images(o, host_img, 1, w, h, stride, stride * (size_t)h, false);
+    if (st) return st;
+    PLF_CUDA(ctx, cudaMemcpyAsync(o->d_okl, host_kl, (size_t)n * sizeof(plf_keyline), cudaMemcpyHostToDevice, ctx->stream));
+    PLF_CUDA(ctx, cudaMemcpyAsync(o->d_onout, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    st = lbd_batch(o, 1, o->d_okl, o->d_onout, cap, n, o->d_odesc, o->d_ofdesc);
+    if (st) return st;
+    if (host_desc) PLF_CUDA(ctx, cudaMemcpyAsync(host_desc, o->d_odesc, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_fdesc) PLF_CUDA(ctx, cudaMemcpyAsync(host_fdesc, o->d_ofdesc, (size_t)n * 72 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PLF_OK;
+}

@@ -1,0 +1,639 @@
+// plf_line_kernels.cuh -- device kernels of the line path:
+// LSD (cv::LineSegmentDetector, refine = 0, as reached from LSDDetector_custom.cpp:246-264) and LBD
+// (binary_descriptor_custom.cpp:350-398, :1026-1372).
+//
+// LSD region growing is sequential in the reference (seeds in descending gradient-bin order, a shared
+// `used` map).  Regions can only contain pixels whose gradient angle is defined, so the 8-connected
+// components of the "defined" mask never interact: the kernels label those components, sort the seeds by
+// (component, bin descending, raster) and grow each component with one thread, as-if-sequentially, which
+// reproduces the reference's regions exactly while thousands of components (x frames) run in parallel.
+#pragma once
+#include "plf_common.cuh"
+
+#define LSD_NOTDEF (-1024.0f)
+#define LSD_USED (-2048.0f)
+#define LSD_PI 3.14159265358979323846
+#define LSD_D2R (LSD_PI / 180)
+#define LSD_3_2_PI (3 * LSD_PI / 2)
+#define LSD_2PI (2 * LSD_PI)
+
+// key layout (64 bit): frame[63:56] | component root[55:34] | (n_bins-1-bin)[33:22] | raster index[21:0]
+#define LSD_KEY_IDX(k) ((int)((k) & 0x3fffffull))
+#define LSD_KEY_TAG(k) ((k) >> 34)
+#define LSD_KEY_FRAME(k) ((int)((k) >> 56))
+#define LSD_KEY_BIN(k) ((int)(((k) >> 22) & 0xfffull))
+
+struct GaussQ8 { int ksize; int q[15]; };
+
+// ---------------- generic separable Q8 Gaussian (cv::GaussianBlur 8U, REFLECT_101) ----------------
+#define GB_TW 128
+#define GB_TH 32
+__global__ void __launch_bounds__(256)
+k_gauss_q8(const uint8_t* __restrict__ src, size_t sframe, int spitch, uint8_t* __restrict__ dst, size_t dframe, int dpitch,
+           int w, int h, GaussQ8 k)
+{
+    __shared__ uint8_t tile[(GB_TH + 14) * (GB_TW + 16)];
+    __shared__ unsigned short hbuf[(GB_TH + 14) * GB_TW];
+    const int r = k.ksize >> 1;
+    const int tx0 = blockIdx.x * GB_TW, ty0 = blockIdx.y * GB_TH;
+    const uint8_t* s = src + (size_t)blockIdx.z * sframe;
+    uint8_t* d = dst + (size_t)blockIdx.z * dframe;
+    const int tid = threadIdx.x;
+    const int TWP = GB_TW + 16, cols = GB_TW + 2 * r, rows = GB_TH + 2 * r;
+    for (int i = tid; i < rows * cols; i += 256) {
+        int ry = i / cols, rx = i - ry * cols;
+        int sy = plf_reflect101(ty0 + ry - r, h), sx = plf_reflect101(tx0 + rx - r, w);
+        tile[ry * TWP + rx] = s[(size_t)sy * spitch + sx];
+    }
+    __syncthreads();
+    for (int i = tid; i < rows * GB_TW; i += 256) {
+        int ry = i / GB_TW, rx = i - ry * GB_TW;
+        const uint8_t* t = &tile[ry * TWP + rx];
+        unsigned v = 0;
+        for (int j = 0; j < k.ksize; j++) v += (unsigned)k.q[j] * t[j];
+        hbuf[i] = (unsigned short)v;
+    }
+    __syncthreads();
+    for (int i = tid; i < GB_TH * GB_TW; i += 256) {
+        int ry = i / GB_TW, rx = i - ry * GB_TW;
+        int x = tx0 + rx, y = ty0 + ry;
+        if (x < w && y < h) {
+            unsigned v = 32768u;
+            for (int j = 0; j < k.ksize; j++) v += (unsigned)k.q[j] * hbuf[(ry + j) * GB_TW + rx];
+            d[(size_t)y * dpitch + x] = (uint8_t)(v >> 16);
+        }
+    }
+}
+
+// ---------------- cv::resize INTER_LINEAR_EXACT; tab: .x = offset, .y = c1 (Q8) ----------------
+__global__ void __launch_bounds__(256)
+k_resize_exact(const uint8_t* __restrict__ src, size_t sframe, int spitch, int sw, int sh,
+               uint8_t* __restrict__ dst, size_t dframe, int dpitch, int dw, int dh,
+               const int2* __restrict__ xtab, const int2* __restrict__ ytab)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const uint8_t* s = src + (size_t)blockIdx.z * sframe;
+    const int2 ty = ytab[y], tx = xtab[x];
+    const int sy0 = ty.x, sy1 = min(sy0 + 1, sh - 1), sx0 = tx.x, sx1 = min(sx0 + 1, sw - 1);
+    const int cy1 = ty.y, cy0 = 256 - cy1, cx1 = tx.y, cx0 = 256 - cx1;
+    const uint8_t* r0 = s + (size_t)sy0 * spitch;
+    const uint8_t* r1 = s + (size_t)sy1 * spitch;
+    int h0 = cx0 * r0[sx0] + cx1 * r0[sx1];
+    int h1 = cx0 * r1[sx0] + cx1 * r1[sx1];
+    dst[(size_t)blockIdx.z * dframe + (size_t)y * dpitch + x] = (uint8_t)((cy0 * h0 + cy1 * h1 + 32768) >> 16);
+}
+
+// ---------------- cv::pyrDown to (w/2, h/2) ----------------
+__global__ void __launch_bounds__(256)
+k_pyrdown(const uint8_t* __restrict__ src, size_t sframe, int spitch, int w, int h,
+          uint8_t* __restrict__ dst, size_t dframe, int dpitch)
+{
+    const int dw = w >> 1, dh = h >> 1;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const uint8_t* s = src + (size_t)blockIdx.z * sframe;
+    int xs[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) xs[i] = plf_reflect101(2 * x + i - 2, w);
+    int acc = 128;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const uint8_t* r = s + (size_t)plf_reflect101(2 * y + j - 2, h) * spitch;
+        int hsum = r[xs[0]] + 4 * r[xs[1]] + 6 * r[xs[2]] + 4 * r[xs[3]] + r[xs[4]];
+        const int kj = (j == 0 || j == 4) ? 1 : (j == 2 ? 6 : 4);
+        acc += kj * hsum;
+    }
+    dst[(size_t)blockIdx.z * dframe + (size_t)y * dpitch + x] = (uint8_t)(acc >> 8);
+}
+
+// ---------------- cv::Sobel 3x3 -> CV_16S dx, dy (binary_descriptor_custom.cpp:395-396) ----------------
+__global__ void __launch_bounds__(256)
+k_sobel3(const uint8_t* __restrict__ src, size_t sframe, int spitch, int w, int h,
+         short* __restrict__ dx, short* __restrict__ dy, size_t dframe)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t* s = src + (size_t)blockIdx.z * sframe;
+    const uint8_t* r0 = s + (size_t)plf_reflect101(y - 1, h) * spitch;
+    const uint8_t* r1 = s + (size_t)y * spitch;
+    const uint8_t* r2 = s + (size_t)plf_reflect101(y + 1, h) * spitch;
+    const int xl = plf_reflect101(x - 1, w), xr = plf_reflect101(x + 1, w);
+    const size_t o = (size_t)blockIdx.z * dframe + (size_t)y * w + x;
+    dx[o] = (short)((r0[xr] - r0[xl]) + 2 * (r1[xr] - r1[xl]) + (r2[xr] - r2[xl]));
+    dy[o] = (short)((r2[xl] + 2 * r2[x] + r2[xr]) - (r0[xl] + 2 * r0[x] + r0[xr]));
+}
+
+// ---------------- LSD ll_angle: gradient, level-line angle, component label init ----------------
+// per pixel: q = gx^2 + gy^2 (norm = sqrt(q / 4.0)), fa = fastAtan2(gx, -gy) in degrees (or NOTDEF),
+// cs = float cos / sin of the float-cast radian angle (what region_grow accumulates), label = own index.
+__global__ void __launch_bounds__(256)
+k_lsd_grad(const uint8_t* __restrict__ img, size_t iframe, int ipitch, int w, int h, double rho,
+           int* __restrict__ q, float* __restrict__ fa, float2* __restrict__ cs, int* __restrict__ label,
+           int* __restrict__ maxq)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const int f = blockIdx.z;
+    int myq = -1;
+    if (x < w && y < h) {
+        const size_t o = (size_t)f * w * h + (size_t)y * w + x;
+        float a = LSD_NOTDEF;
+        int qq = 0;
+        if (x < w - 1 && y < h - 1) {
+            const uint8_t* r0 = img + (size_t)f * iframe + (size_t)y * ipitch + x;
+            const uint8_t* r1 = r0 + ipitch;
+            const int DA = r1[1] - r0[0], BC = r0[1] - r1[0];
+            const int gx = DA + BC, gy = DA - BC;
+            qq = gx * gx + gy * gy;
+            const double norm = sqrt((double)qq / 4.0);
+            if (!(norm <= rho)) {
+                a = plf_fast_atan2((float)gx, (float)(-gy));
+                const float af = (float)((double)a * LSD_D2R);
+                cs[o] = make_float2((float)cos((double)af), (float)sin((double)af));
+                myq = qq;
+            }
+        }
+        q[o] = qq;
+        fa[o] = a;
+        label[o] = a == LSD_NOTDEF ? -1 : y * w + x;
+    }
+    // block max of q over defined pixels -> one atomic per warp
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) myq = max(myq, __shfl_xor_sync(0xffffffffu, myq, s));
+    if (((threadIdx.y * 32 + threadIdx.x) & 31) == 0 && myq >= 0) atomicMax(&maxq[f], myq);
+}
+
+__device__ __forceinline__ int ccl_find(const int* L, int a)
+{
+    int p = ((volatile const int*)L)[a];
+    while (p != a) { a = p; p = ((volatile const int*)L)[a]; }
+    return a;
+}
+__device__ __forceinline__ void ccl_union(int* L, int a, int b)
+{
+    bool done;
+    do {
+        a = ccl_find(L, a);
+        b = ccl_find(L, b);
+        if (a < b) { int old = atomicMin(&L[b], a); done = (old == b); b = old; }
+        else if (b < a) { int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+        else done = true;
+    } while (!done);
+}
+// 8-connected components of the defined mask: link every defined pixel to its W, NW, N, NE neighbours
+__global__ void __launch_bounds__(256)
+k_ccl_merge(int* __restrict__ label, int w, int h)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    int* L = label + (size_t)blockIdx.z * w * h;
+    const int p = y * w + x;
+    if (L[p] < 0) return;
+    if (x > 0 && L[p - 1] >= 0) ccl_union(L, p, p - 1);
+    if (y > 0) {
+        if (x > 0 && L[p - w - 1] >= 0) ccl_union(L, p, p - w - 1);
+        if (L[p - w] >= 0) ccl_union(L, p, p - w);
+        if (x < w - 1 && L[p - w + 1] >= 0) ccl_union(L, p, p - w + 1);
+    }
+}
+
+// emit one sort key per defined pixel (root label, bin, raster index); warp-aggregated append
+__global__ void __launch_bounds__(256)
+k_lsd_keys(const int* __restrict__ label, const int* __restrict__ q, const int* __restrict__ maxq, int w, int h,
+           int n_bins, unsigned long long* __restrict__ keys, int* __restrict__ nkeys, int keycap)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const int f = blockIdx.z;
+    bool have = false;
+    unsigned long long key = 0;
+    if (x < w && y < h) {
+        const size_t o = (size_t)f * w * h + (size_t)y * w + x;
+        if (label[o] >= 0) {
+            const int root = ccl_find(label + (size_t)f * w * h, y * w + x);
+            const int mq = maxq[f];
+            const double max_grad = mq >= 0 ? sqrt((double)mq / 4.0) : -1.0;
+            const double bin_coef = max_grad > 0 ? (double)(n_bins - 1) / max_grad : 0.0;
+            int bin = (int)(sqrt((double)q[o] / 4.0) * bin_coef);
+            if (bin < 0) bin = 0;
+            if (bin > n_bins - 1) bin = n_bins - 1;
+            key = ((unsigned long long)f << 56) | ((unsigned long long)root << 34) |
+                  ((unsigned long long)(n_bins - 1 - bin) << 22) | (unsigned long long)(y * w + x);
+            have = true;
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, have);
+    const int lane = (threadIdx.y * 32 + threadIdx.x) & 31;
+    int base = 0;
+    if (m) {
+        const int leader = __ffs((int)m) - 1;
+        if (lane == leader) base = atomicAdd(nkeys, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (have) {
+            const int o = base + __popc(m & ((1u << lane) - 1));
+            if (o < keycap) keys[o] = key;
+        }
+    }
+}
+
+// component heads in the sorted key array
+__global__ void __launch_bounds__(256)
+k_lsd_heads(const unsigned long long* __restrict__ keys, int n, int* __restrict__ comp, int* __restrict__ ncomp)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    if (i == 0 || LSD_KEY_TAG(keys[i]) != LSD_KEY_TAG(keys[i - 1])) comp[atomicAdd(ncomp, 1)] = i;
+}
+
+struct LsdRegion {
+    int start, n;                 // slice of the region point arena
+    double reg_angle;
+    unsigned long long seedkey;   // key of the seed pixel (frame, bin, raster index)
+};
+
+// region_grow for every seed of one component, one thread per component, dynamic work distribution
+__global__ void __launch_bounds__(128)
+k_lsd_grow(const unsigned long long* __restrict__ keys, int n, const int* __restrict__ comp, const int* __restrict__ ncomp_p,
+           int* __restrict__ next, float* __restrict__ fa, const float2* __restrict__ cs, int w, int h, double prec,
+           int min_reg_size, int* __restrict__ regpts, LsdRegion* __restrict__ regions, int* __restrict__ nregions, int regcap)
+{
+    const int ncomp = *ncomp_p;
+    const size_t px = (size_t)w * h;
+    for (;;) {
+        const int c = atomicAdd(next, 1);
+        if (c >= ncomp) break;
+        const int start = comp[c];
+        const unsigned long long tag = LSD_KEY_TAG(keys[start]);
+        float* F = fa + (size_t)LSD_KEY_FRAME(keys[start]) * px;
+        const float2* CS = cs + (size_t)LSD_KEY_FRAME(keys[start]) * px;
+        int arena = start;
+        for (int i = start; i < n; i++) {
+            const unsigned long long key = keys[i];
+            if (LSD_KEY_TAG(key) != tag) break;
+            const int p = LSD_KEY_IDX(key);
+            const float v0 = F[p];
+            if (v0 < -500.f) continue;   // already used by an earlier region
+            const int r0 = arena;
+            regpts[arena++] = p;
+            double reg_angle = (double)v0 * LSD_D2R;
+            float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
+            F[p] = LSD_USED;
+            for (int r = r0; r < arena; r++) {
+                const int pp = regpts[r];
+                const int y = pp / w, x = pp - y * w;
+                const int xx_min = max(x - 1, 0), xx_max = min(x + 1, w - 1);
+                const int yy_min = max(y - 1, 0), yy_max = min(y + 1, h - 1);
+                for (int yy = yy_min; yy <= yy_max; ++yy)
+                    for (int xx = xx_min; xx <= xx_max; ++xx) {
+                        const int qi = yy * w + xx;
+                        const float v = F[qi];
+                        if (v < -500.f) continue;   // NOTDEF or USED
+                        double n_theta = reg_angle - (double)v * LSD_D2R;
+                        if (n_theta < 0) n_theta = -n_theta;
+                        if (n_theta > LSD_3_2_PI) {
+                            n_theta -= LSD_2PI;
+                            if (n_theta < 0) n_theta = -n_theta;
+                        }
+                        if (n_theta <= prec) {
+                            F[qi] = LSD_USED;
+                            regpts[arena++] = qi;
+                            const float2 c2 = CS[qi];
+                            sumdx += c2.x;
+                            sumdy += c2.y;
+                            reg_angle = (double)plf_fast_atan2(sumdy, sumdx) * LSD_D2R;
+                        }
+                    }
+            }
+            const int nreg = arena - r0;
+            if (nreg >= min_reg_size) {
+                const int rr = atomicAdd(nregions, 1);
+                if (rr < regcap) {
+                    LsdRegion R;
+                    R.start = r0; R.n = nreg; R.reg_angle = reg_angle; R.seedkey = key;
+                    regions[rr] = R;
+                }
+            }
+        }
+    }
+}
+
+// region2rect + get_theta (OpenCV lsd.cpp, refine = 0): one thread per region; sums in region order.
+// Output: line end points (float, +0.5, / SCALE) and an order key (frame, bin descending, raster).
+__global__ void __launch_bounds__(128)
+k_lsd_rect(const LsdRegion* __restrict__ regions, const int* __restrict__ nregions, int regcap, const int* __restrict__ regpts,
+           const int* __restrict__ q, int w, int h, double prec, double scale, float4* __restrict__ lines,
+           unsigned long long* __restrict__ linekey, int* __restrict__ lineidx, int* __restrict__ errflag)
+{
+    const int rr = blockIdx.x * 128 + threadIdx.x;
+    if (rr >= regcap) return;
+    int nr = *nregions;
+    if (nr > regcap) { nr = regcap; if (rr == 0) *errflag = 1; }
+    lineidx[rr] = rr;
+    if (rr >= nr) { linekey[rr] = ~0ull; return; }
+    const LsdRegion R = regions[rr];
+    const int f = LSD_KEY_FRAME(R.seedkey);
+    const int* Q = q + (size_t)f * w * h;
+    const int* pts = regpts + R.start;
+    double x = 0, y = 0, sum = 0;
+    for (int i = 0; i < R.n; i++) {
+        const int p = pts[i];
+        const int py = p / w, pxx = p - py * w;
+        const double weight = sqrt((double)Q[p] / 4.0);
+        x += (double)pxx * weight;
+        y += (double)py * weight;
+        sum += weight;
+    }
+    x /= sum; y /= sum;
+    double Ixx = 0, Iyy = 0, Ixy = 0;
+    for (int i = 0; i < R.n; i++) {
+        const int p = pts[i];
+        const int py = p / w, pxx = p - py * w;
+        const double weight = sqrt((double)Q[p] / 4.0);
+        const double dx = (double)pxx - x, dy = (double)py - y;
+        Ixx += dy * dy * weight;
+        Iyy += dx * dx * weight;
+        Ixy -= dx * dy * weight;
+    }
+    const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+    double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)plf_fast_atan2((float)(lambda - Ixx), (float)Ixy)
+                                           : (double)plf_fast_atan2((float)Ixy, (float)(lambda - Iyy));
+    theta *= LSD_D2R;
+    double diff = theta - R.reg_angle;
+    while (diff <= -LSD_PI) diff += LSD_2PI;
+    while (diff > LSD_PI) diff -= LSD_2PI;
+    if (fabs(diff) > prec) theta += LSD_PI;
+    const double dx = cos(theta), dy = sin(theta);
+    double l_min = 0, l_max = 0;
+    for (int i = 0; i < R.n; i++) {
+        const int p = pts[i];
+        const int py = p / w, pxx = p - py * w;
+        const double regdx = (double)pxx - x, regdy = (double)py - y;
+        const double l = regdx * dx + regdy * dy;
+        if (l > l_max) l_max = l;
+        else if (l < l_min) l_min = l;
+    }
+    double x1 = x + l_min * dx, y1 = y + l_min * dy, x2 = x + l_max * dx, y2 = y + l_max * dy;
+    x1 += 0.5; y1 += 0.5; x2 += 0.5; y2 += 0.5;
+    if (scale != 1) { x1 /= scale; y1 /= scale; x2 /= scale; y2 /= scale; }
+    float4 L;
+    L.x = (float)x1; L.y = (float)y1; L.z = (float)x2; L.w = (float)y2;
+    lines[rr] = L;
+    linekey[rr] = ((unsigned long long)f << 40) | ((R.seedkey >> 22 & 0xfffull) << 22) | (R.seedkey & 0x3fffffull);
+}
+
+// KeyLine assembly for one octave (LSDDetector_custom.cpp:266-308): one thread per sorted line.
+// det layout: [frame][octave][detcap] keylines in seed order, with a per (frame, octave) count.
+__global__ void __launch_bounds__(128)
+k_lsd_keylines(const unsigned long long* __restrict__ skeys, const int* __restrict__ sidx, int nsorted,
+               const float4* __restrict__ lines, int nframes, int octave, int noct, int ow, int oh, double min_length,
+               plf_keyline* __restrict__ det, int* __restrict__ detcount, int detcap)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= nsorted) return;
+    const unsigned long long key = skeys[i];
+    if (key == ~0ull) return;
+    const int f = (int)(key >> 40);
+    if (f >= nframes) return;
+    // position inside the frame = i - first index of the frame (binary search on the sorted keys)
+    int lo = 0, hi = i;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if ((int)(skeys[mid] >> 40) < f) lo = mid + 1; else hi = mid;
+    }
+    const int pos = i - lo;
+    plf_keyline* out = det + ((size_t)f * noct + octave) * detcap;
+    if (pos == 0) {
+        // the last line of the frame publishes the count: find the end of the frame's run
+        int l2 = i, h2 = nsorted;
+        while (l2 < h2) {
+            int mid = (l2 + h2) >> 1;
+            if (skeys[mid] != ~0ull && (int)(skeys[mid] >> 40) <= f) l2 = mid + 1; else h2 = mid;
+        }
+        detcount[f * noct + octave] = l2 - lo;
+    }
+    if (pos >= detcap) return;
+    const float4 L = lines[sidx[i]];
+    float e0 = L.x, e1 = L.y, e2 = L.z, e3 = L.w;
+    // checkLineExtremes (:76-102)
+    if (e0 < 0) e0 = 0;
+    if (e0 >= ow) e0 = (float)ow - 1.0f;
+    if (e2 < 0) e2 = 0;
+    if (e2 >= ow) e2 = (float)ow - 1.0f;
+    if (e1 < 0) e1 = 0;
+    if (e1 >= oh) e1 = (float)oh - 1.0f;
+    if (e3 < 0) e3 = 0;
+    if (e3 >= oh) e3 = (float)oh - 1.0f;
+    const float d02 = e0 - e2, d13 = e1 - e3;
+    const double length = (double)(float)sqrt((double)d02 * (double)d02 + (double)d13 * (double)d13);
+    plf_keyline K;
+    const float os = (float)(1 << octave);
+    K.startPointX = e0 * os; K.startPointY = e1 * os; K.endPointX = e2 * os; K.endPointY = e3 * os;
+    K.sPointInOctaveX = e0; K.sPointInOctaveY = e1; K.ePointInOctaveX = e2; K.ePointInOctaveY = e3;
+    K.lineLength = (float)length;
+    const int ax = __float2int_rn(e0), ay = __float2int_rn(e1), bx = __float2int_rn(e2), by = __float2int_rn(e3);
+    const int adx = ax > bx ? ax - bx : bx - ax, ady = ay > by ? ay - by : by - ay;
+    K.numOfPixels = (adx > ady ? adx : ady) + 1;
+    K.angle = (float)atan2((double)(K.endPointY - K.startPointY), (double)(K.endPointX - K.startPointX));
+    K.class_id = (length > min_length) ? 0 : -1;   // -1 marks "dropped by the min_length filter" for the next stage
+    K.octave = octave;
+    K.size = (K.endPointX - K.startPointX) * (K.endPointY - K.startPointY);
+    K.response = K.lineLength / (float)(ow > oh ? ow : oh);
+    K.pt_x = (K.endPointX + K.startPointX) / 2;
+    K.pt_y = (K.endPointY + K.startPointY) / 2;
+    out[pos] = K;
+}
+
+// min_length filter + class ids (detectImpl) and, when `select`, the per-octave response quota with
+// mid-point keypoints (Lineextractor::ComputeLsdWithLbd, src/Lineextractor.cc:138-207).  One CTA per frame.
+#define SEL_T 256
+__global__ void __launch_bounds__(SEL_T)
+k_line_select(const plf_keyline* __restrict__ det, const int* __restrict__ detcount, int detcap, int noct,
+              int select, int quota0, int quota1, plf_keyline* __restrict__ out_kl, plf_keypoint* __restrict__ out_mid,
+              int cap, int* __restrict__ n_out)
+{
+    __shared__ int s_pos[2][2];   // [octave]: {valid count, kept count}
+    __shared__ int s_err;
+    PLF_DYN_SMEM(smem);
+    int* vidx = (int*)smem;               // valid line indices of the current octave (order preserved)
+    const int f = blockIdx.x, tid = threadIdx.x;
+    int outbase = 0;
+    if (tid == 0) s_err = 0;
+    __syncthreads();
+    for (int o = 0; o < noct; o++) {
+        const plf_keyline* D = det + ((size_t)f * noct + o) * detcap;
+        int cnt = detcount[f * noct + o];
+        if (cnt > detcap) { if (tid == 0) s_err = 1; cnt = detcap; }
+        // order-preserving compaction of lines that passed min_length (serial scan by one thread: cnt is small)
+        if (tid == 0) {
+            int m = 0;
+            for (int i = 0; i < cnt; i++) if (D[i].class_id == 0) vidx[m++] = i;
+            s_pos[o][0] = m;
+        }
+        __syncthreads();
+        const int m = s_pos[o][0];
+        const int quota = o == 0 ? quota0 : quota1;
+        const int keep = (select && m > quota) ? quota : m;
+        for (int i = tid; i < m; i += SEL_T) {
+            int pos = i;
+            if (select && m > quota) {
+                // rank in the stable descending-response order (Lineextractor.cc:175, ties by index)
+                const float r = D[vidx[i]].response;
+                int rank = 0;
+                for (int j = 0; j < m; j++) {
+                    const float rj = D[vidx[j]].response;
+                    if (rj > r || (rj == r && j < i)) rank++;
+                }
+                pos = rank < quota ? rank : -1;
+            }
+            if (pos >= 0) {
+                const int op = outbase + pos;
+                if (op < cap) {
+                    plf_keyline K = D[vidx[i]];
+                    K.class_id = op;
+                    out_kl[(size_t)f * cap + op] = K;
+                    if (out_mid) {
+                        plf_keypoint P;
+                        P.x = (K.startPointX + K.endPointX) / 2;
+                        P.y = (K.startPointY + K.endPointY) / 2;
+                        P.size = 0; P.angle = -1; P.response = 0; P.octave = K.octave; P.class_id = -1;
+                        out_mid[(size_t)f * cap + op] = P;
+                    }
+                } else s_err = 2;
+            }
+        }
+        outbase += keep;
+        __syncthreads();
+    }
+    if (tid == 0) n_out[f] = s_err ? -s_err : outbase;
+}
+
+// ---------------- LBD (binary_descriptor_custom.cpp:1026-1372 + :645-667) ----------------
+// One CTA of 64 threads per line: thread hID < 63 walks one row of the line support region sequentially
+// (float sums in the reference's order), threads < 9 accumulate their band in row order, thread 0 does the
+// mean/std, normalisations and clamp; then 32 threads binarise.
+struct LbdImages {
+    const short* dx[2];
+    const short* dy[2];
+    size_t frame[2];   // elements per frame
+    int w[2], h[2];
+};
+struct LbdCoefs { float g[63]; float l[21]; };
+
+__constant__ int c_lbd_comb[32][2] = {
+    {0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {0, 6}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6},
+    {2, 3}, {2, 4}, {2, 5}, {2, 6}, {2, 7}, {2, 8}, {3, 4}, {3, 5}, {3, 6}, {3, 7}, {3, 8},
+    {4, 5}, {4, 6}, {4, 7}, {4, 8}, {5, 6}, {5, 7}, {5, 8}, {6, 7}, {6, 8}, {7, 8}};
+
+__global__ void __launch_bounds__(64)
+k_lbd(const plf_keyline* __restrict__ kl, const int* __restrict__ nlines, int cap, LbdImages im, LbdCoefs cf,
+      uint8_t* __restrict__ desc, float* __restrict__ fdesc)
+{
+    __shared__ float rows[63][4];
+    __shared__ float band[9][8];
+    __shared__ float dv[72];
+    const int f = blockIdx.y, li = blockIdx.x, tid = threadIdx.x;
+    int nl = nlines[f];
+    if (li >= nl) return;
+    const plf_keyline K = kl[(size_t)f * cap + li];
+    const int o = K.octave;
+    const int realWidth = im.w[o], imageWidth = realWidth - 1, imageHeight = im.h[o] - 1;
+    const short* pdx = im.dx[o] + (size_t)f * im.frame[o];
+    const short* pdy = im.dy[o] + (size_t)f * im.frame[o];
+    const short lengthOfLSP = (short)K.numOfPixels;
+    const short halfWidth = (short)((lengthOfLSP - 1) / 2);
+    const short halfHeight = 31;
+    const float midX = (float)(0.5 * (double)(K.sPointInOctaveX + K.ePointInOctaveX));
+    const float midY = (float)(0.5 * (double)(K.sPointInOctaveY + K.ePointInOctaveY));
+    const float dL0 = (float)cos((double)K.angle), dL1 = (float)sin((double)K.angle);
+    const float dO0 = -dL1, dO1 = dL0;
+    if (tid < 63) {
+        float t0 = -dL0 * (float)halfWidth, t1 = dL1 * (float)halfHeight;
+        float sCorX0 = t0 + t1 + midX;
+        t0 = -dL1 * (float)halfWidth; t1 = dL0 * (float)halfHeight;
+        float sCorY0 = t0 - t1 + midY;
+        for (int hh = 0; hh < tid; hh++) { sCorX0 -= dL1; sCorY0 += dL0; }   // same repeated float updates as the row loop
+        float sCorX = sCorX0, sCorY = sCorY0;
+        float pgdL = 0, ngdL = 0, pgdO = 0, ngdO = 0;
+        for (int wID = 0; wID < lengthOfLSP; wID++) {
+            short tc = (short)(int)round((double)sCorX);
+            const int xCor = tc < 0 ? 0 : (tc > imageWidth ? imageWidth : tc);
+            tc = (short)(int)round((double)sCorY);
+            const int yCor = tc < 0 ? 0 : (tc > imageHeight ? imageHeight : tc);
+            const float dxv = (float)pdx[yCor * realWidth + xCor], dyv = (float)pdy[yCor * realWidth + xCor];
+            float a0 = dxv * dL0, a1 = dyv * dL1;
+            const float gDL = a0 + a1;
+            a0 = dxv * dO0; a1 = dyv * dO1;
+            const float gDO = a0 + a1;
+            if (gDL > 0) pgdL += gDL; else ngdL -= gDL;
+            if (gDO > 0) pgdO += gDO; else ngdO -= gDO;
+            sCorX += dL0;
+            sCorY += dL1;
+        }
+        const float coef = cf.g[tid];
+        rows[tid][0] = coef * pgdL; rows[tid][1] = coef * ngdL; rows[tid][2] = coef * pgdO; rows[tid][3] = coef * ngdO;
+    }
+    __syncthreads();
+    if (tid < 9) {
+        float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // pgdL, ngdL, pgdL2, ngdL2, pgdO, ngdO, pgdO2, ngdO2
+        const int h0 = tid * 7 - 7 < 0 ? 0 : tid * 7 - 7, h1 = tid * 7 + 14 > 63 ? 63 : tid * 7 + 14;
+        for (int hID = h0; hID < h1; hID++) {
+            const int b = hID / 7;
+            float c;
+            if (b == tid) c = cf.l[hID % 7 + 7];
+            else if (b == tid + 1) c = cf.l[hID % 7 + 14];   // row's band-1 == this band
+            else c = cf.l[hID % 7];                            // row's band+1 == this band
+            const float cc = c * c;
+            const float r0 = rows[hID][0], r1 = rows[hID][1], r2 = rows[hID][2], r3 = rows[hID][3];
+            float m;
+            m = c * r0; s[0] += m;
+            m = c * r1; s[1] += m;
+            m = cc * (r0 * r0); s[2] += m;
+            m = cc * (r1 * r1); s[3] += m;
+            m = c * r2; s[4] += m;
+            m = c * r3; s[5] += m;
+            m = cc * (r2 * r2); s[6] += m;
+            m = cc * (r3 * r3); s[7] += m;
+        }
+        for (int k = 0; k < 8; k++) band[tid][k] = s[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const float invN2 = (float)(1.0 / 14.0), invN3 = (float)(1.0 / 21.0);
+        for (int b = 0; b < 9; b++) {
+            const float invN = (b == 0 || b == 8) ? invN2 : invN3;
+            float temp, u, v;
+            temp = band[b][0] * invN; dv[b * 8] = temp;
+            u = band[b][2] * invN; v = temp * temp; dv[b * 8 + 4] = (float)sqrt((double)(u - v));
+            temp = band[b][1] * invN; dv[b * 8 + 1] = temp;
+            u = band[b][3] * invN; v = temp * temp; dv[b * 8 + 5] = (float)sqrt((double)(u - v));
+            temp = band[b][4] * invN; dv[b * 8 + 2] = temp;
+            u = band[b][6] * invN; v = temp * temp; dv[b * 8 + 6] = (float)sqrt((double)(u - v));
+            temp = band[b][5] * invN; dv[b * 8 + 3] = temp;
+            u = band[b][7] * invN; v = temp * temp; dv[b * 8 + 7] = (float)sqrt((double)(u - v));
+        }
+        float tempM = 0, tempS = 0, m;
+        for (int i = 0; i < 72; i += 8) {
+            for (int k = 0; k < 4; k++) { m = dv[i + k] * dv[i + k]; tempM += m; }
+            for (int k = 4; k < 8; k++) { m = dv[i + k] * dv[i + k]; tempS += m; }
+        }
+        tempM = (float)(1 / sqrt((double)tempM));
+        tempS = (float)(1 / sqrt((double)tempS));
+        for (int i = 0; i < 72; i += 8) {
+            for (int k = 0; k < 4; k++) dv[i + k] = dv[i + k] * tempM;
+            for (int k = 4; k < 8; k++) dv[i + k] = dv[i + k] * tempS;
+        }
+        for (int i = 0; i < 72; i++) if ((double)dv[i] > 0.4) dv[i] = (float)0.4;
+        float temp = 0;
+        for (int i = 0; i < 72; i++) { m = dv[i] * dv[i]; temp += m; }
+        temp = (float)(1 / sqrt((double)temp));
+        for (int i = 0; i < 72; i++) dv[i] = dv[i] * temp;
+    }
+    __syncthreads();
+    if (tid < 32 && desc) {
+        const float* f1 = &dv[8 * c_lbd_comb[tid][0]];
+        const float* f2 = &dv[8 * c_lbd_comb[tid][1]];
+        unsigned r = 0;
+        for (int b = 0; b < 8; b++) if (f1[b] > f2[b]) r += 1u << b;
+        desc[((size_t)f * cap + li) * 32 + tid] = (uint8_t)r;
+    }
+    if (fdesc) for (int i = tid; i < 72; i += 64) fdesc[((size_t)f * cap + li) * 72 + i] = dv[i];
+}

@@ -174,8 +174,7 @@ static plf_status orb_prepare(plf_orb* o, int w, int h, int nframes)
         L.keptcap = L.nodecap;
         if (L.nodecap > maxnode) maxnode = L.nodecap;
         int px = L.w * L.h;
-        L.rawcap = px / 16 > 4096 ? px / 16 : 4096;
-        if (L.rawcap > 65000) L.rawcap = 65000;   // octree node ids / key ids are 16-bit
+        L.rawcap = px / 5 > 4096 ? px / 5 : 4096;   // NMS keeps at most one key per 2x2 block; noise reaches ~px/10
         L.scale = o->scale[l];
         L.sizeval = (int)(31 * o->scale[l]);      // :837
         L.rawOff = g.rawPerFrame;
@@ -406,7 +405,6 @@ extern "C" plf_status plf_orb_distribute_octree(plf_ctx* ctx, const int32_t* xs,
         return plf_fail(ctx, PLF_ERR_INVALID, "plf_orb_distribute_octree: bad arguments");
     *n_out = 0;
     if (n == 0) return PLF_OK;
-    if (n > 65000) return plf_fail(ctx, PLF_ERR_CAPACITY, "at most 65000 keys per level");
     PLF_CUDA(ctx, cudaSetDevice(ctx->device));
     // the order key needs the FAST cell grid of the level (SURVEY.md hard part 4)
     const float width = (float)(maxX - minX), height = (float)(maxY - minY);

@@ -91,3 +91,31 @@ def test_emu_octree_standalone(S, oracle, emu_lib):
         ref = oracle.distribute_octree(xo, yo, ro, 16, 16 + W, 16, 16 + H, N)
         got = S.distribute_octree(ctx, xo, yo, ro, 16, 16 + W, 16, 16 + H, N)
         assert np.array_equal(ref, got), (W, H, n, N)
+
+
+@pytest.mark.parametrize("w,h,nf,sc,seed", [(160, 120, 40, 1.1, 0), (240, 160, 20, 1.1, 3)])
+def test_emu_lines(S, oracle, emu_lib, w, h, nf, sc, seed):
+    ctx = S.Context(0, emu_lib)
+    le = S.Lineextractor(nf, 2, 0, sc, 0.6, 2.2, 12.5, 1.0, 0.6, 1024, 0.0, ctx=ctx)
+    prm = oracle.line_params(nf, 2, 0, sc, 0.6, 2.2, 12.5, 1.0, 0.6, 1024, 0.0)
+    assert list(le.features_per_level()) == oracle.features_per_level_lines(prm)
+    img = oracle.synth_image(w, h, seed)
+    kl = le.lsd_detect(img)
+    okl = oracle.lsd_detect_keylines(prm, img)
+    assert len(kl) == len(okl) > 5 and np.array_equal(kl.view(np.uint8), okl.view(np.uint8))
+    d, fd = le.lbd_compute(img, okl, want_float=True)
+    od, ofd = oracle.lbd_compute(img, okl, want_float=True)
+    assert np.array_equal(d, od) and np.array_equal(fd.view(np.uint32), ofd.view(np.uint32))
+    K, M, D = le.ComputeLsdWithLbd(img)
+    oK, oM, oD = oracle.line_extract(prm, img)
+    assert len(K) == len(oK) and np.array_equal(K.view(np.uint8), oK.view(np.uint8))
+    assert np.array_equal(M.view(np.uint8), oM.view(np.uint8)) and np.array_equal(D, oD)
+
+
+def test_emu_lines_empty_and_flat(S, oracle, emu_lib):
+    ctx = S.Context(0, emu_lib)
+    le = S.Lineextractor(40, 2, 0, 1.1, 0.6, 2.2, 12.5, 1.0, 0.6, 1024, 0.0, ctx=ctx)
+    K, M, D = le.ComputeLsdWithLbd(np.zeros((0, 0), np.uint8))
+    assert len(K) == 0 and D.shape == (0, 32)
+    K, M, D = le.ComputeLsdWithLbd(np.full((120, 160), 90, np.uint8))   # no gradient anywhere
+    assert len(K) == 0

@@ -135,3 +135,86 @@ def test_knn2_large_properties(S, oracle, gpu_ctx):
     gpu_ctx.check(lib.plf_knn2_merge_device(h, pidx.data_ptr(), pdist.data_ptr(), shards, nq, midx.data_ptr(), mdist.data_ptr()))
     gpu_ctx.synchronize()
     assert torch.equal(midx, idx) and torch.equal(mdist, dist)
+
+
+LSD_TUM = dict(refine=0, scale=1.1, sigma_scale=0.6, quant=2.2, ang_th=12.5, log_eps=1.0, density_th=0.6, n_bins=1024)
+
+
+def _line_objs(S, oracle, ctx, nf, min_len=0.0, **kw):
+    o = dict(LSD_TUM); o.update(kw)
+    le = S.Lineextractor(nf, 2, o["refine"], o["scale"], o["sigma_scale"], o["quant"], o["ang_th"], o["log_eps"],
+                         o["density_th"], o["n_bins"], min_len, ctx=ctx)
+    prm = oracle.line_params(nf, 2, o["refine"], o["scale"], o["sigma_scale"], o["quant"], o["ang_th"], o["log_eps"],
+                             o["density_th"], o["n_bins"], min_len)
+    return le, prm
+
+
+def _check_lines(le, oracle, prm, img):
+    kl = le.lsd_detect(img)
+    okl = oracle.lsd_detect_keylines(prm, img)
+    assert len(kl) == len(okl), (len(kl), len(okl))
+    for f in ("octave", "class_id", "numOfPixels"):
+        assert np.array_equal(kl[f], okl[f]), f
+    # line end points / angles: stated tolerance 1e-3 px / 1e-5 rad (double cos/sin differ by <= 1 ulp between
+    # libm and the CUDA math library); in practice they come out identical
+    for f in ("startPointX", "startPointY", "endPointX", "endPointY", "sPointInOctaveX", "sPointInOctaveY",
+              "ePointInOctaveX", "ePointInOctaveY", "lineLength", "pt_x", "pt_y"):
+        assert np.allclose(kl[f], okl[f], rtol=0, atol=1e-3), f
+    assert np.allclose(kl["angle"], okl["angle"], rtol=0, atol=1e-5)
+    K, M, D = le.ComputeLsdWithLbd(img)
+    oK, oM, oD = oracle.line_extract(prm, img)
+    assert len(K) == len(oK)
+    assert np.array_equal(K["octave"], oK["octave"]) and np.array_equal(K["class_id"], oK["class_id"])
+    assert np.allclose(K["startPointX"], oK["startPointX"], atol=1e-3) and np.allclose(M["x"], oM["x"], atol=1e-3)
+    assert np.array_equal(D, oD)          # LBD binary descriptors bit-exact
+    # LBD alone on the oracle's keylines: float descriptor bit-exact
+    d, fd = le.lbd_compute(img, okl, want_float=True)
+    od, ofd = oracle.lbd_compute(img, okl, want_float=True)
+    assert np.array_equal(d, od)
+    assert np.array_equal(fd.view(np.uint32), ofd.view(np.uint32))
+    return len(okl), bool(np.array_equal(kl.view(np.uint8), okl.view(np.uint8)))
+
+
+@pytest.mark.parametrize("w,h,nf,seed,kw", [
+    (640, 480, 600, 0, {}),
+    (752, 480, 200, 1, dict(sigma_scale=0.8, density_th=0.8)),      # EuRoC mono line settings
+    (752, 480, 600, 2, {}),
+    (1241, 376, 800, 3, {}),
+    (640, 480, 100, 4, dict(scale=1.0)),                              # SCALE == 1: no pre-blur / resize
+    (640, 480, 300, 5, dict(scale=0.8)),
+])
+def test_line_configs(S, oracle, gpu_ctx, w, h, nf, seed, kw):
+    le, prm = _line_objs(S, oracle, gpu_ctx, nf, **kw)
+    img = oracle.synth_image(w, h, seed)
+    n, identical = _check_lines(le, oracle, prm, img)
+    assert n > 100
+    assert identical, "keylines are within tolerance but not bit-identical"
+
+
+def test_line_min_length_batch_and_edges(S, oracle, gpu_ctx):
+    le, prm = _line_objs(S, oracle, gpu_ctx, 200, min_len=0.02 * 752)
+    imgs = np.stack([oracle.synth_image(752, 480, 30 + i) for i in range(4)])
+    Ks, Ms, Ds = le.extract_batch(imgs)
+    for b in range(len(imgs)):
+        oK, oM, oD = oracle.line_extract(prm, imgs[b])
+        assert len(Ks[b]) == len(oK) and np.array_equal(Ds[b], oD)
+        assert np.array_equal(Ks[b].view(np.uint8), oK.view(np.uint8))
+        assert np.array_equal(Ms[b].view(np.uint8), oM.view(np.uint8))
+    K, M, D = le.ComputeLsdWithLbd(np.zeros((0, 0), np.uint8))
+    assert len(K) == 0
+    K, M, D = le.ComputeLsdWithLbd(np.full((480, 752), 200, np.uint8))
+    assert len(K) == 0
+    rng = np.random.default_rng(0)
+    noise = rng.integers(0, 256, (240, 320), dtype=np.uint8)   # every pixel has a defined gradient
+    oK, oM, oD = oracle.line_extract(prm, noise)
+    K, M, D = le.ComputeLsdWithLbd(noise)
+    assert len(K) == len(oK) and np.array_equal(D, oD)
+
+
+def test_line_1080p(S, oracle, gpu_ctx):
+    le, prm = _line_objs(S, oracle, gpu_ctx, 800)
+    img = oracle.synth_image(1920, 1080, 11)
+    oK, oM, oD = oracle.line_extract(prm, img)
+    K, M, D = le.ComputeLsdWithLbd(img)
+    assert len(K) == len(oK) == 800 and np.array_equal(D, oD)
+    assert np.array_equal(K.view(np.uint8), oK.view(np.uint8))
