@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of ORB + LSD/LBD extraction (BASELINE.json metric) on N B200.
+
+Workload (BASELINE.json configs[1]): EuRoC-style stereo 752x480 pairs, 1200 ORB points
+(8 levels x1.2, FAST 20/7) + LSD/LBD lines (EuRoC line settings: 200 lines, 2 octaves, LSD scale 1.1,
+sigma_scale 0.8, quant 2.2, ang_th 12.5, n_bins 1024) per image.  A "frame" is one image; a stereo pair is
+two frames (left -> rank 2k, right -> rank 2k+1 when N > 1; both on the one GPU when N = 1).
+A step = one batch of FRAMES_PER_GPU frames per GPU through the whole hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  (N > 1: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...)
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM (device-timed, max over
+ranks); `e2e` = the same through the C-ABI host-buffer calls (pinned host memory, H2D + D2H inside the
+timed region); `roofline` = the dominant kernel against the measured HBM peak; `cpu_baseline` = the oracle
+(CPU port of the reference algorithm) on the box's host cores on a bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 752, 480
+ORB = dict(nfeatures=1200, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7)
+LINE = dict(nfeatures=200, nlevels=2, refine=0, scale=1.1, sigma_scale=0.8, quant=2.2, ang_th=12.5, log_eps=1.0,
+            density_th=0.8, n_bins=1024, min_line_length=0.0)   # Examples/Monocular/EuRoC.yaml (Camera.width absent -> 0)
+FRAMES_PER_GPU = 128          # 64 stereo pairs
+WORKLOAD = "EuRoC-style stereo 752x480 pairs, 1200 ORB (8 lv x1.2, FAST 20/7) + LSD/LBD 200 lines per image"
+
+
+def make_frames(n_pairs, seed0):
+    """Synthetic stereo pairs: right = left shifted by a disparity + small noise."""
+    from oracle import oracle as O   # synthetic image generator only (inputs, not the measured path)
+    frames = []
+    for p in range(n_pairs):
+        left = O.synth_image(W, H, seed0 + p)
+        rng = np.random.default_rng(10_000 + seed0 + p)
+        right = np.roll(left, -int(rng.integers(4, 24)), axis=1).astype(np.int16) + rng.integers(-2, 3, left.shape)
+        frames.append(left)
+        frames.append(np.clip(right, 0, 255).astype(np.uint8))
+    return np.stack(frames)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_throughput(frames, nthreads):
+    """Oracle (CPU restatement of the reference algorithm) on `frames`, one frame per worker thread.
+    Mirrors the reference's per-frame work: ORBextractor::operator() + Lineextractor::ComputeLsdWithLbd."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    O.build()
+    prm = O.line_params(**LINE)
+    local = threading.local()
+
+    def work(i):
+        if not hasattr(local, "orb"):
+            local.orb = O.ORBextractor(ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"])
+        k, d = local.orb(frames[i])
+        kl, mid, ld = O.line_extract(prm, frames[i])
+        return len(k) + len(kl)
+
+    with ThreadPoolExecutor(nthreads) as ex:
+        list(ex.map(work, range(min(len(frames), nthreads))))   # warm-up (ctypes releases the GIL)
+        t0 = time.perf_counter()
+        list(ex.map(work, range(len(frames))))
+        dt = time.perf_counter() - t0
+    return len(frames) / dt, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port: the reference itself cannot be compiled
+    here -- no OpenCV C++/Eigen/Pangolin) on the host cores, all threads, bounded sample."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nfr = max(2 * cores, 32)
+    frames = make_frames(nfr // 2, 0)
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_oracle_throughput(frames[:cores], cores)
+    tot_t, tot_f = 0.0, 0
+    for _ in range(args.steps):
+        fps, dt = cpu_oracle_throughput(frames, cores)
+        tot_t += dt; tot_f += len(frames)
+    value = tot_f / tot_t
+    line = {"impl": "reference", "metric": "frames/s ORB+LSD/LBD extraction", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": len(frames)},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": "%d frames per step, one frame per thread on %d threads (C oracle, -O3)" % (len(frames), cores)},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import spl_slam_b200 as S
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = args.frames
+    assert B % 2 == 0 and B <= 254
+    # global frame i -> rank i mod world; this rank's frames: pairs p where frame index = 2p (+1)
+    n_pairs_global = B * world // 2
+    allf = make_frames(n_pairs_global, 0) if world == 1 else None
+    if world > 1:
+        mine = [i for i in range(B * world) if i % world == rank]
+        # generate only the pairs this rank touches
+        cache = {}
+        frames = []
+        for i in mine:
+            p = i // 2
+            if p not in cache:
+                cache[p] = make_frames(1, p)
+            frames.append(cache[p][i % 2])
+        frames = np.stack(frames)
+    else:
+        frames = allf
+    dev = local_rank
+    ctx_o = S.Context(dev)   # ORB stream
+    ctx_l = S.Context(dev)   # line stream
+    lib = ctx_o.lib
+    orb = S.ORBextractor(ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"], ctx=ctx_o)
+    le = S.Lineextractor(LINE["nfeatures"], LINE["nlevels"], LINE["refine"], LINE["scale"], LINE["sigma_scale"], LINE["quant"],
+                         LINE["ang_th"], LINE["log_eps"], LINE["density_th"], LINE["n_bins"], LINE["min_line_length"], ctx=ctx_l)
+    capk, capl = orb.max_keypoints, le.max_keylines
+    # device-resident inputs / outputs (torch only provides the memory)
+    d_img = torch.from_numpy(frames).cuda()
+    d_kps = torch.empty((B, capk, 28), dtype=torch.uint8, device="cuda"); d_desc = torch.empty((B, capk, 32), dtype=torch.uint8, device="cuda")
+    d_nk = torch.empty(B, dtype=torch.int32, device="cuda")
+    d_kl = torch.empty((B, capl, 68), dtype=torch.uint8, device="cuda"); d_mid = torch.empty((B, capl, 28), dtype=torch.uint8, device="cuda")
+    d_ld = torch.empty((B, capl, 32), dtype=torch.uint8, device="cuda"); d_nl = torch.empty(B, dtype=torch.int32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    # pinned host buffers for the end-to-end path
+    h_img = torch.from_numpy(frames).pin_memory()
+    h_kps = torch.empty((B, capk, 28), dtype=torch.uint8).pin_memory(); h_desc = torch.empty((B, capk, 32), dtype=torch.uint8).pin_memory()
+    h_kl = torch.empty((B, capl, 68), dtype=torch.uint8).pin_memory(); h_mid = torch.empty((B, capl, 28), dtype=torch.uint8).pin_memory()
+    h_ld = torch.empty((B, capl, 32), dtype=torch.uint8).pin_memory()
+    n_k = np.zeros(B, np.int32); n_l = np.zeros(B, np.int32)
+
+    def step_device():
+        ctx_o.check(lib.plf_orb_extract_batch_device(orb.h, d_img.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), capk, d_nk.data_ptr()))
+        ctx_l.check(lib.plf_line_extract_batch_device(le.h, d_img.data_ptr(), B, W, H, W, W * H, d_kl.data_ptr(), d_mid.data_ptr(), d_ld.data_ptr(), capl, d_nl.data_ptr()))
+
+    def timed_device_step():
+        flush.zero_()                      # L2 flush between timed iterations (untimed)
+        torch.cuda.synchronize()
+        ctx_o.timer_start()
+        step_device()
+        ctx_o.wait(ctx_l)                  # the ORB stream's stop event waits for the line stream
+        return ctx_o.timer_stop()
+
+    errs = []
+
+    def e2e_orb():
+        try:
+            ctx_o.check(lib.plf_orb_extract_batch(orb.h, h_img.data_ptr(), B, W, H, W, W * H, h_kps.data_ptr(), h_desc.data_ptr(), capk, n_k.ctypes.data))
+        except Exception as e:   # noqa
+            errs.append(e)
+
+    def e2e_line():
+        try:
+            ctx_l.check(lib.plf_line_extract_batch(le.h, h_img.data_ptr(), B, W, H, W, W * H, h_kl.data_ptr(), h_mid.data_ptr(), h_ld.data_ptr(), capl, n_l.ctypes.data))
+        except Exception as e:   # noqa
+            errs.append(e)
+
+    def timed_e2e_step():
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ta = threading.Thread(target=e2e_orb); tb = threading.Thread(target=e2e_line)   # the reference's two threads (Frame.cc:301-304)
+        ta.start(); tb.start(); ta.join(); tb.join()
+        if errs:
+            raise errs[0]
+        return (time.perf_counter() - t0) * 1e3
+
+    # ---- device-resident throughput ----
+    for _ in range(args.warmup):
+        timed_device_step()
+    barrier()
+    sampler = ClockSampler(dev) if rank == 0 else None
+    l0 = ctx_o.launch_count() + ctx_l.launch_count()
+    ms_dev = 0.0
+    for _ in range(args.steps):
+        ms_dev += timed_device_step()
+    barrier()
+    launches = ctx_o.launch_count() + ctx_l.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    nk = d_nk.cpu().numpy(); nl = d_nl.cpu().numpy()
+    assert (nk > 0).all() and (nl >= 0).all(), "extraction reported an overflow"
+
+    # ---- per-kernel times for the roofline (separate profiled steps, CUDA events per launch) ----
+    ctx_o.profile_enable(True); ctx_l.profile_enable(True)
+    PROF_STEPS = 3
+    for _ in range(PROF_STEPS):
+        flush.zero_(); torch.cuda.synchronize()
+        step_device()
+        ctx_o.synchronize(); ctx_l.synchronize()
+    prof = {}
+    for c in (ctx_o, ctx_l):
+        for k, v in c.profile_report().items():
+            prof[k] = (v[0] / PROF_STEPS, v[1] // PROF_STEPS)
+    ctx_o.profile_enable(False); ctx_l.profile_enable(False)
+
+    # ---- end to end ----
+    for _ in range(args.warmup):
+        timed_e2e_step()
+    barrier()
+    ms_e2e = 0.0
+    for _ in range(args.steps):
+        ms_e2e += timed_e2e_step()
+    barrier()
+
+    def maxr(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_dev = maxr(ms_dev); ms_e2e = maxr(ms_e2e)
+    total_frames = B * world * args.steps
+    value = total_frames / (ms_dev / 1e3)
+    e2e_value = total_frames / (ms_e2e / 1e3)
+    h2d = 2 * B * W * H                                              # each extractor uploads the batch once
+    d2h = B * (capk * 60 + 4 + capl * (68 + 28 + 32) + 4)
+
+    if rank == 0:
+        # roofline of the dominant kernel (by measured time share)
+        peak, peak_src = peaks()
+        sw, sh = int(round(W * LINE["scale"])), int(round(H * LINE["scale"]))
+        spx = sw * sh + (int(round((W // 2) * LINE["scale"])) * int(round((H // 2) * LINE["scale"])))   # scaled px, both octaves
+        lv = [(int(np.rint(np.float32(W) / np.float32(1.2) ** l)), int(np.rint(np.float32(H) / np.float32(1.2) ** l))) for l in range(8)]
+        sumpx = sum(a * b for a, b in lv)
+        # algorithmic bytes per frame per kernel (DESIGN.md "kernels and their bytes")
+        alg = {
+            "k_lsd_grow": 6 * spx, "k_lsd_grad": (1 + 20) * spx, "k_ccl_merge": 8 * spx, "k_lsd_keys": 8 * spx + 8 * spx // 10,
+            "k_fast_cells": sumpx, "k_blur7": 2 * sumpx, "k_resize_linear": 2 * sumpx - W * H,
+            "k_gauss_q8": 2 * (W * H + W * H // 4) * 2, "k_resize_exact": (W * H + W * H // 4) + spx,
+            "cub_radix_sort_keys": 2 * 8 * 8 * spx // 10,
+        }
+        top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, (0, 0))
+        step_kernel_ms = sum(v[0] for v in prof.values())
+        roof = None
+        if top[0]:
+            name, (ms_k, n_k_l) = top
+            bytes_launch = alg.get(name, 0) * B / max(n_k_l, 1)
+            achieved = bytes_launch / (ms_k / max(n_k_l, 1) / 1e3) / 1e9 if ms_k > 0 else 0.0
+            roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "launches_per_step": n_k_l, "ms_per_step": ms_k,
+                    "share_of_kernel_time": ms_k / step_kernel_ms if step_kernel_ms else None,
+                    "algorithmic_bytes_per_frame": alg.get(name, 0),
+                    "kernels_ms_per_step": {k: round(v[0], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+        cpu = None
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            sample = frames[:max(2 * cores, 32)] if len(frames) >= max(2 * cores, 32) else frames
+            fps, dt = cpu_oracle_throughput(sample, cores)
+            cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                   "sample": "%d of the step's frames, one frame per thread on %d threads, %.1f s (C oracle of the reference algorithm)" % (len(sample), cores, dt)}
+        line = {"metric": "frames/s ORB+LSD/LBD extraction", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "frame": "one 752x480 image; a stereo pair is 2 frames",
+                           "sharding": "frame i -> rank i mod N (left/right of a pair on separate GPUs for N > 1), no collective",
+                           "l2": "256 MiB buffer written between timed iterations; per-step working set ~%.1f GB" % (B * (45 * spx + 3 * sumpx) / 1e9)},
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "outputs": {"mean_keypoints": float(nk.mean()), "mean_lines": float(nl.mean())}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

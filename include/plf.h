@@ -68,6 +68,13 @@ plf_status plf_timer_start(plf_ctx* ctx);
 plf_status plf_timer_stop(plf_ctx* ctx, float* elapsed_ms);
 /* number of kernels this context has launched since creation (bench "gpu_launches") */
 uint64_t plf_ctx_launch_count(const plf_ctx* ctx);
+/* make ctx wait, on the device, for everything queued so far on `other` (the reference runs the ORB and the
+ * line extractor in two threads, src/Frame.cc:301-304; here they are two contexts / streams) */
+plf_status plf_ctx_wait(plf_ctx* ctx, plf_ctx* other);
+/* optional per-kernel timing: every launch is bracketed by CUDA events on the context stream and summed per
+ * kernel name; plf_profile_report writes "name total_ms launches" lines */
+plf_status plf_profile_enable(plf_ctx* ctx, int on);
+plf_status plf_profile_report(plf_ctx* ctx, char* buf, size_t bufsize);
 
 /* ---- ORB extractor: replaces PL_SLAM::ORBextractor
  * (include/ORBextractor.h:45-113, src/ORBextractor.cc:410-470, :1043-1132) ---- */

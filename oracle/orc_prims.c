@@ -280,6 +280,15 @@ static inline int fast_score(const uint8_t* p, const int* off, int th)
      * corner iff result > th */
     int v = p[0], d[25];
     int any_hi = 0, any_lo = 0;
+    /* quick reject (speed only): a 9-long arc contains one pixel of every opposite pair (k, k+8) */
+    {
+        int cls = 3;
+        for (int k = 0; k < 8 && cls; k++) {
+            int a = v - p[off[k]], b = v - p[off[k + 8]];
+            cls &= ((a > th) | (b > th)) | (((a < -th) | (b < -th)) << 1);
+        }
+        if (!cls) return 0;
+    }
     for (int k = 0; k < 16; k++) {
         d[k] = v - p[off[k]];
         any_hi |= d[k] > th;

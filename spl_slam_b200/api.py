@@ -69,6 +69,9 @@ def load(path=None):
         "plf_timer_start": (C.c_int, [vp]),
         "plf_timer_stop": (C.c_int, [vp, P(C.c_float)]),
         "plf_ctx_launch_count": (C.c_uint64, [vp]),
+        "plf_ctx_wait": (C.c_int, [vp, vp]),
+        "plf_profile_enable": (C.c_int, [vp, C.c_int]),
+        "plf_profile_report": (C.c_int, [vp, C.c_char_p, C.c_size_t]),
         "plf_orb_create": (C.c_int, [vp, P(OrbParams), P(vp)]),
         "plf_orb_destroy": (None, [vp]),
         "plf_orb_tables": (C.c_int, [vp, f32p, f32p, f32p, f32p, i32p]),
@@ -148,6 +151,22 @@ class Context:
 
     def stream(self):
         return self.lib.plf_ctx_stream(self.h)
+
+    def wait(self, other):
+        self.check(self.lib.plf_ctx_wait(self.h, other.h))
+
+    def profile_enable(self, on=True):
+        self.check(self.lib.plf_profile_enable(self.h, 1 if on else 0))
+
+    def profile_report(self):
+        """{kernel name: (total_ms, launches)} accumulated since profile_enable(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        self.check(self.lib.plf_profile_report(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, n = line.split()
+            out[name] = (float(ms), int(n))
+        return out
 
     def close(self):
         if getattr(self, "h", None):

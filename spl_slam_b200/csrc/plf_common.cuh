@@ -7,7 +7,13 @@
 #include "cuda_emu.h"
 #else
 #include <cuda_runtime.h>
-#define PLF_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// every launch site has a `plf_ctx* ctx` in scope; with profiling on, each launch is bracketed by CUDA events
+#define PLF_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
+    do {                                                                   \
+        plf_prof_begin(ctx, #kernel);                                      \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);        \
+        plf_prof_end(ctx);                                                 \
+    } while (0)
 #define PLF_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 #include <stdint.h>
@@ -30,7 +36,18 @@ struct plf_ctx {
     // pinned host staging (grown on demand)
     void* pinned;
     size_t pinned_bytes;
+    // optional per-kernel profiling (plf_profile_enable): event pairs per launch, summed per kernel name
+    int prof_on, prof_n;
+    struct plf_prof_state* prof;
 };
+
+#ifdef PLF_EMU
+static inline void plf_prof_begin(plf_ctx*, const char*) {}
+static inline void plf_prof_end(plf_ctx*) {}
+#else
+void plf_prof_begin(plf_ctx* ctx, const char* name);
+void plf_prof_end(plf_ctx* ctx);
+#endif
 
 static inline plf_status plf_fail(plf_ctx* ctx, plf_status st, const char* fmt, ...)
 {

@@ -91,3 +91,101 @@ plf_status plf_ctx_pinned(plf_ctx* c, size_t bytes, void** out)
     *out = c->pinned;
     return PLF_OK;
 }
+
+// ---------------- per-kernel profiling (bench.py roofline: CUDA events on the launching stream) ----------------
+#define PLF_PROF_MAX 8192
+#define PLF_PROF_NAMES 64
+struct plf_prof_state {
+    cudaEvent_t ev[PLF_PROF_MAX][2];
+    const char* name[PLF_PROF_MAX];
+    int created;
+    const char* names[PLF_PROF_NAMES];
+    double total_ms[PLF_PROF_NAMES];
+    long count[PLF_PROF_NAMES];
+    int nnames;
+};
+
+#ifndef PLF_EMU
+void plf_prof_begin(plf_ctx* c, const char* name)
+{
+    if (!c->prof_on || c->prof_n >= PLF_PROF_MAX) return;
+    plf_prof_state* p = c->prof;
+    if (c->prof_n >= p->created) {
+        cudaEventCreate(&p->ev[p->created][0]);
+        cudaEventCreate(&p->ev[p->created][1]);
+        p->created++;
+    }
+    p->name[c->prof_n] = name;
+    cudaEventRecord(p->ev[c->prof_n][0], c->stream);
+}
+void plf_prof_end(plf_ctx* c)
+{
+    if (!c->prof_on || c->prof_n >= PLF_PROF_MAX) return;
+    cudaEventRecord(c->prof->ev[c->prof_n][1], c->stream);
+    c->prof_n++;
+}
+#endif
+
+static void prof_collect(plf_ctx* c)
+{
+#ifndef PLF_EMU
+    plf_prof_state* p = c->prof;
+    if (!p) return;
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < c->prof_n; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p->ev[i][0], p->ev[i][1]) != cudaSuccess) continue;
+        int k = 0;
+        for (; k < p->nnames; k++) if (p->names[k] == p->name[i] || !strcmp(p->names[k], p->name[i])) break;
+        if (k == p->nnames) {
+            if (p->nnames >= PLF_PROF_NAMES) continue;
+            p->names[k] = p->name[i]; p->total_ms[k] = 0; p->count[k] = 0; p->nnames++;
+        }
+        p->total_ms[k] += ms; p->count[k]++;
+    }
+    c->prof_n = 0;
+#endif
+}
+
+// enable/disable per-launch event timing; enabling resets the accumulated table
+extern "C" plf_status plf_profile_enable(plf_ctx* c, int on)
+{
+    if (!c) return PLF_ERR_INVALID;
+    if (on) {
+        if (!c->prof) c->prof = (plf_prof_state*)calloc(1, sizeof(plf_prof_state));
+        c->prof->nnames = 0;
+        c->prof_n = 0;
+    } else if (c->prof_on) {
+        prof_collect(c);
+    }
+    c->prof_on = on ? 1 : 0;
+    return PLF_OK;
+}
+
+// writes "name total_ms launches\n" lines into buf; returns PLF_ERR_CAPACITY if buf is too small
+extern "C" plf_status plf_profile_report(plf_ctx* c, char* buf, size_t bufsize)
+{
+    if (!c || !buf || bufsize < 2) return PLF_ERR_INVALID;
+    buf[0] = 0;
+    if (!c->prof) return PLF_OK;
+    prof_collect(c);
+    size_t o = 0;
+    for (int k = 0; k < c->prof->nnames; k++) {
+        int n = snprintf(buf + o, bufsize - o, "%s %.6f %ld\n", c->prof->names[k], c->prof->total_ms[k], c->prof->count[k]);
+        if (n < 0 || (size_t)n >= bufsize - o) return PLF_ERR_CAPACITY;
+        o += n;
+    }
+    return PLF_OK;
+}
+
+// make `ctx` wait (on the device) for everything queued so far on `other` (ORB and line contexts run on two streams)
+extern "C" plf_status plf_ctx_wait(plf_ctx* c, plf_ctx* other)
+{
+    if (!c || !other) return PLF_ERR_INVALID;
+    cudaEvent_t e;
+    PLF_CUDA(c, cudaEventCreate(&e));
+    PLF_CUDA(c, cudaEventRecord(e, other->stream));
+    PLF_CUDA(c, cudaStreamWaitEvent(c->stream, e, 0));
+    PLF_CUDA(c, cudaEventDestroy(e));
+    return PLF_OK;
+}

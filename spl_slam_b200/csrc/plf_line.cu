@@ -284,8 +284,10 @@ static plf_status sort_keys(plf_line* o, int n)
     memcpy(o->d_keys2, o->d_keys, (size_t)n * 8);
 #else
     size_t tb = o->cubtmp_bytes;
-    PLF_CUDA(ctx, cub::DeviceRadixSort::SortKeys(o->d_cubtmp, tb, o->d_keys, o->d_keys2, n, 0, 64, ctx->stream));
-    ctx->launches += 8;
+    plf_prof_begin(ctx, "cub_radix_sort_keys");
+    cudaError_t e = cub::DeviceRadixSort::SortKeys(o->d_cubtmp, tb, o->d_keys, o->d_keys2, n, 0, 64, ctx->stream);
+    plf_prof_end(ctx);
+    PLF_CUDA(ctx, e);
 #endif
     return PLF_OK;
 }
@@ -301,8 +303,10 @@ static plf_status sort_lines(plf_line* o)
 #else
     size_t tb = o->cubtmp_bytes;
     // padding keys are ~0: sort all 64 bits so they land at the end
-    PLF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(o->d_cubtmp, tb, o->d_linekey, o->d_linekey2, o->d_lineidx, o->d_lineidx2, o->regcap, 0, 64, ctx->stream));
-    ctx->launches += 8;
+    plf_prof_begin(ctx, "cub_radix_sort_lines");
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(o->d_cubtmp, tb, o->d_linekey, o->d_linekey2, o->d_lineidx, o->d_lineidx2, o->regcap, 0, 64, ctx->stream);
+    plf_prof_end(ctx);
+    PLF_CUDA(ctx, e);
 #endif
     return PLF_OK;
 }
