@@ -30,7 +30,8 @@ struct plf_line {
     uint8_t *d_oct[LINE_MAX_OCT], *d_tmp, *d_scaled;       // images (pitch == width)
     uint8_t *d_lbdimg[LINE_MAX_OCT];
     short *d_dx[LINE_MAX_OCT], *d_dy[LINE_MAX_OCT];
-    int *d_q, *d_label, *d_regpts, *d_comp, *d_lineidx, *d_lineidx2, *d_cnt, *d_detcount;
+    int2* d_comp;
+    int *d_q, *d_label, *d_regpts, *d_lineidx, *d_lineidx2, *d_cnt, *d_detcount;
     float* d_fa;
     float2* d_cs;
     unsigned long long *d_keys, *d_keys2, *d_linekey, *d_linekey2;
@@ -52,8 +53,8 @@ struct plf_line {
     int out_frames, out_cap;
 };
 
-// d_cnt layout (ints): [0]=nkeys [1]=ncomp [2]=next [3]=nregions [4]=sticky overflow flag [8..8+frames) = maxq
-enum { CNT_NKEYS = 0, CNT_NCOMP = 1, CNT_NEXT = 2, CNT_NREG = 3, CNT_ERR = 4, CNT_MAXQ = 8 };
+// d_cnt layout (ints): [0]=nkeys [1]=ncomp [2]=next [3]=nregions [4]=sticky overflow flag [8..32) bucket counts [32..56) bucket fill [64..64+frames) = maxq
+enum { CNT_NKEYS = 0, CNT_NCOMP = 1, CNT_NEXT = 2, CNT_NREG = 3, CNT_ERR = 4, CNT_BCOUNT = 8, CNT_BFILL = 32, CNT_MAXQ = 64 };
 
 static int gauss_kernel_q8(int ksize, double sigma, int* q)
 {
@@ -221,7 +222,7 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
     }
     need(F * (size_t)w * h, 1); need(F * maxpx, 1);
     need(F * maxpx, 4); need(F * maxpx, 4); need(F * maxpx, 4); need(F * maxpx, 8);   // q, label, fa, cs
-    need(o->keycap, 8); need(o->keycap, 8); need(o->keycap, 4); need(o->keycap, 4);    // keys, keys2, regpts, comp
+    need(o->keycap, 8); need(o->keycap, 8); need(o->keycap, 4); need(o->keycap, 8);    // keys, keys2, regpts, comp
     need(o->regcap, sizeof(LsdRegion)); need(o->regcap, sizeof(float4));
     need(o->regcap, 8); need(o->regcap, 8); need(o->regcap, 4); need(o->regcap, 4);
     need(F * noct * LINE_DETCAP, sizeof(plf_keyline));
@@ -244,7 +245,7 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
     o->d_keys = carve<unsigned long long>(p, o->keycap);
     o->d_keys2 = carve<unsigned long long>(p, o->keycap);
     o->d_regpts = carve<int>(p, o->keycap);
-    o->d_comp = carve<int>(p, o->keycap);
+    o->d_comp = carve<int2>(p, o->keycap);
     o->d_regions = carve<LsdRegion>(p, o->regcap);
     o->d_lines = carve<float4>(p, o->regcap);
     o->d_linekey = carve<unsigned long long>(p, o->regcap);
@@ -338,6 +339,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             scaled = o->d_scaled;
         }
         PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt, 0, 4 * sizeof(int), st));
+        PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt + CNT_BCOUNT, 0, (CNT_MAXQ - CNT_BCOUNT) * sizeof(int), st));
         PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt + CNT_MAXQ, 0xff, (size_t)nframes * sizeof(int), st));   // maxq = -1
         dim3 g2(plf_div_up(sw, 32), plf_div_up(sh, 8), nframes), b2(32, 8);
         PLF_LAUNCH(k_lsd_grad, g2, b2, 0, st, scaled, (size_t)sw * sh, sw, sw, sh, o->rho, o->d_q, o->d_fa, o->d_cs, o->d_label,
@@ -355,12 +357,26 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         if (nkeys > 0) {
             plf_status s = sort_keys(o, nkeys);
             if (s) return s;
-            PLF_LAUNCH(k_lsd_heads, dim3(plf_div_up(nkeys, 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2, nkeys, o->d_comp,
-                       o->d_cnt + CNT_NCOMP);
-            PLF_CHECK_LAUNCH(ctx);
-            PLF_LAUNCH(k_lsd_grow, dim3(148 * 4), dim3(128), 0, st, (const unsigned long long*)o->d_keys2, nkeys, (const int*)o->d_comp,
-                       (const int*)(o->d_cnt + CNT_NCOMP), o->d_cnt + CNT_NEXT, o->d_fa, (const float2*)o->d_cs, sw, sh, o->prec,
-                       o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap);
+            for (int pass = 0; pass < 2; pass++) {
+                PLF_LAUNCH(k_lsd_heads, dim3(plf_div_up(nkeys, 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2, nkeys, o->d_comp,
+                           o->d_cnt + CNT_BCOUNT, o->d_cnt + CNT_BFILL, pass);
+                PLF_CHECK_LAUNCH(ctx);
+            }
+            // big components first (one CTA each, `used` bitmap in shared memory) when the bitmap fits
+            const size_t bm = (((size_t)sw * sh + 31) / 32) * 4;
+            const int use_big = bm <= 160 * 1024;
+            if (use_big) {
+#ifndef PLF_EMU
+                PLF_CUDA(ctx, cudaFuncSetAttribute(k_lsd_grow_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm));
+#endif
+                PLF_LAUNCH(k_lsd_grow_big, dim3(nframes * 4 < 64 ? 64 : nframes * 4), dim3(32), bm, st, (const unsigned long long*)o->d_keys2,
+                           (const int2*)o->d_comp, (const int*)(o->d_cnt + CNT_BCOUNT), (const float*)o->d_fa, (const float2*)o->d_cs, sw, sh,
+                           o->prec, o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap);
+                PLF_CHECK_LAUNCH(ctx);
+            }
+            PLF_LAUNCH(k_lsd_grow, dim3(148 * 4), dim3(128), 0, st, (const unsigned long long*)o->d_keys2, nkeys, (const int2*)o->d_comp,
+                       (const int*)(o->d_cnt + CNT_BCOUNT), o->d_cnt + CNT_NEXT, o->d_fa, (const float2*)o->d_cs, sw, sh, o->prec,
+                       o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap, use_big);
             PLF_CHECK_LAUNCH(ctx);
         }
         PLF_LAUNCH(k_lsd_rect, dim3(plf_div_up(o->regcap, 128)), dim3(128), 0, st, (const LsdRegion*)o->d_regions,

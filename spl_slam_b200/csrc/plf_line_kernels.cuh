@@ -235,13 +235,30 @@ k_lsd_keys(const int* __restrict__ label, const int* __restrict__ q, const int* 
     }
 }
 
-// component heads in the sorted key array
+// component heads in the sorted key array.  Two passes (count, fill) bucket the components by
+// floor(log2(size)) so that the grow kernel starts the largest components first (longest-chain-first).
+#define LSD_NBUCKET 24
+#define LSD_BIG_BUCKET 11   // components with >= 2048 seeds get a CTA of their own (k_lsd_grow_big)
 __global__ void __launch_bounds__(256)
-k_lsd_heads(const unsigned long long* __restrict__ keys, int n, int* __restrict__ comp, int* __restrict__ ncomp)
+k_lsd_heads(const unsigned long long* __restrict__ keys, int n, int2* __restrict__ comp, int* __restrict__ bcount,
+            int* __restrict__ bfill, int pass)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
-    if (i == 0 || LSD_KEY_TAG(keys[i]) != LSD_KEY_TAG(keys[i - 1])) comp[atomicAdd(ncomp, 1)] = i;
+    const unsigned long long tag = LSD_KEY_TAG(keys[i]);
+    if (i != 0 && LSD_KEY_TAG(keys[i - 1]) == tag) return;
+    int lo = i + 1, hi = n;   // first index whose tag differs
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (LSD_KEY_TAG(keys[mid]) == tag) lo = mid + 1; else hi = mid;
+    }
+    const int size = lo - i;
+    int b = 31 - __clz(size);
+    if (b >= LSD_NBUCKET) b = LSD_NBUCKET - 1;
+    if (pass == 0) { atomicAdd(&bcount[b], 1); return; }
+    int base = 0;
+    for (int k = LSD_NBUCKET - 1; k > b; k--) base += bcount[k];
+    comp[base + atomicAdd(&bfill[b], 1)] = make_int2(i, size);
 }
 
 struct LsdRegion {
@@ -250,58 +267,177 @@ struct LsdRegion {
     unsigned long long seedkey;   // key of the seed pixel (frame, bin, raster index)
 };
 
-// region_grow for every seed of one component, one thread per component, dynamic work distribution
+// region_grow for every seed of one component, one thread per component, dynamic work distribution.
+// Region points are stored packed (x | y << 16).  The 3x3 neighbourhood of a popped point is loaded in one
+// batch (the only writes in between are this thread's own USED marks on distinct pixels), so a pop costs
+// one memory round trip instead of nine.
 __global__ void __launch_bounds__(128)
-k_lsd_grow(const unsigned long long* __restrict__ keys, int n, const int* __restrict__ comp, const int* __restrict__ ncomp_p,
+k_lsd_grow(const unsigned long long* __restrict__ keys, int n, const int2* __restrict__ comp, const int* __restrict__ bcount,
            int* __restrict__ next, float* __restrict__ fa, const float2* __restrict__ cs, int w, int h, double prec,
-           int min_reg_size, int* __restrict__ regpts, LsdRegion* __restrict__ regions, int* __restrict__ nregions, int regcap)
+           int min_reg_size, int* __restrict__ regpts, LsdRegion* __restrict__ regions, int* __restrict__ nregions, int regcap, int skip_big)
 {
-    const int ncomp = *ncomp_p;
+    int ncomp = 0, cbase = 0;
+    for (int k = 0; k < LSD_NBUCKET; k++) ncomp += bcount[k];
+    if (skip_big) for (int k = LSD_BIG_BUCKET; k < LSD_NBUCKET; k++) cbase += bcount[k];   // done by k_lsd_grow_big
+    ncomp -= cbase;
+    comp += cbase;
     const size_t px = (size_t)w * h;
+    // components are listed largest first.  Lanes of one warp execute divergent chains one after another, so
+    // the first round gives every WARP one of the largest components (lane 0), then the next largest to lane 1,
+    // ...; later rounds draw from the shared counter.
+    const int lane = threadIdx.x & 31;
+    const int totalWarps = (gridDim.x * blockDim.x) >> 5;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    bool first = true;
     for (;;) {
-        const int c = atomicAdd(next, 1);
-        if (c >= ncomp) break;
-        const int start = comp[c];
-        const unsigned long long tag = LSD_KEY_TAG(keys[start]);
+        int c;
+        if (first) { c = lane * totalWarps + gwarp; first = false; }
+        else c = 32 * totalWarps + atomicAdd(next, 1);
+        if (c >= ncomp) { if (c >= 32 * totalWarps) break; else continue; }
+        const int start = comp[c].x, end = start + comp[c].y;
         float* F = fa + (size_t)LSD_KEY_FRAME(keys[start]) * px;
         const float2* CS = cs + (size_t)LSD_KEY_FRAME(keys[start]) * px;
         int arena = start;
-        for (int i = start; i < n; i++) {
+        for (int i = start; i < end; i++) {
             const unsigned long long key = keys[i];
-            if (LSD_KEY_TAG(key) != tag) break;
             const int p = LSD_KEY_IDX(key);
             const float v0 = F[p];
             if (v0 < -500.f) continue;   // already used by an earlier region
             const int r0 = arena;
-            regpts[arena++] = p;
+            {
+                const int sy = p / w;
+                regpts[arena++] = (p - sy * w) | (sy << 16);
+            }
             double reg_angle = (double)v0 * LSD_D2R;
             float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
             F[p] = LSD_USED;
+            int pp = regpts[r0];
             for (int r = r0; r < arena; r++) {
-                const int pp = regpts[r];
-                const int y = pp / w, x = pp - y * w;
-                const int xx_min = max(x - 1, 0), xx_max = min(x + 1, w - 1);
-                const int yy_min = max(y - 1, 0), yy_max = min(y + 1, h - 1);
-                for (int yy = yy_min; yy <= yy_max; ++yy)
-                    for (int xx = xx_min; xx <= xx_max; ++xx) {
-                        const int qi = yy * w + xx;
-                        const float v = F[qi];
-                        if (v < -500.f) continue;   // NOTDEF or USED
-                        double n_theta = reg_angle - (double)v * LSD_D2R;
+                const int x = pp & 0xffff, y = pp >> 16;
+                float v[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    const int xx = x + (k % 3) - 1, yy = y + (k / 3) - 1;
+                    const bool inb = xx >= 0 && yy >= 0 && xx < w && yy < h;
+                    v[k] = inb ? F[yy * w + xx] : LSD_NOTDEF;
+                }
+                if (r + 1 < arena) pp = regpts[r + 1];   // overlap the next pop with this point's tests
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    if (v[k] < -500.f) continue;   // NOTDEF, USED or outside
+                    double n_theta = reg_angle - (double)v[k] * LSD_D2R;
+                    if (n_theta < 0) n_theta = -n_theta;
+                    if (n_theta > LSD_3_2_PI) {
+                        n_theta -= LSD_2PI;
                         if (n_theta < 0) n_theta = -n_theta;
-                        if (n_theta > LSD_3_2_PI) {
-                            n_theta -= LSD_2PI;
-                            if (n_theta < 0) n_theta = -n_theta;
-                        }
-                        if (n_theta <= prec) {
-                            F[qi] = LSD_USED;
-                            regpts[arena++] = qi;
-                            const float2 c2 = CS[qi];
-                            sumdx += c2.x;
-                            sumdy += c2.y;
-                            reg_angle = (double)plf_fast_atan2(sumdy, sumdx) * LSD_D2R;
-                        }
                     }
+                    if (n_theta <= prec) {
+                        const int xx = x + (k % 3) - 1, yy = y + (k / 3) - 1;
+                        const int qi = yy * w + xx;
+                        F[qi] = LSD_USED;
+                        if (arena == r + 1) pp = xx | (yy << 16);   // it is the next point to pop
+                        regpts[arena++] = xx | (yy << 16);
+                        const float2 c2 = CS[qi];
+                        sumdx += c2.x;
+                        sumdy += c2.y;
+                        reg_angle = (double)plf_fast_atan2(sumdy, sumdx) * LSD_D2R;
+                    }
+                }
+            }
+            const int nreg = arena - r0;
+            if (nreg >= min_reg_size) {
+                const int rr = atomicAdd(nregions, 1);
+                if (rr < regcap) {
+                    LsdRegion R;
+                    R.start = r0; R.n = nreg; R.reg_angle = reg_angle; R.seedkey = key;
+                    regions[rr] = R;
+                }
+            }
+        }
+    }
+}
+
+// Large components (>= LSD_BIG_SIZE seeds): one CTA per component, lane 0 walks the chain.  The `used` state of
+// the whole scaled image lives in a shared-memory bitmap, so the angle / cos-sin arrays stay read-only
+// (L1-resident along the edge being followed) and a pop costs tens of cycles instead of an L2 round trip.
+// Valid because a component's regions only ever test pixels of the same component or NOTDEF pixels.
+__global__ void __launch_bounds__(32)
+k_lsd_grow_big(const unsigned long long* __restrict__ keys, const int2* __restrict__ comp, const int* __restrict__ bcount,
+               const float* __restrict__ fa, const float2* __restrict__ cs, int w, int h, double prec, int min_reg_size,
+               int* __restrict__ regpts, LsdRegion* __restrict__ regions, int* __restrict__ nregions, int regcap)
+{
+    PLF_DYN_SMEM(smem);
+    unsigned* used = (unsigned*)smem;
+    int nbig = 0;
+    for (int k = LSD_BIG_BUCKET; k < LSD_NBUCKET; k++) nbig += bcount[k];
+    const size_t px = (size_t)w * h;
+    const int words = (int)((px + 31) >> 5);
+    for (int c = blockIdx.x; c < nbig; c += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < words; i += 32) used[i] = 0u;
+        __syncthreads();
+        if (threadIdx.x != 0) continue;
+        const int start = comp[c].x, end = start + comp[c].y;
+        const float* F = fa + (size_t)LSD_KEY_FRAME(keys[start]) * px;
+        const float2* CS = cs + (size_t)LSD_KEY_FRAME(keys[start]) * px;
+        int arena = start;
+        for (int i = start; i < end; i++) {
+            const unsigned long long key = keys[i];
+            const int p = LSD_KEY_IDX(key);
+            if ((used[p >> 5] >> (p & 31)) & 1u) continue;
+            const int r0 = arena;
+            {
+                const int sy = p / w;
+                regpts[arena++] = (p - sy * w) | (sy << 16);
+            }
+            double reg_angle = (double)F[p] * LSD_D2R;
+            float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
+            used[p >> 5] |= 1u << (p & 31);
+            int pp = regpts[r0];
+            for (int r = r0; r < arena; r++) {
+                const int x = pp & 0xffff, y = pp >> 16;
+                // all loads of this pop are issued unconditionally (clamped addresses) so they overlap
+                float v[9];
+                float2 cv[9];
+                int qa[9];
+                unsigned ub[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    const int xx = min(max(x + (k % 3) - 1, 0), w - 1), yy = min(max(y + (k / 3) - 1, 0), h - 1);
+                    qa[k] = yy * w + xx;
+                }
+#pragma unroll
+                for (int k = 0; k < 9; k++) v[k] = __ldg(&F[qa[k]]);
+#pragma unroll
+                for (int k = 0; k < 9; k++) cv[k] = __ldg(&CS[qa[k]]);
+#pragma unroll
+                for (int k = 0; k < 9; k++) ub[k] = (used[qa[k] >> 5] >> (qa[k] & 31)) & 1u;
+                if (r + 1 < arena) pp = regpts[r + 1];
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    const int xx = x + (k % 3) - 1, yy = y + (k / 3) - 1;
+                    if (ub[k] || xx < 0 || yy < 0 || xx >= w || yy >= h) v[k] = LSD_USED;
+                }
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    if (v[k] < -500.f) continue;
+                    double n_theta = reg_angle - (double)v[k] * LSD_D2R;
+                    if (n_theta < 0) n_theta = -n_theta;
+                    if (n_theta > LSD_3_2_PI) {
+                        n_theta -= LSD_2PI;
+                        if (n_theta < 0) n_theta = -n_theta;
+                    }
+                    if (n_theta <= prec) {
+                        const int xx = x + (k % 3) - 1, yy = y + (k / 3) - 1;
+                        const int qi = yy * w + xx;
+                        used[qi >> 5] |= 1u << (qi & 31);
+                        if (arena == r + 1) pp = xx | (yy << 16);
+                        regpts[arena++] = xx | (yy << 16);
+                        sumdx += cv[k].x;
+                        sumdy += cv[k].y;
+                        reg_angle = (double)plf_fast_atan2(sumdy, sumdx) * LSD_D2R;
+                    }
+                }
             }
             const int nreg = arena - r0;
             if (nreg >= min_reg_size) {
@@ -335,9 +471,9 @@ k_lsd_rect(const LsdRegion* __restrict__ regions, const int* __restrict__ nregio
     const int* pts = regpts + R.start;
     double x = 0, y = 0, sum = 0;
     for (int i = 0; i < R.n; i++) {
-        const int p = pts[i];
-        const int py = p / w, pxx = p - py * w;
-        const double weight = sqrt((double)Q[p] / 4.0);
+        const int pk = pts[i];
+        const int py = pk >> 16, pxx = pk & 0xffff;
+        const double weight = sqrt((double)Q[py * w + pxx] / 4.0);
         x += (double)pxx * weight;
         y += (double)py * weight;
         sum += weight;
@@ -345,9 +481,9 @@ k_lsd_rect(const LsdRegion* __restrict__ regions, const int* __restrict__ nregio
     x /= sum; y /= sum;
     double Ixx = 0, Iyy = 0, Ixy = 0;
     for (int i = 0; i < R.n; i++) {
-        const int p = pts[i];
-        const int py = p / w, pxx = p - py * w;
-        const double weight = sqrt((double)Q[p] / 4.0);
+        const int pk = pts[i];
+        const int py = pk >> 16, pxx = pk & 0xffff;
+        const double weight = sqrt((double)Q[py * w + pxx] / 4.0);
         const double dx = (double)pxx - x, dy = (double)py - y;
         Ixx += dy * dy * weight;
         Iyy += dx * dx * weight;
@@ -364,8 +500,8 @@ k_lsd_rect(const LsdRegion* __restrict__ regions, const int* __restrict__ nregio
     const double dx = cos(theta), dy = sin(theta);
     double l_min = 0, l_max = 0;
     for (int i = 0; i < R.n; i++) {
-        const int p = pts[i];
-        const int py = p / w, pxx = p - py * w;
+        const int pk = pts[i];
+        const int py = pk >> 16, pxx = pk & 0xffff;
         const double regdx = (double)pxx - x, regdy = (double)py - y;
         const double l = regdx * dx + regdy * dy;
         if (l > l_max) l_max = l;

@@ -1,0 +1,62 @@
+"""Multi-GPU sharding of the hot path (one process per GPU, torch.distributed for the plumbing).
+
+Extraction shards by frame with no data-path collective (frame i -> rank i mod N; the left/right images of
+a stereo pair land on neighbouring ranks).  Brute-force matching shards the TRAIN set by rows; every rank
+computes its local top-2 with global indices, the per-shard tables are all-gathered (NCCL over NVLink on
+GPUs, 16 B per query per rank) and merged by (distance, index), which reproduces the single-GPU
+cv::BFMatcher ordering exactly, ties included.
+"""
+import numpy as np
+
+
+def frame_shard(nframes, rank, world):
+    """Global frame ids processed by `rank`."""
+    return list(range(rank, nframes, world))
+
+
+def train_shard(nt, rank, world):
+    """Row range [begin, end) of the train set owned by `rank`: row j -> shard floor(j * world / nt)."""
+    begin = -(-rank * nt // world)          # ceil(rank * nt / world)
+    end = -(-(rank + 1) * nt // world)
+    return begin, min(end, nt)
+
+
+def knn2_sharded(ctx, q, t_local, index_base, group=None):
+    """Top-2 of every query over the union of all ranks' train shards.
+
+    q: (nq, 32) uint8 torch tensor (replicated on every rank); t_local: this rank's (nt_local, 32) shard;
+    index_base: global row index of t_local[0].  Tensors live where the context's library computes
+    (CUDA for libplf.so).  Returns (idx, dist) int32 (nq, 2) tensors, identical on every rank.
+    """
+    import torch
+    import torch.distributed as dist
+    nq = q.shape[0]
+    idx = torch.empty((nq, 2), dtype=torch.int32, device=q.device)
+    dst = torch.empty((nq, 2), dtype=torch.int32, device=q.device)
+    lib = ctx.lib
+    ctx.check(lib.plf_hamming_knn2_device(ctx.h, q.data_ptr(), nq, t_local.data_ptr() if t_local.numel() else None,
+                                          int(t_local.shape[0]), int(index_base), idx.data_ptr(), dst.data_ptr()))
+    ctx.synchronize()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return idx, dst
+    pidx = torch.empty((world, nq, 2), dtype=torch.int32, device=q.device)
+    pdst = torch.empty((world, nq, 2), dtype=torch.int32, device=q.device)
+    dist.all_gather_into_tensor(pidx, idx, group=group)
+    dist.all_gather_into_tensor(pdst, dst, group=group)
+    if q.is_cuda:
+        torch.cuda.current_stream().synchronize()
+    ctx.check(lib.plf_knn2_merge_device(ctx.h, pidx.data_ptr(), pdst.data_ptr(), world, nq, idx.data_ptr(), dst.data_ptr()))
+    ctx.synchronize()
+    return idx, dst
+
+
+def nnr_from_knn2(ctx, idx, dst, nnr):
+    """Ratio test of Linematcher::matchNNR (src/Linematcher.cc:534-538) on a merged top-2 table."""
+    import torch
+    nq = idx.shape[0]
+    m12 = torch.empty(nq, dtype=torch.int32, device=idx.device)
+    nm = torch.zeros(1, dtype=torch.int32, device=idx.device)
+    ctx.check(ctx.lib.plf_nnr_from_knn2_device(ctx.h, idx.data_ptr(), dst.data_ptr(), nq, float(nnr), m12.data_ptr(), nm.data_ptr()))
+    ctx.synchronize()
+    return m12, int(nm.item())
