@@ -1,0 +1,217 @@
+// plf_slam_shim.hpp -- C++ drop-in classes with the reference's signatures on top of the C ABI (plf.h).
+//
+// Include this INSTEAD of the reference's include/ORBextractor.h / include/Lineextractor.h and link libplf.so:
+//   PL_SLAM::ORBextractor        include/ORBextractor.h:45-113      (ctor, operator(), six getters, mvImagePyramid)
+//   PL_SLAM::Lineextractor       include/Lineextractor.h:44-181     (LSD ctor, ComputeLsdWithLbd, six getters)
+//   PL_SLAM::PlfMatcher          Linematcher::DescriptorDistance / matchNNR / the SearchByKNN mutual step
+//                                (include/Linematcher.h:41,68; src/Linematcher.cc:50-66, :454-471, :520-541) and
+//                                ORBmatcher::DescriptorDistance (include/ORBmatcher.h:44)
+// The translation to the reference's conventions happens here: silent return on empty images, assert on non
+// CV_8UC1 input, std::runtime_error where line_descriptor / matchNNR throw, keypoints.clear() +
+// descriptors.create() for ORB, append semantics for ComputeLsdWithLbd.
+//
+// Needs OpenCV's core headers (cv::Mat, cv::KeyPoint) and the vendored KeyLine type.  When built without OpenCV
+// (unit test of this header) define PLF_SHIM_MOCK_OPENCV and provide layout-compatible stand-ins first.
+#pragma once
+#include <cassert>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <cstring>
+#include "plf.h"
+#ifndef PLF_SHIM_MOCK_OPENCV
+#include <opencv2/core/core.hpp>
+#include <line_descriptor_custom.hpp>   // cv::line_descriptor::KeyLine (Thirdparty/line_descriptor)
+#endif
+
+namespace PL_SLAM {
+
+using cv::line_descriptor::KeyLine;
+static_assert(sizeof(cv::KeyPoint) == sizeof(plf_keypoint), "cv::KeyPoint layout");
+static_assert(sizeof(KeyLine) == sizeof(plf_keyline), "KeyLine layout");
+
+// one GPU context per extractor / matcher object: the reference calls distinct instances from concurrent
+// std::threads (src/Frame.cc:116-119, :301-304), never one instance from two threads
+class PlfContext {
+public:
+    explicit PlfContext(int device = 0) : ctx_(nullptr)
+    {
+        if (plf_ctx_create(device, &ctx_) != PLF_OK) throw std::runtime_error("plf: no usable CUDA device (there is no CPU fallback)");
+    }
+    ~PlfContext() { plf_ctx_destroy(ctx_); }
+    PlfContext(const PlfContext&) = delete;
+    PlfContext& operator=(const PlfContext&) = delete;
+    plf_ctx* get() const { return ctx_; }
+    void check(plf_status st) const
+    {
+        if (st != PLF_OK) throw std::runtime_error(std::string("plf: ") + plf_last_error(ctx_));
+    }
+private:
+    plf_ctx* ctx_;
+};
+
+class ORBextractor {
+public:
+    enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int device = 0)
+        : ctx_(device), orb_(nullptr), nlevels(nlevels), scaleFactor(scaleFactor)
+    {
+        plf_orb_params p = {nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST};
+        ctx_.check(plf_orb_create(ctx_.get(), &p, &orb_));
+        mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels);
+        mvLevelSigma2.resize(nlevels); mvInvLevelSigma2.resize(nlevels);
+        plf_orb_tables(orb_, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(), mvInvLevelSigma2.data(), nullptr);
+        mvImagePyramid.resize(nlevels);
+        cap_ = plf_orb_max_keypoints(orb_);
+    }
+    ~ORBextractor() { plf_orb_destroy(orb_); }
+
+    // Compute the ORB features and descriptors on an image; mask is ignored (as in the reference).
+    void operator()(cv::InputArray _image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& _keypoints,
+                    cv::OutputArray _descriptors)
+    {
+        if (_image.empty()) return;                         // src/ORBextractor.cc:1046-1047
+        cv::Mat image = _image.getMat();
+        assert(image.type() == CV_8UC1);                    // :1050
+        kps_.resize(cap_);
+        desc_.resize((size_t)cap_ * 32);
+        int n = 0;
+        ctx_.check(plf_orb_extract(orb_, image.data, image.cols, image.rows, image.step, (plf_keypoint*)kps_.data(),
+                                   desc_.data(), cap_, &n));
+        _keypoints.clear();                                 // :1072
+        if (n == 0) { _descriptors.release(); return; }     // :1064-1065
+        _descriptors.create(n, 32, CV_8U);
+        cv::Mat d = _descriptors.getMat();
+        for (int i = 0; i < n; i++) std::memcpy(d.ptr(i), &desc_[(size_t)i * 32], 32);
+        _keypoints.assign(kps_.begin(), kps_.begin() + n);
+        // mvImagePyramid (include/ORBextractor.h:85) is read by Frame::ComputeStereoMatches (src/Frame.cc:967-1007)
+        for (int l = 0; l < nlevels; l++) {
+            int w = 0, h = 0;
+            ctx_.check(plf_orb_pyramid_level(orb_, 0, l, nullptr, 0, &w, &h));
+            mvImagePyramid[l].create(h, w, CV_8UC1);
+            ctx_.check(plf_orb_pyramid_level(orb_, 0, l, mvImagePyramid[l].data, mvImagePyramid[l].step, &w, &h));
+        }
+    }
+
+    int inline GetLevels() { return nlevels; }
+    float inline GetScaleFactor() { return (float)scaleFactor; }
+    std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }
+    std::vector<float> inline GetInverseScaleFactors() { return mvInvScaleFactor; }
+    std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
+    std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
+
+    std::vector<cv::Mat> mvImagePyramid;
+
+protected:
+    PlfContext ctx_;
+    plf_orb* orb_;
+    int nlevels;
+    double scaleFactor;
+    int cap_;
+    std::vector<cv::KeyPoint> kps_;
+    std::vector<unsigned char> desc_;
+    std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+};
+
+class Lineextractor {
+public:
+    // LSD-LBD constructor (include/Lineextractor.h:49-51)
+    Lineextractor(int nfeatures = 240, int nlevels = 3, int refine = 0, double scale = 1.05, double sigma_scale = 0.6,
+                  double quant = 2.0, double ang_th = 22.5, double log_eps = 1.0, double density_th = 0.7, int n_bins = 1024,
+                  double min_line_length = 32.0, bool busingLSD = true, int device = 0)
+        : busingLSD(busingLSD), ctx_(device), le_(nullptr), nlevels(nlevels), scale(scale)
+    {
+        if (!busingLSD) throw std::runtime_error("plf: the FLD branch is not part of the GPU hot path");
+        plf_line_params p = {nfeatures, nlevels, refine, scale, sigma_scale, quant, ang_th, log_eps, density_th, n_bins, min_line_length};
+        ctx_.check(plf_line_create(ctx_.get(), &p, &le_));
+        mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels);
+        mvLevelSigma2.resize(nlevels); mvInvLevelSigma2.resize(nlevels);
+        plf_line_tables(le_, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(), mvInvLevelSigma2.data(), nullptr);
+        cap_ = plf_line_max_keylines(le_);
+    }
+    ~Lineextractor() { plf_line_destroy(le_); }
+
+    // src/Lineextractor.cc:112-212: appends to keyLines / keypoints, overwrites descriptors
+    void ComputeLsdWithLbd(const cv::Mat& image, std::vector<KeyLine>& keyLines, std::vector<cv::KeyPoint>& keypoints,
+                           cv::Mat& descriptors)
+    {
+        if (image.empty()) return;                                                       // :115-116
+        if (image.depth() != 0 || image.channels() != 1) throw std::runtime_error("Error, depth image!= 0");   // LSDDetector_custom.cpp:236-237
+        std::vector<KeyLine> kl(cap_);
+        std::vector<cv::KeyPoint> mid(cap_);
+        std::vector<unsigned char> desc((size_t)cap_ * 32);
+        int n = 0;
+        ctx_.check(plf_line_extract(le_, image.data, image.cols, image.rows, image.step, (plf_keyline*)kl.data(),
+                                    (plf_keypoint*)mid.data(), desc.data(), cap_, &n));
+        // the reference clears keyLines (which held only this frame's detections) and refills it (:184-201)
+        keyLines.assign(kl.begin(), kl.begin() + n);
+        keypoints.insert(keypoints.end(), mid.begin(), mid.begin() + n);
+        if (n == 0) return;   // BinaryDescriptor::compute prints an error and leaves descriptors untouched
+        descriptors.create(n, 32, CV_8UC1);
+        for (int i = 0; i < n; i++) std::memcpy(descriptors.ptr(i), &desc[(size_t)i * 32], 32);
+    }
+
+    int inline GetLevels() { return nlevels; }
+    float inline GetScaleFactor() { return (float)scale; }
+    std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }
+    std::vector<float> inline GetInverseScaleFactors() { return mvInvScaleFactor; }
+    std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
+    std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
+
+    bool busingLSD;
+    std::vector<cv::Mat> mvImagePyramid;   // only filled by the FLD branch in the reference
+
+protected:
+    PlfContext ctx_;
+    plf_line* le_;
+    int nlevels;
+    double scale;
+    int cap_;
+    std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+};
+
+// The brute-force pieces of ORBmatcher / Linematcher.  The candidate-list Search* routines stay on the host in the
+// reference's own code and can call DescriptorDistance below unchanged.
+class PlfMatcher {
+public:
+    explicit PlfMatcher(int device = 0) : ctx_(device) {}
+
+    // ORBmatcher::DescriptorDistance / Linematcher::DescriptorDistance: one pair is cheaper on the CPU than a kernel
+    // launch, so this keeps the reference's bit-twiddling popcount (src/ORBmatcher.cc:1656-1672) for single pairs.
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b)
+    {
+        const int* pa = a.ptr<int32_t>();
+        const int* pb = b.ptr<int32_t>();
+        int dist = 0;
+        for (int i = 0; i < 8; i++, pa++, pb++) dist += __builtin_popcount((unsigned)(*pa ^ *pb));
+        return dist;
+    }
+
+    // Linematcher::matchNNR (src/Linematcher.cc:520-541)
+    void matchNNR(const cv::Mat& desc1, const cv::Mat& desc2, float nnr, std::vector<int>& matches_12, int& nmatches)
+    {
+        matches_12.resize(desc1.rows, -1);
+        if (desc1.rows == 0) return;
+        if (desc1.cols != 32 || (desc2.rows && desc2.cols != 32) || !desc1.isContinuous() || !desc2.isContinuous())
+            throw std::runtime_error("[matchNNR] descriptors must be continuous N x 32 CV_8U");
+        int n = 0;
+        ctx_.check(plf_match_nnr(ctx_.get(), desc1.data, desc1.rows, desc2.data, desc2.rows, nnr, matches_12.data(), &n));
+        nmatches += n;   // the reference increments the caller's counter
+    }
+
+    // both directions + mutual-consistency filter of SearchByKNN / SearchForTriangulation (:454-471, :825-839)
+    int matchNNRMutual(const cv::Mat& desc1, const cv::Mat& desc2, float nnr, std::vector<int>& matches_12)
+    {
+        matches_12.assign(desc1.rows, -1);
+        if (desc1.rows == 0 || desc2.rows == 0) return 0;
+        int n = 0;
+        ctx_.check(plf_match_nnr_mutual(ctx_.get(), desc1.data, desc1.rows, desc2.data, desc2.rows, nnr, matches_12.data(), &n));
+        return n;
+    }
+
+private:
+    PlfContext ctx_;
+};
+
+}  // namespace PL_SLAM

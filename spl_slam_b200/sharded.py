@@ -40,8 +40,9 @@ def knn2_sharded(ctx, q, t_local, index_base, group=None):
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return idx, dst
-    pidx = torch.empty((world, nq, 2), dtype=torch.int32, device=q.device)
-    pdst = torch.empty((world, nq, 2), dtype=torch.int32, device=q.device)
+    # [shard][nq][2] contiguous, shaped as the dim-0 concatenation both gloo and NCCL accept
+    pidx = torch.empty((world * nq, 2), dtype=torch.int32, device=q.device)
+    pdst = torch.empty((world * nq, 2), dtype=torch.int32, device=q.device)
     dist.all_gather_into_tensor(pidx, idx, group=group)
     dist.all_gather_into_tensor(pdst, dst, group=group)
     if q.is_cuda:
