@@ -54,7 +54,7 @@ struct plf_line {
 };
 
 // d_cnt layout (ints): [0]=nkeys [1]=ncomp [2]=next [3]=nregions [4]=sticky overflow flag [8..32) bucket counts [32..56) bucket fill [64..64+frames) = maxq
-enum { CNT_NKEYS = 0, CNT_NCOMP = 1, CNT_NEXT = 2, CNT_NREG = 3, CNT_ERR = 4, CNT_BCOUNT = 8, CNT_BFILL = 32, CNT_MAXQ = 64 };
+enum { CNT_NKEYS = 0, CNT_NCOMP = 1, CNT_NEXT = 2, CNT_NREG = 3, CNT_ERR = 4, CNT_BCOUNT = 8, CNT_BFILL = 32, CNT_STATS = 64, CNT_MAXQ = 96 };
 
 static int gauss_kernel_q8(int ksize, double sigma, int* q)
 {
@@ -227,6 +227,7 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
     need(o->regcap, 8); need(o->regcap, 8); need(o->regcap, 4); need(o->regcap, 4);
     need(F * noct * LINE_DETCAP, sizeof(plf_keyline));
     need(CNT_MAXQ + F, 4); need(F * noct, 4);
+
     PLF_CUDA(ctx, cudaMalloc((void**)&o->d_base, bytes + 4096));
     uint8_t* p = o->d_base;
     for (int k = 0; k < noct; k++) {
@@ -362,21 +363,22 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
                            o->d_cnt + CNT_BCOUNT, o->d_cnt + CNT_BFILL, pass);
                 PLF_CHECK_LAUNCH(ctx);
             }
-            // big components first (one CTA each, `used` bitmap in shared memory) when the bitmap fits
-            const size_t bm = (((size_t)sw * sh + 31) / 32) * 4;
-            const int use_big = bm <= 160 * 1024;
-            if (use_big) {
+            // the sorted position of every defined pixel (compact component index), then the big components with
+            // warp-cooperative ordered growth (one warp each) and everything else with one thread per component
+            PLF_LAUNCH(k_lsd_cid, dim3(plf_div_up(nkeys, 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2, nkeys, o->d_label,
+                       (size_t)sw * sh);
+            PLF_CHECK_LAUNCH(ctx);
+            const int wg_smem = WARPGROW_MAXC / 8;
 #ifndef PLF_EMU
-                PLF_CUDA(ctx, cudaFuncSetAttribute(k_lsd_grow_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm));
+            PLF_CUDA(ctx, cudaFuncSetAttribute(k_lsd_grow_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem));
 #endif
-                PLF_LAUNCH(k_lsd_grow_big, dim3(nframes * 4 < 64 ? 64 : nframes * 4), dim3(32), bm, st, (const unsigned long long*)o->d_keys2,
-                           (const int2*)o->d_comp, (const int*)(o->d_cnt + CNT_BCOUNT), (const float*)o->d_fa, (const float2*)o->d_cs, sw, sh,
-                           o->prec, o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap);
-                PLF_CHECK_LAUNCH(ctx);
-            }
+            PLF_LAUNCH(k_lsd_grow_warp, dim3(nframes * 4 < 148 ? 148 : nframes * 4), dim3(32), wg_smem, st, (const unsigned long long*)o->d_keys2,
+                       (const int2*)o->d_comp, (const int*)(o->d_cnt + CNT_BCOUNT), (const float*)o->d_fa, (const float2*)o->d_cs,
+                       (const int*)o->d_label, sw, sh, o->prec, o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap);
+            PLF_CHECK_LAUNCH(ctx);
             PLF_LAUNCH(k_lsd_grow, dim3(148 * 4), dim3(128), 0, st, (const unsigned long long*)o->d_keys2, nkeys, (const int2*)o->d_comp,
                        (const int*)(o->d_cnt + CNT_BCOUNT), o->d_cnt + CNT_NEXT, o->d_fa, (const float2*)o->d_cs, sw, sh, o->prec,
-                       o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap, use_big);
+                       o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap, 1, WARPGROW_MAXC);
             PLF_CHECK_LAUNCH(ctx);
         }
         PLF_LAUNCH(k_lsd_rect, dim3(plf_div_up(o->regcap, 128)), dim3(128), 0, st, (const LsdRegion*)o->d_regions,
@@ -613,3 +615,4 @@ extern "C" plf_status plf_lbd_compute(plf_line* o, const uint8_t* host_img, int 
     PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PLF_OK;
 }
+

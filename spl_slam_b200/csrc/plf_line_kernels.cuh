@@ -238,7 +238,9 @@ k_lsd_keys(const int* __restrict__ label, const int* __restrict__ q, const int* 
 // component heads in the sorted key array.  Two passes (count, fill) bucket the components by
 // floor(log2(size)) so that the grow kernel starts the largest components first (longest-chain-first).
 #define LSD_NBUCKET 24
-#define LSD_BIG_BUCKET 11   // components with >= 2048 seeds get a CTA of their own (k_lsd_grow_big)
+#ifndef LSD_BIG_BUCKET
+#define LSD_BIG_BUCKET 11   // components with >= 2048 seeds get a warp of their own (k_lsd_grow_warp)
+#endif
 __global__ void __launch_bounds__(256)
 k_lsd_heads(const unsigned long long* __restrict__ keys, int n, int2* __restrict__ comp, int* __restrict__ bcount,
             int* __restrict__ bfill, int pass)
@@ -274,13 +276,10 @@ struct LsdRegion {
 __global__ void __launch_bounds__(128)
 k_lsd_grow(const unsigned long long* __restrict__ keys, int n, const int2* __restrict__ comp, const int* __restrict__ bcount,
            int* __restrict__ next, float* __restrict__ fa, const float2* __restrict__ cs, int w, int h, double prec,
-           int min_reg_size, int* __restrict__ regpts, LsdRegion* __restrict__ regions, int* __restrict__ nregions, int regcap, int skip_big)
+           int min_reg_size, int* __restrict__ regpts, LsdRegion* __restrict__ regions, int* __restrict__ nregions, int regcap, int skip_big, int spec_maxc)
 {
-    int ncomp = 0, cbase = 0;
+    int ncomp = 0;
     for (int k = 0; k < LSD_NBUCKET; k++) ncomp += bcount[k];
-    if (skip_big) for (int k = LSD_BIG_BUCKET; k < LSD_NBUCKET; k++) cbase += bcount[k];   // done by k_lsd_grow_big
-    ncomp -= cbase;
-    comp += cbase;
     const size_t px = (size_t)w * h;
     // components are listed largest first.  Lanes of one warp execute divergent chains one after another, so
     // the first round gives every WARP one of the largest components (lane 0), then the next largest to lane 1,
@@ -295,6 +294,7 @@ k_lsd_grow(const unsigned long long* __restrict__ keys, int n, const int2* __res
         else c = 32 * totalWarps + atomicAdd(next, 1);
         if (c >= ncomp) { if (c >= 32 * totalWarps) break; else continue; }
         const int start = comp[c].x, end = start + comp[c].y;
+        if (skip_big && comp[c].y >= (1 << LSD_BIG_BUCKET) && comp[c].y <= spec_maxc) continue;   // k_lsd_grow_warp does these
         float* F = fa + (size_t)LSD_KEY_FRAME(keys[start]) * px;
         const float2* CS = cs + (size_t)LSD_KEY_FRAME(keys[start]) * px;
         int arena = start;
@@ -357,96 +357,127 @@ k_lsd_grow(const unsigned long long* __restrict__ keys, int n, const int2* __res
     }
 }
 
-// Large components (>= LSD_BIG_SIZE seeds): one CTA per component, lane 0 walks the chain.  The `used` state of
-// the whole scaled image lives in a shared-memory bitmap, so the angle / cos-sin arrays stay read-only
-// (L1-resident along the edge being followed) and a pop costs tens of cycles instead of an L2 round trip.
-// Valid because a component's regions only ever test pixels of the same component or NOTDEF pixels.
+// ------------------------------------------------------------------------------------------------
+// Large components: one WARP per component, still strictly in the reference's order.
+// A single GPU thread needs ~250 dependent instructions per region pixel; here the nine neighbours of the
+// popped point are handled by nine lanes at once (address, component index, used bit, angle, cos/sin and the
+// alignment test), and only the part that is sequential by definition stays sequential: neighbours are
+// accepted in k order, and after each acceptance the region angle is updated and the neighbours AFTER it are
+// re-tested (the reference's loop never goes back to an earlier neighbour of the same pop).
+// `used` is a shared-memory bitmap indexed by the pixel's position in the sorted seed list (`cid`, written
+// into the label array after the sort), so the angle / cos-sin arrays stay read-only and L1-resident.
+// ------------------------------------------------------------------------------------------------
+#define WARPGROW_MAXC (512 * 1024)          // component pixels one CTA can track (64 KB of used bits)
+
+__global__ void __launch_bounds__(256)
+k_lsd_cid(const unsigned long long* __restrict__ keys, int n, int* __restrict__ label, size_t px)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    label[(size_t)LSD_KEY_FRAME(k) * px + LSD_KEY_IDX(k)] = i;
+}
+
 __global__ void __launch_bounds__(32)
-k_lsd_grow_big(const unsigned long long* __restrict__ keys, const int2* __restrict__ comp, const int* __restrict__ bcount,
-               const float* __restrict__ fa, const float2* __restrict__ cs, int w, int h, double prec, int min_reg_size,
-               int* __restrict__ regpts, LsdRegion* __restrict__ regions, int* __restrict__ nregions, int regcap)
+k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restrict__ comp, const int* __restrict__ bcount,
+                const float* __restrict__ fa, const float2* __restrict__ cs, const int* __restrict__ cid, int w, int h,
+                double prec, int min_reg_size, int* __restrict__ regpts, LsdRegion* __restrict__ regions,
+                int* __restrict__ nregions, int regcap)
 {
     PLF_DYN_SMEM(smem);
     unsigned* used = (unsigned*)smem;
+    const int lane = threadIdx.x;
     int nbig = 0;
     for (int k = LSD_BIG_BUCKET; k < LSD_NBUCKET; k++) nbig += bcount[k];
     const size_t px = (size_t)w * h;
-    const int words = (int)((px + 31) >> 5);
+    const int dxk = (lane % 3) - 1, dyk = (lane / 3) - 1;   // lanes 0..8 own one neighbour each (row-major 3x3)
     for (int c = blockIdx.x; c < nbig; c += gridDim.x) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < words; i += 32) used[i] = 0u;
-        __syncthreads();
-        if (threadIdx.x != 0) continue;
-        const int start = comp[c].x, end = start + comp[c].y;
-        const float* F = fa + (size_t)LSD_KEY_FRAME(keys[start]) * px;
-        const float2* CS = cs + (size_t)LSD_KEY_FRAME(keys[start]) * px;
+        const int start = comp[c].x, C = comp[c].y, end = start + C;
+        if (C > WARPGROW_MAXC) continue;   // handled by k_lsd_grow
+        const size_t foff = (size_t)LSD_KEY_FRAME(keys[start]) * px;
+        const float* F = fa + foff;
+        const float2* CS = cs + foff;
+        const int* CID = cid + foff;
+        __syncwarp();
+        for (int i = lane; i < (C + 31) / 32; i += 32) used[i] = 0u;
+        __syncwarp();
         int arena = start;
-        for (int i = start; i < end; i++) {
-            const unsigned long long key = keys[i];
-            const int p = LSD_KEY_IDX(key);
-            if ((used[p >> 5] >> (p & 31)) & 1u) continue;
-            const int r0 = arena;
-            {
-                const int sy = p / w;
-                regpts[arena++] = (p - sy * w) | (sy << 16);
-            }
-            double reg_angle = (double)F[p] * LSD_D2R;
-            float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
-            used[p >> 5] |= 1u << (p & 31);
-            int pp = regpts[r0];
-            for (int r = r0; r < arena; r++) {
-                const int x = pp & 0xffff, y = pp >> 16;
-                // all loads of this pop are issued unconditionally (clamped addresses) so they overlap
-                float v[9];
-                float2 cv[9];
-                int qa[9];
-                unsigned ub[9];
-#pragma unroll
-                for (int k = 0; k < 9; k++) {
-                    const int xx = min(max(x + (k % 3) - 1, 0), w - 1), yy = min(max(y + (k / 3) - 1, 0), h - 1);
-                    qa[k] = yy * w + xx;
-                }
-#pragma unroll
-                for (int k = 0; k < 9; k++) v[k] = __ldg(&F[qa[k]]);
-#pragma unroll
-                for (int k = 0; k < 9; k++) cv[k] = __ldg(&CS[qa[k]]);
-#pragma unroll
-                for (int k = 0; k < 9; k++) ub[k] = (used[qa[k] >> 5] >> (qa[k] & 31)) & 1u;
-                if (r + 1 < arena) pp = regpts[r + 1];
-#pragma unroll
-                for (int k = 0; k < 9; k++) {
-                    const int xx = x + (k % 3) - 1, yy = y + (k / 3) - 1;
-                    if (ub[k] || xx < 0 || yy < 0 || xx >= w || yy >= h) v[k] = LSD_USED;
-                }
-#pragma unroll
-                for (int k = 0; k < 9; k++) {
-                    if (v[k] < -500.f) continue;
-                    double n_theta = reg_angle - (double)v[k] * LSD_D2R;
-                    if (n_theta < 0) n_theta = -n_theta;
-                    if (n_theta > LSD_3_2_PI) {
-                        n_theta -= LSD_2PI;
-                        if (n_theta < 0) n_theta = -n_theta;
-                    }
-                    if (n_theta <= prec) {
-                        const int xx = x + (k % 3) - 1, yy = y + (k / 3) - 1;
+        for (int i0 = start; i0 < end; i0 += 32) {
+            // 32 seeds at a time: which of them are still unused?
+            const int ii = i0 + lane;
+            unsigned long long mykey = 0;
+            if (ii < end) mykey = keys[ii];
+            for (int s = 0; s < 32 && i0 + s < end; s++) {
+                const int sc = i0 + s - start;
+                if ((used[sc >> 5] >> (sc & 31)) & 1u) continue;            // warp-uniform
+                const unsigned long long key = __shfl_sync(0xffffffffu, mykey, s);
+                const int p = LSD_KEY_IDX(key);
+                const int r0 = arena;
+                const int sy = p / w, sx = p - sy * w;
+                if (lane == 0) { regpts[arena] = sx | (sy << 16); used[sc >> 5] |= 1u << (sc & 31); }
+                arena++;
+                double reg_angle = (double)__ldg(&F[p]) * LSD_D2R;
+                float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
+                int pp = sx | (sy << 16);
+                __syncwarp();
+                for (int r = r0; r < arena; r++) {
+                    const int x = pp & 0xffff, y = pp >> 16;
+                    // lanes 0..8: neighbour state
+                    const int xx = x + dxk, yy = y + dyk;
+                    bool cand = lane < 9 && lane != 4 && xx >= 0 && yy >= 0 && xx < w && yy < h;
+                    float fv = 0.f;
+                    float2 cv = make_float2(0.f, 0.f);
+                    int cc = 0;
+                    if (cand) {
                         const int qi = yy * w + xx;
-                        used[qi >> 5] |= 1u << (qi & 31);
-                        if (arena == r + 1) pp = xx | (yy << 16);
-                        regpts[arena++] = xx | (yy << 16);
-                        sumdx += cv[k].x;
-                        sumdy += cv[k].y;
+                        const int ci = __ldg(&CID[qi]);
+                        fv = __ldg(&F[qi]);
+                        cv = __ldg(&CS[qi]);
+                        cc = ci - start;
+                        cand = ci >= 0 && !((used[cc >> 5] >> (cc & 31)) & 1u);
+                    }
+                    int nextpp = 0;
+                    if (r + 1 < arena) nextpp = regpts[r + 1];   // uniform load, overlaps the tests below
+                    const double a = (double)fv * LSD_D2R;
+                    for (;;) {
+                        bool pass = false;
+                        if (cand) {
+                            double n_theta = reg_angle - a;
+                            if (n_theta < 0) n_theta = -n_theta;
+                            if (n_theta > LSD_3_2_PI) {
+                                n_theta -= LSD_2PI;
+                                if (n_theta < 0) n_theta = -n_theta;
+                            }
+                            pass = n_theta <= prec;
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, pass);
+                        if (!m) break;
+                        const int k0 = __ffs((int)m) - 1;                  // first aligned neighbour in the reference's order
+                        if (lane == k0) {
+                            used[cc >> 5] |= 1u << (cc & 31);              // only this lane writes during the pop
+                            regpts[arena] = xx | (yy << 16);
+                        }
+                        if (arena == r + 1) nextpp = __shfl_sync(0xffffffffu, xx | (yy << 16), k0);
+                        else (void)__shfl_sync(0xffffffffu, 0, k0);
+                        arena++;
+                        sumdx += __shfl_sync(0xffffffffu, cv.x, k0);
+                        sumdy += __shfl_sync(0xffffffffu, cv.y, k0);
                         reg_angle = (double)plf_fast_atan2(sumdy, sumdx) * LSD_D2R;
+                        cand = cand && lane > k0;                          // earlier neighbours are not revisited
+                    }
+                    __syncwarp();
+                    pp = nextpp;
+                }
+                const int nreg = arena - r0;
+                if (lane == 0 && nreg >= min_reg_size) {
+                    const int rr = atomicAdd(nregions, 1);
+                    if (rr < regcap) {
+                        LsdRegion R;
+                        R.start = r0; R.n = nreg; R.reg_angle = reg_angle; R.seedkey = key;
+                        regions[rr] = R;
                     }
                 }
-            }
-            const int nreg = arena - r0;
-            if (nreg >= min_reg_size) {
-                const int rr = atomicAdd(nregions, 1);
-                if (rr < regcap) {
-                    LsdRegion R;
-                    R.start = r0; R.n = nreg; R.reg_angle = reg_angle; R.seedkey = key;
-                    regions[rr] = R;
-                }
+                __syncwarp();
             }
         }
     }
