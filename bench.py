@@ -176,7 +176,7 @@ def main():
         torch.cuda.synchronize()
 
     B = args.frames
-    assert B % 2 == 0 and B <= 254
+    assert B % 2 == 0 and B <= 4096
     # global frame i -> rank i mod world; this rank's frames: pairs p where frame index = 2p (+1)
     n_pairs_global = B * world // 2
     allf = make_frames(n_pairs_global, 0) if world == 1 else None
@@ -269,10 +269,12 @@ def main():
     # ---- per-kernel times for the roofline (separate profiled steps, CUDA events per launch) ----
     ctx_o.profile_enable(True); ctx_l.profile_enable(True)
     PROF_STEPS = 3
-    for _ in range(PROF_STEPS):
+    for _ in range(PROF_STEPS):   # the two streams run one after the other here so that kernel times are not mixed
         flush.zero_(); torch.cuda.synchronize()
-        step_device()
-        ctx_o.synchronize(); ctx_l.synchronize()
+        ctx_o.check(lib.plf_orb_extract_batch_device(orb.h, d_img.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), capk, d_nk.data_ptr()))
+        ctx_o.synchronize()
+        ctx_l.check(lib.plf_line_extract_batch_device(le.h, d_img.data_ptr(), B, W, H, W, W * H, d_kl.data_ptr(), d_mid.data_ptr(), d_ld.data_ptr(), capl, d_nl.data_ptr()))
+        ctx_l.synchronize()
     prof = {}
     for c in (ctx_o, ctx_l):
         for k, v in c.profile_report().items():

@@ -10,8 +10,8 @@
 #endif
 
 #define LINE_MAX_OCT 2
-#define LINE_DETCAP 8192       // detected lines per (frame, octave) before the response quota
-#define LINE_REGCAP_PER_FRAME 16384
+#define LINE_DETCAP 4096       // detected lines per (frame, octave) before the response quota
+#define LINE_REGCAP_PER_FRAME 4096
 
 struct plf_line {
     plf_ctx* ctx;
@@ -25,7 +25,7 @@ struct plf_line {
     LbdCoefs lbd_coefs;
     // workspace
     int ws_w, ws_h, ws_frames;
-    int ow[LINE_MAX_OCT], oh[LINE_MAX_OCT], sw[LINE_MAX_OCT], sh[LINE_MAX_OCT], min_reg[LINE_MAX_OCT];
+    int ow[LINE_MAX_OCT], oh[LINE_MAX_OCT], sw[LINE_MAX_OCT], sh[LINE_MAX_OCT], min_reg[LINE_MAX_OCT], kbits[LINE_MAX_OCT];
     uint8_t* d_base;
     uint8_t *d_oct[LINE_MAX_OCT], *d_tmp, *d_scaled;       // images (pitch == width)
     uint8_t *d_lbdimg[LINE_MAX_OCT];
@@ -196,7 +196,6 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
     if (o->ws_w == w && o->ws_h == h && o->ws_frames >= nframes) return PLF_OK;
     PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     line_free_ws(o);
-    if (nframes > 255) return plf_fail(ctx, PLF_ERR_INVALID, "at most 255 frames per line batch");
     const int noct = o->prm.nlevels;
     const double S = o->prm.scale;
     size_t maxpx = 0, tabCount = 0;
@@ -207,6 +206,10 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         o->sh[k] = S != 1 ? (int)lrint(o->oh[k] * S) : o->oh[k];
         if ((size_t)o->sw[k] * o->sh[k] > maxpx) maxpx = (size_t)o->sw[k] * o->sh[k];
         if ((size_t)o->sw[k] * o->sh[k] >= (1u << 22)) return plf_fail(ctx, PLF_ERR_INVALID, "scaled octave larger than 4M pixels");
+        o->kbits[k] = 1;
+        while ((1u << o->kbits[k]) < (unsigned)(o->sw[k] * o->sh[k])) o->kbits[k]++;
+        if (52 - 2 * o->kbits[k] < 31 && nframes > (1 << (52 - 2 * o->kbits[k])))
+            return plf_fail(ctx, PLF_ERR_INVALID, "at most %d frames of this size per line batch", 1 << (52 - 2 * o->kbits[k]));
         const double LOG_NT = 5 * (log10((double)o->sw[k]) + log10((double)o->sh[k])) / 2 + log10(11.0);
         o->min_reg[k] = (int)(size_t)(-LOG_NT / log10(o->prm.ang_th / 180));
         tabCount += (size_t)o->sw[k] + o->sh[k];
@@ -349,7 +352,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         PLF_LAUNCH(k_ccl_merge, g2, b2, 0, st, o->d_label, sw, sh);
         PLF_CHECK_LAUNCH(ctx);
         PLF_LAUNCH(k_lsd_keys, g2, b2, 0, st, (const int*)o->d_label, (const int*)o->d_q, (const int*)(o->d_cnt + CNT_MAXQ), sw, sh,
-                   o->prm.n_bins, o->d_keys, o->d_cnt + CNT_NKEYS, (int)o->keycap);
+                   o->prm.n_bins, o->d_keys, o->d_cnt + CNT_NKEYS, (int)o->keycap, o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
         int nkeys = 0;
         PLF_CUDA(ctx, cudaMemcpyAsync(&nkeys, o->d_cnt + CNT_NKEYS, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -360,30 +363,39 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             if (s) return s;
             for (int pass = 0; pass < 2; pass++) {
                 PLF_LAUNCH(k_lsd_heads, dim3(plf_div_up(nkeys, 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2, nkeys, o->d_comp,
-                           o->d_cnt + CNT_BCOUNT, o->d_cnt + CNT_BFILL, pass);
+                           o->d_cnt + CNT_BCOUNT, o->d_cnt + CNT_BFILL, pass, o->kbits[k]);
                 PLF_CHECK_LAUNCH(ctx);
             }
             // the sorted position of every defined pixel (compact component index), then the big components with
             // warp-cooperative ordered growth (one warp each) and everything else with one thread per component
             PLF_LAUNCH(k_lsd_cid, dim3(plf_div_up(nkeys, 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2, nkeys, o->d_label,
-                       (size_t)sw * sh);
+                       (size_t)sw * sh, o->kbits[k]);
             PLF_CHECK_LAUNCH(ctx);
-            const int wg_smem = WARPGROW_MAXC / 8;
+            // size the used-bitmap of the warp kernel from the largest component present (bucket counts)
+            int bc[LSD_NBUCKET];
+            PLF_CUDA(ctx, cudaMemcpyAsync(bc, o->d_cnt + CNT_BCOUNT, sizeof(bc), cudaMemcpyDeviceToHost, st));
+            PLF_CUDA(ctx, cudaStreamSynchronize(st));
+            int topb = 0, nbig = 0;
+            for (int b = 0; b < LSD_NBUCKET; b++) { if (bc[b]) topb = b; if (b >= LSD_BIG_BUCKET) nbig += bc[b]; }
+            int wg_maxc = 1 << (topb + 1);
+            if (wg_maxc > WARPGROW_MAXC) wg_maxc = WARPGROW_MAXC;
+            if (wg_maxc < 1024) wg_maxc = 1024;
+            const int wg_smem = wg_maxc / 8;
 #ifndef PLF_EMU
             PLF_CUDA(ctx, cudaFuncSetAttribute(k_lsd_grow_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem));
 #endif
-            PLF_LAUNCH(k_lsd_grow_warp, dim3(nframes * 4 < 148 ? 148 : nframes * 4), dim3(32), wg_smem, st, (const unsigned long long*)o->d_keys2,
+            if (nbig > 0) PLF_LAUNCH(k_lsd_grow_warp, dim3(nbig < 148 * 16 ? nbig : 148 * 16), dim3(32), wg_smem, st, (const unsigned long long*)o->d_keys2,
                        (const int2*)o->d_comp, (const int*)(o->d_cnt + CNT_BCOUNT), (const float*)o->d_fa, (const float2*)o->d_cs,
-                       (const int*)o->d_label, sw, sh, o->prec, o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap);
+                       (const int*)o->d_label, sw, sh, o->prec, o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap, o->kbits[k], wg_maxc);
             PLF_CHECK_LAUNCH(ctx);
             PLF_LAUNCH(k_lsd_grow, dim3(148 * 4), dim3(128), 0, st, (const unsigned long long*)o->d_keys2, nkeys, (const int2*)o->d_comp,
                        (const int*)(o->d_cnt + CNT_BCOUNT), o->d_cnt + CNT_NEXT, o->d_fa, (const float2*)o->d_cs, sw, sh, o->prec,
-                       o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap, 1, WARPGROW_MAXC);
+                       o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap, 1, wg_maxc, o->kbits[k]);
             PLF_CHECK_LAUNCH(ctx);
         }
         PLF_LAUNCH(k_lsd_rect, dim3(plf_div_up(o->regcap, 128)), dim3(128), 0, st, (const LsdRegion*)o->d_regions,
                    (const int*)(o->d_cnt + CNT_NREG), o->regcap, (const int*)o->d_regpts, (const int*)o->d_q, sw, sh, o->prec, S, o->d_lines,
-                   o->d_linekey, o->d_lineidx, o->d_cnt + CNT_ERR);
+                   o->d_linekey, o->d_lineidx, o->d_cnt + CNT_ERR, o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
         plf_status s = sort_lines(o);
         if (s) return s;
