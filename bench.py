@@ -33,7 +33,8 @@ W, H = 752, 480
 ORB = dict(nfeatures=1200, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7)
 LINE = dict(nfeatures=200, nlevels=2, refine=0, scale=1.1, sigma_scale=0.8, quant=2.2, ang_th=12.5, log_eps=1.0,
             density_th=0.8, n_bins=1024, min_line_length=0.0)   # Examples/Monocular/EuRoC.yaml (Camera.width absent -> 0)
-FRAMES_PER_GPU = 128          # 64 stereo pairs
+FRAMES_PER_GPU = 1024         # 512 stereo pairs per GPU per step
+LINE_CONTEXTS = 4             # line extractor instances (own context/stream + host thread each), frames split evenly
 WORKLOAD = "EuRoC-style stereo 752x480 pairs, 1200 ORB (8 lv x1.2, FAST 20/7) + LSD/LBD 200 lines per image"
 
 
@@ -150,6 +151,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--line-contexts", type=int, default=LINE_CONTEXTS)
+    ap.add_argument("--line-sub", type=int, default=0, help="frames per line call (0 = one call per context)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,13 +197,17 @@ def main():
     else:
         frames = allf
     dev = local_rank
+    from concurrent.futures import ThreadPoolExecutor
     ctx_o = S.Context(dev)   # ORB stream
-    ctx_l = S.Context(dev)   # line stream
-    lib = ctx_o.lib
+    NL = args.line_contexts if B % (2 * args.line_contexts) == 0 else 1
+    ctx_ls = [S.Context(dev) for _ in range(NL)]   # line streams: the region-growing chain of one sub-batch overlaps
+    lib = ctx_o.lib                                 # the bandwidth-bound kernels of the others
     orb = S.ORBextractor(ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"], ctx=ctx_o)
-    le = S.Lineextractor(LINE["nfeatures"], LINE["nlevels"], LINE["refine"], LINE["scale"], LINE["sigma_scale"], LINE["quant"],
-                         LINE["ang_th"], LINE["log_eps"], LINE["density_th"], LINE["n_bins"], LINE["min_line_length"], ctx=ctx_l)
-    capk, capl = orb.max_keypoints, le.max_keylines
+    les = [S.Lineextractor(LINE["nfeatures"], LINE["nlevels"], LINE["refine"], LINE["scale"], LINE["sigma_scale"], LINE["quant"],
+                           LINE["ang_th"], LINE["log_eps"], LINE["density_th"], LINE["n_bins"], LINE["min_line_length"], ctx=c) for c in ctx_ls]
+    capk, capl = orb.max_keypoints, les[0].max_keylines
+    BL = B // NL
+    pool = ThreadPoolExecutor(NL + 1)
     # device-resident inputs / outputs (torch only provides the memory)
     d_img = torch.from_numpy(frames).cuda()
     d_kps = torch.empty((B, capk, 28), dtype=torch.uint8, device="cuda"); d_desc = torch.empty((B, capk, 32), dtype=torch.uint8, device="cuda")
@@ -215,40 +222,46 @@ def main():
     h_ld = torch.empty((B, capl, 32), dtype=torch.uint8).pin_memory()
     n_k = np.zeros(B, np.int32); n_l = np.zeros(B, np.int32)
 
-    def step_device():
+    def dev_orb():
         ctx_o.check(lib.plf_orb_extract_batch_device(orb.h, d_img.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), capk, d_nk.data_ptr()))
-        ctx_l.check(lib.plf_line_extract_batch_device(le.h, d_img.data_ptr(), B, W, H, W, W * H, d_kl.data_ptr(), d_mid.data_ptr(), d_ld.data_ptr(), capl, d_nl.data_ptr()))
+
+    SUB = args.line_sub if args.line_sub and BL % args.line_sub == 0 else BL
+
+    def dev_line(i):
+        for j in range(i * BL, (i + 1) * BL, SUB):     # sub-batches keep the contexts out of lockstep: one context's
+            s = slice(j, j + SUB)                      # region-growing chain overlaps the others' bandwidth kernels
+            ctx_ls[i].check(lib.plf_line_extract_batch_device(les[i].h, d_img[s].data_ptr(), SUB, W, H, W, W * H, d_kl[s].data_ptr(),
+                                                              d_mid[s].data_ptr(), d_ld[s].data_ptr(), capl, d_nl[s].data_ptr()))
+
+    def step_device():
+        dev_orb()                                              # asynchronous on the ORB stream
+        list(pool.map(dev_line, range(NL)))                    # line calls contain stream syncs: one host thread each
 
     def timed_device_step():
         flush.zero_()                      # L2 flush between timed iterations (untimed)
         torch.cuda.synchronize()
         ctx_o.timer_start()
         step_device()
-        ctx_o.wait(ctx_l)                  # the ORB stream's stop event waits for the line stream
+        for c in ctx_ls:
+            ctx_o.wait(c)                  # the ORB stream's stop event waits for every line stream
         return ctx_o.timer_stop()
 
-    errs = []
-
     def e2e_orb():
-        try:
-            ctx_o.check(lib.plf_orb_extract_batch(orb.h, h_img.data_ptr(), B, W, H, W, W * H, h_kps.data_ptr(), h_desc.data_ptr(), capk, n_k.ctypes.data))
-        except Exception as e:   # noqa
-            errs.append(e)
+        ctx_o.check(lib.plf_orb_extract_batch(orb.h, h_img.data_ptr(), B, W, H, W, W * H, h_kps.data_ptr(), h_desc.data_ptr(), capk, n_k.ctypes.data))
 
-    def e2e_line():
-        try:
-            ctx_l.check(lib.plf_line_extract_batch(le.h, h_img.data_ptr(), B, W, H, W, W * H, h_kl.data_ptr(), h_mid.data_ptr(), h_ld.data_ptr(), capl, n_l.ctypes.data))
-        except Exception as e:   # noqa
-            errs.append(e)
+    def e2e_line(i):
+        for j in range(i * BL, (i + 1) * BL, SUB):
+            s = slice(j, j + SUB)
+            ctx_ls[i].check(lib.plf_line_extract_batch(les[i].h, h_img[s].data_ptr(), SUB, W, H, W, W * H, h_kl[s].data_ptr(), h_mid[s].data_ptr(),
+                                                       h_ld[s].data_ptr(), capl, n_l[s].ctypes.data))
 
     def timed_e2e_step():
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        ta = threading.Thread(target=e2e_orb); tb = threading.Thread(target=e2e_line)   # the reference's two threads (Frame.cc:301-304)
-        ta.start(); tb.start(); ta.join(); tb.join()
-        if errs:
-            raise errs[0]
+        fo = pool.submit(e2e_orb)          # the reference's ORB thread and line thread(s) (Frame.cc:301-304)
+        list(pool.map(e2e_line, range(NL)))
+        fo.result()
         return (time.perf_counter() - t0) * 1e3
 
     # ---- device-resident throughput ----
@@ -256,30 +269,33 @@ def main():
         timed_device_step()
     barrier()
     sampler = ClockSampler(dev) if rank == 0 else None
-    l0 = ctx_o.launch_count() + ctx_l.launch_count()
+    l0 = ctx_o.launch_count() + sum(c.launch_count() for c in ctx_ls)
     ms_dev = 0.0
     for _ in range(args.steps):
         ms_dev += timed_device_step()
     barrier()
-    launches = ctx_o.launch_count() + ctx_l.launch_count() - l0
+    launches = ctx_o.launch_count() + sum(c.launch_count() for c in ctx_ls) - l0
     clocks = sampler.stop() if sampler else None
     nk = d_nk.cpu().numpy(); nl = d_nl.cpu().numpy()
     assert (nk > 0).all() and (nl >= 0).all(), "extraction reported an overflow"
 
     # ---- per-kernel times for the roofline (separate profiled steps, CUDA events per launch) ----
-    ctx_o.profile_enable(True); ctx_l.profile_enable(True)
+    for c in [ctx_o] + ctx_ls:
+        c.profile_enable(True)
     PROF_STEPS = 3
-    for _ in range(PROF_STEPS):   # the two streams run one after the other here so that kernel times are not mixed
+    for _ in range(PROF_STEPS):   # one stream at a time here, so that kernel times are not mixed
         flush.zero_(); torch.cuda.synchronize()
-        ctx_o.check(lib.plf_orb_extract_batch_device(orb.h, d_img.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), capk, d_nk.data_ptr()))
+        dev_orb()
         ctx_o.synchronize()
-        ctx_l.check(lib.plf_line_extract_batch_device(le.h, d_img.data_ptr(), B, W, H, W, W * H, d_kl.data_ptr(), d_mid.data_ptr(), d_ld.data_ptr(), capl, d_nl.data_ptr()))
-        ctx_l.synchronize()
+        for i in range(NL):
+            dev_line(i)
+            ctx_ls[i].synchronize()
     prof = {}
-    for c in (ctx_o, ctx_l):
+    for c in [ctx_o] + ctx_ls:
         for k, v in c.profile_report().items():
-            prof[k] = (v[0] / PROF_STEPS, v[1] // PROF_STEPS)
-    ctx_o.profile_enable(False); ctx_l.profile_enable(False)
+            a = prof.get(k, (0.0, 0))
+            prof[k] = (a[0] + v[0] / PROF_STEPS, a[1] + v[1] // PROF_STEPS)
+        c.profile_enable(False)
 
     # ---- end to end ----
     for _ in range(args.warmup):
@@ -333,14 +349,14 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            sample = frames[:max(2 * cores, 32)] if len(frames) >= max(2 * cores, 32) else frames
+            sample = frames[:min(len(frames), 512)]
             fps, dt = cpu_oracle_throughput(sample, cores)
             cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                    "sample": "%d of the step's frames, one frame per thread on %d threads, %.1f s (C oracle of the reference algorithm)" % (len(sample), cores, dt)}
         line = {"metric": "frames/s ORB+LSD/LBD extraction", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "frame": "one 752x480 image; a stereo pair is 2 frames",
+                "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "line_contexts": NL, "frames_per_line_call": SUB, "frame": "one 752x480 image; a stereo pair is 2 frames",
                            "sharding": "frame i -> rank i mod N (left/right of a pair on separate GPUs for N > 1), no collective",
                            "l2": "256 MiB buffer written between timed iterations; per-step working set ~%.1f GB" % (B * (45 * spx + 3 * sumpx) / 1e9)},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -15,6 +15,10 @@
         plf_prof_end(ctx);                                                 \
     } while (0)
 #define PLF_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define PLF_PREFETCH_L1(ptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr))
+#endif
+#ifdef PLF_EMU
+#define PLF_PREFETCH_L1(ptr) ((void)(ptr))
 #endif
 #include <stdint.h>
 #include <stddef.h>

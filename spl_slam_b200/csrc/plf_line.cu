@@ -5,6 +5,7 @@
 #include <math.h>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 #ifndef PLF_EMU
 #include <cub/device/device_radix_sort.cuh>   // library radix sort (a plain sort, like cuBLAS for a plain GEMM)
 #endif
@@ -316,6 +317,12 @@ static plf_status sort_lines(plf_line* o)
     return PLF_OK;
 }
 
+// Several line contexts (host threads) may run at once.  The phase of an octave before region growing is
+// bandwidth-bound and fills the GPU; region growing is a latency-bound dependent chain that leaves it mostly
+// idle.  Contexts therefore take turns for the first phase (this mutex) and overlap their growing phases with
+// the other contexts' first phases instead of marching in lockstep.
+static std::mutex g_lsd_prephase;
+
 // LSDDetectorC::detect for a batch resident in d_oct[0]: fills d_det / d_detcount
 static plf_status lsd_detect_batch(plf_line* o, int nframes)
 {
@@ -327,6 +334,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
     PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt + CNT_ERR, 0, sizeof(int), st));
     for (int k = 0; k < noct; k++) {
         const int ow = o->ow[k], oh = o->oh[k], sw = o->sw[k], sh = o->sh[k];
+        std::unique_lock<std::mutex> prephase(g_lsd_prephase);
         if (k > 0) {   // computeGaussianPyramid: pyrDown, no pre-blur (LSDDetector_custom.cpp:56-73)
             PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(ow, 32), plf_div_up(oh, 8), nframes), dim3(32, 8), 0, st, (const uint8_t*)o->d_oct[k - 1],
                        (size_t)o->ow[k - 1] * o->oh[k - 1], o->ow[k - 1], o->ow[k - 1], o->oh[k - 1], o->d_oct[k], (size_t)ow * oh, ow);
@@ -375,6 +383,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             int bc[LSD_NBUCKET];
             PLF_CUDA(ctx, cudaMemcpyAsync(bc, o->d_cnt + CNT_BCOUNT, sizeof(bc), cudaMemcpyDeviceToHost, st));
             PLF_CUDA(ctx, cudaStreamSynchronize(st));
+            prephase.unlock();   // everything up to here has finished on the GPU; growing may overlap other contexts
             int topb = 0, nbig = 0;
             for (int b = 0; b < LSD_NBUCKET; b++) { if (bc[b]) topb = b; if (b >= LSD_BIG_BUCKET) nbig += bc[b]; }
             int wg_maxc = 1 << (topb + 1);
