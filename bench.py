@@ -124,7 +124,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    nfr = max(2 * cores, 32)
+    nfr = 256
     frames = make_frames(nfr // 2, 0)
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_oracle_throughput(frames[:cores], cores)
@@ -169,6 +169,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -306,6 +308,30 @@ def main():
         ms_e2e += timed_e2e_step()
     barrier()
 
+    # ---- matching (BASELINE config 5): 1e4 queries x 1e6 train rows, train-sharded across ranks ----
+    from spl_slam_b200 import sharded
+    NQ, NT = 10000, 1000000
+    gq = torch.Generator(device="cuda"); gq.manual_seed(1234)
+    dq = torch.randint(0, 256, (NQ, 32), dtype=torch.uint8, device="cuda", generator=gq)
+    tb, te = sharded.train_shard(NT, rank, world)
+    gt = torch.Generator(device="cuda"); gt.manual_seed(4321 + rank)
+    dt = torch.randint(0, 256, (te - tb, 32), dtype=torch.uint8, device="cuda", generator=gt)
+    ctx_m = S.Context(dev)
+    for _ in range(2):
+        idx, dst = sharded.knn2_sharded(ctx_m, dq, dt, tb)
+    barrier()
+    ms_match = 0.0
+    MREP = 5
+    for _ in range(MREP):
+        flush.zero_(); torch.cuda.synchronize()
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        ctx_m.timer_start()
+        idx, dst = sharded.knn2_sharded(ctx_m, dq, dt, tb)       # local top-2 + NCCL all-gather + merge (world > 1)
+        m12, nm = sharded.nnr_from_knn2(ctx_m, idx, dst, 0.75)
+        ms_match += ctx_m.timer_stop()
+    barrier()
+    popc_peak = ctx_m.popc_peak()
+
     def maxr(v):
         if world == 1:
             return v
@@ -313,7 +339,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    ms_dev = maxr(ms_dev); ms_e2e = maxr(ms_e2e)
+    ms_dev = maxr(ms_dev); ms_e2e = maxr(ms_e2e); ms_match = maxr(ms_match) / MREP
     total_frames = B * world * args.steps
     value = total_frames / (ms_dev / 1e3)
     e2e_value = total_frames / (ms_e2e / 1e3)
@@ -362,7 +388,14 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "outputs": {"mean_keypoints": float(nk.mean()), "mean_lines": float(nl.mean())}}
+                "outputs": {"mean_keypoints": float(nk.mean()), "mean_lines": float(nl.mean())},
+                "matching": {"metric": "Hamming matches/s", "value": NQ / (ms_match / 1e3), "unit": "queries/s at 1e6 train rows",
+                             "pairs_per_s": NQ * NT / (ms_match / 1e3), "ms": ms_match,
+                             "config": "1e4 queries x 1e6 train, 256-bit, top-2 + ratio 0.75, train rows sharded over %d GPU(s)%s" %
+                                       (world, " + NCCL all-gather + merge" if world > 1 else ""),
+                             "roofline": {"bound": "popc", "achieved": 8 * NQ * NT / (ms_match / 1e3) / world, "peak": popc_peak,
+                                          "unit": "popc32/s per GPU", "frac": 8 * NQ * NT / (ms_match / 1e3) / world / popc_peak,
+                                          "peak_source": "plf_popc_peak micro-benchmark on this GPU"}}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -195,6 +195,10 @@ plf_status plf_nnr_from_knn2_device(plf_ctx* ctx, const int32_t* dev_idx, const 
 plf_status plf_match_nnr_mutual(plf_ctx* ctx, const uint8_t* host_d1, int n1, const uint8_t* host_d2, int n2,
                                 float nnr, int32_t* host_matches12, int* nmatches);
 
+/* measured POPC issue rate of the device (popc32 results per second; XOR + POPC + ADD per result): the roofline
+ * denominator of the matching kernels */
+plf_status plf_popc_peak(plf_ctx* ctx, double* popc_per_s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,7 @@ def load(path=None):
         "plf_knn2_merge_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp]),
         "plf_match_nnr": (C.c_int, [vp, vp, C.c_int, vp, C.c_int64, C.c_float, i32p, P(C.c_int)]),
         "plf_nnr_from_knn2_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_float, vp, vp]),
+        "plf_popc_peak": (C.c_int, [vp, P(C.c_double)]),
         "plf_match_nnr_mutual": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_float, i32p, P(C.c_int)]),
     }
     missing = []
@@ -151,6 +152,11 @@ class Context:
 
     def stream(self):
         return self.lib.plf_ctx_stream(self.h)
+
+    def popc_peak(self):
+        v = C.c_double()
+        self.check(self.lib.plf_popc_peak(self.h, C.byref(v)))
+        return v.value
 
     def wait(self, other):
         self.check(self.lib.plf_ctx_wait(self.h, other.h))

@@ -316,3 +316,47 @@ extern "C" plf_status plf_descriptor_distance(plf_ctx* ctx, const uint8_t* ha, c
     cudaFree(da); cudaFree(db); cudaFree(dd);
     return st;
 }
+
+// ---- POPC issue-rate micro-benchmark: the roofline denominator for the matching kernels ----
+__global__ void __launch_bounds__(256)
+popc_peak_kernel(unsigned* __restrict__ out, int iters)
+{
+    unsigned x0 = threadIdx.x * 2654435761u + blockIdx.x, x1 = x0 ^ 0x9e3779b9u, x2 = x0 * 3u, x3 = x1 * 5u;
+    unsigned x4 = x0 + 17u, x5 = x1 + 31u, x6 = x2 ^ 0x55555555u, x7 = x3 ^ 0xaaaaaaaau;
+    unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
+#pragma unroll 4
+    for (int i = 0; i < iters; i++) {
+        a0 += __popc(x0 ^ i); a1 += __popc(x1 ^ i); a2 += __popc(x2 ^ i); a3 += __popc(x3 ^ i);
+        a4 += __popc(x4 ^ i); a5 += __popc(x5 ^ i); a6 += __popc(x6 ^ i); a7 += __popc(x7 ^ i);
+    }
+    out[blockIdx.x * 256 + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// measured popc32 results per second of this GPU (XOR + POPC + ADD per result, like the Hamming inner loop)
+extern "C" plf_status plf_popc_peak(plf_ctx* ctx, double* popc_per_s)
+{
+    if (!ctx || !popc_per_s) return PLF_ERR_INVALID;
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int blocks = 148 * 8, iters = 1 << 14;
+    void* s;
+    plf_status st = plf_ctx_scratch(ctx, (size_t)blocks * 256 * sizeof(unsigned), &s);
+    if (st) return st;
+    cudaEvent_t e0, e1;
+    PLF_CUDA(ctx, cudaEventCreate(&e0));
+    PLF_CUDA(ctx, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        PLF_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        PLF_LAUNCH(popc_peak_kernel, dim3(blocks), dim3(256), 0, ctx->stream, (unsigned*)s, iters);
+        PLF_CHECK_LAUNCH(ctx);
+        PLF_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        PLF_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0;
+        PLF_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *popc_per_s = (double)blocks * 256 * 8.0 * iters / (best * 1e-3);
+    return PLF_OK;
+}
