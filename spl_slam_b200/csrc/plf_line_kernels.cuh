@@ -249,7 +249,7 @@ k_lsd_keys(const int* __restrict__ label, const int* __restrict__ q, const int* 
 // floor(log2(size)) so that the grow kernel starts the largest components first (longest-chain-first).
 #define LSD_NBUCKET 24
 #ifndef LSD_BIG_BUCKET
-#define LSD_BIG_BUCKET 11   // components with >= 2048 seeds get a warp of their own (k_lsd_grow_warp)
+#define LSD_BIG_BUCKET 8    // components with >= 256 seeds get a warp of their own (k_lsd_grow_warp)
 #endif
 __global__ void __launch_bounds__(256)
 k_lsd_heads(const unsigned long long* __restrict__ keys, int n, int2* __restrict__ comp, int* __restrict__ bcount,
@@ -378,6 +378,7 @@ k_lsd_grow(const unsigned long long* __restrict__ keys, int n, const int2* __res
 // into the label array after the sort), so the angle / cos-sin arrays stay read-only and L1-resident.
 // ------------------------------------------------------------------------------------------------
 #define WARPGROW_MAXC (512 * 1024)          // component pixels one CTA can track (64 KB of used bits)
+#define WG_RING 1024                        // queue entries kept in shared memory
 
 __global__ void __launch_bounds__(256)
 k_lsd_cid(const unsigned long long* __restrict__ keys, int n, int* __restrict__ label, size_t px, int kb)
@@ -396,11 +397,11 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
 {
     PLF_DYN_SMEM(smem);
     unsigned* used = (unsigned*)smem;
+    __shared__ int ring[WG_RING];
     const int lane = threadIdx.x;
     int nbig = 0;
     for (int k = LSD_BIG_BUCKET; k < LSD_NBUCKET; k++) nbig += bcount[k];
     const size_t px = (size_t)w * h;
-    const int dxk = (lane % 3) - 1, dyk = (lane / 3) - 1;   // lanes 0..8 own one neighbour each (row-major 3x3)
     for (int c = blockIdx.x; c < nbig; c += gridDim.x) {
         const int start = comp[c].x, C = comp[c].y, end = start + C;
         if (C > maxc) continue;   // handled by k_lsd_grow
@@ -424,20 +425,34 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
                 const int p = LSD_KEY_IDX(key);
                 const int r0 = arena;
                 const int sy = p / w, sx = p - sy * w;
-                if (lane == 0) { regpts[arena] = sx | (sy << 16); used[sc >> 5] |= 1u << (sc & 31); }
+                if (lane == 0) {
+                    regpts[arena] = sx | (sy << 16);
+                    ring[arena & (WG_RING - 1)] = sx | (sy << 16);
+                    used[sc >> 5] |= 1u << (sc & 31);
+                }
                 arena++;
                 double reg_angle = (double)__ldg(&F[p]) * LSD_D2R;
                 float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
-                int pp = sx | (sy << 16);
                 __syncwarp();
-                for (int r = r0; r < arena; r++) {
-                    const int x = pp & 0xffff, y = pp >> 16;
-                    // lanes 0..8: neighbour state
-                    const int xx = x + dxk, yy = y + dyk;
-                    bool cand = lane < 9 && lane != 4 && xx >= 0 && yy >= 0 && xx < w && yy < h;
+                // Up to three queue entries are expanded per iteration: lane 9g + k handles neighbour k of entry r + g.
+                // Lane order equals the reference's test order (entry, then neighbour), so "first aligned lane"
+                // is the reference's next acceptance; after each acceptance the region angle changes and every
+                // LATER lane is re-tested, exactly what the sequential loop would see.
+                const int grp = lane / 9, kk = lane - grp * 9;
+                const int gdx = (kk % 3) - 1, gdy = (kk / 3) - 1;
+                for (int r = r0; r < arena;) {
+                    const int ng = min(3, arena - r);
+                    bool cand = grp < ng && kk != 4;
+                    int xx = 0, yy = 0, cc = -1;
                     float fv = 0.f;
                     float2 cv = make_float2(0.f, 0.f);
-                    int cc = 0;
+                    if (cand) {
+                        const int qidx = r + grp;
+                        // the queue tail lives in a shared-memory ring; older entries come from the global arena
+                        const int pp = (arena - qidx <= WG_RING) ? ring[qidx & (WG_RING - 1)] : regpts[qidx];
+                        xx = (pp & 0xffff) + gdx; yy = (pp >> 16) + gdy;
+                        cand = xx >= 0 && yy >= 0 && xx < w && yy < h;
+                    }
                     if (cand) {
                         const int qi = yy * w + xx;
                         const int ci = __ldg(&CID[qi]);
@@ -445,9 +460,8 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
                         cv = __ldg(&CS[qi]);
                         cc = ci - start;
                         cand = ci >= 0 && !((used[cc >> 5] >> (cc & 31)) & 1u);
+                        if (!cand) cc = -1;
                     }
-                    int nextpp = 0;
-                    if (r + 1 < arena) nextpp = regpts[r + 1];   // uniform load, overlaps the tests below
                     const double a = (double)fv * LSD_D2R;
                     for (;;) {
                         bool pass = false;
@@ -462,21 +476,21 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
                         }
                         const unsigned m = __ballot_sync(0xffffffffu, pass);
                         if (!m) break;
-                        const int k0 = __ffs((int)m) - 1;                  // first aligned neighbour in the reference's order
+                        const int k0 = __ffs((int)m) - 1;                  // next acceptance in the reference's order
                         if (lane == k0) {
-                            used[cc >> 5] |= 1u << (cc & 31);              // only this lane writes during the pop
+                            used[cc >> 5] |= 1u << (cc & 31);              // only this lane writes in this round
                             regpts[arena] = xx | (yy << 16);
+                            ring[arena & (WG_RING - 1)] = xx | (yy << 16);
                         }
-                        if (arena == r + 1) nextpp = __shfl_sync(0xffffffffu, xx | (yy << 16), k0);
-                        else (void)__shfl_sync(0xffffffffu, 0, k0);
                         arena++;
+                        const int cc0 = __shfl_sync(0xffffffffu, cc, k0);
                         sumdx += __shfl_sync(0xffffffffu, cv.x, k0);
                         sumdy += __shfl_sync(0xffffffffu, cv.y, k0);
                         reg_angle = (double)plf_fast_atan2(sumdy, sumdx) * LSD_D2R;
-                        cand = cand && lane > k0;                          // earlier neighbours are not revisited
+                        cand = cand && lane > k0 && cc != cc0;             // earlier tests stand; the same pixel seen from another entry is now used
                     }
                     __syncwarp();
-                    pp = nextpp;
+                    r += ng;
                 }
                 const int nreg = arena - r0;
                 if (lane == 0 && nreg >= min_reg_size) {
