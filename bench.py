@@ -35,6 +35,7 @@ LINE = dict(nfeatures=200, nlevels=2, refine=0, scale=1.1, sigma_scale=0.8, quan
             density_th=0.8, n_bins=1024, min_line_length=0.0)   # Examples/Monocular/EuRoC.yaml (Camera.width absent -> 0)
 FRAMES_PER_GPU = 1024         # 512 stereo pairs per GPU per step
 LINE_CONTEXTS = 4             # line extractor instances (own context/stream + host thread each), frames split evenly
+ORB_CONTEXTS = 2              # ORB extractor instances, same idea (uploads of one overlap kernels of the other)
 WORKLOAD = "EuRoC-style stereo 752x480 pairs, 1200 ORB (8 lv x1.2, FAST 20/7) + LSD/LBD 200 lines per image"
 
 
@@ -152,6 +153,7 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--line-contexts", type=int, default=LINE_CONTEXTS)
+    ap.add_argument("--orb-contexts", type=int, default=ORB_CONTEXTS)
     ap.add_argument("--line-sub", type=int, default=0, help="frames per line call (0 = one call per context)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -200,16 +202,20 @@ def main():
         frames = allf
     dev = local_rank
     from concurrent.futures import ThreadPoolExecutor
-    ctx_o = S.Context(dev)   # ORB stream
+    NO = args.orb_contexts if B % (2 * args.orb_contexts) == 0 else 1
+    ctx_os = [S.Context(dev) for _ in range(NO)]    # ORB streams
+    ctx_o = ctx_os[0]
     NL = args.line_contexts if B % (2 * args.line_contexts) == 0 else 1
     ctx_ls = [S.Context(dev) for _ in range(NL)]   # line streams: the region-growing chain of one sub-batch overlaps
     lib = ctx_o.lib                                 # the bandwidth-bound kernels of the others
-    orb = S.ORBextractor(ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"], ctx=ctx_o)
+    orbs = [S.ORBextractor(ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"], ctx=c) for c in ctx_os]
+    orb = orbs[0]
     les = [S.Lineextractor(LINE["nfeatures"], LINE["nlevels"], LINE["refine"], LINE["scale"], LINE["sigma_scale"], LINE["quant"],
                            LINE["ang_th"], LINE["log_eps"], LINE["density_th"], LINE["n_bins"], LINE["min_line_length"], ctx=c) for c in ctx_ls]
     capk, capl = orb.max_keypoints, les[0].max_keylines
     BL = B // NL
-    pool = ThreadPoolExecutor(NL + 1)
+    BO = B // NO
+    pool = ThreadPoolExecutor(NL + NO)
     # device-resident inputs / outputs (torch only provides the memory)
     d_img = torch.from_numpy(frames).cuda()
     d_kps = torch.empty((B, capk, 28), dtype=torch.uint8, device="cuda"); d_desc = torch.empty((B, capk, 32), dtype=torch.uint8, device="cuda")
@@ -224,8 +230,14 @@ def main():
     h_ld = torch.empty((B, capl, 32), dtype=torch.uint8).pin_memory()
     n_k = np.zeros(B, np.int32); n_l = np.zeros(B, np.int32)
 
+    def dev_orb_i(i):
+        s = slice(i * BO, (i + 1) * BO)
+        ctx_os[i].check(lib.plf_orb_extract_batch_device(orbs[i].h, d_img[s].data_ptr(), BO, W, H, W, W * H, d_kps[s].data_ptr(),
+                                                         d_desc[s].data_ptr(), capk, d_nk[s].data_ptr()))
+
     def dev_orb():
-        ctx_o.check(lib.plf_orb_extract_batch_device(orb.h, d_img.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), capk, d_nk.data_ptr()))
+        for i in range(NO):   # asynchronous launches, one stream per ORB context
+            dev_orb_i(i)
 
     SUB = args.line_sub if args.line_sub and BL % args.line_sub == 0 else BL
 
@@ -244,12 +256,14 @@ def main():
         torch.cuda.synchronize()
         ctx_o.timer_start()
         step_device()
-        for c in ctx_ls:
-            ctx_o.wait(c)                  # the ORB stream's stop event waits for every line stream
+        for c in ctx_os[1:] + ctx_ls:
+            ctx_o.wait(c)                  # the first ORB stream's stop event waits for every other stream
         return ctx_o.timer_stop()
 
-    def e2e_orb():
-        ctx_o.check(lib.plf_orb_extract_batch(orb.h, h_img.data_ptr(), B, W, H, W, W * H, h_kps.data_ptr(), h_desc.data_ptr(), capk, n_k.ctypes.data))
+    def e2e_orb(i):
+        s = slice(i * BO, (i + 1) * BO)
+        ctx_os[i].check(lib.plf_orb_extract_batch(orbs[i].h, h_img[s].data_ptr(), BO, W, H, W, W * H, h_kps[s].data_ptr(), h_desc[s].data_ptr(),
+                                                  capk, n_k[s].ctypes.data))
 
     def e2e_line(i):
         for j in range(i * BL, (i + 1) * BL, SUB):
@@ -261,9 +275,10 @@ def main():
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        fo = pool.submit(e2e_orb)          # the reference's ORB thread and line thread(s) (Frame.cc:301-304)
+        fo = [pool.submit(e2e_orb, i) for i in range(NO)]   # the reference's ORB thread(s) and line thread(s) (Frame.cc:301-304)
         list(pool.map(e2e_line, range(NL)))
-        fo.result()
+        for f in fo:
+            f.result()
         return (time.perf_counter() - t0) * 1e3
 
     # ---- device-resident throughput ----
@@ -271,29 +286,30 @@ def main():
         timed_device_step()
     barrier()
     sampler = ClockSampler(dev) if rank == 0 else None
-    l0 = ctx_o.launch_count() + sum(c.launch_count() for c in ctx_ls)
+    l0 = sum(c.launch_count() for c in ctx_os + ctx_ls)
     ms_dev = 0.0
     for _ in range(args.steps):
         ms_dev += timed_device_step()
     barrier()
-    launches = ctx_o.launch_count() + sum(c.launch_count() for c in ctx_ls) - l0
+    launches = sum(c.launch_count() for c in ctx_os + ctx_ls) - l0
     clocks = sampler.stop() if sampler else None
     nk = d_nk.cpu().numpy(); nl = d_nl.cpu().numpy()
     assert (nk > 0).all() and (nl >= 0).all(), "extraction reported an overflow"
 
     # ---- per-kernel times for the roofline (separate profiled steps, CUDA events per launch) ----
-    for c in [ctx_o] + ctx_ls:
+    for c in ctx_os + ctx_ls:
         c.profile_enable(True)
     PROF_STEPS = 3
     for _ in range(PROF_STEPS):   # one stream at a time here, so that kernel times are not mixed
         flush.zero_(); torch.cuda.synchronize()
-        dev_orb()
-        ctx_o.synchronize()
+        for i in range(NO):
+            dev_orb_i(i)
+            ctx_os[i].synchronize()
         for i in range(NL):
             dev_line(i)
             ctx_ls[i].synchronize()
     prof = {}
-    for c in [ctx_o] + ctx_ls:
+    for c in ctx_os + ctx_ls:
         for k, v in c.profile_report().items():
             a = prof.get(k, (0.0, 0))
             prof[k] = (a[0] + v[0] / PROF_STEPS, a[1] + v[1] // PROF_STEPS)
@@ -382,7 +398,7 @@ def main():
         line = {"metric": "frames/s ORB+LSD/LBD extraction", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "line_contexts": NL, "frames_per_line_call": SUB, "frame": "one 752x480 image; a stereo pair is 2 frames",
+                "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "orb_contexts": NO, "line_contexts": NL, "frames_per_line_call": SUB, "frame": "one 752x480 image; a stereo pair is 2 frames",
                            "sharding": "frame i -> rank i mod N (left/right of a pair on separate GPUs for N > 1), no collective",
                            "l2": "256 MiB buffer written between timed iterations; per-step working set ~%.1f GB" % (B * (45 * spx + 3 * sumpx) / 1e9)},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

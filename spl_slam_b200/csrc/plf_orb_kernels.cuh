@@ -109,10 +109,14 @@ __device__ __forceinline__ int fast_best(const uint8_t* c, int pitch, int th)
     // returns max(A, B) if the pixel is a FAST-9 corner at threshold th, else 0
     const int v = c[0];
     int d[16];
-    d[0] = v - c[3 * pitch];      d[1] = v - c[3 * pitch + 1];  d[2] = v - c[2 * pitch + 2];  d[3] = v - c[pitch + 3];
-    d[4] = v - c[3];              d[5] = v - c[-pitch + 3];     d[6] = v - c[-2 * pitch + 2]; d[7] = v - c[-3 * pitch + 1];
-    d[8] = v - c[-3 * pitch];     d[9] = v - c[-3 * pitch - 1]; d[10] = v - c[-2 * pitch - 2]; d[11] = v - c[-pitch - 3];
-    d[12] = v - c[-3];            d[13] = v - c[pitch - 3];     d[14] = v - c[2 * pitch - 2]; d[15] = v - c[3 * pitch - 1];
+    // quick reject on the four compass points: a 9-long arc contains one pixel of every opposite pair (k, k + 8),
+    // so both pixels of a pair inside [v - th, v + th] rules the corner out (whole warps leave here on smooth areas)
+    d[0] = v - c[3 * pitch];  d[8] = v - c[-3 * pitch];  d[4] = v - c[3];  d[12] = v - c[-3];
+    if (!((d[0] > th || d[8] > th || d[0] < -th || d[8] < -th) && (d[4] > th || d[12] > th || d[4] < -th || d[12] < -th))) return 0;
+    d[1] = v - c[3 * pitch + 1];  d[2] = v - c[2 * pitch + 2];  d[3] = v - c[pitch + 3];
+    d[5] = v - c[-pitch + 3];     d[6] = v - c[-2 * pitch + 2]; d[7] = v - c[-3 * pitch + 1];
+    d[9] = v - c[-3 * pitch - 1]; d[10] = v - c[-2 * pitch - 2]; d[11] = v - c[-pitch - 3];
+    d[13] = v - c[pitch - 3];     d[14] = v - c[2 * pitch - 2]; d[15] = v - c[3 * pitch - 1];
     unsigned hi = 0, lo = 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
