@@ -63,6 +63,7 @@ def lib():
         L.orc_orb_level_raw_count.argtypes = [vp, C.c_int]
         L.orc_orb_level_raw.argtypes = [vp, C.c_int, i32p, i32p, i32p]
         L.orc_orb_level_kept_count.argtypes = [vp, C.c_int]
+        L.orc_stereo_match.argtypes = [vp, vp, vp, u8p, C.c_int, vp, u8p, C.c_int, C.c_float, C.c_float, f32p, f32p]
         L.orc_distribute_octree.argtypes = [i32p, i32p, i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_int, i32p, C.c_int]
         L.orc_resize_linear_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, u8p, C.c_int, C.c_int, C.c_size_t]
@@ -234,6 +235,16 @@ class ORBextractor:
 
     def level_kept_count(self, level):
         return lib().orc_orb_level_kept_count(self._h, level)
+
+
+def stereo_match(orbL, orbR, kL, dL, kR, dR, mb, mbf):
+    """Frame::ComputeStereoMatches (src/Frame.cc:881-1055): orbL/orbR are oracle extractors that just processed the
+    left/right image (their pyramids are read).  Returns (mvuRight, mvDepth)."""
+    kL = np.ascontiguousarray(kL, KEYPOINT_DTYPE); kR = np.ascontiguousarray(kR, KEYPOINT_DTYPE)
+    dL = np.ascontiguousarray(dL, np.uint8); dR = np.ascontiguousarray(dR, np.uint8)
+    u = np.empty(len(kL), np.float32); z = np.empty(len(kL), np.float32)
+    lib().orc_stereo_match(orbL._h, orbR._h, _p(kL), _p(dL), len(kL), _p(kR), _p(dR), len(kR), mb, mbf, _p(u), _p(z))
+    return u, z
 
 
 # ---------------- lines ----------------

@@ -490,3 +490,101 @@ void orc_orb_level_raw(const orc_orb* o, int level, int* xs, int* ys, int* resp)
     memcpy(resp, L->rr, sizeof(int) * (size_t)L->nraw);
 }
 int orc_orb_level_kept_count(const orc_orb* o, int level) { return o->lv[level].nkept; }
+
+/* ---------------- Frame::ComputeStereoMatches, src/Frame.cc:881-1055 ----------------
+ * Row-band best-1 Hamming (octave +-1, disparity window, TH_HIGH init, first-best on ties) + 11x11 SAD slide
+ * on the two extractors' pyramids + parabola sub-pixel + 2.1 x median SAD filter.  oL / oR must hold the
+ * pyramids of the two images (state after orc_orb_extract).  Windows that would leave the level image are
+ * skipped (the reference would throw in cv::Mat::colRange); an empty match list is a no-op (reference UB). */
+static int cmp_pair(const void* a, const void* b)
+{
+    const int* x = (const int*)a; const int* y = (const int*)b;
+    if (x[0] != y[0]) return x[0] < y[0] ? -1 : 1;
+    return x[1] < y[1] ? -1 : (x[1] > y[1]);
+}
+
+void orc_stereo_match(const orc_orb* oL, const orc_orb* oR, const orc_keypoint* kL, const uint8_t* dL, int nL,
+                      const orc_keypoint* kR, const uint8_t* dR, int nR, float mb, float mbf,
+                      float* uRight, float* depth)
+{
+    const int TH_HIGH = 100, TH_LOW = 50, thOrbDist = (TH_HIGH + TH_LOW) / 2;
+    const int nRows = oL->lv[0].h;
+    for (int i = 0; i < nL; i++) { uRight[i] = -1.0f; depth[i] = -1.0f; }
+    const float minZ = mb, minD = 0, maxD = mbf / minZ;
+    int (*pairs)[2] = (int (*)[2])malloc(sizeof(int[2]) * (size_t)(nL > 0 ? nL : 1));
+    int np = 0;
+    for (int iL = 0; iL < nL; iL++) {
+        const int levelL = kL[iL].octave;
+        const float vL = kL[iL].y, uL = kL[iL].x;
+        const int row = (int)vL;
+        if (row < 0 || row >= nRows) continue;
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = TH_HIGH, bestIdxR = 0;
+        for (int iR = 0; iR < nR; iR++) {
+            /* iR is in vRowIndices[row] iff floor(y - r) <= row <= ceil(y + r) */
+            const float r = 2.0f * oL->scale[kR[iR].octave];
+            const int maxr = (int)ceilf(kR[iR].y + r), minr = (int)floorf(kR[iR].y - r);
+            if (row < minr || row > maxr) continue;
+            if (kR[iR].octave < levelL - 1 || kR[iR].octave > levelL + 1) continue;
+            const float uR = kR[iR].x;
+            if (uR >= minU && uR <= maxU) {
+                int dist = orc_descriptor_distance(dL + (size_t)iL * 32, dR + (size_t)iR * 32);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (!(bestDist < thOrbDist)) continue;
+        const float uR0 = kR[bestIdxR].x;
+        const float scaleFactor = oL->inv_scale[levelL];
+        const float scaleduL = roundf(kL[iL].x * scaleFactor), scaledvL = roundf(kL[iL].y * scaleFactor);
+        const float scaleduR0 = roundf(uR0 * scaleFactor);
+        const int w = 5, L = 5;
+        const orb_level* PL = &oL->lv[levelL];
+        const orb_level* PR = &oR->lv[levelL];
+        const uint8_t* imL = PL->buf + EDGE_THRESHOLD * PL->stride + EDGE_THRESHOLD;
+        const uint8_t* imR = PR->buf + EDGE_THRESHOLD * PR->stride + EDGE_THRESHOLD;
+        const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+        if (iniu < 0 || endu >= PR->w) continue;
+        const int cu = (int)scaleduL, cv = (int)scaledvL, cr = (int)scaleduR0;
+        if (cv - w < 0 || cv + w >= PL->h || cu - w < 0 || cu + w >= PL->w || cr - L - w < 0 || cr + L + w >= PR->w || cv + w >= PR->h)
+            continue;
+        int bestSad = 2147483647, bestincR = 0;
+        float vDists[11];
+        const int cL = imL[(size_t)cv * PL->stride + cu];
+        for (int incR = -L; incR <= L; incR++) {
+            const int cR = imR[(size_t)cv * PR->stride + cr + incR];
+            int sad = 0;
+            for (int dy = -w; dy <= w; dy++)
+                for (int dx = -w; dx <= w; dx++) {
+                    int a = imL[(size_t)(cv + dy) * PL->stride + cu + dx] - cL;
+                    int b = imR[(size_t)(cv + dy) * PR->stride + cr + incR + dx] - cR;
+                    sad += abs(a - b);
+                }
+            float dist = (float)sad;
+            if (dist < (float)bestSad) { bestSad = (int)dist; bestincR = incR; }
+            vDists[L + incR] = dist;
+        }
+        if (bestincR == -L || bestincR == L) continue;
+        const float dist1 = vDists[L + bestincR - 1], dist2 = vDists[L + bestincR], dist3 = vDists[L + bestincR + 1];
+        const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+        if (deltaR < -1 || deltaR > 1) continue;
+        float bestuR = oL->scale[levelL] * ((float)scaleduR0 + (float)bestincR + deltaR);
+        float disparity = (uL - bestuR);
+        if (disparity >= minD && disparity < maxD) {
+            if (disparity <= 0) { disparity = (float)0.01; bestuR = (float)(uL - 0.01); }
+            depth[iL] = mbf / disparity;
+            uRight[iL] = bestuR;
+            pairs[np][0] = bestSad; pairs[np][1] = iL; np++;
+        }
+    }
+    if (np > 0) {
+        qsort(pairs, (size_t)np, sizeof(int[2]), cmp_pair);
+        const float median = (float)pairs[np / 2][0];
+        const float thDist = 1.5f * 1.4f * median;
+        for (int i = np - 1; i >= 0; i--) {
+            if ((float)pairs[i][0] < thDist) break;
+            uRight[pairs[i][1]] = -1; depth[pairs[i][1]] = -1;
+        }
+    }
+    free(pairs);
+}

@@ -80,6 +80,11 @@ int  orc_orb_level_raw_count(const orc_orb*, int level);
 void orc_orb_level_raw(const orc_orb*, int level, int* xs, int* ys, int* resp);
 int  orc_orb_level_kept_count(const orc_orb*, int level);
 
+/* Frame::ComputeStereoMatches (src/Frame.cc:881-1055); oL/oR hold the two images' pyramids (after extract) */
+void orc_stereo_match(const orc_orb* oL, const orc_orb* oR, const orc_keypoint* kL, const uint8_t* dL, int nL,
+                      const orc_keypoint* kR, const uint8_t* dR, int nR, float mb, float mbf,
+                      float* uRight, float* depth);
+
 /* DistributeOctTree alone (ORBextractor.cc:539-763); keys relative to (minX,minY).
  * out_idx receives indices into the input arrays in final list order; returns count. */
 int  orc_distribute_octree(const int* xs, const int* ys, const int* resp, int n,
