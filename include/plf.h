@@ -195,6 +195,40 @@ plf_status plf_nnr_from_knn2_device(plf_ctx* ctx, const int32_t* dev_idx, const 
 plf_status plf_match_nnr_mutual(plf_ctx* ctx, const uint8_t* host_d1, int n1, const uint8_t* host_d2, int n2,
                                 float nnr, int32_t* host_matches12, int* nmatches);
 
+/* Candidate-list matching: the data-parallel core of ORBmatcher::SearchForInitialization / SearchByProjection /
+ * SearchByBoW and Linematcher::SearchForInitialization / SearchByProjection (src/ORBmatcher.cc:45-129, :406-521;
+ * src/Linematcher.cc:146-286, :544-646).  Query q scans its candidate train rows cand_idx[cand_off[q] ..
+ * cand_off[q+1]) in list order with the reference's update rule (`dist < bestDist` strict, else
+ * `dist < bestDist2`): best[q] = {first minimum, second entry in (distance, list position) order} as train
+ * indices (-1 where the list is shorter), best_dist likewise.  cand_dist (may be NULL) receives every
+ * candidate's distance so the order-dependent greedy steps (vMatchedDistance, rotation histogram) can stay on
+ * the host.  cand_off has nq + 1 entries. */
+plf_status plf_hamming_candidates(plf_ctx* ctx, const uint8_t* host_q, int nq, const uint8_t* host_t, int nt,
+                                  const int32_t* host_cand_off, const int32_t* host_cand_idx,
+                                  int32_t* host_best_idx, int32_t* host_best_dist, int32_t* host_cand_dist);
+plf_status plf_hamming_candidates_device(plf_ctx* ctx, const uint8_t* dev_q, int nq, const uint8_t* dev_t, int nt,
+                                         const int32_t* dev_cand_off, const int32_t* dev_cand_idx,
+                                         int32_t* dev_best_idx, int32_t* dev_best_dist, int32_t* dev_cand_dist);
+
+/* ---- stereo: replaces Frame::ComputeStereoMatches (src/Frame.cc:881-1055).  Reads the pyramids the two
+ * extractors hold after their last extraction (the reference reads mpORBextractorLeft/Right->mvImagePyramid),
+ * so `left` / `right` must have processed the pair's images (the same extractor with two frames of one batch is
+ * fine).  mb = baseline in metres, mbf = baseline * fx.  Outputs mvuRight / mvDepth (-1 where unmatched).
+ * Defined behaviour where the reference has none: an SAD window that would leave the level image skips the
+ * keypoint (the reference throws from cv::Mat::colRange); no match at all leaves everything at -1. ---- */
+plf_status plf_stereo_match(plf_orb* left, int frame_l, plf_orb* right, int frame_r,
+                            const plf_keypoint* host_kl, const uint8_t* host_dl, int nl,
+                            const plf_keypoint* host_kr, const uint8_t* host_dr, int nr,
+                            float mb, float mbf, float* host_uright, float* host_depth);
+/* batched, device resident: pair p uses frame left_first + p * left_step of `left`'s last batch and
+ * right_first + p * right_step of `right`'s; dev_k* / dev_d* / dev_n* are the [frame][cap] outputs of
+ * plf_orb_extract_batch_device; dev_uright / dev_depth are [npairs][cap]. */
+plf_status plf_stereo_match_batch_device(plf_orb* left, plf_orb* right, int npairs, int left_first, int left_step,
+                                         int right_first, int right_step,
+                                         const plf_keypoint* dev_kl, const uint8_t* dev_dl, const int32_t* dev_nl,
+                                         const plf_keypoint* dev_kr, const uint8_t* dev_dr, const int32_t* dev_nr,
+                                         int cap, float mb, float mbf, float* dev_uright, float* dev_depth);
+
 /* measured POPC issue rate of the device (popc32 results per second; XOR + POPC + ADD per result): the roofline
  * denominator of the matching kernels */
 plf_status plf_popc_peak(plf_ctx* ctx, double* popc_per_s);

@@ -86,6 +86,7 @@ def lib():
         L.orc_descriptor_distance.argtypes = [u8p, u8p]
         L.orc_knn2.argtypes = [u8p, C.c_int, u8p, C.c_long, i32p, i32p]
         L.orc_match_nnr.argtypes = [u8p, C.c_int, u8p, C.c_long, C.c_float, i32p]
+        L.orc_hamming_candidates.argtypes = [u8p, C.c_int, u8p, i32p, i32p, i32p, i32p, i32p]
         _LIB = L
     return _LIB
 
@@ -309,6 +310,17 @@ def knn2(q, t):
     idx = np.empty((len(q), 2), np.int32); dist = np.empty((len(q), 2), np.int32)
     lib().orc_knn2(_p(q), len(q), _p(t), len(t), _p(idx), _p(dist))
     return idx, dist
+
+
+def candidates_top2(q, t, cand_lists):
+    """Sequential top-2 over candidate lists (src/ORBmatcher.cc:430-456) -> (best_idx, best_dist, cand_dist)."""
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    off = np.zeros(len(q) + 1, np.int32)
+    off[1:] = np.cumsum([len(c) for c in cand_lists])
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(c, np.int32) for c in cand_lists]), np.int32)
+    bi = np.empty((len(q), 2), np.int32); bd = np.empty((len(q), 2), np.int32); cd = np.empty(max(len(flat), 1), np.int32)
+    lib().orc_hamming_candidates(_p(q), len(q), _p(t), _p(off), _p(flat), _p(bi), _p(bd), _p(cd))
+    return bi, bd, cd[:len(flat)]
 
 
 def match_nnr(q, t, nnr):

@@ -299,3 +299,22 @@ int orc_match_nnr(const uint8_t* q, int nq, const uint8_t* t, long nt, float nnr
     free(idx);
     return nm;
 }
+
+/* top-2 over a candidate list with the reference's update rule (ORBmatcher::SearchForInitialization,
+ * src/ORBmatcher.cc:430-456: `dist < bestDist` -> shift, `else if (dist < bestDist2)`); also tracks which
+ * candidate holds the second place (bestLevel2 bookkeeping of SearchByProjection, :88-104). */
+void orc_hamming_candidates(const uint8_t* q, int nq, const uint8_t* t, const int32_t* off, const int32_t* cidx,
+                            int32_t* bidx, int32_t* bdist, int32_t* cdist)
+{
+    for (int i = 0; i < nq; i++) {
+        int bestDist = 2147483647, bestDist2 = 2147483647, bestIdx = -1, bestIdx2 = -1;
+        for (int c = off[i]; c < off[i + 1]; c++) {
+            const int dist = orc_descriptor_distance(q + (size_t)i * 32, t + (size_t)cidx[c] * 32);
+            if (cdist) cdist[c] = dist;
+            if (dist < bestDist) { bestDist2 = bestDist; bestIdx2 = bestIdx; bestDist = dist; bestIdx = cidx[c]; }
+            else if (dist < bestDist2) { bestDist2 = dist; bestIdx2 = cidx[c]; }
+        }
+        bidx[2 * i] = bestIdx; bidx[2 * i + 1] = bestIdx2;
+        bdist[2 * i] = bestIdx >= 0 ? bestDist : -1; bdist[2 * i + 1] = bestIdx2 >= 0 ? bestDist2 : -1;
+    }
+}

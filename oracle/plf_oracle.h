@@ -119,6 +119,9 @@ int  orc_descriptor_distance(const uint8_t* a, const uint8_t* b);
 /* knnMatch k=2 semantics: idx/dist are nq x 2; missing entries -1 */
 void orc_knn2(const uint8_t* q, int nq, const uint8_t* t, long nt, int32_t* idx, int32_t* dist);
 /* matchNNR: matches12[q] = trainIdx or -1; returns nmatches. nt<2 -> all -1 (defined behaviour) */
+/* candidate-list top-2, reference update rule (src/ORBmatcher.cc:430-456) */
+void orc_hamming_candidates(const uint8_t* q, int nq, const uint8_t* t, const int32_t* off, const int32_t* cidx,
+                            int32_t* bidx, int32_t* bdist, int32_t* cdist);
 int  orc_match_nnr(const uint8_t* q, int nq, const uint8_t* t, long nt, float nnr, int32_t* matches12);
 
 #ifdef __cplusplus

@@ -100,6 +100,11 @@ def load(path=None):
         "plf_nnr_from_knn2_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_float, vp, vp]),
         "plf_popc_peak": (C.c_int, [vp, P(C.c_double)]),
         "plf_match_nnr_mutual": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_float, i32p, P(C.c_int)]),
+        "plf_hamming_candidates": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, i32p, i32p, i32p, i32p, i32p]),
+        "plf_hamming_candidates_device": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp]),
+        "plf_stereo_match": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_float, f32p, f32p]),
+        "plf_stereo_match_batch_device": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
+                                                    C.c_int, C.c_float, C.c_float, vp, vp]),
     }
     missing = []
     for name, (res, args) in sig.items():
@@ -268,6 +273,16 @@ class ORBextractor:
     @property
     def mvImagePyramid(self):
         return [self.pyramid_level(l) for l in range(self.nlevels)]
+
+    def ComputeStereoMatches(self, right, keysL, descL, keysR, descR, mb, mbf, frame_l=0, frame_r=0):
+        """Frame::ComputeStereoMatches (src/Frame.cc:881-1055) for the images this extractor (left) and `right`
+        processed last: -> (mvuRight, mvDepth)."""
+        kl = np.ascontiguousarray(keysL, KEYPOINT_DTYPE); kr = np.ascontiguousarray(keysR, KEYPOINT_DTYPE)
+        dl = np.ascontiguousarray(descL, np.uint8); dr = np.ascontiguousarray(descR, np.uint8)
+        u = np.full(len(kl), -1.0, np.float32); z = np.full(len(kl), -1.0, np.float32)
+        self.ctx.check(self.lib.plf_stereo_match(self.h, frame_l, right.h, frame_r, _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr),
+                                                 mb, mbf, _p(u), _p(z)))
+        return u, z
 
     def debug_blurred(self, level, frame=0):
         w, h = C.c_int(), C.c_int()
@@ -439,6 +454,20 @@ class Linematcher:
         self.ctx.check(self.lib.plf_match_nnr_mutual(self.ctx.h, _p(a), len(a), _p(b), len(b),
                                                      self.mfNNratio if nnr is None else nnr, _p(m), C.byref(n)))
         return m, n.value
+
+    def candidates_top2(self, desc1, desc2, cand_lists, want_dist=False):
+        """The distance / top-2 core of the candidate-list matchers (ORBmatcher::SearchForInitialization,
+        src/ORBmatcher.cc:430-456, and the other Search* loops): cand_lists[q] = train rows query q scans, in
+        order.  Returns (best_idx[nq,2], best_dist[nq,2]) (+ the flat per-candidate distances)."""
+        q, t = _desc(desc1), _desc(desc2)
+        off = np.zeros(len(q) + 1, np.int32)
+        off[1:] = np.cumsum([len(c) for c in cand_lists])
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(c, np.int32) for c in cand_lists]) if len(cand_lists) else np.zeros(0, np.int32), np.int32)
+        bi = np.empty((len(q), 2), np.int32); bd = np.empty((len(q), 2), np.int32)
+        cd = np.empty(max(len(flat), 1), np.int32) if want_dist else None
+        self.ctx.check(self.lib.plf_hamming_candidates(self.ctx.h, _p(q), len(q), _p(t), len(t), _p(off), _p(flat) if len(flat) else None,
+                                                       _p(bi), _p(bd), _p(cd) if want_dist else None))
+        return (bi, bd, cd[:len(flat)]) if want_dist else (bi, bd)
 
 
 ORBmatcher = Linematcher  # ORBmatcher::DescriptorDistance is the same function (src/ORBmatcher.cc:1656-1672)

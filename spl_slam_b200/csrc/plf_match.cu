@@ -317,6 +317,104 @@ extern "C" plf_status plf_descriptor_distance(plf_ctx* ctx, const uint8_t* ha, c
     return st;
 }
 
+// ---- candidate-list top-2 (ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:430-456, and the other
+// Search* loops): one warp per query; lane l takes list positions l, l+32, ...; the per-lane and cross-lane
+// merges order entries by (distance, list position), which is what the reference's sequential
+// `dist < bestDist` / `else if (dist < bestDist2)` scan produces. ----
+__global__ void __launch_bounds__(256)
+cand_top2_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, const int* __restrict__ off,
+                 const int* __restrict__ cidx, int* __restrict__ bidx, int* __restrict__ bdist, int* __restrict__ cdist)
+{
+    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (qi >= nq) return;
+    const uint4 a0 = q[2 * (size_t)qi], a1 = q[2 * (size_t)qi + 1];
+    const int beg = off[qi], end = off[qi + 1];
+    // keys: distance << 22 | list position (lists up to 4M entries); KNN_INF = none
+    long long k0 = 0x7fffffffffffffffLL, k1 = 0x7fffffffffffffffLL;
+    for (int c = beg + lane; c < end; c += 32) {
+        const int ti = cidx[c];
+        int d = -1;
+        if (ti >= 0 && ti < nt) {
+            const uint4 b0 = t[2 * (size_t)ti], b1 = t[2 * (size_t)ti + 1];
+            d = hamming256(a0, a1, b0, b1);
+            const long long key = ((long long)d << 32) | (unsigned)(c - beg);
+            if (key < k0) { k1 = k0; k0 = key; }
+            else if (key < k1) k1 = key;
+        }
+        if (cdist) cdist[c] = d;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const long long o0 = __shfl_xor_sync(0xffffffffu, k0, s), o1 = __shfl_xor_sync(0xffffffffu, k1, s);
+        // merge two sorted pairs
+        const long long lo = k0 < o0 ? k0 : o0, hi = k0 < o0 ? o0 : k0;
+        const long long m1 = k1 < o1 ? k1 : o1;
+        k0 = lo;
+        k1 = hi < m1 ? hi : m1;
+    }
+    if (lane == 0) {
+        const bool h0 = k0 != 0x7fffffffffffffffLL, h1 = k1 != 0x7fffffffffffffffLL;
+        bidx[2 * (size_t)qi] = h0 ? cidx[beg + (int)(k0 & 0xffffffffLL)] : -1;
+        bidx[2 * (size_t)qi + 1] = h1 ? cidx[beg + (int)(k1 & 0xffffffffLL)] : -1;
+        bdist[2 * (size_t)qi] = h0 ? (int)(k0 >> 32) : -1;
+        bdist[2 * (size_t)qi + 1] = h1 ? (int)(k1 >> 32) : -1;
+    }
+}
+
+extern "C" plf_status plf_hamming_candidates_device(plf_ctx* ctx, const uint8_t* dq, int nq, const uint8_t* dt, int nt, const int32_t* doff,
+                                                    const int32_t* dcidx, int32_t* dbidx, int32_t* dbdist, int32_t* dcdist)
+{
+    if (!ctx || nq < 0 || nt < 0 || (nq > 0 && (!dq || !doff || !dbidx || !dbdist)))
+        return plf_fail(ctx, PLF_ERR_INVALID, "plf_hamming_candidates_device: bad arguments");
+    if (((uintptr_t)dq | (uintptr_t)dt) & 15) return plf_fail(ctx, PLF_ERR_INVALID, "descriptor pointers must be 16-byte aligned");
+    if (nq == 0) return PLF_OK;
+    PLF_LAUNCH(cand_top2_kernel, dim3(plf_div_up(nq, 8)), dim3(256), 0, ctx->stream, (const uint4*)dq, nq, (const uint4*)dt, nt, doff, dcidx,
+               dbidx, dbdist, dcdist);
+    PLF_CHECK_LAUNCH(ctx);
+    return PLF_OK;
+}
+
+extern "C" plf_status plf_hamming_candidates(plf_ctx* ctx, const uint8_t* hq, int nq, const uint8_t* ht, int nt, const int32_t* hoff,
+                                             const int32_t* hcidx, int32_t* hbidx, int32_t* hbdist, int32_t* hcdist)
+{
+    if (!ctx || nq < 0 || nt < 0 || (nq > 0 && (!hq || !hoff || !hbidx || !hbdist)) || (nt > 0 && !ht))
+        return plf_fail(ctx, PLF_ERR_INVALID, "plf_hamming_candidates: bad arguments");
+    if (nq == 0) return PLF_OK;
+    for (int i = 0; i < nq; i++)
+        if (hoff[i] < 0 || hoff[i + 1] < hoff[i]) return plf_fail(ctx, PLF_ERR_INVALID, "cand_off must be non-decreasing");
+    const int ncand = hoff[nq];
+    if (ncand > 0 && !hcidx) return plf_fail(ctx, PLF_ERR_INVALID, "plf_hamming_candidates: cand_idx is NULL");
+    for (int c = hoff[0]; c < ncand; c++)
+        if (hcidx[c] < 0 || hcidx[c] >= nt) return plf_fail(ctx, PLF_ERR_INVALID, "candidate %d: train index %d out of range", c, hcidx[c]);
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t qb = plf_align_up((size_t)nq * 32, 256), tb = plf_align_up((size_t)(nt > 0 ? nt : 1) * 32, 256);
+    const size_t ob = plf_align_up((size_t)(nq + 1) * 4, 256), cb = plf_align_up((size_t)(ncand > 0 ? ncand : 1) * 4, 256);
+    const size_t bb = plf_align_up((size_t)nq * 2 * 4, 256);
+    void* s;
+    plf_status st = plf_ctx_scratch(ctx, qb + tb + ob + 2 * cb + 2 * bb, &s);
+    if (st) return st;
+    uint8_t* p = (uint8_t*)s;
+    uint8_t* dq = p; p += qb;
+    uint8_t* dt = p; p += tb;
+    int* doff = (int*)p; p += ob;
+    int* dcidx = (int*)p; p += cb;
+    int* dcdist = (int*)p; p += cb;
+    int* dbidx = (int*)p; p += bb;
+    int* dbdist = (int*)p;
+    cudaStream_t sq = ctx->stream;
+    PLF_CUDA(ctx, cudaMemcpyAsync(dq, hq, (size_t)nq * 32, cudaMemcpyHostToDevice, sq));
+    if (nt > 0) PLF_CUDA(ctx, cudaMemcpyAsync(dt, ht, (size_t)nt * 32, cudaMemcpyHostToDevice, sq));
+    PLF_CUDA(ctx, cudaMemcpyAsync(doff, hoff, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, sq));
+    if (ncand > 0) PLF_CUDA(ctx, cudaMemcpyAsync(dcidx, hcidx, (size_t)ncand * 4, cudaMemcpyHostToDevice, sq));
+    st = plf_hamming_candidates_device(ctx, dq, nq, dt, nt, doff, dcidx, dbidx, dbdist, hcdist ? dcdist : nullptr);
+    if (st) return st;
+    PLF_CUDA(ctx, cudaMemcpyAsync(hbidx, dbidx, (size_t)nq * 2 * 4, cudaMemcpyDeviceToHost, sq));
+    PLF_CUDA(ctx, cudaMemcpyAsync(hbdist, dbdist, (size_t)nq * 2 * 4, cudaMemcpyDeviceToHost, sq));
+    if (hcdist && ncand > 0) PLF_CUDA(ctx, cudaMemcpyAsync(hcdist, dcdist, (size_t)ncand * 4, cudaMemcpyDeviceToHost, sq));
+    PLF_CUDA(ctx, cudaStreamSynchronize(sq));
+    return PLF_OK;
+}
+
 // ---- POPC issue-rate micro-benchmark: the roofline denominator for the matching kernels ----
 __global__ void __launch_bounds__(256)
 popc_peak_kernel(unsigned* __restrict__ out, int iters)

@@ -446,3 +446,133 @@ extern "C" plf_status plf_orb_distribute_octree(plf_ctx* ctx, const int32_t* xs,
     *n_out = cnt;
     return PLF_OK;
 }
+
+// ---------------- Frame::ComputeStereoMatches (src/Frame.cc:881-1055) ----------------
+#include "plf_stereo_kernels.cuh"
+
+static void stereo_side(const plf_orb* o, StereoSide* S)
+{
+    memset(S, 0, sizeof(*S));
+    for (int l = 0; l < o->geom.nlevels; l++) {
+        S->lvl[l] = o->ptrs.lvl[l]; S->frameStride[l] = o->ptrs.frameStride[l]; S->pitch[l] = o->ptrs.pitch[l];
+        S->w[l] = o->geom.lv[l].w; S->h[l] = o->geom.lv[l].h;
+    }
+}
+
+static plf_status stereo_run(plf_orb* left, plf_orb* right, int npairs, StereoSide SL, StereoSide SR, int cap, float mb, float mbf,
+                             float* d_uright, float* d_depth, int* d_sad)
+{
+    plf_ctx* ctx = left->ctx;
+    StereoTables T;
+    memset(&T, 0, sizeof(T));
+    T.nlevels = left->geom.nlevels;
+    for (int l = 0; l < T.nlevels; l++) { T.scale[l] = left->scale[l]; T.inv_scale[l] = left->inv_scale[l]; }
+    if (right->ctx != ctx) {
+        plf_status st = plf_ctx_wait(ctx, right->ctx);   // the right extractor's pyramid must be complete
+        if (st) return st;
+    }
+    PLF_LAUNCH(k_stereo_match, dim3(plf_div_up(cap, 8), npairs), dim3(256), 0, ctx->stream, SL, SR, T, cap, mb, mbf, d_uright, d_depth, d_sad);
+    PLF_CHECK_LAUNCH(ctx);
+    PLF_LAUNCH(k_stereo_filter, dim3(npairs), dim3(256), (size_t)cap * sizeof(int), ctx->stream, cap, d_uright, d_depth, (const int*)d_sad);
+    PLF_CHECK_LAUNCH(ctx);
+    return PLF_OK;
+}
+
+static plf_status stereo_check(plf_orb* left, plf_orb* right, int cap)
+{
+    plf_ctx* ctx = left->ctx;
+    if (left->last_frames < 1 || right->last_frames < 1) return plf_fail(ctx, PLF_ERR_STATE, "stereo matching needs both extractors' pyramids (run the extraction first)");
+    if (left->ctx->device != right->ctx->device) return plf_fail(ctx, PLF_ERR_INVALID, "both extractors must live on the same device");
+    if (left->geom.nlevels != right->geom.nlevels || left->ws_w != right->ws_w || left->ws_h != right->ws_h)
+        return plf_fail(ctx, PLF_ERR_INVALID, "left and right extractors differ in image size or pyramid levels");
+    if (cap < 1 || cap > 0xffff || (size_t)cap * sizeof(int) > 200 * 1024) return plf_fail(ctx, PLF_ERR_INVALID, "stereo matching supports up to 51200 keypoints per image");
+    return PLF_OK;
+}
+
+extern "C" plf_status plf_stereo_match_batch_device(plf_orb* left, plf_orb* right, int npairs, int left_first, int left_step,
+                                                    int right_first, int right_step, const plf_keypoint* dev_kl, const uint8_t* dev_dl,
+                                                    const int32_t* dev_nl, const plf_keypoint* dev_kr, const uint8_t* dev_dr,
+                                                    const int32_t* dev_nr, int cap, float mb, float mbf, float* dev_uright, float* dev_depth)
+{
+    if (!left || !right) return PLF_ERR_INVALID;
+    plf_ctx* ctx = left->ctx;
+    if (npairs < 1 || !dev_kl || !dev_dl || !dev_nl || !dev_kr || !dev_dr || !dev_nr || !dev_uright || !dev_depth || !(mb > 0))
+        return plf_fail(ctx, PLF_ERR_INVALID, "plf_stereo_match_batch_device: bad arguments");
+    plf_status st = stereo_check(left, right, cap);
+    if (st) return st;
+    const int lastL = left_first + (npairs - 1) * left_step, lastR = right_first + (npairs - 1) * right_step;
+    if (left_first < 0 || lastL < 0 || left_first >= left->last_frames || lastL >= left->last_frames || right_first < 0 || lastR < 0 ||
+        right_first >= right->last_frames || lastR >= right->last_frames)
+        return plf_fail(ctx, PLF_ERR_INVALID, "stereo pair frames outside the extractors' last batch");
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+#ifndef PLF_EMU
+    PLF_CUDA(ctx, cudaFuncSetAttribute(k_stereo_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)cap * sizeof(int))));
+#endif
+    void* s;
+    st = plf_ctx_scratch(ctx, (size_t)npairs * cap * sizeof(int), &s);
+    if (st) return st;
+    StereoSide SL, SR;
+    stereo_side(left, &SL); stereo_side(right, &SR);
+    SL.kps = dev_kl; SL.desc = dev_dl; SL.n = dev_nl; SL.first = left_first; SL.step = left_step;
+    SR.kps = dev_kr; SR.desc = dev_dr; SR.n = dev_nr; SR.first = right_first; SR.step = right_step;
+    return stereo_run(left, right, npairs, SL, SR, cap, mb, mbf, dev_uright, dev_depth, (int*)s);
+}
+
+extern "C" plf_status plf_stereo_match(plf_orb* left, int frame_l, plf_orb* right, int frame_r, const plf_keypoint* host_kl,
+                                       const uint8_t* host_dl, int nl, const plf_keypoint* host_kr, const uint8_t* host_dr, int nr,
+                                       float mb, float mbf, float* host_uright, float* host_depth)
+{
+    if (!left || !right) return PLF_ERR_INVALID;
+    plf_ctx* ctx = left->ctx;
+    if (nl < 0 || nr < 0 || (nl > 0 && (!host_kl || !host_dl || !host_uright || !host_depth)) || (nr > 0 && (!host_kr || !host_dr)) || !(mb > 0))
+        return plf_fail(ctx, PLF_ERR_INVALID, "plf_stereo_match: bad arguments");
+    if (nl == 0) return PLF_OK;
+    const int cap = nl > nr ? nl : nr;
+    plf_status st = stereo_check(left, right, cap);
+    if (st) return st;
+    if (frame_l < 0 || frame_l >= left->last_frames || frame_r < 0 || frame_r >= right->last_frames)
+        return plf_fail(ctx, PLF_ERR_INVALID, "stereo frames outside the extractors' last batch");
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+#ifndef PLF_EMU
+    PLF_CUDA(ctx, cudaFuncSetAttribute(k_stereo_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)cap * sizeof(int))));
+#endif
+    // scratch layout: kps L, kps R, desc L, desc R, n[2], uright, depth, sad
+    const size_t kb = plf_align_up((size_t)cap * sizeof(plf_keypoint), 256), db = plf_align_up((size_t)cap * 32, 256), fb = plf_align_up((size_t)cap * 4, 256);
+    void* s;
+    st = plf_ctx_scratch(ctx, 2 * kb + 2 * db + 256 + 3 * fb, &s);
+    if (st) return st;
+    uint8_t* p = (uint8_t*)s;
+    plf_keypoint* dkl = (plf_keypoint*)p; p += kb;
+    plf_keypoint* dkr = (plf_keypoint*)p; p += kb;
+    uint8_t* ddl = p; p += db;
+    uint8_t* ddr = p; p += db;
+    int* dn = (int*)p; p += 256;
+    float* du = (float*)p; p += fb;
+    float* dz = (float*)p; p += fb;
+    int* dsad = (int*)p;
+    cudaStream_t stq = ctx->stream;
+    const int nn[2] = {nl, nr};
+    PLF_CUDA(ctx, cudaMemcpyAsync(dkl, host_kl, (size_t)nl * sizeof(plf_keypoint), cudaMemcpyHostToDevice, stq));
+    PLF_CUDA(ctx, cudaMemcpyAsync(ddl, host_dl, (size_t)nl * 32, cudaMemcpyHostToDevice, stq));
+    if (nr > 0) {
+        PLF_CUDA(ctx, cudaMemcpyAsync(dkr, host_kr, (size_t)nr * sizeof(plf_keypoint), cudaMemcpyHostToDevice, stq));
+        PLF_CUDA(ctx, cudaMemcpyAsync(ddr, host_dr, (size_t)nr * 32, cudaMemcpyHostToDevice, stq));
+    }
+    PLF_CUDA(ctx, cudaMemcpyAsync(dn, nn, sizeof(nn), cudaMemcpyHostToDevice, stq));
+    StereoSide SL, SR;
+    stereo_side(left, &SL); stereo_side(right, &SR);
+    // the keypoint tables of this call hold one frame each; the pyramid frames are frame_l / frame_r
+    for (int l = 0; l < left->geom.nlevels; l++) {
+        SL.lvl[l] += (size_t)frame_l * SL.frameStride[l];
+        SR.lvl[l] += (size_t)frame_r * SR.frameStride[l];
+    }
+    SL.kps = dkl; SL.desc = ddl; SL.n = dn; SL.first = 0; SL.step = 0;
+    SR.kps = dkr; SR.desc = ddr; SR.n = dn + 1; SR.first = 0; SR.step = 0;
+    // frame index 0 for the tables, so the right count is read through n[0] of its own pointer
+    st = stereo_run(left, right, 1, SL, SR, cap, mb, mbf, du, dz, dsad);
+    if (st) return st;
+    PLF_CUDA(ctx, cudaMemcpyAsync(host_uright, du, (size_t)nl * sizeof(float), cudaMemcpyDeviceToHost, stq));
+    PLF_CUDA(ctx, cudaMemcpyAsync(host_depth, dz, (size_t)nl * sizeof(float), cudaMemcpyDeviceToHost, stq));
+    PLF_CUDA(ctx, cudaStreamSynchronize(stq));
+    return PLF_OK;
+}

@@ -119,3 +119,47 @@ def test_emu_lines_empty_and_flat(S, oracle, emu_lib):
     assert len(K) == 0 and D.shape == (0, 32)
     K, M, D = le.ComputeLsdWithLbd(np.full((120, 160), 90, np.uint8))   # no gradient anywhere
     assert len(K) == 0
+
+
+def _stereo_pair(oracle, w, h, seed, shift):
+    left = oracle.synth_image(w, h, seed)
+    rng = np.random.default_rng(seed + 1000)
+    right = np.roll(left, -shift, axis=1).astype(np.int16)
+    right[h // 2:] = np.roll(left, -(shift + 6), axis=1)[h // 2:]      # two disparity bands
+    right = np.clip(right + rng.integers(-2, 3, right.shape), 0, 255).astype(np.uint8)
+    return left, right
+
+
+def test_emu_stereo_match(S, oracle, emu_lib):
+    ctx = S.Context(0, emu_lib)
+    left, right = _stereo_pair(oracle, 320, 240, 3, 9)
+    exL = S.ORBextractor(400, 1.2, 4, 20, 7, ctx=ctx); exR = S.ORBextractor(400, 1.2, 4, 20, 7, ctx=ctx)
+    oxL = oracle.ORBextractor(400, 1.2, 4, 20, 7); oxR = oracle.ORBextractor(400, 1.2, 4, 20, 7)
+    kL, dL = exL(left); kR, dR = exR(right)
+    okL, odL = oxL(left); okR, odR = oxR(right)
+    assert np.array_equal(kL.view(np.uint8), okL.view(np.uint8)) and np.array_equal(kR.view(np.uint8), okR.view(np.uint8))
+    u, z = exL.ComputeStereoMatches(exR, kL, dL, kR, dR, 0.11, 0.11 * 200.0)
+    ou, oz = oracle.stereo_match(oxL, oxR, okL, odL, okR, odR, 0.11, 0.11 * 200.0)
+    assert (ou >= 0).sum() > 20                      # the case is not vacuous
+    assert np.array_equal(u.view(np.uint32), ou.view(np.uint32)) and np.array_equal(z.view(np.uint32), oz.view(np.uint32))
+    # one extractor, the pair as two frames of one batch
+    ks, ds = exL.extract_batch(np.stack([left, right]))
+    u2, z2 = exL.ComputeStereoMatches(exL, ks[0], ds[0], ks[1], ds[1], 0.11, 0.11 * 200.0, frame_l=0, frame_r=1)
+    assert np.array_equal(u2.view(np.uint32), ou.view(np.uint32)) and np.array_equal(z2.view(np.uint32), oz.view(np.uint32))
+    # no right keypoints -> nothing matched
+    u3, z3 = exL.ComputeStereoMatches(exL, ks[0], ds[0], ks[1][:0], ds[1][:0], 0.11, 22.0, frame_l=0, frame_r=1)
+    assert (u3 == -1).all() and (z3 == -1).all()
+
+
+def test_emu_candidates(S, oracle, emu_lib):
+    ctx = S.Context(0, emu_lib)
+    m = S.ORBmatcher(0.9, ctx=ctx)
+    rng = np.random.default_rng(5)
+    for hi in (256, 3):                                # hi = 3: tie-heavy
+        q = rng.integers(0, hi, (70, 32), dtype=np.uint8)
+        t = rng.integers(0, hi, (150, 32), dtype=np.uint8)
+        lists = [rng.integers(0, 150, int(n)).astype(np.int32) for n in rng.integers(0, 90, 70)]
+        lists[0] = np.zeros(0, np.int32); lists[1] = np.array([7], np.int32)
+        bi, bd, cd = m.candidates_top2(q, t, lists, want_dist=True)
+        obi, obd, ocd = oracle.candidates_top2(q, t, lists)
+        assert np.array_equal(bi, obi) and np.array_equal(bd, obd) and np.array_equal(cd, ocd)

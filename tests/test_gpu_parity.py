@@ -218,3 +218,66 @@ def test_line_1080p(S, oracle, gpu_ctx):
     K, M, D = le.ComputeLsdWithLbd(img)
     assert len(K) == len(oK) == 800 and np.array_equal(D, oD)
     assert np.array_equal(K.view(np.uint8), oK.view(np.uint8))
+
+
+def _stereo_pair(oracle, w, h, seed, shift):
+    left = oracle.synth_image(w, h, seed)
+    rng = np.random.default_rng(seed + 1000)
+    right = np.roll(left, -shift, axis=1).astype(np.int16)
+    right[h // 2:] = np.roll(left, -(shift + 6), axis=1)[h // 2:]      # two disparity bands
+    right = np.clip(right + rng.integers(-2, 3, right.shape), 0, 255).astype(np.uint8)
+    return left, right
+
+
+@pytest.mark.parametrize("w,h,nf,mb,fx,seed", [(752, 480, 1200, 0.11, 435.2, 40), (1241, 376, 2000, 0.537, 718.9, 41)])
+def test_stereo_matches(S, oracle, gpu_ctx, w, h, nf, mb, fx, seed):
+    """BASELINE configs 2 / 3: Frame::ComputeStereoMatches on an EuRoC- / KITTI-style pair, bit-exact mvuRight, mvDepth."""
+    import torch
+    left, right = _stereo_pair(oracle, w, h, seed, 11)
+    ctx2 = S.Context(0)                                   # the right extractor on its own stream, as in Frame.cc:116-119
+    exL = S.ORBextractor(nf, 1.2, 8, 20, 7, ctx=gpu_ctx); exR = S.ORBextractor(nf, 1.2, 8, 20, 7, ctx=ctx2)
+    oxL = oracle.ORBextractor(nf, 1.2, 8, 20, 7); oxR = oracle.ORBextractor(nf, 1.2, 8, 20, 7)
+    kL, dL = exL(left); kR, dR = exR(right)
+    okL, odL = oxL(left); okR, odR = oxR(right)
+    assert np.array_equal(kL.view(np.uint8), okL.view(np.uint8)) and np.array_equal(kR.view(np.uint8), okR.view(np.uint8))
+    mbf = np.float32(mb * fx)
+    u, z = exL.ComputeStereoMatches(exR, kL, dL, kR, dR, mb, mbf)
+    ou, oz = oracle.stereo_match(oxL, oxR, okL, odL, okR, odR, mb, mbf)
+    assert (ou >= 0).sum() > nf // 10
+    assert np.array_equal(u.view(np.uint32), ou.view(np.uint32)) and np.array_equal(z.view(np.uint32), oz.view(np.uint32))
+    # batched device-resident variant: 3 pairs interleaved (L, R, L, R, ...) in one extractor batch
+    pairs = [(left, right), _stereo_pair(oracle, w, h, seed + 1, 5), _stereo_pair(oracle, w, h, seed + 2, 20)]
+    imgs = torch.from_numpy(np.stack([im for p in pairs for im in p])).cuda()
+    cap = exL.max_keypoints
+    nfr = len(imgs)
+    dk = torch.zeros((nfr, cap, 7), dtype=torch.float32, device="cuda"); dd = torch.zeros((nfr, cap, 32), dtype=torch.uint8, device="cuda")
+    dn = torch.zeros(nfr, dtype=torch.int32, device="cuda")
+    du = torch.zeros((3, cap), dtype=torch.float32, device="cuda"); dz = torch.zeros_like(du)
+    torch.cuda.synchronize()
+    lib = gpu_ctx.lib
+    gpu_ctx.check(lib.plf_orb_extract_batch_device(exL.h, imgs.data_ptr(), nfr, w, h, w, w * h, dk.data_ptr(), dd.data_ptr(), cap, dn.data_ptr()))
+    gpu_ctx.check(lib.plf_stereo_match_batch_device(exL.h, exL.h, 3, 0, 2, 1, 2, dk.data_ptr(), dd.data_ptr(), dn.data_ptr(),
+                                                    dk.data_ptr(), dd.data_ptr(), dn.data_ptr(), cap, mb, mbf, du.data_ptr(), dz.data_ptr()))
+    gpu_ctx.synchronize()
+    for p, (l, r) in enumerate(pairs):
+        okL, odL = oxL(l); okR, odR = oxR(r)
+        ou, oz = oracle.stereo_match(oxL, oxR, okL, odL, okR, odR, mb, mbf)
+        n = len(okL)
+        assert int(dn[2 * p]) == n
+        assert np.array_equal(du[p, :n].cpu().numpy().view(np.uint32), ou.view(np.uint32))
+        assert np.array_equal(dz[p, :n].cpu().numpy().view(np.uint32), oz.view(np.uint32))
+
+
+def test_candidate_lists(S, oracle, gpu_ctx):
+    m = S.ORBmatcher(0.9, ctx=gpu_ctx)
+    rng = np.random.default_rng(5)
+    for hi, nq, nt, maxc in [(256, 2000, 2000, 60), (3, 500, 800, 300), (256, 3, 10, 5000)]:
+        q = rng.integers(0, hi, (nq, 32), dtype=np.uint8)
+        t = rng.integers(0, hi, (nt, 32), dtype=np.uint8)
+        lists = [rng.integers(0, nt, int(n)).astype(np.int32) for n in rng.integers(0, maxc, nq)]
+        lists[0] = np.zeros(0, np.int32); lists[1] = np.array([7], np.int32)
+        bi, bd, cd = m.candidates_top2(q, t, lists, want_dist=True)
+        obi, obd, ocd = oracle.candidates_top2(q, t, lists)
+        assert np.array_equal(bi, obi) and np.array_equal(bd, obd) and np.array_equal(cd, ocd)
+    with pytest.raises(S.PlfError):
+        m.candidates_top2(q, t, [np.array([nt], np.int32)] + [np.zeros(0, np.int32)] * (nq - 1))
