@@ -389,6 +389,72 @@ k_lsd_cid(const unsigned long long* __restrict__ keys, int n, int* __restrict__ 
     label[(size_t)LSD_KEY_FRAME(k) * px + LSD_KEY_IDX(k)] = i;
 }
 
+// One candidate: neighbour `nb` of queue entry q.  The queue tail lives in a shared-memory ring; older entries
+// come from the global arena.  The three loads are independent of each other (one memory round trip).
+struct WgCand { int xx, yy, ci, pp; float fv; float2 cv; bool inb; };
+__device__ __forceinline__ WgCand wg_load(int q, int arena, const int* ring, const int* __restrict__ regpts, int gdx, int gdy, int w, int h,
+                                          const int* __restrict__ CID, const float* __restrict__ F, const float2* __restrict__ CS)
+{
+    WgCand c;
+    const int pp = (arena - q <= WG_RING) ? ring[q & (WG_RING - 1)] : regpts[q];
+    c.pp = pp;
+    c.xx = (pp & 0xffff) + gdx; c.yy = (pp >> 16) + gdy;
+    c.inb = c.xx >= 0 && c.yy >= 0 && c.xx < w && c.yy < h;
+    c.ci = -1; c.fv = 0.f; c.cv = make_float2(0.f, 0.f);
+    if (c.inb) {
+        const int qi = c.yy * w + c.xx;
+        c.ci = __ldg(&CID[qi]);
+        c.fv = __ldg(&F[qi]);
+        c.cv = __ldg(&CS[qi]);
+        // the entries accepted from here will look one pixel further: pull the 5x5 ring towards L1 now
+        const int x2 = c.xx + gdx, y2 = c.yy + gdy;
+        if (x2 >= 0 && y2 >= 0 && x2 < w && y2 < h) {
+            const int q2 = y2 * w + x2;
+            PLF_PREFETCH_L1(&CID[q2]);
+            PLF_PREFETCH_L1(&F[q2]);
+            PLF_PREFETCH_L1(&CS[q2]);
+        }
+    }
+    return c;
+}
+
+// lanes (of earlier queue entries) that test the same pixel as lane (grp, nbr) of entry pp: the pixel is a
+// neighbour of entry e' = pp_other iff it lies within one pixel of it
+__device__ __forceinline__ unsigned wg_dupmask(int xx, int yy, int grp, int pp_other, int g_other)
+{
+    if (g_other >= grp) return 0u;
+    const int dx = xx - (pp_other & 0xffff), dy = yy - (pp_other >> 16);
+    if (dx < -1 || dx > 1 || dy < -1 || dy > 1 || (dx == 0 && dy == 0)) return 0u;
+    const int nb = (dy + 1) * 3 + dx + 1;
+    return 1u << (g_other * 8 + (nb < 4 ? nb : nb - 1));
+}
+
+__device__ __forceinline__ double wg_ntheta(double reg_angle, double a)
+{
+    double n_theta = reg_angle - a;
+    if (n_theta < 0) n_theta = -n_theta;
+    if (n_theta > LSD_3_2_PI) {
+        n_theta -= LSD_2PI;
+        if (n_theta < 0) n_theta = -n_theta;
+    }
+    return n_theta;
+}
+
+// Four queue entries are expanded per iteration: lane 8g + k handles the k-th neighbour (centre skipped) of
+// entry r + g, so lane order equals the reference's test order (entry, then neighbour in raster order).
+//
+// Sequential rule: neighbours are accepted in that order, and after every acceptance the region angle
+// reg_angle = fastAtan2(sumdy, sumdx) changes, so every LATER test sees the new angle.
+// Batched rule (the common case): with m candidates passing the test at the iteration's starting angle, the
+// angle can move by at most D = 1.02 m sin(prec + 0.1) / |sum| + 1e-3 rad while they are accepted (each
+// accepted unit vector lies within prec + D + E of the current direction and |sum| only grows; E = 1.7e-4 rad
+// is the fastAtan2 model error, 2E < 1e-3).  If every candidate's |n_theta - prec| exceeds D, no decision can
+// flip, so all passing candidates are accepted at once (first lane per pixel), the float sums are added in
+// lane order, and one fastAtan2 closes the iteration -- bit-identical to the sequential rule.  Otherwise the
+// iteration falls back to one acceptance per round.
+// The loads of the NEXT iteration's candidates are issued before this iteration's tests (their used bits are
+// checked when they are consumed), which hides the L2 round trip behind the arithmetic.
+#define WG_E 4
 __global__ void __launch_bounds__(32)
 k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restrict__ comp, const int* __restrict__ bcount,
                 const float* __restrict__ fa, const float2* __restrict__ cs, const int* __restrict__ cid, int w, int h,
@@ -398,10 +464,17 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
     PLF_DYN_SMEM(smem);
     unsigned* used = (unsigned*)smem;
     __shared__ int ring[WG_RING];
+    __shared__ float2 acc[32];
     const int lane = threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
     int nbig = 0;
     for (int k = LSD_BIG_BUCKET; k < LSD_NBUCKET; k++) nbig += bcount[k];
     const size_t px = (size_t)w * h;
+    const int grp = lane >> 3, kk = lane & 7;
+    const int nbr = kk < 4 ? kk : kk + 1;
+    const int gdx = (nbr % 3) - 1, gdy = (nbr / 3) - 1;
+    const bool fast_ok = prec < 1.4;
+    const float sphi = (float)sin(prec + 0.1) * 1.05f;   // 1.05 covers the float rounding of this product and of rsqrtf below
     for (int c = blockIdx.x; c < nbig; c += gridDim.x) {
         const int start = comp[c].x, C = comp[c].y, end = start + C;
         if (C > maxc) continue;   // handled by k_lsd_grow
@@ -414,14 +487,22 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
         __syncwarp();
         int arena = start;
         for (int i0 = start; i0 < end; i0 += 32) {
-            // 32 seeds at a time: which of them are still unused?
+            // 32 seeds at a time; only the ones still unused at this point can start a region
             const int ii = i0 + lane;
             unsigned long long mykey = 0;
-            if (ii < end) mykey = keys[ii];
-            for (int s = 0; s < 32 && i0 + s < end; s++) {
+            bool mine = false;
+            if (ii < end) {
+                mykey = keys[ii];
+                const int sc = ii - start;
+                mine = !((used[sc >> 5] >> (sc & 31)) & 1u);
+            }
+            unsigned todo = __ballot_sync(FULL, mine);
+            while (todo) {
+                const int s = __ffs((int)todo) - 1;
+                todo &= todo - 1;
                 const int sc = i0 + s - start;
-                if ((used[sc >> 5] >> (sc & 31)) & 1u) continue;            // warp-uniform
-                const unsigned long long key = __shfl_sync(0xffffffffu, mykey, s);
+                if ((used[sc >> 5] >> (sc & 31)) & 1u) continue;            // taken by a region grown meanwhile (warp-uniform)
+                const unsigned long long key = __shfl_sync(FULL, mykey, s);
                 const int p = LSD_KEY_IDX(key);
                 const int r0 = arena;
                 const int sy = p / w, sx = p - sy * w;
@@ -434,63 +515,89 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
                 double reg_angle = (double)__ldg(&F[p]) * LSD_D2R;
                 float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
                 __syncwarp();
-                // Up to three queue entries are expanded per iteration: lane 9g + k handles neighbour k of entry r + g.
-                // Lane order equals the reference's test order (entry, then neighbour), so "first aligned lane"
-                // is the reference's next acceptance; after each acceptance the region angle changes and every
-                // LATER lane is re-tested, exactly what the sequential loop would see.
-                const int grp = lane / 9, kk = lane - grp * 9;
-                const int gdx = (kk % 3) - 1, gdy = (kk / 3) - 1;
+                int npf = 0;              // entries whose candidates were prefetched for the coming iteration
+                WgCand pf;
+                pf.xx = pf.yy = pf.pp = 0; pf.ci = -1; pf.fv = 0.f; pf.cv = make_float2(0.f, 0.f); pf.inb = false;
                 for (int r = r0; r < arena;) {
-                    const int ng = min(3, arena - r);
-                    bool cand = grp < ng && kk != 4;
-                    int xx = 0, yy = 0, cc = -1;
-                    float fv = 0.f;
-                    float2 cv = make_float2(0.f, 0.f);
-                    if (cand) {
-                        const int qidx = r + grp;
-                        // the queue tail lives in a shared-memory ring; older entries come from the global arena
-                        const int pp = (arena - qidx <= WG_RING) ? ring[qidx & (WG_RING - 1)] : regpts[qidx];
-                        xx = (pp & 0xffff) + gdx; yy = (pp >> 16) + gdy;
-                        cand = xx >= 0 && yy >= 0 && xx < w && yy < h;
+                    const int ng = min(WG_E, arena - r);
+                    WgCand cd = pf;
+                    if (grp >= npf) {
+                        cd.inb = false; cd.ci = -1; cd.pp = -(4 << 16);   // far outside: never adjacent to a pixel
+                        if (grp < ng) cd = wg_load(r + grp, arena, ring, regpts, gdx, gdy, w, h, CID, F, CS);
                     }
+                    // lanes of earlier entries looking at the same pixel (off the critical path: entries are known here)
+                    unsigned dupmask = 0u;
+#pragma unroll
+                    for (int g2 = 0; g2 < WG_E - 1; g2++) dupmask |= wg_dupmask(cd.xx, cd.yy, grp, __shfl_sync(FULL, cd.pp, g2 * 8), g2);
+                    const int rn = r + ng;
+                    npf = min(WG_E, arena - rn);
+                    if (grp < npf) pf = wg_load(rn + grp, arena, ring, regpts, gdx, gdy, w, h, CID, F, CS);
+                    int cc = -1 - lane;       // position of the pixel in the component's seed list (negative: none)
+                    bool cand = cd.inb && cd.ci >= 0;
                     if (cand) {
-                        const int qi = yy * w + xx;
-                        const int ci = __ldg(&CID[qi]);
-                        fv = __ldg(&F[qi]);
-                        cv = __ldg(&CS[qi]);
-                        cc = ci - start;
-                        cand = ci >= 0 && !((used[cc >> 5] >> (cc & 31)) & 1u);
-                        if (!cand) cc = -1;
+                        cc = cd.ci - start;
+                        cand = !((used[cc >> 5] >> (cc & 31)) & 1u);
+                        if (!cand) cc = -1 - lane;
                     }
-                    const double a = (double)fv * LSD_D2R;
-                    for (;;) {
-                        bool pass = false;
-                        if (cand) {
-                            double n_theta = reg_angle - a;
-                            if (n_theta < 0) n_theta = -n_theta;
-                            if (n_theta > LSD_3_2_PI) {
-                                n_theta -= LSD_2PI;
-                                if (n_theta < 0) n_theta = -n_theta;
+                    const double a = (double)cd.fv * LSD_D2R;
+                    double n_theta = wg_ntheta(reg_angle, a);
+                    bool pass = cand && n_theta <= prec;
+                    unsigned m = __ballot_sync(FULL, pass);
+                    if (m) {
+                        bool fast = false;
+                        if (fast_ok) {
+                            const float L2 = sumdx * sumdx + sumdy * sumdy;
+                            if (L2 >= 16.f) {
+                                const float D = (float)__popc(m) * sphi * rsqrtf(L2) + 1e-3f;
+                                double margin = n_theta - prec;
+                                if (margin < 0) margin = -margin;
+                                const bool risky = cand && (float)margin <= D * 1.0001f;
+                                fast = D <= 0.09f && !__any_sync(FULL, risky);
                             }
-                            pass = n_theta <= prec;
                         }
-                        const unsigned m = __ballot_sync(0xffffffffu, pass);
-                        if (!m) break;
-                        const int k0 = __ffs((int)m) - 1;                  // next acceptance in the reference's order
-                        if (lane == k0) {
-                            used[cc >> 5] |= 1u << (cc & 31);              // only this lane writes in this round
-                            regpts[arena] = xx | (yy << 16);
-                            ring[arena & (WG_RING - 1)] = xx | (yy << 16);
+                        if (fast) {
+                            const bool win = pass && !(m & dupmask);     // first lane per pixel
+                            const unsigned mw = __ballot_sync(FULL, win);
+                            const int nw = __popc(mw);
+                            if (win) {
+                                const int rank = __popc(mw & ((1u << lane) - 1u));
+                                atomicOr(&used[cc >> 5], 1u << (cc & 31));
+                                regpts[arena + rank] = cd.xx | (cd.yy << 16);
+                                ring[(arena + rank) & (WG_RING - 1)] = cd.xx | (cd.yy << 16);
+                                acc[rank] = cd.cv;
+                            }
+                            __syncwarp();
+                            // float sums in acceptance (lane) order, read back as broadcasts
+                            for (int j = 0; j < nw; j += 4) {
+                                const float2 v0 = acc[j], v1 = acc[(j + 1) & 31], v2 = acc[(j + 2) & 31], v3 = acc[(j + 3) & 31];
+                                sumdx += v0.x; sumdy += v0.y;
+                                if (j + 1 < nw) { sumdx += v1.x; sumdy += v1.y; }
+                                if (j + 2 < nw) { sumdx += v2.x; sumdy += v2.y; }
+                                if (j + 3 < nw) { sumdx += v3.x; sumdy += v3.y; }
+                            }
+                            arena += nw;
+                            reg_angle = (double)plf_fast_atan2(sumdy, sumdx) * LSD_D2R;
+                        } else {
+                            for (;;) {
+                                const int k0 = __ffs((int)m) - 1;                  // next acceptance in the reference's order
+                                if (lane == k0) {
+                                    used[cc >> 5] |= 1u << (cc & 31);              // only this lane writes in this round
+                                    regpts[arena] = cd.xx | (cd.yy << 16);
+                                    ring[arena & (WG_RING - 1)] = cd.xx | (cd.yy << 16);
+                                }
+                                arena++;
+                                sumdx += __shfl_sync(FULL, cd.cv.x, k0);
+                                sumdy += __shfl_sync(FULL, cd.cv.y, k0);
+                                reg_angle = (double)plf_fast_atan2(sumdy, sumdx) * LSD_D2R;
+                                cand = cand && lane > k0 && !((dupmask >> k0) & 1u);   // earlier tests stand; the same pixel seen from another entry is now used
+                                pass = cand && wg_ntheta(reg_angle, a) <= prec;
+                                m = __ballot_sync(FULL, pass);
+                                if (!m) break;
+                            }
                         }
-                        arena++;
-                        const int cc0 = __shfl_sync(0xffffffffu, cc, k0);
-                        sumdx += __shfl_sync(0xffffffffu, cv.x, k0);
-                        sumdy += __shfl_sync(0xffffffffu, cv.y, k0);
-                        reg_angle = (double)plf_fast_atan2(sumdy, sumdx) * LSD_D2R;
-                        cand = cand && lane > k0 && cc != cc0;             // earlier tests stand; the same pixel seen from another entry is now used
                     }
                     __syncwarp();
-                    r += ng;
+                    r = rn;
                 }
                 const int nreg = arena - r0;
                 if (lane == 0 && nreg >= min_reg_size) {

@@ -144,6 +144,15 @@ template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int x, in
     int lane = emu_lane_linear & 31;
     return emu_shfl(mask, v, lane ^ x);
 }
+template <class T> static inline unsigned __match_any_sync(unsigned mask, T v)
+{
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) {
+        T o = emu_shfl(mask, v, i);
+        if (o == v) r |= 1u << i;
+    }
+    return r;
+}
 
 // ---- atomics ----
 template <class T> static inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
@@ -200,6 +209,7 @@ static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 using std::max;
 using std::min;
