@@ -119,3 +119,100 @@ __host__ __device__ __forceinline__ int plf_reflect101(int p, int n)
     }
     return p;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Separable Q8 Gaussian with 2R+1 taps (cv::GaussianBlur on 8U, BORDER_REFLECT_101):
+//   H = sum_t k[t] * src[x + t - R]   (<= 65280),   dst = (sum_t k[t] * H[y + t - R] + 32768) >> 16.
+// A thread produces a 4-px wide column strip of `rows` rows with a register sliding window: per input row it
+// loads three aligned 32-bit words (bytes x0-4 .. x0+7; the overlap between neighbouring threads is served
+// by L1), forms the horizontal sums for its four pixels two at a time (stride-2 byte pairs packed in 16-bit
+// halves: b[i] | b[i+2] << 16, products <= 65280 never carry between the halves), keeps the last 2R+1 rows of
+// sums in registers and emits one packed 32-bit store per output row.  No shared memory, no barriers.
+// Strips that touch the left/right image edge (or unaligned buffers) gather their 12 bytes with reflection.
+// ------------------------------------------------------------------------------------------------
+struct BlurTaps { int k[8]; };   // k[0..2R]
+
+template <int R>
+__device__ __forceinline__ void plf_blur_hrow(const uint8_t* __restrict__ rp, int x0, int w, bool fastx, const int (&kc)[2 * R + 1], int (&out)[4])
+{
+    unsigned w0, w1, w2;
+    if (fastx) {
+        const unsigned* p = (const unsigned*)(rp + x0 - 4);
+        w0 = p[0]; w1 = p[1]; w2 = p[2];
+    } else {
+        unsigned b[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) b[i] = (i >= 4 - R && i < 8 + R) ? rp[plf_reflect101(x0 - 4 + i, w)] : 0u;
+        w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+        w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+    }
+    // q[i] = byte(i) | byte(i + 2) << 16, byte index relative to x0 - 4
+    unsigned q[10];
+    q[0] = __byte_perm(w0, 0u, 0x4240); q[1] = __byte_perm(w0, 0u, 0x4341);
+    q[4] = __byte_perm(w1, 0u, 0x4240); q[5] = __byte_perm(w1, 0u, 0x4341);
+    q[8] = __byte_perm(w2, 0u, 0x4240); q[9] = __byte_perm(w2, 0u, 0x4341);
+    q[2] = __funnelshift_r(q[0], q[4], 16); q[3] = __funnelshift_r(q[1], q[5], 16);
+    q[6] = __funnelshift_r(q[4], q[8], 16); q[7] = __funnelshift_r(q[5], q[9], 16);
+    unsigned h02 = (unsigned)kc[R] * q[4], h13 = (unsigned)kc[R] * q[5];
+#pragma unroll
+    for (int t = 0; t < R; t++) {
+        h02 += (unsigned)kc[t] * (q[4 - R + t] + q[4 + R - t]);
+        h13 += (unsigned)kc[t] * (q[5 - R + t] + q[5 + R - t]);
+    }
+    out[0] = (int)(h02 & 0xffffu); out[2] = (int)(h02 >> 16);
+    out[1] = (int)(h13 & 0xffffu); out[3] = (int)(h13 >> 16);
+}
+
+template <int R>
+__device__ __forceinline__ void plf_blur_strip(const uint8_t* __restrict__ src, int spitch, uint8_t* __restrict__ dst, int dpitch,
+                                               int w, int h, int x0, int y0, int rows, const BlurTaps& taps)
+{
+    constexpr int K = 2 * R + 1;
+    if (x0 >= w) return;
+    int kc[K];
+#pragma unroll
+    for (int t = 0; t < K; t++) kc[t] = taps.k[t];
+    const bool aligned = ((((size_t)src) | ((size_t)dst) | (size_t)spitch | (size_t)dpitch) & 3) == 0;
+    const bool fastx = aligned && x0 >= 4 && x0 + 8 <= w;
+    const bool fullw = aligned && x0 + 4 <= w;
+    int ring[K][4];
+    // prime the window with rows y0 - R .. y0 + R - 1 (slots 0 .. K-2); h > R, so one reflection is enough
+#pragma unroll
+    for (int t = 0; t < K - 1; t++) {
+        int yy = y0 - R + t;
+        yy = yy < 0 ? -yy : yy;
+        yy = yy >= h ? 2 * (h - 1) - yy : yy;
+        plf_blur_hrow<R>(src + (size_t)yy * spitch, x0, w, fastx, kc, ring[t]);
+    }
+    const int yend = min(y0 + rows, h);
+    // rows are processed K at a time so that the ring slots are compile-time; rows past the image bottom are
+    // computed from clamped addresses and simply not stored (no branch around the loads)
+    for (int yb = y0; yb < yend; yb += K) {
+#pragma unroll
+        for (int s = 0; s < K; s++) {        // slot (s + K - 1) % K receives row y + R
+            const int y = yb + s;
+            int yy = min(y, h - 1) + R;
+            yy = yy >= h ? 2 * (h - 1) - yy : yy;
+            plf_blur_hrow<R>(src + (size_t)yy * spitch, x0, w, fastx, kc, ring[(s + K - 1) % K]);
+            unsigned o = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                unsigned v = 32768u + (unsigned)kc[R] * (unsigned)ring[(s + R) % K][j];
+#pragma unroll
+                for (int t = 0; t < R; t++)
+                    v += (unsigned)kc[t] * (unsigned)(ring[(s + t) % K][j] + ring[(s + K - 1 - t) % K][j]);
+                o |= (v >> 16) << (8 * j);
+            }
+            if (y < yend) {
+                uint8_t* dp = dst + (size_t)y * dpitch + x0;
+                if (fullw) *(unsigned*)dp = o;
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (x0 + j < w) dp[j] = (uint8_t)(o >> (8 * j));
+                }
+            }
+        }
+    }
+}

@@ -317,6 +317,26 @@ static plf_status sort_lines(plf_line* o)
     return PLF_OK;
 }
 
+
+// cv::GaussianBlur 8U for a batch: 5 / 7 taps go to the register sliding-window kernel, other sizes to the generic one
+static plf_status gauss_batch(plf_ctx* ctx, const uint8_t* src, uint8_t* dst, int w, int h, int nframes, const GaussQ8& k)
+{
+    cudaStream_t st = ctx->stream;
+    const size_t frame = (size_t)w * h;
+    if (k.ksize == 5 || k.ksize == 7) {
+        BlurTaps taps;
+        memset(&taps, 0, sizeof(taps));
+        for (int i = 0; i < k.ksize; i++) taps.k[i] = k.q[i];
+        dim3 grid(plf_div_up(w, 128), plf_div_up(h, 128), nframes), block(32, 4);
+        if (k.ksize == 5) PLF_LAUNCH(k_gauss_strip<2>, grid, block, 0, st, src, frame, w, dst, frame, w, w, h, taps);
+        else PLF_LAUNCH(k_gauss_strip<3>, grid, block, 0, st, src, frame, w, dst, frame, w, w, h, taps);
+    } else {
+        PLF_LAUNCH(k_gauss_q8, dim3(plf_div_up(w, GB_TW), plf_div_up(h, GB_TH), nframes), dim3(256), 0, st, src, frame, w, dst, frame, w, w, h, k);
+    }
+    PLF_CHECK_LAUNCH(ctx);
+    return PLF_OK;
+}
+
 // Several line contexts (host threads) may run at once.  The phase of an octave before region growing is
 // bandwidth-bound and fills the GPU; region growing is a latency-bound dependent chain that leaves it mostly
 // idle.  Contexts therefore take turns for the first phase (this mutex) and overlap their growing phases with
@@ -342,9 +362,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         }
         const uint8_t* scaled = o->d_oct[k];
         if (S != 1) {
-            PLF_LAUNCH(k_gauss_q8, dim3(plf_div_up(ow, GB_TW), plf_div_up(oh, GB_TH), nframes), dim3(256), 0, st, (const uint8_t*)o->d_oct[k],
-                       (size_t)ow * oh, ow, o->d_tmp, (size_t)ow * oh, ow, ow, oh, o->lsd_gauss);
-            PLF_CHECK_LAUNCH(ctx);
+            { plf_status gs = gauss_batch(ctx, o->d_oct[k], o->d_tmp, ow, oh, nframes, o->lsd_gauss); if (gs) return gs; }
             PLF_LAUNCH(k_resize_exact, dim3(plf_div_up(sw, 32), plf_div_up(sh, 8), nframes), dim3(32, 8), 0, st, (const uint8_t*)o->d_tmp,
                        (size_t)ow * oh, ow, ow, oh, o->d_scaled, (size_t)sw * sh, sw, sw, sh, o->xtab[k], o->ytab[k]);
             PLF_CHECK_LAUNCH(ctx);
@@ -440,8 +458,7 @@ static plf_status lbd_batch(plf_line* o, int nframes, const plf_keyline* d_kl, c
     for (int k = 0; k < noct; k++) {
         const int ow = o->ow[k], oh = o->oh[k];
         if (k == 0) {   // computeGaussianPyramid (binary_descriptor_custom.cpp:350-370): blur 5x5 sigma 1, then pyrDown
-            PLF_LAUNCH(k_gauss_q8, dim3(plf_div_up(ow, GB_TW), plf_div_up(oh, GB_TH), nframes), dim3(256), 0, st, (const uint8_t*)o->d_oct[0],
-                       (size_t)ow * oh, ow, o->d_lbdimg[0], (size_t)ow * oh, ow, ow, oh, o->lbd_gauss);
+            { plf_status gs = gauss_batch(ctx, o->d_oct[0], o->d_lbdimg[0], ow, oh, nframes, o->lbd_gauss); if (gs) return gs; }
         } else {
             PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(ow, 32), plf_div_up(oh, 8), nframes), dim3(32, 8), 0, st, (const uint8_t*)o->d_lbdimg[k - 1],
                        (size_t)o->ow[k - 1] * o->oh[k - 1], o->ow[k - 1], o->ow[k - 1], o->oh[k - 1], o->d_lbdimg[k], (size_t)ow * oh, ow);

@@ -67,6 +67,18 @@ k_gauss_q8(const uint8_t* __restrict__ src, size_t sframe, int spitch, uint8_t* 
     }
 }
 
+// 5- and 7-tap kernels (everything the reference's settings reach): register sliding window, see plf_blur_strip.
+// block = (32, 4): lane = 4-px column strip, threadIdx.y = 32-row band of a 128 x 128 tile.
+template <int R>
+__global__ void __launch_bounds__(128)
+k_gauss_strip(const uint8_t* __restrict__ src, size_t sframe, int spitch, uint8_t* __restrict__ dst, size_t dframe, int dpitch,
+              int w, int h, BlurTaps taps)
+{
+    const int x0 = blockIdx.x * 128 + 4 * threadIdx.x, y0 = (blockIdx.y * 4 + threadIdx.y) * 32;
+    if (y0 >= h) return;
+    plf_blur_strip<R>(src + (size_t)blockIdx.z * sframe, spitch, dst + (size_t)blockIdx.z * dframe, dpitch, w, h, x0, y0, 32, taps);
+}
+
 // ---------------- cv::resize INTER_LINEAR_EXACT; tab: .x = offset, .y = c1 (Q8) ----------------
 __global__ void __launch_bounds__(256)
 k_resize_exact(const uint8_t* __restrict__ src, size_t sframe, int spitch, int sw, int sh,
@@ -207,7 +219,9 @@ k_ccl_merge(int* __restrict__ label, int w, int h)
     }
 }
 
-// emit one sort key per defined pixel (root label, bin, raster index); warp-aggregated append
+// emit one sort key per defined pixel (root label, bin, raster index); warp-aggregated append.
+// (A CTA-aggregated variant with several rows per thread measured slower: the kernel is bound by the
+// dependent label chases of ccl_find, which want as many independent threads as possible.)
 __global__ void __launch_bounds__(256)
 k_lsd_keys(const int* __restrict__ label, const int* __restrict__ q, const int* __restrict__ maxq, int w, int h,
            int n_bins, unsigned long long* __restrict__ keys, int* __restrict__ nkeys, int keycap, int kb)

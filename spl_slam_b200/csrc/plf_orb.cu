@@ -247,9 +247,12 @@ static plf_status orb_run(plf_orb* o, const uint8_t* lvl0, size_t stride0, size_
                    o->lvl_own[l], D.frameBytes, D.pitch, D.w, D.h, o->xtab[l], o->ytab[l]);
         PLF_CHECK_LAUNCH(ctx);
     }
-    PLF_LAUNCH(k_fast_cells, dim3(g.totalCells, nframes), dim3(256), 0, st, g, P);
+    int fw = 0, fh = 0;   // largest FAST cell window of the geometry -> shared-memory map size
+    for (int l = 0; l < g.nlevels; l++) { fw = g.lv[l].wCell + 6 > fw ? g.lv[l].wCell + 6 : fw; fh = g.lv[l].hCell + 6 > fh ? g.lv[l].hCell + 6 : fh; }
+    const int ftp = (fw + 3 + 3) & ~3;
+    PLF_LAUNCH(k_fast_cells, dim3(plf_div_up(g.totalCells, FAST_WARPS), nframes), dim3(32 * FAST_WARPS), (size_t)FAST_WARPS * 2 * ftp * fh, st, g, P, ftp, fh);
     PLF_CHECK_LAUNCH(ctx);
-    PLF_LAUNCH(k_blur7, dim3(g.totalBlurTiles, nframes), dim3(256), 0, st, g, P);
+    PLF_LAUNCH(k_blur7, dim3(plf_div_up(g.totalBlurTiles, BLUR_WARPS), nframes), dim3(32 * BLUR_WARPS), 0, st, g, P);
     PLF_CHECK_LAUNCH(ctx);
     PLF_LAUNCH(k_octree, dim3(g.nlevels, nframes), dim3(OCT_T), o->oct_smem, st, g, P, o->oct_cap);
     PLF_CHECK_LAUNCH(ctx);

@@ -55,44 +55,22 @@ k_resize_linear(const uint8_t* __restrict__ src, size_t srcFrameStride, int spit
 // ------------------------------------------------------------------------------------------------
 #define BLUR_TW 128
 #define BLUR_TH 32
-__global__ void __launch_bounds__(256)
+#define BLUR_WARPS 4
+// one WARP per 128 x 32 tile (lane = 4-px column strip, see plf_blur_strip); tiles of all levels in one launch
+__global__ void __launch_bounds__(32 * BLUR_WARPS, 8)
 k_blur7(OrbGeom g, OrbPtrs p)
 {
-    __shared__ uint8_t tile[(BLUR_TH + 6) * (BLUR_TW + 8)];
-    __shared__ unsigned short hbuf[(BLUR_TH + 6) * BLUR_TW];
-    int tileId = blockIdx.x, l = 0;
+    int tileId = blockIdx.x * BLUR_WARPS + (threadIdx.x >> 5), l = 0;
+    if (tileId >= g.totalBlurTiles) return;
     while (l + 1 < g.nlevels && tileId >= g.lv[l + 1].blurTileBase) l++;
     tileId -= g.lv[l].blurTileBase;
     const OrbLevelGeom& L = g.lv[l];
     const int tx0 = (tileId % L.blurTilesX) * BLUR_TW, ty0 = (tileId / L.blurTilesX) * BLUR_TH;
     const uint8_t* src = p.lvl[l] + (size_t)blockIdx.y * p.frameStride[l];
-    const int spitch = p.pitch[l];
     uint8_t* dst = p.blr[l] + (size_t)blockIdx.y * L.frameBytes;
-    const int tid = threadIdx.x;
-    const int TWP = BLUR_TW + 8;
-    for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
-        int ry = i / (BLUR_TW + 6), rx = i - ry * (BLUR_TW + 6);
-        int sy = plf_reflect101(ty0 + ry - 3, L.h), sx = plf_reflect101(tx0 + rx - 3, L.w);
-        tile[ry * TWP + rx] = src[(size_t)sy * spitch + sx];
-    }
-    __syncthreads();
-    for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
-        int ry = i / BLUR_TW, rx = i - ry * BLUR_TW;
-        const uint8_t* t = &tile[ry * TWP + rx];
-        unsigned v = 18u * (t[0] + t[6]) + 34u * (t[1] + t[5]) + 48u * (t[2] + t[4]) + 56u * t[3];
-        hbuf[i] = (unsigned short)v;
-    }
-    __syncthreads();
-    for (int i = tid; i < BLUR_TH * BLUR_TW; i += 256) {
-        int ry = i / BLUR_TW, rx = i - ry * BLUR_TW;
-        int x = tx0 + rx, y = ty0 + ry;
-        if (x < L.w && y < L.h) {
-            const unsigned short* hcol = &hbuf[ry * BLUR_TW + rx];
-            unsigned v = 18u * (hcol[0] + hcol[6 * BLUR_TW]) + 34u * (hcol[BLUR_TW] + hcol[5 * BLUR_TW]) +
-                         48u * (hcol[2 * BLUR_TW] + hcol[4 * BLUR_TW]) + 56u * hcol[3 * BLUR_TW] + 32768u;
-            dst[(size_t)y * L.pitch + x] = (uint8_t)(v >> 16);
-        }
-    }
+    BlurTaps taps;
+    taps.k[0] = 18; taps.k[1] = 34; taps.k[2] = 48; taps.k[3] = 56; taps.k[4] = 48; taps.k[5] = 34; taps.k[6] = 18; taps.k[7] = 0;
+    plf_blur_strip<3>(src, p.pitch[l], dst, L.pitch, L.w, L.h, tx0 + 4 * (threadIdx.x & 31), ty0, BLUR_TH, taps);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -102,21 +80,40 @@ k_blur7(OrbGeom g, OrbPtrs p)
 // (cell row, cell column, y, x) that restates the reference's push_back order.
 // ------------------------------------------------------------------------------------------------
 #define FAST_MAXC 72          // max cell window edge (wCell + 6); geometry setup checks this
-#define FAST_MAXKEYS 1024     // per cell after NMS (<= interior / 4)
+#define FAST_WARPS 4          // cells per CTA (one warp each)
 
-__device__ __forceinline__ int fast_best(const uint8_t* c, int pitch, int th)
+// 16 differences centre - ring pixel (ring order of cv::FAST, k and k + 8 opposite)
+__device__ __forceinline__ void fast_ring(const uint8_t* c, int pitch, int v, int (&d)[16])
 {
-    // returns max(A, B) if the pixel is a FAST-9 corner at threshold th, else 0
-    const int v = c[0];
-    int d[16];
-    // quick reject on the four compass points: a 9-long arc contains one pixel of every opposite pair (k, k + 8),
-    // so both pixels of a pair inside [v - th, v + th] rules the corner out (whole warps leave here on smooth areas)
-    d[0] = v - c[3 * pitch];  d[8] = v - c[-3 * pitch];  d[4] = v - c[3];  d[12] = v - c[-3];
-    if (!((d[0] > th || d[8] > th || d[0] < -th || d[8] < -th) && (d[4] > th || d[12] > th || d[4] < -th || d[12] < -th))) return 0;
     d[1] = v - c[3 * pitch + 1];  d[2] = v - c[2 * pitch + 2];  d[3] = v - c[pitch + 3];
     d[5] = v - c[-pitch + 3];     d[6] = v - c[-2 * pitch + 2]; d[7] = v - c[-3 * pitch + 1];
     d[9] = v - c[-3 * pitch - 1]; d[10] = v - c[-2 * pitch - 2]; d[11] = v - c[-pitch - 3];
     d[13] = v - c[pitch - 3];     d[14] = v - c[2 * pitch - 2]; d[15] = v - c[3 * pitch - 1];
+}
+
+// max over the 16 nine-long arcs of the arc minimum of d (three-input min / max trees)
+__device__ __forceinline__ int fast_arc_maxmin(const int (&d)[16])
+{
+    int m3[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) m3[k] = min(min(d[k], d[(k + 1) & 15]), d[(k + 2) & 15]);
+    int best = -1000;
+#pragma unroll
+    for (int k = 0; k < 16; k++) best = max(best, min(min(m3[k], m3[(k + 3) & 15]), m3[(k + 6) & 15]));
+    return best;
+}
+
+// returns max(A, B) (the FAST score + 1) if the pixel is a FAST-9 corner at threshold th, else 0.
+// Quick reject on the four compass points: a 9-long arc contains one pixel of every opposite pair (k, k + 8),
+// so both pixels of a pair inside [v - th, v + th] rules the corner out.  Only the side (brighter / darker) that
+// has a 9-run can reach a score above th, so only that side's arcs are evaluated.
+__device__ __forceinline__ int fast_best(const uint8_t* c, int pitch, int th)
+{
+    const int v = c[0];
+    int d[16];
+    d[0] = v - c[3 * pitch];  d[8] = v - c[-3 * pitch];  d[4] = v - c[3];  d[12] = v - c[-3];
+    if (!((d[0] > th || d[8] > th || d[0] < -th || d[8] < -th) && (d[4] > th || d[12] > th || d[4] < -th || d[12] < -th))) return 0;
+    fast_ring(c, pitch, v, d);
     unsigned hi = 0, lo = 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -127,30 +124,29 @@ __device__ __forceinline__ int fast_best(const uint8_t* c, int pitch, int th)
     unsigned h = hi & (hi >> 1); h &= h >> 2; h &= h >> 4; h &= hi >> 8;  // runs of 9
     unsigned w = lo & (lo >> 1); w &= w >> 2; w &= w >> 4; w &= lo >> 8;
     if (!(h | w)) return 0;
-    int A = -1000, B = -1000;
+    int best = 0;
+    if (h) best = fast_arc_maxmin(d);
+    if (w) {
 #pragma unroll
-    for (int s = 0; s < 16; s++) {
-        int mn = d[s], mx = d[s];
-#pragma unroll
-        for (int k = 1; k < 9; k++) {
-            int t = d[(s + k) & 15];
-            mn = min(mn, t);
-            mx = max(mx, t);
-        }
-        A = max(A, mn);
-        B = max(B, -mx);
+        for (int k = 0; k < 16; k++) d[k] = -d[k];
+        best = max(best, fast_arc_maxmin(d));
     }
-    return max(A, B);
+    return best;
 }
 
-__global__ void __launch_bounds__(256)
-k_fast_cells(OrbGeom g, OrbPtrs p)
+// One WARP per 30-px cell, no block barriers.  Pass A evaluates the cell at iniTh; only a cell that yields no
+// keypoint there is evaluated again at minTh (src/ORBextractor.cc:809-816) -- corner scores do not depend on the
+// threshold, so scores found in pass A stay valid.  Keys go straight to the (frame, level) list with
+// warp-aggregated atomics.
+// Dynamic shared memory: per warp two byte maps (pixels, scores) of `rows` x `tp` (tp = window width + 3
+// alignment bytes rounded up to a multiple of 4), sized by the host from the largest cell of the geometry.
+__global__ void __launch_bounds__(32 * FAST_WARPS)
+k_fast_cells(OrbGeom g, OrbPtrs p, int tp, int rows)
 {
-    __shared__ uint8_t tile[FAST_MAXC * FAST_MAXC];
-    __shared__ uint8_t best[FAST_MAXC * FAST_MAXC];
-    __shared__ unsigned keys[FAST_MAXKEYS];
-    __shared__ int s_count, s_base;
-    int cell = blockIdx.x, l = 0;
+    PLF_DYN_SMEM(smem);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int cell = blockIdx.x * FAST_WARPS + wid, l = 0;
+    if (cell >= g.totalCells) return;
     while (l + 1 < g.nlevels && cell >= g.lv[l + 1].cellBase) l++;
     cell -= g.lv[l].cellBase;
     const OrbLevelGeom& L = g.lv[l];
@@ -161,55 +157,72 @@ k_fast_cells(OrbGeom g, OrbPtrs p)
     const int maxY = min(iniY + L.hCell + 6, maxBorderY), maxX = min(iniX + L.wCell + 6, maxBorderX);
     const int cw = maxX - iniX, ch = maxY - iniY;
     if (cw < 7 || ch < 7) return;
-    const int tid = threadIdx.x;
-    const uint8_t* src = p.lvl[l] + (size_t)blockIdx.y * p.frameStride[l] + (size_t)iniY * p.pitch[l] + iniX;
+    uint8_t* tile = smem + (size_t)wid * 2 * tp * rows;
+    uint8_t* best = tile + (size_t)tp * rows;
+    const int FAST_TP = tp;
     const int spitch = p.pitch[l];
-    for (int i = tid; i < cw * ch; i += 256) {
-        int ry = i / cw, rx = i - ry * cw;
-        tile[ry * FAST_MAXC + rx] = src[(size_t)ry * spitch + rx];
-        best[ry * FAST_MAXC + rx] = 0;
+    const uint8_t* src = p.lvl[l] + (size_t)blockIdx.y * p.frameStride[l] + (size_t)iniY * spitch + iniX;
+    // window -> shared memory; aligned buffers are read as 32-bit words (16 words x 2 rows per step)
+    const int off = (int)((size_t)src & 3);            // window column rx lives at tile column rx + off
+    if (((size_t)spitch & 3) == 0) {
+        const unsigned* s4 = (const unsigned*)(src - off);
+        const int nW = (off + cw + 3) >> 2, wx = lane & 15;
+        for (int ry = lane >> 4; ry < ch; ry += 2)
+            if (wx < nW) {
+                ((unsigned*)tile)[ry * (FAST_TP / 4) + wx] = s4[(size_t)ry * (spitch >> 2) + wx];
+                ((unsigned*)best)[ry * (FAST_TP / 4) + wx] = 0u;
+            }
+    } else {
+        for (int ry = 0; ry < ch; ry++)
+            for (int rx = lane; rx < cw; rx += 32) {
+                tile[ry * FAST_TP + rx + off] = src[(size_t)ry * spitch + rx];
+                best[ry * FAST_TP + rx + off] = 0;
+            }
     }
-    if (tid == 0) s_count = 0;
-    __syncthreads();
-    const int iw = cw - 6, ih = ch - 6;
-    for (int i = tid; i < iw * ih; i += 256) {
-        int ry = i / iw + 3, rx = i - (ry - 3) * iw + 3;
-        int b = fast_best(&tile[ry * FAST_MAXC + rx], FAST_MAXC, g.minTh);
-        best[ry * FAST_MAXC + rx] = (uint8_t)b;   // b <= 255
-    }
-    __syncthreads();
+    __syncwarp();
+    int* cnt = p.rawcount + (size_t)blockIdx.y * g.nlevels + l;
+    unsigned* out = p.rawkeys + (size_t)blockIdx.y * g.rawPerFrame + L.rawOff;
+    int found = 0;
     for (int pass = 0; pass < 2; pass++) {
         const int th = pass == 0 ? g.iniTh : g.minTh;
-        for (int i = tid; i < iw * ih; i += 256) {
-            int ry = i / iw + 3, rx = i - (ry - 3) * iw + 3;
-            const uint8_t* b = &best[ry * FAST_MAXC + rx];
-            int s = b[0];
-            if (s <= th) continue;
-            // strict maximum over the 8 neighbours; scores below the threshold (and the non-interior ring,
-            // which stays 0) count as 0, and score = best - 1 is monotone so best values compare the same
-#define NB(o) ((int)b[o] > th ? (int)b[o] : 0)
-            if (s > NB(-1) && s > NB(1) && s > NB(-FAST_MAXC - 1) && s > NB(-FAST_MAXC) && s > NB(-FAST_MAXC + 1) &&
-                s > NB(FAST_MAXC - 1) && s > NB(FAST_MAXC) && s > NB(FAST_MAXC + 1)) {
-                int slot = atomicAdd(&s_count, 1);
-                int kx = rx + cj * L.wCell, ky = ry + ci * L.hCell;   // relative to minBorder, :822-823
-                if (slot < FAST_MAXKEYS) keys[slot] = (unsigned)kx | ((unsigned)ky << 12) | ((unsigned)(s - 1) << 24);
+        for (int ry = 3; ry < ch - 3; ry++)
+            for (int rx = 3 + lane; rx < cw - 3; rx += 32) {
+                const int o = ry * FAST_TP + rx + off;
+                if (pass == 0 || best[o] == 0) best[o] = (uint8_t)fast_best(&tile[o], FAST_TP, th);   // <= 255
             }
+        __syncwarp();
+        for (int ry = 3; ry < ch - 3; ry++)
+            for (int rx0 = 3; rx0 < cw - 3; rx0 += 32) {
+                const int rx = rx0 + lane;
+                bool key = false;
+                int sc = 0;
+                if (rx < cw - 3) {
+                    const uint8_t* b = &best[ry * FAST_TP + rx + off];
+                    sc = b[0];
+                    if (sc > th) {
+                        // strict maximum over the 8 neighbours; scores at or below the threshold (and the ring around the
+                        // interior, which stays 0) count as 0; score = best - 1 is monotone, so best values compare the same
+#define NB(o) ((int)b[o] > th ? (int)b[o] : 0)
+                        key = sc > NB(-1) && sc > NB(1) && sc > NB(-FAST_TP - 1) && sc > NB(-FAST_TP) && sc > NB(-FAST_TP + 1) &&
+                              sc > NB(FAST_TP - 1) && sc > NB(FAST_TP) && sc > NB(FAST_TP + 1);
 #undef NB
-        }
-        __syncthreads();
-        const int found = s_count;
-        __syncthreads();          // every thread has read the count before the retry pass can change it
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, key);
+                if (m) {
+                    int base = 0;
+                    const int leader = __ffs((int)m) - 1;
+                    if (lane == leader) base = atomicAdd(cnt, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (key) {
+                        const int oo = base + __popc(m & ((1u << lane) - 1u));
+                        const int kx = rx + cj * L.wCell, ky = ry + ci * L.hCell;   // relative to minBorder, :822-823
+                        if (oo < L.rawcap) out[oo] = (unsigned)kx | ((unsigned)ky << 12) | ((unsigned)(sc - 1) << 24);
+                    }
+                    found += __popc(m);
+                }
+            }
         if (found > 0) break;
-    }
-    const int n = min(s_count, FAST_MAXKEYS);
-    if (n == 0) return;
-    int* cnt = p.rawcount + (size_t)blockIdx.y * g.nlevels + l;
-    if (tid == 0) s_base = atomicAdd(cnt, n);
-    __syncthreads();
-    unsigned* out = p.rawkeys + (size_t)blockIdx.y * g.rawPerFrame + L.rawOff;
-    for (int i = tid; i < n; i += 256) {
-        int o = s_base + i;
-        if (o < L.rawcap) out[o] = keys[i];
     }
 }
 

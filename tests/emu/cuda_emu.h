@@ -209,6 +209,23 @@ static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
+{
+    unsigned long long v = ((unsigned long long)b << 32) | a;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        unsigned n = (sel >> (4 * i)) & 0xf;
+        unsigned byte = (unsigned)((v >> (8 * (n & 7))) & 0xff);
+        if (n & 8) byte = (byte & 0x80) ? 0xff : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh)
+{
+    unsigned long long v = ((unsigned long long)hi << 32) | lo;
+    return (unsigned)(v >> (sh & 31));
+}
 static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 using std::max;
