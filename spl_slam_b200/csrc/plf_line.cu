@@ -33,6 +33,9 @@ struct plf_line {
     short *d_dx[LINE_MAX_OCT], *d_dy[LINE_MAX_OCT];
     int2* d_comp;
     int *d_q, *d_label, *d_regpts, *d_lineidx, *d_lineidx2, *d_cnt, *d_detcount;
+    unsigned* d_mask;       // one bit per scaled pixel: gradient defined
+    double* d_bincoef;      // per frame
+    int qthr;               // defined <=> gx^2 + gy^2 > qthr
     float* d_fa;
     float2* d_cs;
     unsigned long long *d_keys, *d_keys2, *d_linekey, *d_linekey2;
@@ -107,6 +110,14 @@ extern "C" plf_status plf_line_create(plf_ctx* ctx, const plf_line_params* p, pl
     // LSD constants (OpenCV lsd.cpp flsd)
     o->prec = LSD_PI * p->ang_th / 180;
     o->rho = p->quant / sin(o->prec);
+    {   // largest integer q with sqrt(q / 4.0) <= rho in double arithmetic (the reference's NOTDEF test, monotone in q)
+        long qq = (long)floor(4.0 * o->rho * o->rho);
+        if (qq < 0) qq = 0;
+        if (qq > 600000) qq = 600000;
+        while (qq > 0 && !(sqrt((double)qq / 4.0) <= o->rho)) qq--;
+        while (sqrt((double)(qq + 1) / 4.0) <= o->rho && qq < 600000) qq++;
+        o->qthr = (sqrt((double)qq / 4.0) <= o->rho) ? (int)qq : -1;
+    }
     if (p->scale != 1) {
         const double sigma = (p->scale < 1) ? (p->sigma_scale / p->scale) : p->sigma_scale;
         const unsigned hh = (unsigned)(ceil(sigma * sqrt(2 * 3.0 * log(10.0))));
@@ -231,6 +242,7 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
     need(o->regcap, 8); need(o->regcap, 8); need(o->regcap, 4); need(o->regcap, 4);
     need(F * noct * LINE_DETCAP, sizeof(plf_keyline));
     need(CNT_MAXQ + F, 4); need(F * noct, 4);
+    need(F * (maxpx / 32 + 8192), 4); need(F, 8);   // mask (rows x ceil(w / 32) words), bin coefficients
 
     PLF_CUDA(ctx, cudaMalloc((void**)&o->d_base, bytes + 4096));
     uint8_t* p = o->d_base;
@@ -260,6 +272,8 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
     o->d_det = carve<plf_keyline>(p, F * noct * LINE_DETCAP);
     o->d_cnt = carve<int>(p, CNT_MAXQ + F);
     o->d_detcount = carve<int>(p, F * noct);
+    o->d_mask = carve<unsigned>(p, F * (maxpx / 32 + 8192));
+    o->d_bincoef = carve<double>(p, F);
     // INTER_LINEAR_EXACT tables
     PLF_CUDA(ctx, cudaMalloc((void**)&o->d_tabs, (tabCount + 1) * sizeof(int2)));
     if (S != 1) {
@@ -372,13 +386,17 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt + CNT_BCOUNT, 0, (CNT_MAXQ - CNT_BCOUNT) * sizeof(int), st));
         PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt + CNT_MAXQ, 0xff, (size_t)nframes * sizeof(int), st));   // maxq = -1
         dim3 g2(plf_div_up(sw, 32), plf_div_up(sh, 8), nframes), b2(32, 8);
-        PLF_LAUNCH(k_lsd_grad, g2, b2, 0, st, scaled, (size_t)sw * sh, sw, sw, sh, o->rho, o->d_q, o->d_fa, o->d_cs, o->d_label,
-                   o->d_cnt + CNT_MAXQ);
+        const int mw = plf_div_up(sw, 32);
+        PLF_LAUNCH(k_lsd_grad, g2, b2, 0, st, scaled, (size_t)sw * sh, sw, sw, sh, o->qthr, o->d_q, o->d_fa, o->d_label,
+                   o->d_mask, mw, o->d_cnt + CNT_MAXQ);
         PLF_CHECK_LAUNCH(ctx);
-        PLF_LAUNCH(k_ccl_merge, g2, b2, 0, st, o->d_label, sw, sh);
+        PLF_LAUNCH(k_lsd_bincoef, dim3(plf_div_up(nframes, 128)), dim3(128), 0, st, (const int*)(o->d_cnt + CNT_MAXQ), nframes, o->prm.n_bins,
+                   o->d_bincoef);
         PLF_CHECK_LAUNCH(ctx);
-        PLF_LAUNCH(k_lsd_keys, g2, b2, 0, st, (const int*)o->d_label, (const int*)o->d_q, (const int*)(o->d_cnt + CNT_MAXQ), sw, sh,
-                   o->prm.n_bins, o->d_keys, o->d_cnt + CNT_NKEYS, (int)o->keycap, o->kbits[k]);
+        PLF_LAUNCH(k_ccl_merge, g2, b2, 0, st, o->d_label, (const unsigned*)o->d_mask, mw, sw, sh);
+        PLF_CHECK_LAUNCH(ctx);
+        PLF_LAUNCH(k_lsd_keys, g2, b2, 0, st, (const int*)o->d_label, (const int*)o->d_q, (const unsigned*)o->d_mask, mw,
+                   (const double*)o->d_bincoef, sw, sh, o->prm.n_bins, o->d_keys, o->d_cnt + CNT_NKEYS, (int)o->keycap, o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
         int nkeys = 0;
         PLF_CUDA(ctx, cudaMemcpyAsync(&nkeys, o->d_cnt + CNT_NKEYS, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -395,7 +413,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             // the sorted position of every defined pixel (compact component index), then the big components with
             // warp-cooperative ordered growth (one warp each) and everything else with one thread per component
             PLF_LAUNCH(k_lsd_cid, dim3(plf_div_up(nkeys, 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2, nkeys, o->d_label,
-                       (size_t)sw * sh, o->kbits[k]);
+                       (const float*)o->d_fa, o->d_cs, (size_t)sw * sh, o->kbits[k]);
             PLF_CHECK_LAUNCH(ctx);
             // size the used-bitmap of the warp kernel from the largest component present (bucket counts)
             int bc[LSD_NBUCKET];
@@ -420,7 +438,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
                        o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap, 1, wg_maxc, o->kbits[k]);
             PLF_CHECK_LAUNCH(ctx);
         }
-        PLF_LAUNCH(k_lsd_rect, dim3(plf_div_up(o->regcap, 128)), dim3(128), 0, st, (const LsdRegion*)o->d_regions,
+        PLF_LAUNCH(k_lsd_rect, dim3(plf_div_up(o->regcap, RECT_WARPS)), dim3(32 * RECT_WARPS), 0, st, (const LsdRegion*)o->d_regions,
                    (const int*)(o->d_cnt + CNT_NREG), o->regcap, (const int*)o->d_regpts, (const int*)o->d_q, sw, sh, o->prec, S, o->d_lines,
                    o->d_linekey, o->d_lineidx, o->d_cnt + CNT_ERR, o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);

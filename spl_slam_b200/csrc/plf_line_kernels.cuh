@@ -139,42 +139,65 @@ k_sobel3(const uint8_t* __restrict__ src, size_t sframe, int spitch, int w, int 
 }
 
 // ---------------- LSD ll_angle: gradient, level-line angle, component label init ----------------
-// per pixel: q = gx^2 + gy^2 (norm = sqrt(q / 4.0)), fa = fastAtan2(gx, -gy) in degrees (or NOTDEF),
-// cs = float cos / sin of the float-cast radian angle (what region_grow accumulates), label = own index.
+// A pixel is "defined" iff norm = sqrt(q / 4.0) > rho, q = gx^2 + gy^2: the host turns that into the integer
+// test q > qthr (qthr = largest q whose correctly rounded double norm is <= rho), so only the defined pixels
+// (a few percent) do any floating point.  Per pixel: fa = fastAtan2(gx, -gy) in degrees or NOTDEF (all pixels);
+// for defined pixels also q, cs = float cos / sin of the float-cast radian angle (what region_grow
+// accumulates) and label = first pixel of the pixel's horizontal run inside its 32-px row segment.
+// mask holds one bit per pixel (one word per warp: 32 consecutive pixels of a row); it is what the CCL and key
+// kernels test, so they skip empty segments without touching the per-pixel arrays.
 __global__ void __launch_bounds__(256)
-k_lsd_grad(const uint8_t* __restrict__ img, size_t iframe, int ipitch, int w, int h, double rho,
-           int* __restrict__ q, float* __restrict__ fa, float2* __restrict__ cs, int* __restrict__ label,
-           int* __restrict__ maxq)
+k_lsd_grad(const uint8_t* __restrict__ img, size_t iframe, int ipitch, int w, int h, int qthr,
+           int* __restrict__ q, float* __restrict__ fa, int* __restrict__ label,
+           unsigned* __restrict__ mask, int mw, int* __restrict__ maxq)
 {
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     const int f = blockIdx.z;
     int myq = -1;
-    if (x < w && y < h) {
-        const size_t o = (size_t)f * w * h + (size_t)y * w + x;
-        float a = LSD_NOTDEF;
-        int qq = 0;
-        if (x < w - 1 && y < h - 1) {
-            const uint8_t* r0 = img + (size_t)f * iframe + (size_t)y * ipitch + x;
-            const uint8_t* r1 = r0 + ipitch;
-            const int DA = r1[1] - r0[0], BC = r0[1] - r1[0];
-            const int gx = DA + BC, gy = DA - BC;
-            qq = gx * gx + gy * gy;
-            const double norm = sqrt((double)qq / 4.0);
-            if (!(norm <= rho)) {
-                a = plf_fast_atan2((float)gx, (float)(-gy));
-                const float af = (float)((double)a * LSD_D2R);
-                cs[o] = make_float2((float)cos((double)af), (float)sin((double)af));
-                myq = qq;
-            }
-        }
-        q[o] = qq;
-        fa[o] = a;
-        label[o] = a == LSD_NOTDEF ? -1 : y * w + x;
+    bool def = false;
+    const size_t o = (size_t)f * w * h + (size_t)y * w + x;
+    int gx = 0, gy = 0;
+    if (x < w - 1 && y < h - 1) {
+        const uint8_t* r0 = img + (size_t)f * iframe + (size_t)y * ipitch + x;
+        const uint8_t* r1 = r0 + ipitch;
+        const int DA = r1[1] - r0[0], BC = r0[1] - r1[0];
+        gx = DA + BC; gy = DA - BC;
+        myq = gx * gx + gy * gy;
+        def = myq > qthr;
     }
+    const unsigned m = __ballot_sync(0xffffffffu, def);
+    if (y < h) {
+        if (threadIdx.x == 0) mask[((size_t)f * h + y) * mw + blockIdx.x] = m;
+        if (x < w) {
+            float a = LSD_NOTDEF;
+            if (def) {
+                a = plf_fast_atan2((float)gx, (float)(-gy));
+                q[o] = myq;     // (cos / sin of the angle are filled in densely by k_lsd_cid after the sort)
+                // head of the run of defined pixels this lane belongs to (inside the warp's segment)
+                const unsigned below = ~m & ((1u << threadIdx.x) - 1u);
+                const int head = below ? 32 - __clz((int)below) : 0;
+                label[o] = y * w + blockIdx.x * 32 + head;
+            }
+            fa[o] = a;
+        }
+    }
+    if (!def) myq = -1;
     // block max of q over defined pixels -> one atomic per warp
+    if (m) {
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) myq = max(myq, __shfl_xor_sync(0xffffffffu, myq, s));
-    if (((threadIdx.y * 32 + threadIdx.x) & 31) == 0 && myq >= 0) atomicMax(&maxq[f], myq);
+        for (int s = 16; s > 0; s >>= 1) myq = max(myq, __shfl_xor_sync(0xffffffffu, myq, s));
+        if (threadIdx.x == 0) atomicMax(&maxq[f], myq);
+    }
+}
+
+// per frame: bin_coef = (n_bins - 1) / max_grad (OpenCV lsd.cpp ll_angle), once instead of per pixel
+__global__ void k_lsd_bincoef(const int* __restrict__ maxq, int nframes, int n_bins, double* __restrict__ coef)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    const int mq = maxq[f];
+    const double max_grad = mq >= 0 ? sqrt((double)mq / 4.0) : -1.0;
+    coef[f] = max_grad > 0 ? (double)(n_bins - 1) / max_grad : 0.0;
 }
 
 __device__ __forceinline__ int ccl_find(const int* L, int a)
@@ -195,27 +218,40 @@ __device__ __forceinline__ void ccl_union(int* L, int a, int b)
     } while (!done);
 }
 // 8-connected components of the defined mask: union-find in global memory (atomicMin links the larger root to
-// the smaller).  A block-tiled shared-memory variant measured slower here (CTA overhead at 7 % defined pixels);
-// what mattered was cutting the unions per pixel with the decision tree below (35 ms -> 3 ms per 1024 frames).
+// the smaller).  A warp owns one 32-px row segment and reads the definedness of its neighbours from the bit
+// mask (five warp-uniform words), so empty segments leave at once.  Pixels of one run inside a segment already
+// share a label (k_lsd_grad), so only these links remain, each made once per pair of touching runs:
+//   W  : the run continues from the previous segment (lane 0 only),
+//   N  : first pixel of the overlap with a run above (skipped when the W neighbour made the same link via its N),
+//   NE : N undefined, NE defined (a run above starting one to the right),
+//   NW : N and W undefined, NW defined.
 __global__ void __launch_bounds__(256)
-k_ccl_merge(int* __restrict__ label, int w, int h)
+k_ccl_merge(int* __restrict__ label, const unsigned* __restrict__ mask, int mw, int w, int h)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= w || y >= h) return;
+    const int seg = blockIdx.x, lane = threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (y >= h) return;
+    const unsigned* M = mask + ((size_t)blockIdx.z * h + y) * mw;
+    const unsigned m1 = M[seg];
+    if (!m1) return;
+    const unsigned m1l = seg > 0 ? M[seg - 1] : 0u;
+    unsigned m0 = 0u, m0l = 0u, m0r = 0u;
+    if (y > 0) {
+        m0 = M[seg - mw];
+        m0l = seg > 0 ? M[seg - mw - 1] : 0u;
+        m0r = seg + 1 < mw ? M[seg - mw + 1] : 0u;
+    }
+    if (!((m1 >> lane) & 1u)) return;
+    const bool dW = lane > 0 ? (m1 >> (lane - 1)) & 1u : (m1l >> 31) & 1u;
+    const bool dN = (m0 >> lane) & 1u;
+    const bool dNW = lane > 0 ? (m0 >> (lane - 1)) & 1u : (m0l >> 31) & 1u;
+    const bool dNE = lane < 31 ? (m0 >> (lane + 1)) & 1u : m0r & 1u;
     int* L = label + (size_t)blockIdx.z * w * h;
-    const int p = y * w + x;
-    if (L[p] < 0) return;
-    // decision tree over the backward neighbours (W, NW, N, NE): N is adjacent to the other three, W to NW,
-    // so at most two unions are needed and usually one
-    const bool dW = x > 0 && L[p - 1] >= 0;
-    const bool dN = y > 0 && L[p - w] >= 0;
-    const bool dNW = y > 0 && x > 0 && L[p - w - 1] >= 0;
-    const bool dNE = y > 0 && x < w - 1 && L[p - w + 1] >= 0;
-    if (dN) ccl_union(L, p, p - w);
+    const int p = y * w + seg * 32 + lane;
+    if (lane == 0 && dW) ccl_union(L, p, p - 1);
+    if (dN) { if (!(dW && dNW)) ccl_union(L, p, p - w); }
     else {
         if (dNE) ccl_union(L, p, p - w + 1);
-        if (dW) ccl_union(L, p, p - 1);
-        else if (dNW) ccl_union(L, p, p - w - 1);
+        if (!dW && dNW) ccl_union(L, p, p - w - 1);
     }
 }
 
@@ -223,39 +259,34 @@ k_ccl_merge(int* __restrict__ label, int w, int h)
 // (A CTA-aggregated variant with several rows per thread measured slower: the kernel is bound by the
 // dependent label chases of ccl_find, which want as many independent threads as possible.)
 __global__ void __launch_bounds__(256)
-k_lsd_keys(const int* __restrict__ label, const int* __restrict__ q, const int* __restrict__ maxq, int w, int h,
-           int n_bins, unsigned long long* __restrict__ keys, int* __restrict__ nkeys, int keycap, int kb)
+k_lsd_keys(const int* __restrict__ label, const int* __restrict__ q, const unsigned* __restrict__ mask, int mw,
+           const double* __restrict__ coef, int w, int h, int n_bins, unsigned long long* __restrict__ keys,
+           int* __restrict__ nkeys, int keycap, int kb)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const int lane = threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     const int f = blockIdx.z;
-    bool have = false;
+    if (y >= h) return;
+    const unsigned m = mask[((size_t)f * h + y) * mw + blockIdx.x];
+    if (!m) return;
+    const bool have = (m >> lane) & 1u;
     unsigned long long key = 0;
-    if (x < w && y < h) {
-        const size_t o = (size_t)f * w * h + (size_t)y * w + x;
-        if (label[o] >= 0) {
-            const int root = ccl_find(label + (size_t)f * w * h, y * w + x);
-            const int mq = maxq[f];
-            const double max_grad = mq >= 0 ? sqrt((double)mq / 4.0) : -1.0;
-            const double bin_coef = max_grad > 0 ? (double)(n_bins - 1) / max_grad : 0.0;
-            int bin = (int)(sqrt((double)q[o] / 4.0) * bin_coef);
-            if (bin < 0) bin = 0;
-            if (bin > n_bins - 1) bin = n_bins - 1;
-            key = ((unsigned long long)f << (2 * kb + 12)) | ((unsigned long long)root << (kb + 12)) |
-                  ((unsigned long long)(n_bins - 1 - bin) << kb) | (unsigned long long)(y * w + x);
-            have = true;
-        }
+    if (have) {
+        const int p = y * w + blockIdx.x * 32 + lane;
+        const size_t o = (size_t)f * w * h + p;
+        const int root = ccl_find(label + (size_t)f * w * h, p);
+        int bin = (int)(sqrt((double)q[o] / 4.0) * coef[f]);
+        if (bin < 0) bin = 0;
+        if (bin > n_bins - 1) bin = n_bins - 1;
+        key = ((unsigned long long)f << (2 * kb + 12)) | ((unsigned long long)root << (kb + 12)) |
+              ((unsigned long long)(n_bins - 1 - bin) << kb) | (unsigned long long)p;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, have);
-    const int lane = (threadIdx.y * 32 + threadIdx.x) & 31;
     int base = 0;
-    if (m) {
-        const int leader = __ffs((int)m) - 1;
-        if (lane == leader) base = atomicAdd(nkeys, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (have) {
-            const int o = base + __popc(m & ((1u << lane) - 1));
-            if (o < keycap) keys[o] = key;
-        }
+    const int leader = __ffs((int)m) - 1;
+    if (lane == leader) base = atomicAdd(nkeys, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (have) {
+        const int oo = base + __popc(m & ((1u << lane) - 1));
+        if (oo < keycap) keys[oo] = key;
     }
 }
 
@@ -394,13 +425,20 @@ k_lsd_grow(const unsigned long long* __restrict__ keys, int n, const int2* __res
 #define WARPGROW_MAXC (512 * 1024)          // component pixels one CTA can track (64 KB of used bits)
 #define WG_RING 1024                        // queue entries kept in shared memory
 
+// after the sort: the sorted position of every defined pixel (its compact index inside the component), and -- one
+// thread per defined pixel, no divergence -- cs = float cos / sin of the float-cast radian angle, which is what
+// region_grow accumulates (OpenCV lsd.cpp: sumdx += cos(float(angle)))
 __global__ void __launch_bounds__(256)
-k_lsd_cid(const unsigned long long* __restrict__ keys, int n, int* __restrict__ label, size_t px, int kb)
+k_lsd_cid(const unsigned long long* __restrict__ keys, int n, int* __restrict__ label, const float* __restrict__ fa,
+          float2* __restrict__ cs, size_t px, int kb)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const unsigned long long k = keys[i];
-    label[(size_t)LSD_KEY_FRAME(k) * px + LSD_KEY_IDX(k)] = i;
+    const size_t o = (size_t)LSD_KEY_FRAME(k) * px + LSD_KEY_IDX(k);
+    label[o] = i;
+    const float af = (float)((double)fa[o] * LSD_D2R);
+    cs[o] = make_float2((float)cos((double)af), (float)sin((double)af));
 }
 
 // One candidate: neighbour `nb` of queue entry q.  The queue tail lives in a shared-memory ring; older entries
@@ -547,7 +585,7 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
                     npf = min(WG_E, arena - rn);
                     if (grp < npf) pf = wg_load(rn + grp, arena, ring, regpts, gdx, gdy, w, h, CID, F, CS);
                     int cc = -1 - lane;       // position of the pixel in the component's seed list (negative: none)
-                    bool cand = cd.inb && cd.ci >= 0;
+                    bool cand = cd.inb && cd.fv > -500.f;     // defined (labels of undefined pixels are stale)
                     if (cand) {
                         cc = cd.ci - start;
                         cand = !((used[cc >> 5] >> (cc & 31)) & 1u);
@@ -628,42 +666,64 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
     }
 }
 
-// region2rect + get_theta (OpenCV lsd.cpp, refine = 0): one thread per region; sums in region order.
+// region2rect + get_theta (OpenCV lsd.cpp, refine = 0): one WARP per region.  The double sums are order dependent,
+// so they are accumulated strictly in region order -- but the per-point work (gather, double sqrt, products) is done
+// by 32 lanes at once and only the additions are replayed in order (every lane replays them from shuffles, which
+// keeps the warp converged): ~10 cycles per point instead of a dependent gather + sqrt chain per point.
 // Output: line end points (float, +0.5, / SCALE) and an order key (frame, bin descending, raster).
-__global__ void __launch_bounds__(128)
+#define RECT_WARPS 8
+__global__ void __launch_bounds__(32 * RECT_WARPS)
 k_lsd_rect(const LsdRegion* __restrict__ regions, const int* __restrict__ nregions, int regcap, const int* __restrict__ regpts,
            const int* __restrict__ q, int w, int h, double prec, double scale, float4* __restrict__ lines,
            unsigned long long* __restrict__ linekey, int* __restrict__ lineidx, int* __restrict__ errflag, int kb)
 {
-    const int rr = blockIdx.x * 128 + threadIdx.x;
+    const int rr = blockIdx.x * RECT_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
     if (rr >= regcap) return;
     int nr = *nregions;
-    if (nr > regcap) { nr = regcap; if (rr == 0) *errflag = 1; }
-    lineidx[rr] = rr;
-    if (rr >= nr) { linekey[rr] = ~0ull; return; }
+    if (nr > regcap) { nr = regcap; if (rr == 0 && lane == 0) *errflag = 1; }
+    if (lane == 0) lineidx[rr] = rr;
+    if (rr >= nr) { if (lane == 0) linekey[rr] = ~0ull; return; }
     const LsdRegion R = regions[rr];
     const int f = LSD_KEY_FRAME(R.seedkey);
     const int* Q = q + (size_t)f * w * h;
     const int* pts = regpts + R.start;
     double x = 0, y = 0, sum = 0;
-    for (int i = 0; i < R.n; i++) {
-        const int pk = pts[i];
-        const int py = pk >> 16, pxx = pk & 0xffff;
-        const double weight = sqrt((double)Q[py * w + pxx] / 4.0);
-        x += (double)pxx * weight;
-        y += (double)py * weight;
-        sum += weight;
+    for (int i0 = 0; i0 < R.n; i0 += 32) {
+        const int cnt = min(32, R.n - i0);
+        double wgt = 0, xw = 0, yw = 0;
+        if (lane < cnt) {
+            const int pk = pts[i0 + lane];
+            const int py = pk >> 16, pxx = pk & 0xffff;
+            wgt = sqrt((double)Q[py * w + pxx] / 4.0);
+            xw = (double)pxx * wgt;
+            yw = (double)py * wgt;
+        }
+        for (int j = 0; j < cnt; j++) {
+            x += __shfl_sync(FULL, xw, j);
+            y += __shfl_sync(FULL, yw, j);
+            sum += __shfl_sync(FULL, wgt, j);
+        }
     }
     x /= sum; y /= sum;
     double Ixx = 0, Iyy = 0, Ixy = 0;
-    for (int i = 0; i < R.n; i++) {
-        const int pk = pts[i];
-        const int py = pk >> 16, pxx = pk & 0xffff;
-        const double weight = sqrt((double)Q[py * w + pxx] / 4.0);
-        const double dx = (double)pxx - x, dy = (double)py - y;
-        Ixx += dy * dy * weight;
-        Iyy += dx * dx * weight;
-        Ixy -= dx * dy * weight;
+    for (int i0 = 0; i0 < R.n; i0 += 32) {
+        const int cnt = min(32, R.n - i0);
+        double txx = 0, tyy = 0, txy = 0;
+        if (lane < cnt) {
+            const int pk = pts[i0 + lane];
+            const int py = pk >> 16, pxx = pk & 0xffff;
+            const double wgt = sqrt((double)Q[py * w + pxx] / 4.0);
+            const double dx = (double)pxx - x, dy = (double)py - y;
+            txx = dy * dy * wgt;
+            tyy = dx * dx * wgt;
+            txy = dx * dy * wgt;
+        }
+        for (int j = 0; j < cnt; j++) {
+            Ixx += __shfl_sync(FULL, txx, j);
+            Iyy += __shfl_sync(FULL, tyy, j);
+            Ixy -= __shfl_sync(FULL, txy, j);
+        }
     }
     const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
     double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)plf_fast_atan2((float)(lambda - Ixx), (float)Ixy)
@@ -674,15 +734,24 @@ k_lsd_rect(const LsdRegion* __restrict__ regions, const int* __restrict__ nregio
     while (diff > LSD_PI) diff -= LSD_2PI;
     if (fabs(diff) > prec) theta += LSD_PI;
     const double dx = cos(theta), dy = sin(theta);
+    // l_min = min(0, min l), l_max = max(0, max l): the reference's `if (l > l_max) .. else if (l < l_min) ..` with both
+    // starting at 0 never lets one value update both, so the order of the points does not matter here
     double l_min = 0, l_max = 0;
-    for (int i = 0; i < R.n; i++) {
+    for (int i = lane; i < R.n; i += 32) {
         const int pk = pts[i];
         const int py = pk >> 16, pxx = pk & 0xffff;
         const double regdx = (double)pxx - x, regdy = (double)py - y;
         const double l = regdx * dx + regdy * dy;
         if (l > l_max) l_max = l;
-        else if (l < l_min) l_min = l;
+        if (l < l_min) l_min = l;
     }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const double a = __shfl_xor_sync(FULL, l_max, s), b = __shfl_xor_sync(FULL, l_min, s);
+        if (a > l_max) l_max = a;
+        if (b < l_min) l_min = b;
+    }
+    if (lane != 0) return;
     double x1 = x + l_min * dx, y1 = y + l_min * dy, x2 = x + l_max * dx, y2 = y + l_max * dy;
     x1 += 0.5; y1 += 0.5; x2 += 0.5; y2 += 0.5;
     if (scale != 1) { x1 /= scale; y1 /= scale; x2 /= scale; y2 /= scale; }

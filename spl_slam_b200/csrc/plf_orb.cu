@@ -312,14 +312,18 @@ extern "C" plf_status plf_orb_extract_batch(plf_orb* o, const uint8_t* host_imgs
     if (st) return st;
     const OrbLevelGeom& L0 = o->geom.lv[0];
     cudaStream_t s = ctx->stream;
-    if (stride == (size_t)w && frame_stride == (size_t)w * h && L0.pitch == w) {
+    // level 0 is kept densely packed (pitch = width) when the width is a multiple of 4, so that a contiguous host batch
+    // is ONE DMA transfer; other widths keep the 64-byte aligned pitch (the kernels' 32-bit fast paths need it).  The
+    // level-0 buffer was sized for the aligned pitch, which is at least as large.
+    const size_t p0 = (w & 3) ? (size_t)L0.pitch : (size_t)w;
+    if (stride == p0 && frame_stride == p0 * h) {
         PLF_CUDA(ctx, cudaMemcpyAsync(o->lvl_own[0], host_imgs, (size_t)nframes * frame_stride, cudaMemcpyHostToDevice, s));
     } else {
         for (int f = 0; f < nframes; f++)
-            PLF_CUDA(ctx, cudaMemcpy2DAsync(o->lvl_own[0] + (size_t)f * L0.frameBytes, L0.pitch, host_imgs + (size_t)f * frame_stride,
+            PLF_CUDA(ctx, cudaMemcpy2DAsync(o->lvl_own[0] + (size_t)f * p0 * h, p0, host_imgs + (size_t)f * frame_stride,
                                             stride, w, h, cudaMemcpyHostToDevice, s));
     }
-    st = orb_run(o, o->lvl_own[0], L0.pitch, L0.frameBytes, nframes, o->d_kps, o->d_desc, cap, o->d_nout);
+    st = orb_run(o, o->lvl_own[0], p0, p0 * h, nframes, o->d_kps, o->d_desc, cap, o->d_nout);
     if (st) return st;
     PLF_CUDA(ctx, cudaMemcpyAsync(n_out, o->d_nout, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, s));
     PLF_CUDA(ctx, cudaMemcpyAsync(host_kps, o->d_kps, (size_t)nframes * cap * sizeof(plf_keypoint), cudaMemcpyDeviceToHost, s));
