@@ -250,7 +250,12 @@ static plf_status orb_run(plf_orb* o, const uint8_t* lvl0, size_t stride0, size_
     int fw = 0, fh = 0;   // largest FAST cell window of the geometry -> shared-memory map size
     for (int l = 0; l < g.nlevels; l++) { fw = g.lv[l].wCell + 6 > fw ? g.lv[l].wCell + 6 : fw; fh = g.lv[l].hCell + 6 > fh ? g.lv[l].hCell + 6 : fh; }
     const int ftp = (fw + 3 + 3) & ~3;
-    PLF_LAUNCH(k_fast_cells, dim3(plf_div_up(g.totalCells, FAST_WARPS), nframes), dim3(32 * FAST_WARPS), (size_t)FAST_WARPS * 2 * ftp * fh, st, g, P, ftp, fh);
+    const int flcap = ((fw - 6) * (fh - 6) + 1) & ~1;   // work-list entries: one per interior pixel
+    const size_t fsmem = (size_t)FAST_WARPS * (2 * ftp * fh + 2 * flcap);
+#ifndef PLF_EMU
+    if (fsmem > 48 * 1024) PLF_CUDA(ctx, cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+#endif
+    PLF_LAUNCH(k_fast_cells, dim3(plf_div_up(g.totalCells, FAST_WARPS), nframes), dim3(32 * FAST_WARPS), fsmem, st, g, P, ftp, fh, flcap);
     PLF_CHECK_LAUNCH(ctx);
     PLF_LAUNCH(k_blur7, dim3(plf_div_up(g.totalBlurTiles, BLUR_WARPS), nframes), dim3(32 * BLUR_WARPS), 0, st, g, P);
     PLF_CHECK_LAUNCH(ctx);

@@ -103,17 +103,27 @@ __device__ __forceinline__ int fast_arc_maxmin(const int (&d)[16])
     return best;
 }
 
-// returns max(A, B) (the FAST score + 1) if the pixel is a FAST-9 corner at threshold th, else 0.
-// Quick reject on the four compass points: a 9-long arc contains one pixel of every opposite pair (k, k + 8),
-// so both pixels of a pair inside [v - th, v + th] rules the corner out.  Only the side (brighter / darker) that
-// has a 9-run can reach a score above th, so only that side's arcs are evaluated.
-__device__ __forceinline__ int fast_best(const uint8_t* c, int pitch, int th)
+// Quick reject on the four compass points: a 9-long arc contains one pixel of every opposite pair (k, k + 8), so both
+// pixels of a pair inside [v - th, v + th] rules the corner out.
+__device__ __forceinline__ bool fast_quick(const uint8_t* c, int pitch, int th)
 {
     const int v = c[0];
-    int d[16];
+    const int d0 = v - c[3 * pitch], d8 = v - c[-3 * pitch], d4 = v - c[3], d12 = v - c[-3];
+    return (d0 > th || d8 > th || d0 < -th || d8 < -th) && (d4 > th || d12 > th || d4 < -th || d12 < -th);
+}
+
+__device__ __forceinline__ void fast_ring_all(const uint8_t* c, int pitch, int (&d)[16])
+{
+    const int v = c[0];
     d[0] = v - c[3 * pitch];  d[8] = v - c[-3 * pitch];  d[4] = v - c[3];  d[12] = v - c[-3];
-    if (!((d[0] > th || d[8] > th || d[0] < -th || d[8] < -th) && (d[4] > th || d[12] > th || d[4] < -th || d[12] < -th))) return 0;
     fast_ring(c, pitch, v, d);
+}
+
+// bit 0: a 9-run of ring pixels darker than centre - th exists (d > th), bit 1: a 9-run brighter than centre + th
+__device__ __forceinline__ int fast_sides(const uint8_t* c, int pitch, int th)
+{
+    int d[16];
+    fast_ring_all(c, pitch, d);
     unsigned hi = 0, lo = 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -123,10 +133,18 @@ __device__ __forceinline__ int fast_best(const uint8_t* c, int pitch, int th)
     hi |= hi << 16; lo |= lo << 16;
     unsigned h = hi & (hi >> 1); h &= h >> 2; h &= h >> 4; h &= hi >> 8;  // runs of 9
     unsigned w = lo & (lo >> 1); w &= w >> 2; w &= w >> 4; w &= lo >> 8;
-    if (!(h | w)) return 0;
+    return (h ? 1 : 0) | (w ? 2 : 0);
+}
+
+// max(A, B) = FAST score + 1.  Only a side that has a 9-run can reach a value above the threshold, so only that
+// side's arcs are evaluated.
+__device__ __forceinline__ int fast_score(const uint8_t* c, int pitch, int sides)
+{
+    int d[16];
+    fast_ring_all(c, pitch, d);
     int best = 0;
-    if (h) best = fast_arc_maxmin(d);
-    if (w) {
+    if (sides & 1) best = fast_arc_maxmin(d);
+    if (sides & 2) {
 #pragma unroll
         for (int k = 0; k < 16; k++) d[k] = -d[k];
         best = max(best, fast_arc_maxmin(d));
@@ -135,16 +153,20 @@ __device__ __forceinline__ int fast_best(const uint8_t* c, int pitch, int th)
 }
 
 // One WARP per 30-px cell, no block barriers.  Pass A evaluates the cell at iniTh; only a cell that yields no
-// keypoint there is evaluated again at minTh (src/ORBextractor.cc:809-816) -- corner scores do not depend on the
-// threshold, so scores found in pass A stay valid.  Keys go straight to the (frame, level) list with
-// warp-aggregated atomics.
-// Dynamic shared memory: per warp two byte maps (pixels, scores) of `rows` x `tp` (tp = window width + 3
-// alignment bytes rounded up to a multiple of 4), sized by the host from the largest cell of the geometry.
+// keypoint there is evaluated again at minTh (src/ORBextractor.cc:809-816).  Inside a pass the work is compacted
+// between stages so that the expensive stages run with full warps: (1) compass quick-reject over the interior ->
+// list of survivors, (2) 16-pixel ring + 9-run test on the list -> list of corners, (3) arc scores of the corners
+// into the score map, (4) per-cell NMS of the corners (strict maximum over the 8 neighbours).  Keys go straight to
+// the (frame, level) list with warp-aggregated atomics; their order is irrelevant (the octree breaks response ties
+// with an explicit order key that restates the reference's push_back order).
+// Dynamic shared memory per warp: pixel map and score map of `rows` x `tp` bytes (tp = window width + 3 alignment
+// bytes rounded up to a multiple of 4) and a 16-bit work list of `lcap` entries, sized from the largest cell.
 __global__ void __launch_bounds__(32 * FAST_WARPS)
-k_fast_cells(OrbGeom g, OrbPtrs p, int tp, int rows)
+k_fast_cells(OrbGeom g, OrbPtrs p, int tp, int rows, int lcap)
 {
     PLF_DYN_SMEM(smem);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu, LT = (1u << lane) - 1u;
     int cell = blockIdx.x * FAST_WARPS + wid, l = 0;
     if (cell >= g.totalCells) return;
     while (l + 1 < g.nlevels && cell >= g.lv[l + 1].cellBase) l++;
@@ -157,72 +179,96 @@ k_fast_cells(OrbGeom g, OrbPtrs p, int tp, int rows)
     const int maxY = min(iniY + L.hCell + 6, maxBorderY), maxX = min(iniX + L.wCell + 6, maxBorderX);
     const int cw = maxX - iniX, ch = maxY - iniY;
     if (cw < 7 || ch < 7) return;
-    uint8_t* tile = smem + (size_t)wid * 2 * tp * rows;
+    const size_t per_warp = (size_t)2 * tp * rows + (size_t)2 * lcap;
+    uint8_t* tile = smem + (size_t)wid * per_warp;
     uint8_t* best = tile + (size_t)tp * rows;
-    const int FAST_TP = tp;
+    unsigned short* list = (unsigned short*)(best + (size_t)tp * rows);
     const int spitch = p.pitch[l];
     const uint8_t* src = p.lvl[l] + (size_t)blockIdx.y * p.frameStride[l] + (size_t)iniY * spitch + iniX;
     // window -> shared memory; aligned buffers are read as 32-bit words (16 words x 2 rows per step)
-    const int off = (int)((size_t)src & 3);            // window column rx lives at tile column rx + off
+    const int off = (int)((size_t)src & 3);            // window column rx lives at map column rx + off
     if (((size_t)spitch & 3) == 0) {
         const unsigned* s4 = (const unsigned*)(src - off);
         const int nW = (off + cw + 3) >> 2, wx = lane & 15;
         for (int ry = lane >> 4; ry < ch; ry += 2)
             if (wx < nW) {
-                ((unsigned*)tile)[ry * (FAST_TP / 4) + wx] = s4[(size_t)ry * (spitch >> 2) + wx];
-                ((unsigned*)best)[ry * (FAST_TP / 4) + wx] = 0u;
+                ((unsigned*)tile)[ry * (tp >> 2) + wx] = s4[(size_t)ry * (spitch >> 2) + wx];
+                ((unsigned*)best)[ry * (tp >> 2) + wx] = 0u;
             }
     } else {
         for (int ry = 0; ry < ch; ry++)
             for (int rx = lane; rx < cw; rx += 32) {
-                tile[ry * FAST_TP + rx + off] = src[(size_t)ry * spitch + rx];
-                best[ry * FAST_TP + rx + off] = 0;
+                tile[ry * tp + rx + off] = src[(size_t)ry * spitch + rx];
+                best[ry * tp + rx + off] = 0;
             }
     }
     __syncwarp();
     int* cnt = p.rawcount + (size_t)blockIdx.y * g.nlevels + l;
     unsigned* out = p.rawkeys + (size_t)blockIdx.y * g.rawPerFrame + L.rawOff;
-    int found = 0;
     for (int pass = 0; pass < 2; pass++) {
         const int th = pass == 0 ? g.iniTh : g.minTh;
-        for (int ry = 3; ry < ch - 3; ry++)
-            for (int rx = 3 + lane; rx < cw - 3; rx += 32) {
-                const int o = ry * FAST_TP + rx + off;
-                if (pass == 0 || best[o] == 0) best[o] = (uint8_t)fast_best(&tile[o], FAST_TP, th);   // <= 255
-            }
-        __syncwarp();
+        // (1) compass quick-reject over the interior
+        int n1 = 0;
         for (int ry = 3; ry < ch - 3; ry++)
             for (int rx0 = 3; rx0 < cw - 3; rx0 += 32) {
-                const int rx = rx0 + lane;
-                bool key = false;
-                int sc = 0;
-                if (rx < cw - 3) {
-                    const uint8_t* b = &best[ry * FAST_TP + rx + off];
-                    sc = b[0];
-                    if (sc > th) {
-                        // strict maximum over the 8 neighbours; scores at or below the threshold (and the ring around the
-                        // interior, which stays 0) count as 0; score = best - 1 is monotone, so best values compare the same
-#define NB(o) ((int)b[o] > th ? (int)b[o] : 0)
-                        key = sc > NB(-1) && sc > NB(1) && sc > NB(-FAST_TP - 1) && sc > NB(-FAST_TP) && sc > NB(-FAST_TP + 1) &&
-                              sc > NB(FAST_TP - 1) && sc > NB(FAST_TP) && sc > NB(FAST_TP + 1);
-#undef NB
-                    }
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, key);
-                if (m) {
-                    int base = 0;
-                    const int leader = __ffs((int)m) - 1;
-                    if (lane == leader) base = atomicAdd(cnt, __popc(m));
-                    base = __shfl_sync(0xffffffffu, base, leader);
-                    if (key) {
-                        const int oo = base + __popc(m & ((1u << lane) - 1u));
-                        const int kx = rx + cj * L.wCell, ky = ry + ci * L.hCell;   // relative to minBorder, :822-823
-                        if (oo < L.rawcap) out[oo] = (unsigned)kx | ((unsigned)ky << 12) | ((unsigned)(sc - 1) << 24);
-                    }
-                    found += __popc(m);
-                }
+                const int rx = rx0 + lane, o = ry * tp + rx + off;
+                const bool go = rx < cw - 3 && fast_quick(&tile[o], tp, th);
+                const unsigned m = __ballot_sync(FULL, go);
+                if (go) list[n1 + __popc(m & LT)] = (unsigned short)o;
+                n1 += __popc(m);
             }
+        __syncwarp();
+        // (2) ring + 9-run test, compacted in place (entry: map offset | sides << 14)
+        int n2 = 0;
+        for (int i0 = 0; i0 < n1; i0 += 32) {
+            const int i = i0 + lane;
+            int o = 0, sides = 0;
+            if (i < n1) { o = list[i]; sides = fast_sides(&tile[o], tp, th); }
+            __syncwarp();                                   // every lane has read its entry before slots are reused
+            const unsigned m = __ballot_sync(FULL, sides != 0);
+            if (sides) list[n2 + __popc(m & LT)] = (unsigned short)(o | (sides << 14));
+            n2 += __popc(m);
+        }
+        __syncwarp();
+        // (3) scores of the corners (independent of the threshold; <= 255)
+        for (int i = lane; i < n2; i += 32) {
+            const int e = list[i], o = e & 0x3fff;
+            best[o] = (uint8_t)fast_score(&tile[o], tp, e >> 14);
+        }
+        __syncwarp();
+        // (4) per-cell NMS: scores at or below the threshold (and the ring around the interior, which stays 0) count
+        // as 0; score = best - 1 is monotone, so best values compare the same
+        int found = 0;
+        for (int i0 = 0; i0 < n2; i0 += 32) {
+            const int i = i0 + lane;
+            bool key = false;
+            int sc = 0, o = 0;
+            if (i < n2) {
+                o = list[i] & 0x3fff;
+                const uint8_t* b = &best[o];
+                sc = b[0];
+#define NB(d) ((int)b[d] > th ? (int)b[d] : 0)
+                key = sc > th && sc > NB(-1) && sc > NB(1) && sc > NB(-tp - 1) && sc > NB(-tp) && sc > NB(-tp + 1) &&
+                      sc > NB(tp - 1) && sc > NB(tp) && sc > NB(tp + 1);
+#undef NB
+            }
+            const unsigned m = __ballot_sync(FULL, key);
+            if (m) {
+                int base = 0;
+                const int leader = __ffs((int)m) - 1;
+                if (lane == leader) base = atomicAdd(cnt, __popc(m));
+                base = __shfl_sync(FULL, base, leader);
+                if (key) {
+                    const int oo = base + __popc(m & LT);
+                    const int ry = o / tp, rx = o - ry * tp - off;
+                    const int kx = rx + cj * L.wCell, ky = ry + ci * L.hCell;   // relative to minBorder, :822-823
+                    if (oo < L.rawcap) out[oo] = (unsigned)kx | ((unsigned)ky << 12) | ((unsigned)(sc - 1) << 24);
+                }
+                found += __popc(m);
+            }
+        }
         if (found > 0) break;
+        __syncwarp();
     }
 }
 
