@@ -247,15 +247,21 @@ def main():
             ctx_ls[i].check(lib.plf_line_extract_batch_device(les[i].h, d_img[s].data_ptr(), SUB, W, H, W, W * H, d_kl[s].data_ptr(),
                                                               d_mid[s].data_ptr(), d_ld[s].data_ptr(), capl, d_nl[s].data_ptr()))
 
-    def step_device():
-        dev_orb()                                              # asynchronous on the ORB stream
-        list(pool.map(dev_line, range(NL)))                    # line calls contain stream syncs: one host thread each
+    def dev_line_steps(i, nsteps):
+        for _ in range(nsteps):
+            if i == 0:
+                dev_orb()      # the ORB launches of a step are issued as the first line instance enters that step, so ORB work
+            dev_line(i)        # keeps filling the gaps the line path leaves (host syncs, region-growing chains) in every step
 
-    def timed_device_step():
-        flush.zero_()                      # L2 flush between timed iterations (untimed)
+    def run_device(nsteps):
+        """nsteps steps back to back: every extractor instance (own stream + host thread) walks through its share of each
+        step's batch without a global barrier between steps, so the tail of one step (the last region-growing chain,
+        LBD) overlaps the start of the next, as it does in a running system.  Returns the device time in ms."""
         torch.cuda.synchronize()
         ctx_o.timer_start()
-        step_device()
+        futs = [pool.submit(dev_line_steps, i, nsteps) for i in range(NL)]   # line calls contain stream syncs: one host thread each
+        for f in futs:
+            f.result()
         for c in ctx_os[1:] + ctx_ls:
             ctx_o.wait(c)                  # the first ORB stream's stop event waits for every other stream
         return ctx_o.timer_stop()
@@ -271,31 +277,54 @@ def main():
             ctx_ls[i].check(lib.plf_line_extract_batch(les[i].h, h_img[s].data_ptr(), SUB, W, H, W, W * H, h_kl[s].data_ptr(), h_mid[s].data_ptr(),
                                                        h_ld[s].data_ptr(), capl, n_l[s].ctypes.data))
 
-    def timed_e2e_step():
-        flush.zero_()
+    def e2e_orb_steps(i, nsteps, gate):
+        for _ in range(nsteps):
+            gate.acquire()     # paced by the first line instance: ORB and line work of a step stay interleaved
+            e2e_orb(i)
+
+    def e2e_line_steps(i, nsteps, gates):
+        for _ in range(nsteps):
+            if i == 0:
+                for g_ in gates:
+                    g_.release()
+            e2e_line(i)
+
+    def run_e2e(nsteps):
+        """The same through the host-buffer C-ABI calls: every call uploads its images from pinned host memory and
+        downloads its results (H2D + D2H inside the timed region); one host thread per extractor instance, the
+        reference's ORB thread and line thread (Frame.cc:301-304)."""
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        fo = [pool.submit(e2e_orb, i) for i in range(NO)]   # the reference's ORB thread(s) and line thread(s) (Frame.cc:301-304)
-        list(pool.map(e2e_line, range(NL)))
-        for f in fo:
+        gates = [threading.Semaphore(0) for _ in range(NO)]
+        futs = [pool.submit(e2e_orb_steps, i, nsteps, gates[i]) for i in range(NO)] + [pool.submit(e2e_line_steps, i, nsteps, gates) for i in range(NL)]
+        for f in futs:
             f.result()
+        torch.cuda.synchronize()
         return (time.perf_counter() - t0) * 1e3
 
     # ---- device-resident throughput ----
-    for _ in range(args.warmup):
-        timed_device_step()
+    run_device(args.warmup)
+    flush.zero_()                          # leave nothing of the warm-up in L2; the per-step working set (GBs) exceeds L2 anyway
     barrier()
     sampler = ClockSampler(dev) if rank == 0 else None
     l0 = sum(c.launch_count() for c in ctx_os + ctx_ls)
-    ms_dev = 0.0
-    for _ in range(args.steps):
-        ms_dev += timed_device_step()
+    ms_dev = run_device(args.steps)
     barrier()
     launches = sum(c.launch_count() for c in ctx_os + ctx_ls) - l0
     clocks = sampler.stop() if sampler else None
     nk = d_nk.cpu().numpy(); nl = d_nl.cpu().numpy()
     assert (nk > 0).all() and (nl >= 0).all(), "extraction reported an overflow"
 
+    if os.environ.get("PLF_PROF_CONCURRENT"):   # diagnostic: per-kernel event times while all streams run together
+        for c in ctx_os + ctx_ls:
+            c.profile_enable(True)
+        t_conc = run_device(2) / 2
+        conc = {}
+        for c in ctx_os + ctx_ls:
+            for k, v in c.profile_report().items():
+                conc[k] = conc.get(k, 0.0) + v[0] / 2
+            c.profile_enable(False)
+        print("concurrent step %.1f ms; kernel ms under concurrency: %s" % (t_conc, {k: round(v, 2) for k, v in sorted(conc.items(), key=lambda kv: -kv[1])}), file=sys.stderr)
     # ---- per-kernel times for the roofline (separate profiled steps, CUDA events per launch) ----
     for c in ctx_os + ctx_ls:
         c.profile_enable(True)
@@ -316,12 +345,10 @@ def main():
         c.profile_enable(False)
 
     # ---- end to end ----
-    for _ in range(args.warmup):
-        timed_e2e_step()
+    run_e2e(args.warmup)
+    flush.zero_()
     barrier()
-    ms_e2e = 0.0
-    for _ in range(args.steps):
-        ms_e2e += timed_e2e_step()
+    ms_e2e = run_e2e(args.steps)
     barrier()
 
     # ---- matching (BASELINE config 5): 1e4 queries x 1e6 train rows, train-sharded across ranks ----
@@ -400,7 +427,7 @@ def main():
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "orb_contexts": NO, "line_contexts": NL, "frames_per_line_call": SUB, "frame": "one 752x480 image; a stereo pair is 2 frames",
                            "sharding": "frame i -> rank i mod N (left/right of a pair on separate GPUs for N > 1), no collective",
-                           "l2": "256 MiB buffer written between timed iterations; per-step working set ~%.1f GB" % (B * (45 * spx + 3 * sumpx) / 1e9)},
+                           "l2": "inputs larger than L2: per-step working set ~%.1f GB vs 126 MB (256 MiB flush before the timed region); the K steps run back to back, no barrier between steps" % (B * (45 * spx + 3 * sumpx) / 1e9)},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,

@@ -27,6 +27,7 @@ struct plf_line {
     // workspace
     int ws_w, ws_h, ws_frames;
     int ow[LINE_MAX_OCT], oh[LINE_MAX_OCT], sw[LINE_MAX_OCT], sh[LINE_MAX_OCT], min_reg[LINE_MAX_OCT], kbits[LINE_MAX_OCT];
+    int sp[LINE_MAX_OCT];   // working width of the scaled octave: sw rounded up to 4 (row pitch of every per-pixel LSD array; the pad columns are NOTDEF)
     uint8_t* d_base;
     uint8_t *d_oct[LINE_MAX_OCT], *d_tmp, *d_scaled;       // images (pitch == width)
     uint8_t *d_lbdimg[LINE_MAX_OCT];
@@ -216,10 +217,11 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         if (o->ow[k] < 8 || o->oh[k] < 8) return plf_fail(ctx, PLF_ERR_INVALID, "image too small for %d octaves", noct);
         o->sw[k] = S != 1 ? (int)lrint(o->ow[k] * S) : o->ow[k];
         o->sh[k] = S != 1 ? (int)lrint(o->oh[k] * S) : o->oh[k];
-        if ((size_t)o->sw[k] * o->sh[k] > maxpx) maxpx = (size_t)o->sw[k] * o->sh[k];
-        if ((size_t)o->sw[k] * o->sh[k] >= (1u << 22)) return plf_fail(ctx, PLF_ERR_INVALID, "scaled octave larger than 4M pixels");
+        o->sp[k] = (o->sw[k] + 3) & ~3;
+        if ((size_t)o->sp[k] * o->sh[k] > maxpx) maxpx = (size_t)o->sp[k] * o->sh[k];
+        if ((size_t)o->sp[k] * o->sh[k] >= (1u << 22)) return plf_fail(ctx, PLF_ERR_INVALID, "scaled octave larger than 4M pixels");
         o->kbits[k] = 1;
-        while ((1u << o->kbits[k]) < (unsigned)(o->sw[k] * o->sh[k])) o->kbits[k]++;
+        while ((1u << o->kbits[k]) < (unsigned)(o->sp[k] * o->sh[k])) o->kbits[k]++;
         if (52 - 2 * o->kbits[k] < 31 && nframes > (1 << (52 - 2 * o->kbits[k])))
             return plf_fail(ctx, PLF_ERR_INVALID, "at most %d frames of this size per line batch", 1 << (52 - 2 * o->kbits[k]));
         const double LOG_NT = 5 * (log10((double)o->sw[k]) + log10((double)o->sh[k])) / 2 + log10(11.0);
@@ -341,7 +343,7 @@ static plf_status gauss_batch(plf_ctx* ctx, const uint8_t* src, uint8_t* dst, in
         BlurTaps taps;
         memset(&taps, 0, sizeof(taps));
         for (int i = 0; i < k.ksize; i++) taps.k[i] = k.q[i];
-        dim3 grid(plf_div_up(w, 128), plf_div_up(h, 128), nframes), block(32, 4);
+        dim3 grid(plf_div_up(w, 128), plf_div_up(h, 4 * GS_ROWS), nframes), block(32, 4);
         if (k.ksize == 5) PLF_LAUNCH(k_gauss_strip<2>, grid, block, 0, st, src, frame, w, dst, frame, w, w, h, taps);
         else PLF_LAUNCH(k_gauss_strip<3>, grid, block, 0, st, src, frame, w, dst, frame, w, w, h, taps);
     } else {
@@ -367,36 +369,41 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
     PLF_CUDA(ctx, cudaMemsetAsync(o->d_detcount, 0, (size_t)nframes * noct * sizeof(int), st));
     PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt + CNT_ERR, 0, sizeof(int), st));
     for (int k = 0; k < noct; k++) {
-        const int ow = o->ow[k], oh = o->oh[k], sw = o->sw[k], sh = o->sh[k];
+        const int ow = o->ow[k], oh = o->oh[k], sw = o->sw[k], sh = o->sh[k], sp = o->sp[k];
         std::unique_lock<std::mutex> prephase(g_lsd_prephase);
         if (k > 0) {   // computeGaussianPyramid: pyrDown, no pre-blur (LSDDetector_custom.cpp:56-73)
-            PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(ow, 32), plf_div_up(oh, 8), nframes), dim3(32, 8), 0, st, (const uint8_t*)o->d_oct[k - 1],
+            PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(ow, 128), plf_div_up(oh, 4 * PD_ROWS), nframes), dim3(32, 4), 0, st, (const uint8_t*)o->d_oct[k - 1],
                        (size_t)o->ow[k - 1] * o->oh[k - 1], o->ow[k - 1], o->ow[k - 1], o->oh[k - 1], o->d_oct[k], (size_t)ow * oh, ow);
             PLF_CHECK_LAUNCH(ctx);
         }
+        // the image the gradient is taken of: the octave itself (SCALE == 1, pitch = octave width) or its blurred and
+        // resized copy (pitch = sp)
         const uint8_t* scaled = o->d_oct[k];
+        int spitch = ow;
+        size_t sframe = (size_t)ow * oh;
         if (S != 1) {
             { plf_status gs = gauss_batch(ctx, o->d_oct[k], o->d_tmp, ow, oh, nframes, o->lsd_gauss); if (gs) return gs; }
             PLF_LAUNCH(k_resize_exact, dim3(plf_div_up(sw, 32), plf_div_up(sh, 8), nframes), dim3(32, 8), 0, st, (const uint8_t*)o->d_tmp,
-                       (size_t)ow * oh, ow, ow, oh, o->d_scaled, (size_t)sw * sh, sw, sw, sh, o->xtab[k], o->ytab[k]);
+                       (size_t)ow * oh, ow, ow, oh, o->d_scaled, (size_t)sp * sh, sp, sw, sh, o->xtab[k], o->ytab[k]);
             PLF_CHECK_LAUNCH(ctx);
-            scaled = o->d_scaled;
+            scaled = o->d_scaled; spitch = sp; sframe = (size_t)sp * sh;
         }
         PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt, 0, 4 * sizeof(int), st));
         PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt + CNT_BCOUNT, 0, (CNT_MAXQ - CNT_BCOUNT) * sizeof(int), st));
         PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt + CNT_MAXQ, 0xff, (size_t)nframes * sizeof(int), st));   // maxq = -1
-        dim3 g2(plf_div_up(sw, 32), plf_div_up(sh, 8), nframes), b2(32, 8);
-        const int mw = plf_div_up(sw, 32);
-        PLF_LAUNCH(k_lsd_grad, g2, b2, 0, st, scaled, (size_t)sw * sh, sw, sw, sh, o->qthr, o->d_q, o->d_fa, o->d_label,
-                   o->d_mask, mw, o->d_cnt + CNT_MAXQ);
+        // from here on every per-pixel array has sp columns per row (sw real ones + NOTDEF padding)
+        const int mw = plf_div_up(sp, 32);
+        dim3 g2(mw, plf_div_up(sh, 8), nframes), b2(32, 8);
+        PLF_LAUNCH(k_lsd_grad, dim3(plf_div_up(sp, 128), plf_div_up(sh, 4), nframes), dim3(32, 4), 0, st, scaled, sframe, spitch, sw, sp, sh, o->qthr,
+                   o->d_q, o->d_fa, o->d_label, o->d_mask, mw, o->d_cnt + CNT_MAXQ);
         PLF_CHECK_LAUNCH(ctx);
         PLF_LAUNCH(k_lsd_bincoef, dim3(plf_div_up(nframes, 128)), dim3(128), 0, st, (const int*)(o->d_cnt + CNT_MAXQ), nframes, o->prm.n_bins,
                    o->d_bincoef);
         PLF_CHECK_LAUNCH(ctx);
-        PLF_LAUNCH(k_ccl_merge, g2, b2, 0, st, o->d_label, (const unsigned*)o->d_mask, mw, sw, sh);
+        PLF_LAUNCH(k_ccl_merge, g2, b2, 0, st, o->d_label, (const unsigned*)o->d_mask, mw, sp, sh);
         PLF_CHECK_LAUNCH(ctx);
         PLF_LAUNCH(k_lsd_keys, g2, b2, 0, st, (const int*)o->d_label, (const int*)o->d_q, (const unsigned*)o->d_mask, mw,
-                   (const double*)o->d_bincoef, sw, sh, o->prm.n_bins, o->d_keys, o->d_cnt + CNT_NKEYS, (int)o->keycap, o->kbits[k]);
+                   (const double*)o->d_bincoef, sp, sh, o->prm.n_bins, o->d_keys, o->d_cnt + CNT_NKEYS, (int)o->keycap, o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
         int nkeys = 0;
         PLF_CUDA(ctx, cudaMemcpyAsync(&nkeys, o->d_cnt + CNT_NKEYS, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -413,7 +420,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             // the sorted position of every defined pixel (compact component index), then the big components with
             // warp-cooperative ordered growth (one warp each) and everything else with one thread per component
             PLF_LAUNCH(k_lsd_cid, dim3(plf_div_up(nkeys, 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2, nkeys, o->d_label,
-                       (const float*)o->d_fa, o->d_cs, (size_t)sw * sh, o->kbits[k]);
+                       (const float*)o->d_fa, o->d_cs, (size_t)sp * sh, o->kbits[k]);
             PLF_CHECK_LAUNCH(ctx);
             // size the used-bitmap of the warp kernel from the largest component present (bucket counts)
             int bc[LSD_NBUCKET];
@@ -425,21 +432,22 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             int wg_maxc = 1 << (topb + 1);
             if (wg_maxc > WARPGROW_MAXC) wg_maxc = WARPGROW_MAXC;
             if (wg_maxc < 1024) wg_maxc = 1024;
-            const int wg_smem = wg_maxc / 8;
+            const int wg_smem = WG_WARPS * (wg_maxc / 8);
 #ifndef PLF_EMU
             PLF_CUDA(ctx, cudaFuncSetAttribute(k_lsd_grow_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem));
 #endif
-            if (nbig > 0) PLF_LAUNCH(k_lsd_grow_warp, dim3(nbig < 148 * 16 ? nbig : 148 * 16), dim3(32), wg_smem, st, (const unsigned long long*)o->d_keys2,
+            const int wg_ctas = plf_div_up(nbig, WG_WARPS) < 148 * 4 ? plf_div_up(nbig, WG_WARPS) : 148 * 4;
+            if (nbig > 0) PLF_LAUNCH(k_lsd_grow_warp, dim3(wg_ctas), dim3(32 * WG_WARPS), wg_smem, st, (const unsigned long long*)o->d_keys2,
                        (const int2*)o->d_comp, (const int*)(o->d_cnt + CNT_BCOUNT), (const float*)o->d_fa, (const float2*)o->d_cs,
-                       (const int*)o->d_label, sw, sh, o->prec, o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap, o->kbits[k], wg_maxc);
+                       (const int*)o->d_label, sp, sh, o->prec, o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap, o->kbits[k], wg_maxc);
             PLF_CHECK_LAUNCH(ctx);
             PLF_LAUNCH(k_lsd_grow, dim3(148 * 4), dim3(128), 0, st, (const unsigned long long*)o->d_keys2, nkeys, (const int2*)o->d_comp,
-                       (const int*)(o->d_cnt + CNT_BCOUNT), o->d_cnt + CNT_NEXT, o->d_fa, (const float2*)o->d_cs, sw, sh, o->prec,
+                       (const int*)(o->d_cnt + CNT_BCOUNT), o->d_cnt + CNT_NEXT, o->d_fa, (const float2*)o->d_cs, sp, sh, o->prec,
                        o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap, 1, wg_maxc, o->kbits[k]);
             PLF_CHECK_LAUNCH(ctx);
         }
         PLF_LAUNCH(k_lsd_rect, dim3(plf_div_up(o->regcap, RECT_WARPS)), dim3(32 * RECT_WARPS), 0, st, (const LsdRegion*)o->d_regions,
-                   (const int*)(o->d_cnt + CNT_NREG), o->regcap, (const int*)o->d_regpts, (const int*)o->d_q, sw, sh, o->prec, S, o->d_lines,
+                   (const int*)(o->d_cnt + CNT_NREG), o->regcap, (const int*)o->d_regpts, (const int*)o->d_q, sp, sh, o->prec, S, o->d_lines,
                    o->d_linekey, o->d_lineidx, o->d_cnt + CNT_ERR, o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
         plf_status s = sort_lines(o);
@@ -478,11 +486,11 @@ static plf_status lbd_batch(plf_line* o, int nframes, const plf_keyline* d_kl, c
         if (k == 0) {   // computeGaussianPyramid (binary_descriptor_custom.cpp:350-370): blur 5x5 sigma 1, then pyrDown
             { plf_status gs = gauss_batch(ctx, o->d_oct[0], o->d_lbdimg[0], ow, oh, nframes, o->lbd_gauss); if (gs) return gs; }
         } else {
-            PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(ow, 32), plf_div_up(oh, 8), nframes), dim3(32, 8), 0, st, (const uint8_t*)o->d_lbdimg[k - 1],
+            PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(ow, 128), plf_div_up(oh, 4 * PD_ROWS), nframes), dim3(32, 4), 0, st, (const uint8_t*)o->d_lbdimg[k - 1],
                        (size_t)o->ow[k - 1] * o->oh[k - 1], o->ow[k - 1], o->ow[k - 1], o->oh[k - 1], o->d_lbdimg[k], (size_t)ow * oh, ow);
         }
         PLF_CHECK_LAUNCH(ctx);
-        PLF_LAUNCH(k_sobel3, dim3(plf_div_up(ow, 32), plf_div_up(oh, 8), nframes), dim3(32, 8), 0, st, (const uint8_t*)o->d_lbdimg[k],
+        PLF_LAUNCH(k_sobel3, dim3(plf_div_up(ow, 128), plf_div_up(oh, 4 * SB_ROWS), nframes), dim3(32, 4), 0, st, (const uint8_t*)o->d_lbdimg[k],
                    (size_t)ow * oh, ow, ow, oh, o->d_dx[k], o->d_dy[k], (size_t)ow * oh);
         PLF_CHECK_LAUNCH(ctx);
         im.dx[k] = o->d_dx[k]; im.dy[k] = o->d_dy[k]; im.frame[k] = (size_t)ow * oh; im.w[k] = ow; im.h[k] = oh;

@@ -68,15 +68,16 @@ k_gauss_q8(const uint8_t* __restrict__ src, size_t sframe, int spitch, uint8_t* 
 }
 
 // 5- and 7-tap kernels (everything the reference's settings reach): register sliding window, see plf_blur_strip.
-// block = (32, 4): lane = 4-px column strip, threadIdx.y = 32-row band of a 128 x 128 tile.
+// block = (32, 4): lane = 4-px column strip, threadIdx.y = GS_ROWS-row band.
+#define GS_ROWS 35   // a multiple of both window lengths (5 and 7): no partially used ring turns
 template <int R>
 __global__ void __launch_bounds__(128)
 k_gauss_strip(const uint8_t* __restrict__ src, size_t sframe, int spitch, uint8_t* __restrict__ dst, size_t dframe, int dpitch,
               int w, int h, BlurTaps taps)
 {
-    const int x0 = blockIdx.x * 128 + 4 * threadIdx.x, y0 = (blockIdx.y * 4 + threadIdx.y) * 32;
+    const int x0 = blockIdx.x * 128 + 4 * threadIdx.x, y0 = (blockIdx.y * 4 + threadIdx.y) * GS_ROWS;
     if (y0 >= h) return;
-    plf_blur_strip<R>(src + (size_t)blockIdx.z * sframe, spitch, dst + (size_t)blockIdx.z * dframe, dpitch, w, h, x0, y0, 32, taps);
+    plf_blur_strip<R>(src + (size_t)blockIdx.z * sframe, spitch, dst + (size_t)blockIdx.z * dframe, dpitch, w, h, x0, y0, GS_ROWS, taps);
 }
 
 // ---------------- cv::resize INTER_LINEAR_EXACT; tab: .x = offset, .y = c1 (Q8) ----------------
@@ -98,44 +99,149 @@ k_resize_exact(const uint8_t* __restrict__ src, size_t sframe, int spitch, int s
     dst[(size_t)blockIdx.z * dframe + (size_t)y * dpitch + x] = (uint8_t)((cy0 * h0 + cy1 * h1 + 32768) >> 16);
 }
 
+// 12 bytes x0-4 .. x0+7 of an image row as three words (aligned fast path, or gathered with REFLECT_101)
+__device__ __forceinline__ void row_words3(const uint8_t* __restrict__ rp, int x0, int w, bool fastx, unsigned& w0, unsigned& w1, unsigned& w2)
+{
+    if (fastx) {
+        const unsigned* p = (const unsigned*)(rp + x0 - 4);
+        w0 = p[0]; w1 = p[1]; w2 = p[2];
+    } else {
+        unsigned b[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) b[i] = rp[plf_reflect101(x0 - 4 + i, w)];
+        w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+        w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+    }
+}
+__device__ __forceinline__ int reflect_once(int p, int n)   // valid for -n < p < 2n - 1
+{
+    p = p < 0 ? -p : p;
+    return p >= n ? 2 * (n - 1) - p : p;
+}
+
 // ---------------- cv::pyrDown to (w/2, h/2) ----------------
-__global__ void __launch_bounds__(256)
+// [1 4 6 4 1]^2 / 256, REFLECT_101, rounding (v + 128) >> 8.  A thread produces a 4-px wide strip of PD_ROWS output
+// rows: per input row it loads the 16 bytes 2*x0-4 .. 2*x0+11 (four aligned words), forms the four horizontal sums
+// and keeps the last five rows of sums in registers (two new input rows per output row).
+#define PD_ROWS 15
+__device__ __forceinline__ void pyrdown_hrow(const uint8_t* __restrict__ rp, int sx0, int w, bool fastx, int (&out)[4])
+{
+    unsigned b[16];
+    if (fastx) {
+        const unsigned* pw = (const unsigned*)(rp + sx0 - 4);
+        const unsigned ww[4] = {pw[0], pw[1], pw[2], pw[3]};
+#pragma unroll
+        for (int i = 0; i < 16; i++) b[i] = (ww[i >> 2] >> (8 * (i & 3))) & 0xffu;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) b[i] = (i >= 2 && i <= 12) ? rp[plf_reflect101(sx0 - 4 + i, w)] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)   // source column 2 * (x0 + j) is byte 4 + 2j
+        out[j] = (int)(b[2 + 2 * j] + b[6 + 2 * j] + 4u * (b[3 + 2 * j] + b[5 + 2 * j]) + 6u * b[4 + 2 * j]);
+}
+__global__ void __launch_bounds__(128)
 k_pyrdown(const uint8_t* __restrict__ src, size_t sframe, int spitch, int w, int h,
           uint8_t* __restrict__ dst, size_t dframe, int dpitch)
 {
     const int dw = w >> 1, dh = h >> 1;
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= dw || y >= dh) return;
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, y0 = (blockIdx.y * 4 + threadIdx.y) * PD_ROWS;
+    if (x0 >= dw || y0 >= dh) return;
     const uint8_t* s = src + (size_t)blockIdx.z * sframe;
-    int xs[5];
+    uint8_t* d = dst + (size_t)blockIdx.z * dframe;
+    const int sx0 = 2 * x0;
+    const bool fastx = ((((size_t)s) | (size_t)spitch) & 3) == 0 && sx0 >= 4 && sx0 + 12 <= w;   // four aligned words
+    const bool fullw = ((((size_t)d) | (size_t)dpitch) & 3) == 0 && x0 + 4 <= dw;
+    int ring[5][4];
 #pragma unroll
-    for (int i = 0; i < 5; i++) xs[i] = plf_reflect101(2 * x + i - 2, w);
-    int acc = 128;
+    for (int t = 0; t < 3; t++) pyrdown_hrow(s + (size_t)reflect_once(2 * y0 - 2 + t, h) * spitch, sx0, w, fastx, ring[t]);
+    const int yend = min(y0 + PD_ROWS, dh);
+    // ring slot of input row r (relative to 2*y0 - 2) is r % 5; output row y0 + i uses relative rows 2i .. 2i + 4
+    for (int ib = 0; ib < PD_ROWS; ib += 5) {
 #pragma unroll
-    for (int j = 0; j < 5; j++) {
-        const uint8_t* r = s + (size_t)plf_reflect101(2 * y + j - 2, h) * spitch;
-        int hsum = r[xs[0]] + 4 * r[xs[1]] + 6 * r[xs[2]] + 4 * r[xs[3]] + r[xs[4]];
-        const int kj = (j == 0 || j == 4) ? 1 : (j == 2 ? 6 : 4);
-        acc += kj * hsum;
+        for (int u = 0; u < 5; u++) {
+            const int i = ib + u, y = y0 + i;
+            const int ya = reflect_once(min(2 * y + 1, h + 1), h), yb = reflect_once(min(2 * y + 2, h + 1), h);
+            pyrdown_hrow(s + (size_t)ya * spitch, sx0, w, fastx, ring[(2 * u + 3) % 5]);
+            pyrdown_hrow(s + (size_t)yb * spitch, sx0, w, fastx, ring[(2 * u + 4) % 5]);
+            unsigned o = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int v = ring[(2 * u) % 5][j] + ring[(2 * u + 4) % 5][j] + 4 * (ring[(2 * u + 1) % 5][j] + ring[(2 * u + 3) % 5][j]) +
+                              6 * ring[(2 * u + 2) % 5][j] + 128;
+                o |= (unsigned)(v >> 8) << (8 * j);
+            }
+            if (y < yend) {
+                uint8_t* dp = d + (size_t)y * dpitch + x0;
+                if (fullw) *(unsigned*)dp = o;
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (x0 + j < dw) dp[j] = (uint8_t)(o >> (8 * j));
+                }
+            }
+        }
     }
-    dst[(size_t)blockIdx.z * dframe + (size_t)y * dpitch + x] = (uint8_t)(acc >> 8);
 }
 
-// ---------------- cv::Sobel 3x3 -> CV_16S dx, dy (binary_descriptor_custom.cpp:395-396) ----------------
-__global__ void __launch_bounds__(256)
+// ---------------- cv::Sobel 3x3 -> CV_16S dx, dy (binary_descriptor_custom.cpp:395-396), REFLECT_101 ----------------
+// Same strip scheme: per input row the horizontal difference d[x] = r[x+1] - r[x-1] and smoothing
+// s[x] = r[x-1] + 2 r[x] + r[x+1] of four pixels; dx = d0 + 2 d1 + d2, dy = s2 - s0 over a three-row register window.
+#define SB_ROWS 33
+__device__ __forceinline__ void sobel_hrow(const uint8_t* __restrict__ rp, int x0, int w, bool fastx, int (&dd)[4], int (&ss)[4])
+{
+    unsigned w0, w1, w2;
+    row_words3(rp, x0, w, fastx, w0, w1, w2);
+    int b[6];
+    b[0] = (int)(w0 >> 24);
+    b[1] = (int)(w1 & 0xffu); b[2] = (int)((w1 >> 8) & 0xffu); b[3] = (int)((w1 >> 16) & 0xffu); b[4] = (int)(w1 >> 24);
+    b[5] = (int)(w2 & 0xffu);
+#pragma unroll
+    for (int j = 0; j < 4; j++) { dd[j] = b[j + 2] - b[j]; ss[j] = b[j] + 2 * b[j + 1] + b[j + 2]; }
+}
+__global__ void __launch_bounds__(128)
 k_sobel3(const uint8_t* __restrict__ src, size_t sframe, int spitch, int w, int h,
          short* __restrict__ dx, short* __restrict__ dy, size_t dframe)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= w || y >= h) return;
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, y0 = (blockIdx.y * 4 + threadIdx.y) * SB_ROWS;
+    if (x0 >= w || y0 >= h) return;
     const uint8_t* s = src + (size_t)blockIdx.z * sframe;
-    const uint8_t* r0 = s + (size_t)plf_reflect101(y - 1, h) * spitch;
-    const uint8_t* r1 = s + (size_t)y * spitch;
-    const uint8_t* r2 = s + (size_t)plf_reflect101(y + 1, h) * spitch;
-    const int xl = plf_reflect101(x - 1, w), xr = plf_reflect101(x + 1, w);
-    const size_t o = (size_t)blockIdx.z * dframe + (size_t)y * w + x;
-    dx[o] = (short)((r0[xr] - r0[xl]) + 2 * (r1[xr] - r1[xl]) + (r2[xr] - r2[xl]));
-    dy[o] = (short)((r2[xl] + 2 * r2[x] + r2[xr]) - (r0[xl] + 2 * r0[x] + r0[xr]));
+    short* ox = dx + (size_t)blockIdx.z * dframe;
+    short* oy = dy + (size_t)blockIdx.z * dframe;
+    const bool fastx = ((((size_t)s) | (size_t)spitch) & 3) == 0 && x0 >= 4 && x0 + 8 <= w;
+    const bool fullw = (w & 3) == 0 && ((((size_t)ox) | ((size_t)oy)) & 7) == 0 && x0 + 4 <= w;
+    int D[3][4], S[3][4];
+    sobel_hrow(s + (size_t)reflect_once(y0 - 1, h) * spitch, x0, w, fastx, D[0], S[0]);
+    sobel_hrow(s + (size_t)y0 * spitch, x0, w, fastx, D[1], S[1]);
+    const int yend = min(y0 + SB_ROWS, h);
+    for (int yb = y0; yb < yend; yb += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; u++) {       // rows y-1, y, y+1 live in slots u, u+1, u+2 (mod 3)
+            const int y = yb + u;
+            sobel_hrow(s + (size_t)reflect_once(min(y, h - 1) + 1, h) * spitch, x0, w, fastx, D[(u + 2) % 3], S[(u + 2) % 3]);
+            int gx[4], gy[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                gx[j] = D[u % 3][j] + 2 * D[(u + 1) % 3][j] + D[(u + 2) % 3][j];
+                gy[j] = S[(u + 2) % 3][j] - S[u % 3][j];
+            }
+            if (y < yend) {
+                const size_t o = (size_t)y * w + x0;
+                if (fullw) {
+                    uint2 vx, vy;
+                    vx.x = (unsigned)(gx[0] & 0xffff) | ((unsigned)gx[1] << 16); vx.y = (unsigned)(gx[2] & 0xffff) | ((unsigned)gx[3] << 16);
+                    vy.x = (unsigned)(gy[0] & 0xffff) | ((unsigned)gy[1] << 16); vy.y = (unsigned)(gy[2] & 0xffff) | ((unsigned)gy[3] << 16);
+                    *(uint2*)(ox + o) = vx;
+                    *(uint2*)(oy + o) = vy;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (x0 + j < w) { ox[o + j] = (short)gx[j]; oy[o + j] = (short)gy[j]; }
+                }
+            }
+        }
+    }
 }
 
 // ---------------- LSD ll_angle: gradient, level-line angle, component label init ----------------
@@ -146,47 +252,83 @@ k_sobel3(const uint8_t* __restrict__ src, size_t sframe, int spitch, int w, int 
 // accumulates) and label = first pixel of the pixel's horizontal run inside its 32-px row segment.
 // mask holds one bit per pixel (one word per warp: 32 consecutive pixels of a row); it is what the CCL and key
 // kernels test, so they skip empty segments without touching the per-pixel arrays.
-__global__ void __launch_bounds__(256)
-k_lsd_grad(const uint8_t* __restrict__ img, size_t iframe, int ipitch, int w, int h, int qthr,
+// Layout: every per-pixel array has P = w rounded up to 4 columns per row (the pad columns are NOTDEF), so a thread
+// handles four adjacent pixels with one 32-bit load per image row and one 16-byte store of the angles.
+// block = (32, 4): a warp covers 128 pixels (four mask words) of one row.
+__global__ void __launch_bounds__(128)
+k_lsd_grad(const uint8_t* __restrict__ img, size_t iframe, int ipitch, int w, int P, int h, int qthr,
            int* __restrict__ q, float* __restrict__ fa, int* __restrict__ label,
            unsigned* __restrict__ mask, int mw, int* __restrict__ maxq)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const int lane = threadIdx.x;
+    const int x0 = (blockIdx.x * 32 + lane) * 4, y = blockIdx.y * 4 + threadIdx.y;
     const int f = blockIdx.z;
-    int myq = -1;
-    bool def = false;
-    const size_t o = (size_t)f * w * h + (size_t)y * w + x;
-    int gx = 0, gy = 0;
-    if (x < w - 1 && y < h - 1) {
-        const uint8_t* r0 = img + (size_t)f * iframe + (size_t)y * ipitch + x;
-        const uint8_t* r1 = r0 + ipitch;
-        const int DA = r1[1] - r0[0], BC = r0[1] - r1[0];
-        gx = DA + BC; gy = DA - BC;
-        myq = gx * gx + gy * gy;
-        def = myq > qthr;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, def);
-    if (y < h) {
-        if (threadIdx.x == 0) mask[((size_t)f * h + y) * mw + blockIdx.x] = m;
-        if (x < w) {
-            float a = LSD_NOTDEF;
-            if (def) {
-                a = plf_fast_atan2((float)gx, (float)(-gy));
-                q[o] = myq;     // (cos / sin of the angle are filled in densely by k_lsd_cid after the sort)
-                // head of the run of defined pixels this lane belongs to (inside the warp's segment)
-                const unsigned below = ~m & ((1u << threadIdx.x) - 1u);
-                const int head = below ? 32 - __clz((int)below) : 0;
-                label[o] = y * w + blockIdx.x * 32 + head;
-            }
-            fa[o] = a;
+    const unsigned FULL = 0xffffffffu;
+    if (y >= h) return;                                   // warp-uniform
+    const uint8_t* r0 = img + (size_t)f * iframe + (size_t)y * ipitch;
+    const uint8_t* r1 = r0 + ipitch;
+    // five pixels of both rows: x0 .. x0 + 4 (the fifth comes from the next lane's word)
+    unsigned a = 0, b = 0, a4 = 0, b4 = 0;
+    const bool rows_ok = y < h - 1;
+    if (rows_ok && x0 < w) {
+        if (((((size_t)img) | (size_t)ipitch | iframe) & 3) == 0 && x0 + 4 <= ipitch) {
+            a = *(const unsigned*)(r0 + x0);
+            b = *(const unsigned*)(r1 + x0);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (x0 + j < w) { a |= (unsigned)r0[x0 + j] << (8 * j); b |= (unsigned)r1[x0 + j] << (8 * j); }
         }
     }
-    if (!def) myq = -1;
-    // block max of q over defined pixels -> one atomic per warp
-    if (m) {
+    a4 = __shfl_down_sync(FULL, a, 1) & 0xffu;
+    b4 = __shfl_down_sync(FULL, b, 1) & 0xffu;
+    if (lane == 31 && rows_ok && x0 + 4 < w) { a4 = r0[x0 + 4]; b4 = r1[x0 + 4]; }
+    int pa[5], pb[5];
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) myq = max(myq, __shfl_xor_sync(0xffffffffu, myq, s));
-        if (threadIdx.x == 0) atomicMax(&maxq[f], myq);
+    for (int j = 0; j < 4; j++) { pa[j] = (int)((a >> (8 * j)) & 0xffu); pb[j] = (int)((b >> (8 * j)) & 0xffu); }
+    pa[4] = (int)a4; pb[4] = (int)b4;
+    int gx[4], gy[4], qq[4];
+    unsigned nib = 0;
+    int myq = -1;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int DA = pb[j + 1] - pa[j], BC = pa[j + 1] - pb[j];
+        gx[j] = DA + BC; gy[j] = DA - BC;
+        qq[j] = gx[j] * gx[j] + gy[j] * gy[j];
+        const bool def = rows_ok && x0 + j < w - 1 && qq[j] > qthr;
+        if (def) { nib |= 1u << j; myq = max(myq, qq[j]); }
+    }
+    // the mask word of this lane's 32-px segment: nibbles of its eight lanes
+    unsigned m = nib << (4 * (lane & 7));
+    m |= __shfl_xor_sync(FULL, m, 1);
+    m |= __shfl_xor_sync(FULL, m, 2);
+    m |= __shfl_xor_sync(FULL, m, 4);
+    const int seg = blockIdx.x * 4 + (lane >> 3);
+    if ((lane & 7) == 0 && seg < mw) mask[((size_t)f * h + y) * mw + seg] = m;
+    if (x0 < P) {
+        const size_t o = (size_t)f * P * h + (size_t)y * P + x0;
+        float4 ang = make_float4(LSD_NOTDEF, LSD_NOTDEF, LSD_NOTDEF, LSD_NOTDEF);
+        if (nib) {
+            float* av = &ang.x;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if ((nib >> j) & 1u) {
+                    av[j] = plf_fast_atan2((float)gx[j], (float)(-gy[j]));
+                    q[o + j] = qq[j];     // (cos / sin of the angle are filled in densely by k_lsd_cid after the sort)
+                    // head of the run of defined pixels this pixel belongs to (inside its 32-px segment)
+                    const int bit = 4 * (lane & 7) + j;
+                    const unsigned below = ~m & ((1u << bit) - 1u);
+                    const int head = below ? 32 - __clz((int)below) : 0;
+                    label[o + j] = y * P + seg * 32 + head;
+                }
+        }
+        *(float4*)(fa + o) = ang;
+    }
+    // frame maximum of q over defined pixels -> one atomic per warp that has any
+    if (__any_sync(FULL, nib != 0)) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) myq = max(myq, __shfl_xor_sync(FULL, myq, s));
+        if (lane == 0) atomicMax(&maxq[f], myq);
     }
 }
 
@@ -422,7 +564,7 @@ k_lsd_grow(const unsigned long long* __restrict__ keys, int n, const int2* __res
 // `used` is a shared-memory bitmap indexed by the pixel's position in the sorted seed list (`cid`, written
 // into the label array after the sort), so the angle / cos-sin arrays stay read-only and L1-resident.
 // ------------------------------------------------------------------------------------------------
-#define WARPGROW_MAXC (512 * 1024)          // component pixels one CTA can track (64 KB of used bits)
+#define WARPGROW_MAXC (256 * 1024)          // component pixels one warp can track (32 KB of used bits; four warps per CTA)
 #define WG_RING 1024                        // queue entries kept in shared memory
 
 // after the sort: the sorted position of every defined pixel (its compact index inside the component), and -- one
@@ -506,18 +648,23 @@ __device__ __forceinline__ double wg_ntheta(double reg_angle, double a)
 // iteration falls back to one acceptance per round.
 // The loads of the NEXT iteration's candidates are issued before this iteration's tests (their used bits are
 // checked when they are consumed), which hides the L2 round trip behind the arithmetic.
+// CTAs hold WG_WARPS independent warps (one component each): an SM has only 32 CTA slots, and one-warp CTAs of a few
+// concurrent launches (one per line context) would take them all and starve every other kernel on the device.
 #define WG_E 4
-__global__ void __launch_bounds__(32)
+#define WG_WARPS 4
+__global__ void __launch_bounds__(32 * WG_WARPS)
 k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restrict__ comp, const int* __restrict__ bcount,
                 const float* __restrict__ fa, const float2* __restrict__ cs, const int* __restrict__ cid, int w, int h,
                 double prec, int min_reg_size, int* __restrict__ regpts, LsdRegion* __restrict__ regions,
                 int* __restrict__ nregions, int regcap, int kb, int maxc)
 {
     PLF_DYN_SMEM(smem);
-    unsigned* used = (unsigned*)smem;
-    __shared__ int ring[WG_RING];
-    __shared__ float2 acc[32];
-    const int lane = threadIdx.x;
+    __shared__ int s_ring[WG_WARPS][WG_RING];
+    __shared__ float2 s_acc[WG_WARPS][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned* used = (unsigned*)smem + (size_t)wid * (maxc >> 5);
+    int* ring = s_ring[wid];
+    float2* acc = s_acc[wid];
     const unsigned FULL = 0xffffffffu;
     int nbig = 0;
     for (int k = LSD_BIG_BUCKET; k < LSD_NBUCKET; k++) nbig += bcount[k];
@@ -527,7 +674,7 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
     const int gdx = (nbr % 3) - 1, gdy = (nbr / 3) - 1;
     const bool fast_ok = prec < 1.4;
     const float sphi = (float)sin(prec + 0.1) * 1.05f;   // 1.05 covers the float rounding of this product and of rsqrtf below
-    for (int c = blockIdx.x; c < nbig; c += gridDim.x) {
+    for (int c = blockIdx.x * WG_WARPS + wid; c < nbig; c += gridDim.x * WG_WARPS) {
         const int start = comp[c].x, C = comp[c].y, end = start + C;
         if (C > maxc) continue;   // handled by k_lsd_grow
         const size_t foff = (size_t)LSD_KEY_FRAME(keys[start]) * px;

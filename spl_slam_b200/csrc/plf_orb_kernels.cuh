@@ -54,9 +54,9 @@ k_resize_linear(const uint8_t* __restrict__ src, size_t srcFrameStride, int spit
 // (src/ORBextractor.cc:1086).  One CTA = 128 x 32 output tile of one level of one frame.
 // ------------------------------------------------------------------------------------------------
 #define BLUR_TW 128
-#define BLUR_TH 32
+#define BLUR_TH 35           // a multiple of the 7-row register window
 #define BLUR_WARPS 4
-// one WARP per 128 x 32 tile (lane = 4-px column strip, see plf_blur_strip); tiles of all levels in one launch
+// one WARP per 128 x 35 tile (lane = 4-px column strip, see plf_blur_strip); tiles of all levels in one launch
 __global__ void __launch_bounds__(32 * BLUR_WARPS, 8)
 k_blur7(OrbGeom g, OrbPtrs p)
 {

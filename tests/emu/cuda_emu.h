@@ -45,6 +45,7 @@ static inline uint2 make_uint2(unsigned a, unsigned b) { uint2 r = {a, b}; retur
 static inline int2 make_int2(int a, int b) { int2 r = {a, b}; return r; }
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 r = {a, b, c, d}; return r; }
 static inline float2 make_float2(float a, float b) { float2 r = {a, b}; return r; }
+static inline float4 make_float4(float a, float b, float c, float d) { float4 r = {a, b, c, d}; return r; }
 
 extern thread_local uint3_ threadIdx, blockIdx;
 extern thread_local dim3 blockDim, gridDim;
