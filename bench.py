@@ -203,10 +203,10 @@ def main():
     dev = local_rank
     from concurrent.futures import ThreadPoolExecutor
     NO = args.orb_contexts if B % (2 * args.orb_contexts) == 0 else 1
-    ctx_os = [S.Context(dev) for _ in range(NO)]    # ORB streams
+    ctx_os = [S.Context(dev, priority=-1) for _ in range(NO)]    # ORB streams: filler priority, run one step ahead of the lines
     ctx_o = ctx_os[0]
     NL = args.line_contexts if B % (2 * args.line_contexts) == 0 else 1
-    ctx_ls = [S.Context(dev) for _ in range(NL)]   # line streams: the region-growing chain of one sub-batch overlaps
+    ctx_ls = [S.Context(dev, priority=1) for _ in range(NL)]   # line streams (their chains set the step time): the region-growing chain of one sub-batch overlaps
     lib = ctx_o.lib                                 # the bandwidth-bound kernels of the others
     orbs = [S.ORBextractor(ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"], ctx=c) for c in ctx_os]
     orb = orbs[0]
@@ -248,10 +248,10 @@ def main():
                                                               d_mid[s].data_ptr(), d_ld[s].data_ptr(), capl, d_nl[s].data_ptr()))
 
     def dev_line_steps(i, nsteps):
-        for _ in range(nsteps):
-            if i == 0:
-                dev_orb()      # the ORB launches of a step are issued as the first line instance enters that step, so ORB work
-            dev_line(i)        # keeps filling the gaps the line path leaves (host syncs, region-growing chains) in every step
+        for k in range(nsteps):
+            if i == 0 and k + 1 < nsteps:
+                dev_orb()      # ORB launches of step k + 1 (low-priority streams): filler for the gaps the line path leaves
+            dev_line(i)        # (host syncs, phases where only region-growing chains are running)
 
     def run_device(nsteps):
         """nsteps steps back to back: every extractor instance (own stream + host thread) walks through its share of each
@@ -259,6 +259,7 @@ def main():
         LBD) overlaps the start of the next, as it does in a running system.  Returns the device time in ms."""
         torch.cuda.synchronize()
         ctx_o.timer_start()
+        dev_orb()                                                            # ORB of step 0
         futs = [pool.submit(dev_line_steps, i, nsteps) for i in range(NL)]   # line calls contain stream syncs: one host thread each
         for f in futs:
             f.result()
@@ -283,10 +284,10 @@ def main():
             e2e_orb(i)
 
     def e2e_line_steps(i, nsteps, gates):
-        for _ in range(nsteps):
-            if i == 0:
+        for k in range(nsteps):
+            if i == 0 and k + 1 < nsteps:
                 for g_ in gates:
-                    g_.release()
+                    g_.release()   # ORB instances may start step k + 1 (they run one step ahead, as in run_device)
             e2e_line(i)
 
     def run_e2e(nsteps):
@@ -295,7 +296,7 @@ def main():
         reference's ORB thread and line thread (Frame.cc:301-304)."""
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        gates = [threading.Semaphore(0) for _ in range(NO)]
+        gates = [threading.Semaphore(1) for _ in range(NO)]   # step 0 is free to start
         futs = [pool.submit(e2e_orb_steps, i, nsteps, gates[i]) for i in range(NO)] + [pool.submit(e2e_line_steps, i, nsteps, gates) for i in range(NL)]
         for f in futs:
             f.result()
@@ -315,16 +316,34 @@ def main():
     nk = d_nk.cpu().numpy(); nl = d_nl.cpu().numpy()
     assert (nk > 0).all() and (nl >= 0).all(), "extraction reported an overflow"
 
-    if os.environ.get("PLF_PROF_CONCURRENT"):   # diagnostic: per-kernel event times while all streams run together
+    if os.environ.get("PLF_PROF_CONCURRENT"):   # diagnostic: kernel timeline while all streams run together
         for c in ctx_os + ctx_ls:
             c.profile_enable(True)
-        t_conc = run_device(2) / 2
-        conc = {}
-        for c in ctx_os + ctx_ls:
-            for k, v in c.profile_report().items():
-                conc[k] = conc.get(k, 0.0) + v[0] / 2
+        nst = 3
+        t_conc = run_device(nst) / nst
+        ivs = []
+        for ci, c in enumerate(ctx_os + ctx_ls):
+            for name, t0, t1 in c.profile_timeline(ctx_o):
+                ivs.append((t0, t1, name, ci))
             c.profile_enable(False)
-        print("concurrent step %.1f ms; kernel ms under concurrency: %s" % (t_conc, {k: round(v, 2) for k, v in sorted(conc.items(), key=lambda kv: -kv[1])}), file=sys.stderr)
+
+        def union(iv):
+            tot, cur0, cur1 = 0.0, None, None
+            for a, b in sorted(iv):
+                if cur1 is None or a > cur1:
+                    if cur1 is not None:
+                        tot += cur1 - cur0
+                    cur0, cur1 = a, b
+                else:
+                    cur1 = max(cur1, b)
+            return tot + ((cur1 - cur0) if cur1 is not None else 0.0)
+        thr = [(a, b) for a, b, n, ci in ivs if n != "k_lsd_grow_warp"]
+        allk = [(a, b) for a, b, n, ci in ivs]
+        print("concurrent: %.1f ms/step; busy with any kernel %.1f ms/step; busy with a kernel other than grow_warp %.1f ms/step" %
+              (t_conc, union(allk) / nst, union(thr) / nst), file=sys.stderr)
+        with open(os.path.join(ROOT, "gpurun_out", "timeline.txt"), "w") as fh:
+            for a, b, n, ci in sorted(ivs):
+                fh.write("%.3f %.3f %d %s\n" % (a, b, ci, n))
     # ---- per-kernel times for the roofline (separate profiled steps, CUDA events per launch) ----
     for c in ctx_os + ctx_ls:
         c.profile_enable(True)

@@ -58,6 +58,9 @@ typedef struct plf_line plf_line;
  * matchNNR from concurrent std::threads (src/Frame.cc:116-119, :301-304;
  * src/Linematcher.cc:454-457); give each such thread its own context. ---- */
 plf_status plf_ctx_create(int device, plf_ctx** out);
+/* the same with a stream priority: > 0 latency-critical (e.g. the line extractor, whose region-growing chains set the
+ * frame time), < 0 filler work (e.g. ORB extraction of the next batch), 0 default */
+plf_status plf_ctx_create_prio(int device, int priority, plf_ctx** out);
 void plf_ctx_destroy(plf_ctx* ctx);
 const char* plf_last_error(const plf_ctx* ctx);
 plf_status plf_ctx_synchronize(plf_ctx* ctx);
@@ -75,6 +78,9 @@ plf_status plf_ctx_wait(plf_ctx* ctx, plf_ctx* other);
  * kernel name; plf_profile_report writes "name total_ms launches" lines */
 plf_status plf_profile_enable(plf_ctx* ctx, int on);
 plf_status plf_profile_report(plf_ctx* ctx, char* buf, size_t bufsize);
+/* diagnostic: "name start_ms end_ms" lines for the launches recorded since profiling was enabled, relative to the
+ * last plf_timer_start of `ref` (same device); call before plf_profile_report */
+plf_status plf_profile_timeline(plf_ctx* ctx, plf_ctx* ref, char* buf, size_t bufsize);
 
 /* ---- ORB extractor: replaces PL_SLAM::ORBextractor
  * (include/ORBextractor.h:45-113, src/ORBextractor.cc:410-470, :1043-1132) ---- */

@@ -62,6 +62,7 @@ def load(path=None):
     P = C.POINTER
     sig = {
         "plf_ctx_create": (C.c_int, [C.c_int, P(vp)]),
+        "plf_ctx_create_prio": (C.c_int, [C.c_int, C.c_int, P(vp)]),
         "plf_ctx_destroy": (None, [vp]),
         "plf_last_error": (C.c_char_p, [vp]),
         "plf_ctx_synchronize": (C.c_int, [vp]),
@@ -72,6 +73,7 @@ def load(path=None):
         "plf_ctx_wait": (C.c_int, [vp, vp]),
         "plf_profile_enable": (C.c_int, [vp, C.c_int]),
         "plf_profile_report": (C.c_int, [vp, C.c_char_p, C.c_size_t]),
+        "plf_profile_timeline": (C.c_int, [vp, vp, C.c_char_p, C.c_size_t]),
         "plf_orb_create": (C.c_int, [vp, P(OrbParams), P(vp)]),
         "plf_orb_destroy": (None, [vp]),
         "plf_orb_tables": (C.c_int, [vp, f32p, f32p, f32p, f32p, i32p]),
@@ -128,10 +130,10 @@ def _p(a):
 class Context:
     """plf_ctx: one per host thread / stream (the reference's concurrent std::threads each get one)."""
 
-    def __init__(self, device=0, lib=None):
+    def __init__(self, device=0, lib=None, priority=0):
         self.lib = load(lib)
         h = C.c_void_p()
-        st = self.lib.plf_ctx_create(device, C.byref(h))
+        st = self.lib.plf_ctx_create_prio(device, priority, C.byref(h))
         if st != PLF_OK:
             raise PlfError(st, "plf_ctx_create(device=%d) failed: no usable CUDA device (there is no CPU fallback)" % device)
         self.h = h
@@ -168,6 +170,15 @@ class Context:
 
     def profile_enable(self, on=True):
         self.check(self.lib.plf_profile_enable(self.h, 1 if on else 0))
+
+    def profile_timeline(self, ref):
+        buf = C.create_string_buffer(1 << 22)
+        self.check(self.lib.plf_profile_timeline(self.h, ref.h, buf, len(buf)))
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, t0, t1 = line.rsplit(" ", 2)
+            out.append((name, float(t0), float(t1)))
+        return out
 
     def profile_report(self):
         """{kernel name: (total_ms, launches)} accumulated since profile_enable(True)."""

@@ -1,7 +1,9 @@
 // plf_ctx.cu -- context, stream, timer and scratch management for libplf.so.
 #include "plf_common.cuh"
 
-extern "C" plf_status plf_ctx_create(int device, plf_ctx** out)
+// priority: 0 = default, < 0 = lower than default (filler work), > 0 = higher (latency-critical work); mapped onto the
+// device's stream priority range
+extern "C" plf_status plf_ctx_create_prio(int device, int priority, plf_ctx** out)
 {
     if (!out) return PLF_ERR_INVALID;
     *out = nullptr;
@@ -11,14 +13,27 @@ extern "C" plf_status plf_ctx_create(int device, plf_ctx** out)
     plf_ctx* c = (plf_ctx*)calloc(1, sizeof(plf_ctx));
     if (!c) return PLF_ERR_INVALID;
     c->device = device;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+    int lo = 0, hi = 0;   // numerically: lo = least priority (largest value), hi = greatest priority (smallest value)
+#ifndef PLF_EMU
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+#endif
+    const int prio = priority > 0 ? hi : (priority < 0 ? lo : (lo + hi) / 2);
+    cudaError_t e;
+#ifndef PLF_EMU
+    e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio);
+#else
+    (void)prio;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+#endif
+    if (e != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
         free(c);
         return PLF_ERR_CUDA;
     }
     *out = c;
     return PLF_OK;
 }
+
+extern "C" plf_status plf_ctx_create(int device, plf_ctx** out) { return plf_ctx_create_prio(device, 0, out); }
 
 extern "C" void plf_ctx_destroy(plf_ctx* c)
 {
@@ -175,6 +190,29 @@ extern "C" plf_status plf_profile_report(plf_ctx* c, char* buf, size_t bufsize)
         if (n < 0 || (size_t)n >= bufsize - o) return PLF_ERR_CAPACITY;
         o += n;
     }
+    return PLF_OK;
+}
+
+// diagnostic: "name start_ms end_ms" per recorded launch, times relative to `ref`'s last plf_timer_start event
+// (consumes the pending records; call before plf_profile_report)
+extern "C" plf_status plf_profile_timeline(plf_ctx* c, plf_ctx* ref, char* buf, size_t bufsize)
+{
+    if (!c || !ref || !buf || bufsize < 2) return PLF_ERR_INVALID;
+    buf[0] = 0;
+#ifndef PLF_EMU
+    plf_prof_state* p = c->prof;
+    if (!p) return PLF_OK;
+    cudaStreamSynchronize(c->stream);
+    size_t o = 0;
+    for (int i = 0; i < c->prof_n; i++) {
+        float t0 = 0, t1 = 0;
+        if (cudaEventElapsedTime(&t0, ref->ev0, p->ev[i][0]) != cudaSuccess) continue;
+        if (cudaEventElapsedTime(&t1, ref->ev0, p->ev[i][1]) != cudaSuccess) continue;
+        int n = snprintf(buf + o, bufsize - o, "%s %.4f %.4f\n", p->name[i], t0, t1);
+        if (n < 0 || (size_t)n >= bufsize - o) return PLF_ERR_CAPACITY;
+        o += n;
+    }
+#endif
     return PLF_OK;
 }
 

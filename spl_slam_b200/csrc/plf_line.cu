@@ -370,6 +370,9 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
     PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt + CNT_ERR, 0, sizeof(int), st));
     for (int k = 0; k < noct; k++) {
         const int ow = o->ow[k], oh = o->oh[k], sw = o->sw[k], sh = o->sh[k], sp = o->sp[k];
+        // whatever is still queued on this stream (the image upload of a host-buffer call, the previous octave's tail)
+        // finishes before the turn is taken: the lock must not be held across a PCIe transfer
+        PLF_CUDA(ctx, cudaStreamSynchronize(st));
         std::unique_lock<std::mutex> prephase(g_lsd_prephase);
         if (k > 0) {   // computeGaussianPyramid: pyrDown, no pre-blur (LSDDetector_custom.cpp:56-73)
             PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(ow, 128), plf_div_up(oh, 4 * PD_ROWS), nframes), dim3(32, 4), 0, st, (const uint8_t*)o->d_oct[k - 1],
