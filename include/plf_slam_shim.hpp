@@ -103,6 +103,8 @@ public:
 
     std::vector<cv::Mat> mvImagePyramid;
 
+    plf_orb* handle() const { return orb_; }   // for ComputeStereoMatches below (reads the device-resident pyramid)
+
 protected:
     PlfContext ctx_;
     plf_orb* orb_;
@@ -210,8 +212,43 @@ public:
         return n;
     }
 
+    // The data-parallel core of the candidate-list matchers (ORBmatcher::SearchForInitialization / SearchByProjection /
+    // SearchByBoW, Linematcher::SearchForInitialization / SearchByProjection): query q scans candIdx[candOff[q] ..
+    // candOff[q+1]) in order with the reference's `dist < bestDist` / `else if (dist < bestDist2)` rule
+    // (src/ORBmatcher.cc:430-456).  bestIdx / bestDist are nq x 2; candDist (optional) gets every candidate's distance
+    // for the order-dependent greedy steps, which stay in the reference's host code.
+    void candidatesTop2(const cv::Mat& desc1, const cv::Mat& desc2, const std::vector<int>& candOff, const std::vector<int>& candIdx,
+                        std::vector<int>& bestIdx, std::vector<int>& bestDist, std::vector<int>* candDist = nullptr)
+    {
+        bestIdx.assign((size_t)desc1.rows * 2, -1);
+        bestDist.assign((size_t)desc1.rows * 2, -1);
+        if (candDist) candDist->assign(candIdx.size(), -1);
+        if (desc1.rows == 0) return;
+        if ((int)candOff.size() != desc1.rows + 1) throw std::runtime_error("[candidatesTop2] candOff must have rows + 1 entries");
+        ctx_.check(plf_hamming_candidates(ctx_.get(), desc1.data, desc1.rows, desc2.data, desc2.rows, candOff.data(), candIdx.data(),
+                                          bestIdx.data(), bestDist.data(), candDist ? candDist->data() : nullptr));
+    }
+
 private:
     PlfContext ctx_;
 };
+
+// Frame::ComputeStereoMatches (src/Frame.cc:881-1055) for the pair the two extractors processed last: fills mvuRight
+// and mvDepth exactly like the reference (row-band Hamming best-1, 11x11 SAD slide on the extractors' pyramids,
+// parabola sub-pixel, 2.1 x median SAD filter).  mb = baseline [m], mbf = baseline * fx.
+inline void ComputeStereoMatches(const ORBextractor& left, const ORBextractor& right, const std::vector<cv::KeyPoint>& mvKeys,
+                                 const cv::Mat& mDescriptors, const std::vector<cv::KeyPoint>& mvKeysRight,
+                                 const cv::Mat& mDescriptorsRight, float mb, float mbf, std::vector<float>& mvuRight,
+                                 std::vector<float>& mvDepth)
+{
+    const int N = (int)mvKeys.size(), Nr = (int)mvKeysRight.size();
+    mvuRight.assign(N, -1.0f);
+    mvDepth.assign(N, -1.0f);
+    if (N == 0) return;
+    plf_status st = plf_stereo_match(left.handle(), 0, right.handle(), 0, (const plf_keypoint*)mvKeys.data(), mDescriptors.data, N,
+                                     (const plf_keypoint*)mvKeysRight.data(), mDescriptorsRight.data, Nr, mb, mbf, mvuRight.data(),
+                                     mvDepth.data());
+    if (st != PLF_OK) throw std::runtime_error("plf: ComputeStereoMatches failed");
+}
 
 }  // namespace PL_SLAM

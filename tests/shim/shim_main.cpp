@@ -32,6 +32,17 @@ int main(int argc, char** argv)
     std::vector<cv::KeyPoint> k2(3);
     cv::Mat e, d2;
     orb(e, mask, k2, d2);
+    // stereo: right image = left shifted by 9 px; a second extractor instance, as in Frame.cc:116-119
+    std::vector<unsigned char> rimg((size_t)W * H);
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) rimg[(size_t)y * W + x] = img[(size_t)y * W + (x + 9) % W];
+    cv::Mat imR(H, W, CV_8UC1, rimg.data());
+    PL_SLAM::ORBextractor orbR(500, 1.2f, 6, 20, 7);
+    std::vector<cv::KeyPoint> kpsR;
+    cv::Mat descR;
+    orbR(imR, mask, kpsR, descR);
+    std::vector<float> uRight, depth;
+    PL_SLAM::ComputeStereoMatches(orb, orbR, kps, desc, kpsR, descR, 0.11f, 0.11f * 435.2f, uRight, depth);
     FILE* o = fopen(argv[4], "wb");
     int hdr[8] = {(int)kps.size(), (int)kl.size(), nm, d01, (int)k2.size(), orb.GetLevels(), orb.mvImagePyramid[1].cols, orb.mvImagePyramid[1].rows};
     fwrite(hdr, sizeof(int), 8, o);
@@ -40,6 +51,8 @@ int main(int argc, char** argv)
     fwrite(kl.data(), sizeof(PL_SLAM::KeyLine), kl.size(), o);
     fwrite(ld.data, 32, kl.size(), o);
     fwrite(m12.data(), sizeof(int), m12.size(), o);
+    fwrite(uRight.data(), sizeof(float), uRight.size(), o);
+    fwrite(depth.data(), sizeof(float), depth.size(), o);
     fclose(o);
     printf("shim ok: %zu keypoints, %zu lines, %d self-matches\n", kps.size(), kl.size(), nm);
     return 0;

@@ -38,7 +38,9 @@ def test_shim_results_match_oracle(tmp_path, oracle):
     desc = np.frombuffer(buf, np.uint8, nk * 32, off).reshape(nk, 32); off += nk * 32
     kl = np.frombuffer(buf, oracle.KEYLINE_DTYPE, nl, off); off += nl * 68
     ld = np.frombuffer(buf, np.uint8, nl * 32, off).reshape(nl, 32); off += nl * 32
-    m12 = np.frombuffer(buf, np.int32, nk, off)
+    m12 = np.frombuffer(buf, np.int32, nk, off); off += nk * 4
+    uR = np.frombuffer(buf, np.float32, nk, off); off += nk * 4
+    dep = np.frombuffer(buf, np.float32, nk, off)
     ok, od = oracle.ORBextractor(500, 1.2, 6, 20, 7)(img)
     assert nk == len(ok) and np.array_equal(kps.view(np.uint8), ok.view(np.uint8)) and np.array_equal(desc, od)
     oK, oM, oD = oracle.line_extract(oracle.line_params(100, 2, 0, 1.1, 0.6, 2.2, 12.5, 1.0, 0.6, 1024, 0.0), img)
@@ -46,4 +48,9 @@ def test_shim_results_match_oracle(tmp_path, oracle):
     om, on = oracle.match_nnr(od, od, 0.9)
     assert nm == on and np.array_equal(m12, om)
     assert d01 == oracle.descriptor_distance(od[0], od[1])
+    oxL = oracle.ORBextractor(500, 1.2, 6, 20, 7); oxR = oracle.ORBextractor(500, 1.2, 6, 20, 7)
+    okL, odL = oxL(img); okR, odR = oxR(np.roll(img, -9, axis=1).copy())
+    ou, oz = oracle.stereo_match(oxL, oxR, okL, odL, okR, odR, np.float32(0.11), np.float32(0.11) * np.float32(435.2))
+    assert (ou >= 0).sum() > 20
+    assert np.array_equal(uR.view(np.uint32), ou.view(np.uint32)) and np.array_equal(dep.view(np.uint32), oz.view(np.uint32))
     assert k2 == 3 and levels == 6 and (p1w, p1h) == (533, 400)    # empty image left the caller's vector untouched
