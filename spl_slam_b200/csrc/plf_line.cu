@@ -8,6 +8,18 @@
 #include <mutex>
 #ifndef PLF_EMU
 #include <cub/device/device_radix_sort.cuh>   // library radix sort (a plain sort, like cuBLAS for a plain GEMM)
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+struct PopcOp {
+    __host__ __device__ int operator()(unsigned v) const
+    {
+#ifdef __CUDA_ARCH__
+        return __popc(v);
+#else
+        return __builtin_popcount(v);
+#endif
+    }
+};
 #endif
 
 #define LINE_MAX_OCT 2
@@ -27,6 +39,7 @@ struct plf_line {
     // workspace
     int ws_w, ws_h, ws_frames;
     int ow[LINE_MAX_OCT], oh[LINE_MAX_OCT], sw[LINE_MAX_OCT], sh[LINE_MAX_OCT], min_reg[LINE_MAX_OCT], kbits[LINE_MAX_OCT];
+    int keybits[LINE_MAX_OCT];
     int sp[LINE_MAX_OCT];   // working width of the scaled octave: sw rounded up to 4 (row pitch of every per-pixel LSD array; the pad columns are NOTDEF)
     uint8_t* d_base;
     uint8_t *d_oct[LINE_MAX_OCT], *d_tmp, *d_scaled;       // images (pitch == width)
@@ -35,6 +48,7 @@ struct plf_line {
     int2* d_comp;
     int *d_q, *d_label, *d_regpts, *d_lineidx, *d_lineidx2, *d_cnt, *d_detcount;
     unsigned* d_mask;       // one bit per scaled pixel: gradient defined
+    int* d_offs;            // inclusive prefix sum of the mask popcounts (+ leading 0)
     double* d_bincoef;      // per frame
     int qthr;               // defined <=> gx^2 + gy^2 > qthr
     float* d_fa;
@@ -220,10 +234,13 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         o->sp[k] = (o->sw[k] + 3) & ~3;
         if ((size_t)o->sp[k] * o->sh[k] > maxpx) maxpx = (size_t)o->sp[k] * o->sh[k];
         if ((size_t)o->sp[k] * o->sh[k] >= (1u << 22)) return plf_fail(ctx, PLF_ERR_INVALID, "scaled octave larger than 4M pixels");
-        o->kbits[k] = 1;
-        while ((1u << o->kbits[k]) < (unsigned)(o->sp[k] * o->sh[k])) o->kbits[k]++;
-        if (52 - 2 * o->kbits[k] < 31 && nframes > (1 << (52 - 2 * o->kbits[k])))
-            return plf_fail(ctx, PLF_ERR_INVALID, "at most %d frames of this size per line batch", 1 << (52 - 2 * o->kbits[k]));
+        int kbv = 1, bbv = 1;
+        while ((1u << kbv) < (unsigned)(o->sp[k] * o->sh[k])) kbv++;
+        while ((1 << bbv) < o->prm.n_bins) bbv++;
+        o->kbits[k] = kbv | (bbv << 8);     // packed key geometry (see plf_line_kernels.cuh)
+        o->keybits[k] = 2 * kbv + bbv;      // key bits below the frame field
+        if (64 - o->keybits[k] < 31 && nframes > (1 << (64 - o->keybits[k])))
+            return plf_fail(ctx, PLF_ERR_INVALID, "at most %d frames of this size per line batch", 1 << (64 - o->keybits[k]));
         const double LOG_NT = 5 * (log10((double)o->sw[k]) + log10((double)o->sh[k])) / 2 + log10(11.0);
         o->min_reg[k] = (int)(size_t)(-LOG_NT / log10(o->prm.ang_th / 180));
         tabCount += (size_t)o->sw[k] + o->sh[k];
@@ -244,7 +261,7 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
     need(o->regcap, 8); need(o->regcap, 8); need(o->regcap, 4); need(o->regcap, 4);
     need(F * noct * LINE_DETCAP, sizeof(plf_keyline));
     need(CNT_MAXQ + F, 4); need(F * noct, 4);
-    need(F * (maxpx / 32 + 8192), 4); need(F, 8);   // mask (rows x ceil(w / 32) words), bin coefficients
+    need(F * (maxpx / 32 + 8192), 4); need(F * (maxpx / 32 + 8192) + 64, 4); need(F, 8);   // mask (rows x ceil(w / 32) words), bin coefficients
 
     PLF_CUDA(ctx, cudaMalloc((void**)&o->d_base, bytes + 4096));
     uint8_t* p = o->d_base;
@@ -275,6 +292,7 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
     o->d_cnt = carve<int>(p, CNT_MAXQ + F);
     o->d_detcount = carve<int>(p, F * noct);
     o->d_mask = carve<unsigned>(p, F * (maxpx / 32 + 8192));
+    o->d_offs = carve<int>(p, F * (maxpx / 32 + 8192) + 64);
     o->d_bincoef = carve<double>(p, F);
     // INTER_LINEAR_EXACT tables
     PLF_CUDA(ctx, cudaMalloc((void**)&o->d_tabs, (tabCount + 1) * sizeof(int2)));
@@ -291,14 +309,21 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
     size_t t1 = 0, t2 = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, t1, o->d_keys, o->d_keys2, (int)o->keycap, 0, 64, ctx->stream);
     cub::DeviceRadixSort::SortPairs(nullptr, t2, o->d_linekey, o->d_linekey2, o->d_lineidx, o->d_lineidx2, o->regcap, 0, 48, ctx->stream);
+    size_t t3 = 0;
+    {
+        cub::TransformInputIterator<int, PopcOp, const unsigned*> it(o->d_mask, PopcOp());
+        cub::DeviceScan::InclusiveSum(nullptr, t3, it, o->d_offs + 1, (int)(F * (maxpx / 32 + 8192)), ctx->stream);
+    }
     o->cubtmp_bytes = t1 > t2 ? t1 : t2;
+    if (t3 > o->cubtmp_bytes) o->cubtmp_bytes = t3;
     PLF_CUDA(ctx, cudaMalloc(&o->d_cubtmp, o->cubtmp_bytes + 256));
 #endif
+    PLF_CUDA(ctx, cudaMemset(o->d_offs, 0, sizeof(int)));
     o->ws_w = w; o->ws_h = h; o->ws_frames = nframes;
     return PLF_OK;
 }
 
-static plf_status sort_keys(plf_line* o, int n)
+static plf_status sort_keys(plf_line* o, int n, int end_bit)
 {
     plf_ctx* ctx = o->ctx;
 #ifdef PLF_EMU
@@ -307,7 +332,7 @@ static plf_status sort_keys(plf_line* o, int n)
 #else
     size_t tb = o->cubtmp_bytes;
     plf_prof_begin(ctx, "cub_radix_sort_keys");
-    cudaError_t e = cub::DeviceRadixSort::SortKeys(o->d_cubtmp, tb, o->d_keys, o->d_keys2, n, 0, 64, ctx->stream);
+    cudaError_t e = cub::DeviceRadixSort::SortKeys(o->d_cubtmp, tb, o->d_keys, o->d_keys2, n, 0, end_bit, ctx->stream);
     plf_prof_end(ctx);
     PLF_CUDA(ctx, e);
 #endif
@@ -405,15 +430,31 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         PLF_CHECK_LAUNCH(ctx);
         PLF_LAUNCH(k_ccl_merge, g2, b2, 0, st, o->d_label, (const unsigned*)o->d_mask, mw, sp, sh);
         PLF_CHECK_LAUNCH(ctx);
-        PLF_LAUNCH(k_lsd_keys, g2, b2, 0, st, (const int*)o->d_label, (const int*)o->d_q, (const unsigned*)o->d_mask, mw,
-                   (const double*)o->d_bincoef, sp, sh, o->prm.n_bins, o->d_keys, o->d_cnt + CNT_NKEYS, (int)o->keycap, o->kbits[k]);
+        // key positions: inclusive scan of the mask popcounts (d_offs[0] = 0 is set once per workspace)
+        const int nwords = nframes * sh * mw;
+#ifdef PLF_EMU
+        { int acc = 0; o->d_offs[0] = 0; for (int i = 0; i < nwords; i++) { acc += __builtin_popcount(o->d_mask[i]); o->d_offs[i + 1] = acc; } }
+#else
+        {
+            size_t tb = o->cubtmp_bytes;
+            cub::TransformInputIterator<int, PopcOp, const unsigned*> it(o->d_mask, PopcOp());
+            plf_prof_begin(ctx, "cub_scan_mask");
+            cudaError_t e = cub::DeviceScan::InclusiveSum(o->d_cubtmp, tb, it, o->d_offs + 1, nwords, st);
+            plf_prof_end(ctx);
+            PLF_CUDA(ctx, e);
+        }
+#endif
+        PLF_LAUNCH(k_lsd_keys, g2, b2, 0, st, (const int*)o->d_label, (const int*)o->d_q, (const unsigned*)o->d_mask, mw, (const int*)o->d_offs,
+                   (const double*)o->d_bincoef, sp, sh, o->prm.n_bins, o->d_keys, (int)o->keycap, o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
         int nkeys = 0;
-        PLF_CUDA(ctx, cudaMemcpyAsync(&nkeys, o->d_cnt + CNT_NKEYS, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PLF_CUDA(ctx, cudaMemcpyAsync(&nkeys, o->d_offs + nwords, sizeof(int), cudaMemcpyDeviceToHost, st));
         PLF_CUDA(ctx, cudaStreamSynchronize(st));
         if (nkeys > (int)o->keycap) return plf_fail(ctx, PLF_ERR_CAPACITY, "LSD key buffer overflow");
         if (nkeys > 0) {
-            plf_status s = sort_keys(o, nkeys);
+            int fbits = 1;
+            while ((1 << fbits) < nframes) fbits++;
+            plf_status s = sort_keys(o, nkeys, o->keybits[k] + fbits > 64 ? 64 : o->keybits[k] + fbits);
             if (s) return s;
             for (int pass = 0; pass < 2; pass++) {
                 PLF_LAUNCH(k_lsd_heads, dim3(plf_div_up(nkeys, 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2, nkeys, o->d_comp,

@@ -17,13 +17,17 @@
 #define LSD_3_2_PI (3 * LSD_PI / 2)
 #define LSD_2PI (2 * LSD_PI)
 
-// key layout (64 bit), kb = bits of a raster index of the scaled octave (<= 22):
-//   frame[63 : 2kb+12] | component root[2kb+11 : kb+12] | (n_bins-1-bin)[kb+11 : kb] | raster index[kb-1 : 0]
-// so a batch can hold 2^(52-2kb) frames (16384 at 752x480, 256 at 1080p).
-#define LSD_KEY_IDX(k) ((int)((k) & ((1ull << kb) - 1)))
-#define LSD_KEY_TAG(k) ((k) >> (kb + 12))
-#define LSD_KEY_FRAME(k) ((int)((k) >> (2 * kb + 12)))
-#define LSD_KEY_BIN(k) ((int)(((k) >> kb) & 0xfffull))
+// key layout (64 bit).  Every kernel receives one packed int `kb` = KB | BB << 8: KB = bits of a raster index of the
+// scaled octave (<= 22), BB = bits of the bin field (ceil(log2(n_bins)), <= 12):
+//   frame | component root [KB bits] | n_bins-1-bin [BB bits] | raster index [KB bits]
+// Keeping the fields as narrow as the problem allows saves radix-sort passes (56 instead of 58 bits at 752x480 with
+// 1024 bins and 256 frames: 7 passes instead of 8).
+#define LSD_KB (kb & 0xff)
+#define LSD_BB (kb >> 8)
+#define LSD_KEY_IDX(k) ((int)((k) & ((1ull << LSD_KB) - 1)))
+#define LSD_KEY_TAG(k) ((k) >> (LSD_KB + LSD_BB))
+#define LSD_KEY_FRAME(k) ((int)((k) >> (2 * LSD_KB + LSD_BB)))
+#define LSD_KEY_BIN(k) ((int)(((k) >> LSD_KB) & ((1ull << LSD_BB) - 1)))
 
 struct GaussQ8 { int ksize; int q[15]; };
 
@@ -397,37 +401,35 @@ k_ccl_merge(int* __restrict__ label, const unsigned* __restrict__ mask, int mw, 
     }
 }
 
-// emit one sort key per defined pixel (root label, bin, raster index); warp-aggregated append.
-// (A CTA-aggregated variant with several rows per thread measured slower: the kernel is bound by the
-// dependent label chases of ccl_find, which want as many independent threads as possible.)
+// emit one sort key per defined pixel (root label, bin, raster index).  Positions come from an inclusive prefix sum of
+// the mask popcounts (offs[i + 1] = number of defined pixels in mask words 0 .. i): no atomics, keys in raster order.
 __global__ void __launch_bounds__(256)
 k_lsd_keys(const int* __restrict__ label, const int* __restrict__ q, const unsigned* __restrict__ mask, int mw,
-           const double* __restrict__ coef, int w, int h, int n_bins, unsigned long long* __restrict__ keys,
-           int* __restrict__ nkeys, int keycap, int kb)
+           const int* __restrict__ offs, const double* __restrict__ coef, int w, int h, int n_bins,
+           unsigned long long* __restrict__ keys, int keycap, int kb)
 {
     const int lane = threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     const int f = blockIdx.z;
     if (y >= h) return;
-    const unsigned m = mask[((size_t)f * h + y) * mw + blockIdx.x];
+    const size_t widx = ((size_t)f * h + y) * mw + blockIdx.x;
+    const unsigned m = mask[widx];
     if (!m) return;
     const bool have = (m >> lane) & 1u;
-    unsigned long long key = 0;
+    // pixels of one run share a label (k_lsd_grad): only the head of each run chases its root, the others take it by shuffle
+    const unsigned below = ~m & ((1u << lane) - 1u);
+    const int head = below ? 32 - __clz((int)below) : 0;
+    int root = -1;
+    if (have && head == lane) root = ccl_find(label + (size_t)f * w * h, y * w + blockIdx.x * 32 + lane);
+    root = __shfl_sync(0xffffffffu, root, head);
     if (have) {
         const int p = y * w + blockIdx.x * 32 + lane;
         const size_t o = (size_t)f * w * h + p;
-        const int root = ccl_find(label + (size_t)f * w * h, p);
         int bin = (int)(sqrt((double)q[o] / 4.0) * coef[f]);
         if (bin < 0) bin = 0;
         if (bin > n_bins - 1) bin = n_bins - 1;
-        key = ((unsigned long long)f << (2 * kb + 12)) | ((unsigned long long)root << (kb + 12)) |
-              ((unsigned long long)(n_bins - 1 - bin) << kb) | (unsigned long long)p;
-    }
-    int base = 0;
-    const int leader = __ffs((int)m) - 1;
-    if (lane == leader) base = atomicAdd(nkeys, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (have) {
-        const int oo = base + __popc(m & ((1u << lane) - 1));
+        const unsigned long long key = ((unsigned long long)f << (2 * LSD_KB + LSD_BB)) | ((unsigned long long)root << (LSD_KB + LSD_BB)) |
+                                       ((unsigned long long)(n_bins - 1 - bin) << LSD_KB) | (unsigned long long)p;
+        const int oo = offs[widx] + __popc(m & ((1u << lane) - 1));
         if (oo < keycap) keys[oo] = key;
     }
 }
@@ -1051,7 +1053,7 @@ __constant__ int c_lbd_comb[32][2] = {
     {2, 3}, {2, 4}, {2, 5}, {2, 6}, {2, 7}, {2, 8}, {3, 4}, {3, 5}, {3, 6}, {3, 7}, {3, 8},
     {4, 5}, {4, 6}, {4, 7}, {4, 8}, {5, 6}, {5, 7}, {5, 8}, {6, 7}, {6, 8}, {7, 8}};
 
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, 16)
 k_lbd(const plf_keyline* __restrict__ kl, const int* __restrict__ nlines, int cap, LbdImages im, LbdCoefs cf,
       uint8_t* __restrict__ desc, float* __restrict__ fdesc)
 {

@@ -4,7 +4,7 @@
 #pragma once
 #include "plf_orb.cuh"
 
-__device__ const signed char d_orb_pattern[1024] = {
+__device__ __align__(16) const signed char d_orb_pattern[1024] = {
 #include "orb_pattern.inc"
 };
 
@@ -622,7 +622,15 @@ k_describe(OrbGeom g, OrbPtrs p, plf_keypoint* __restrict__ kps, uint8_t* __rest
     const float ang = angle * factorPI;
     const float a = (float)cos((double)ang), b = (float)sin((double)ang);
     const uint8_t* center = p.blr[l] + (size_t)f * L.frameBytes + (size_t)Y * L.pitch + X;
-    const signed char* pat = d_orb_pattern + lane * 32;
+    // the lane's 16 point pairs (32 signed bytes) as two 16-byte loads
+    signed char pat[32];
+    {
+        const int4* pp = (const int4*)(d_orb_pattern + lane * 32);
+        const int4 q0 = pp[0], q1 = pp[1];
+        const int wds[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int i = 0; i < 32; i++) pat[i] = (signed char)((wds[i >> 2] >> (8 * (i & 3))) & 0xff);
+    }
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
