@@ -826,7 +826,9 @@ k_lsd_rect(const LsdRegion* __restrict__ regions, const int* __restrict__ nregio
            const int* __restrict__ q, int w, int h, double prec, double scale, float4* __restrict__ lines,
            unsigned long long* __restrict__ linekey, int* __restrict__ lineidx, int* __restrict__ errflag, int kb)
 {
+    __shared__ double s_buf[RECT_WARPS][32][3];
     const int rr = blockIdx.x * RECT_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    double (*buf)[3] = s_buf[threadIdx.x >> 5];
     const unsigned FULL = 0xffffffffu;
     if (rr >= regcap) return;
     int nr = *nregions;
@@ -848,10 +850,13 @@ k_lsd_rect(const LsdRegion* __restrict__ regions, const int* __restrict__ nregio
             xw = (double)pxx * wgt;
             yw = (double)py * wgt;
         }
-        for (int j = 0; j < cnt; j++) {
-            x += __shfl_sync(FULL, xw, j);
-            y += __shfl_sync(FULL, yw, j);
-            sum += __shfl_sync(FULL, wgt, j);
+        __syncwarp();
+        buf[lane][0] = xw; buf[lane][1] = yw; buf[lane][2] = wgt;
+        __syncwarp();
+        for (int j = 0; j < cnt; j++) {      // ordered replay from shared-memory broadcasts
+            x += buf[j][0];
+            y += buf[j][1];
+            sum += buf[j][2];
         }
     }
     x /= sum; y /= sum;
@@ -868,10 +873,13 @@ k_lsd_rect(const LsdRegion* __restrict__ regions, const int* __restrict__ nregio
             tyy = dx * dx * wgt;
             txy = dx * dy * wgt;
         }
+        __syncwarp();
+        buf[lane][0] = txx; buf[lane][1] = tyy; buf[lane][2] = txy;
+        __syncwarp();
         for (int j = 0; j < cnt; j++) {
-            Ixx += __shfl_sync(FULL, txx, j);
-            Iyy += __shfl_sync(FULL, tyy, j);
-            Ixy -= __shfl_sync(FULL, txy, j);
+            Ixx += buf[j][0];
+            Iyy += buf[j][1];
+            Ixy -= buf[j][2];
         }
     }
     const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));

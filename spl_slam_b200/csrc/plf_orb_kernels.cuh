@@ -207,16 +207,43 @@ k_fast_cells(OrbGeom g, OrbPtrs p, int tp, int rows, int lcap)
     unsigned* out = p.rawkeys + (size_t)blockIdx.y * g.rawPerFrame + L.rawOff;
     for (int pass = 0; pass < 2; pass++) {
         const int th = pass == 0 ? g.iniTh : g.minTh;
-        // (1) compass quick-reject over the interior
+        // (1) compass quick-reject over the interior, four pixels per lane from 32-bit shared-memory words: a lane owns
+        // one aligned word of a row, a warp covers 32 / (words per row) rows per step
         int n1 = 0;
-        for (int ry = 3; ry < ch - 3; ry++)
-            for (int rx0 = 3; rx0 < cw - 3; rx0 += 32) {
-                const int rx = rx0 + lane, o = ry * tp + rx + off;
-                const bool go = rx < cw - 3 && fast_quick(&tile[o], tp, th);
-                const unsigned m = __ballot_sync(FULL, go);
-                if (go) list[n1 + __popc(m & LT)] = (unsigned short)o;
-                n1 += __popc(m);
+        {
+            const int tpw = tp >> 2;
+            const int c0 = 3 + off, c1 = cw - 3 + off;          // interior map columns [c0, c1)
+            const int w0 = c0 >> 2, nwl = ((c1 + 3) >> 2) - w0;  // words per row that hold interior pixels (<= 19)
+            const int rpi = 32 / nwl;                            // rows per step
+            const int lr = lane / nwl, wq = w0 + lane - lr * nwl;
+            const unsigned* T = (const unsigned*)tile;
+            for (int rb = 3; rb < ch - 3; rb += rpi) {
+                const int ry = rb + lr;
+                unsigned go = 0;
+                if (lr < rpi && ry < ch - 3) {
+                    const unsigned C = T[ry * tpw + wq], Lw = T[ry * tpw + wq - 1], Rw = T[ry * tpw + wq + 1];
+                    const unsigned U = T[(ry - 3) * tpw + wq], D = T[(ry + 3) * tpw + wq];
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int col = 4 * wq + b;
+                        const int v = (int)((C >> (8 * b)) & 0xffu);
+                        const int pu = (int)((U >> (8 * b)) & 0xffu), pd = (int)((D >> (8 * b)) & 0xffu);
+                        const int pl = b < 3 ? (int)((Lw >> (8 * (b + 1))) & 0xffu) : (int)(C & 0xffu);
+                        const int pr = b > 0 ? (int)((Rw >> (8 * (b - 1))) & 0xffu) : (int)(C >> 24);
+                        const int d0 = v - pd, d8 = v - pu, d4 = v - pr, d12 = v - pl;
+                        const bool g1 = (d0 > th || d8 > th || d0 < -th || d8 < -th) && (d4 > th || d12 > th || d4 < -th || d12 < -th);
+                        if (g1 && col >= c0 && col < c1) go |= 1u << b;
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const bool g1 = (go >> b) & 1u;
+                    const unsigned m = __ballot_sync(FULL, g1);
+                    if (g1) list[n1 + __popc(m & LT)] = (unsigned short)(ry * tp + 4 * wq + b);
+                    n1 += __popc(m);
+                }
             }
+        }
         __syncwarp();
         // (2) ring + 9-run test, compacted in place (entry: map offset | sides << 14)
         int n2 = 0;
