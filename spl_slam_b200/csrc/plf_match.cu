@@ -6,7 +6,7 @@
 #include "plf_common.cuh"
 
 #define KNN_THREADS 128
-#define KNN_QPT 2           // queries per thread
+#define KNN_QPT 4           // queries per thread
 #define KNN_TILE 256        // train descriptors staged in shared memory per step
 #define KNN_INF 0x7fffffff
 

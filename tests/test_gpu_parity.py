@@ -108,21 +108,22 @@ def test_knn2_and_nnr(S, oracle, gpu_ctx, nq, nt, hi):
         assert np.array_equal(mu, ref) and nu == int((ref >= 0).sum())
 
 
-def test_knn2_large_properties(S, oracle, gpu_ctx):
-    """1e4 x 1e6 (BASELINE config 5): too slow for the scalar oracle in full, so check a query sample against
-    the oracle and the whole result through the shard/merge property (sharded == unsharded)."""
+@pytest.mark.parametrize("nt,nsample,hi", [(1000000, 16, 256), (10000000, 4, 256), (1000000, 8, 2)])
+def test_knn2_large_properties(S, oracle, gpu_ctx, nt, nsample, hi):
+    """1e4 x 1e6 / 1e7 (BASELINE config 5, incl. a tie-heavy variant): too slow for the scalar oracle in full, so check
+    a query sample against the oracle and the whole result through the shard/merge property (sharded == unsharded)."""
     import torch
     rng = np.random.default_rng(1234)
-    nq, nt = 10000, 1000000
-    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
-    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    nq = 10000
+    q = rng.integers(0, hi, (nq, 32), dtype=np.uint8)
+    t = rng.integers(0, hi, (nt, 32), dtype=np.uint8)
     lib, h = gpu_ctx.lib, gpu_ctx.h
     dq = torch.from_numpy(q).cuda(); dt = torch.from_numpy(t).cuda()
     idx = torch.empty((nq, 2), dtype=torch.int32, device="cuda"); dist = torch.empty_like(idx)
     torch.cuda.synchronize()
     gpu_ctx.check(lib.plf_hamming_knn2_device(h, dq.data_ptr(), nq, dt.data_ptr(), nt, 0, idx.data_ptr(), dist.data_ptr()))
     gpu_ctx.synchronize()
-    sample = rng.choice(nq, 16, replace=False)
+    sample = rng.choice(nq, nsample, replace=False)
     oi, od = oracle.knn2(q[sample], t)
     assert np.array_equal(idx.cpu().numpy()[sample], oi) and np.array_equal(dist.cpu().numpy()[sample], od)
     shards = 4
