@@ -339,7 +339,7 @@ static plf_status sort_keys(plf_line* o, int n, int end_bit)
     return PLF_OK;
 }
 
-static plf_status sort_lines(plf_line* o)
+static plf_status sort_lines(plf_line* o, int nframes)
 {
     plf_ctx* ctx = o->ctx;
 #ifdef PLF_EMU
@@ -349,9 +349,12 @@ static plf_status sort_lines(plf_line* o)
     for (int i = 0; i < o->regcap; i++) { o->d_linekey2[i] = v[i].first; o->d_lineidx2[i] = v[i].second; }
 #else
     size_t tb = o->cubtmp_bytes;
-    // padding keys are ~0: sort all 64 bits so they land at the end
+    // line keys use bits [0, 40 + frame bits); padding keys are ~0, i.e. all ones in that range too (one past the last frame),
+    // so sorting just those bits still puts them at the end
+    int fbits = 1;
+    while ((1 << fbits) < nframes + 1) fbits++;
     plf_prof_begin(ctx, "cub_radix_sort_lines");
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(o->d_cubtmp, tb, o->d_linekey, o->d_linekey2, o->d_lineidx, o->d_lineidx2, o->regcap, 0, 64, ctx->stream);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(o->d_cubtmp, tb, o->d_linekey, o->d_linekey2, o->d_lineidx, o->d_lineidx2, o->regcap, 0, 40 + fbits, ctx->stream);
     plf_prof_end(ctx);
     PLF_CUDA(ctx, e);
 #endif
@@ -494,7 +497,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
                    (const int*)(o->d_cnt + CNT_NREG), o->regcap, (const int*)o->d_regpts, (const int*)o->d_q, sp, sh, o->prec, S, o->d_lines,
                    o->d_linekey, o->d_lineidx, o->d_cnt + CNT_ERR, o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
-        plf_status s = sort_lines(o);
+        plf_status s = sort_lines(o, nframes);
         if (s) return s;
         PLF_LAUNCH(k_lsd_keylines, dim3(plf_div_up(o->regcap, 128)), dim3(128), 0, st, (const unsigned long long*)o->d_linekey2,
                    (const int*)o->d_lineidx2, o->regcap, (const float4*)o->d_lines, nframes, k, noct, ow, oh, o->prm.min_line_length,
