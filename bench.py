@@ -344,6 +344,22 @@ def main():
         with open(os.path.join(ROOT, "gpurun_out", "timeline.txt"), "w") as fh:
             for a, b, n, ci in sorted(ivs):
                 fh.write("%.3f %.3f %d %s\n" % (a, b, ci, n))
+    if os.environ.get("PLF_PROF_E2E"):   # diagnostic: kernel timeline of the host-buffer path
+        run_e2e(2)
+        for c in ctx_os + ctx_ls:
+            c.profile_enable(True)
+        ctx_o.timer_start()
+        nst = 3
+        t_conc = run_e2e(nst) / nst
+        ivs = []
+        for ci, c in enumerate(ctx_os + ctx_ls):
+            for name, t0, t1 in c.profile_timeline(ctx_o):
+                ivs.append((t0, t1, name, ci))
+            c.profile_enable(False)
+        with open(os.path.join(ROOT, "gpurun_out", "timeline_e2e.txt"), "w") as fh:
+            for a, b, n, ci in sorted(ivs):
+                fh.write("%.3f %.3f %d %s\n" % (a, b, ci, n))
+        print("e2e profiled: %.1f ms/step" % t_conc, file=sys.stderr)
     # ---- per-kernel times for the roofline (separate profiled steps, CUDA events per launch) ----
     for c in ctx_os + ctx_ls:
         c.profile_enable(True)

@@ -362,6 +362,19 @@ static plf_status sort_lines(plf_line* o, int nframes)
 }
 
 
+// small device -> host reads go through pinned staging: a copy into pageable memory makes the driver wait for the stream
+// inside the call (holding its lock), which stalls the launches of every other context's host thread
+static plf_status read_ints(plf_ctx* ctx, const int* dev, int n, int* host)
+{
+    void* pin;
+    plf_status st = plf_ctx_pinned(ctx, (size_t)(n > 64 ? n : 64) * sizeof(int), &pin);
+    if (st) return st;
+    PLF_CUDA(ctx, cudaMemcpyAsync(pin, dev, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(host, pin, (size_t)n * sizeof(int));
+    return PLF_OK;
+}
+
 // cv::GaussianBlur 8U for a batch: 5 / 7 taps go to the register sliding-window kernel, other sizes to the generic one
 static plf_status gauss_batch(plf_ctx* ctx, const uint8_t* src, uint8_t* dst, int w, int h, int nframes, const GaussQ8& k)
 {
@@ -451,8 +464,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
                    (const double*)o->d_bincoef, sp, sh, o->prm.n_bins, o->d_keys, (int)o->keycap, o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
         int nkeys = 0;
-        PLF_CUDA(ctx, cudaMemcpyAsync(&nkeys, o->d_offs + nwords, sizeof(int), cudaMemcpyDeviceToHost, st));
-        PLF_CUDA(ctx, cudaStreamSynchronize(st));
+        { plf_status rs = read_ints(ctx, o->d_offs + nwords, 1, &nkeys); if (rs) return rs; }
         if (nkeys > (int)o->keycap) return plf_fail(ctx, PLF_ERR_CAPACITY, "LSD key buffer overflow");
         if (nkeys > 0) {
             int fbits = 1;
@@ -471,8 +483,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             PLF_CHECK_LAUNCH(ctx);
             // size the used-bitmap of the warp kernel from the largest component present (bucket counts)
             int bc[LSD_NBUCKET];
-            PLF_CUDA(ctx, cudaMemcpyAsync(bc, o->d_cnt + CNT_BCOUNT, sizeof(bc), cudaMemcpyDeviceToHost, st));
-            PLF_CUDA(ctx, cudaStreamSynchronize(st));
+            { plf_status rs = read_ints(ctx, o->d_cnt + CNT_BCOUNT, LSD_NBUCKET, bc); if (rs) return rs; }
             prephase.unlock();   // everything up to here has finished on the GPU; growing may overlap other contexts
             int topb = 0, nbig = 0;
             for (int b = 0; b < LSD_NBUCKET; b++) { if (bc[b]) topb = b; if (b >= LSD_BIG_BUCKET) nbig += bc[b]; }
@@ -621,8 +632,7 @@ static plf_status check_regions(plf_line* o)
 {
     plf_ctx* ctx = o->ctx;
     int err = 0;
-    PLF_CUDA(ctx, cudaMemcpyAsync(&err, o->d_cnt + CNT_ERR, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    { plf_status rs = read_ints(ctx, o->d_cnt + CNT_ERR, 1, &err); if (rs) return rs; }
     if (err) return plf_fail(ctx, PLF_ERR_CAPACITY, "LSD region buffer overflow (more than %d regions in the batch)", o->regcap);
     return PLF_OK;
 }
@@ -649,10 +659,11 @@ extern "C" plf_status plf_line_extract_batch(plf_line* o, const uint8_t* host_im
     st = line_extract_device_impl(o, nframes, o->d_okl, o->d_omid, o->d_odesc, cap, o->d_onout);
     if (st) return st;
     cudaStream_t s = ctx->stream;
-    PLF_CUDA(ctx, cudaMemcpyAsync(n_out, o->d_onout, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, s));
     PLF_CUDA(ctx, cudaMemcpyAsync(host_kl, o->d_okl, (size_t)nframes * cap * sizeof(plf_keyline), cudaMemcpyDeviceToHost, s));
     if (host_mid) PLF_CUDA(ctx, cudaMemcpyAsync(host_mid, o->d_omid, (size_t)nframes * cap * sizeof(plf_keypoint), cudaMemcpyDeviceToHost, s));
     PLF_CUDA(ctx, cudaMemcpyAsync(host_desc, o->d_odesc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, s));
+    st = read_ints(ctx, o->d_onout, nframes, n_out);       // also completes the result copies above
+    if (st) return st;
     st = check_regions(o);
     if (st) return st;
     return check_counts(ctx, n_out, nframes);
@@ -687,7 +698,8 @@ extern "C" plf_status plf_lsd_detect(plf_line* o, const uint8_t* host_img, int w
     st = line_select(o, 1, false, o->d_okl, nullptr, cap, o->d_onout);
     if (st) return st;
     int32_t n = 0;
-    PLF_CUDA(ctx, cudaMemcpyAsync(&n, o->d_onout, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    st = read_ints(ctx, o->d_onout, 1, &n);
+    if (st) return st;
     st = check_regions(o);
     if (st) return st;
     st = check_counts(ctx, &n, 1);

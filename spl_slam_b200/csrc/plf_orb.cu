@@ -322,7 +322,10 @@ extern "C" plf_status plf_orb_extract_batch(plf_orb* o, const uint8_t* host_imgs
     // level-0 buffer was sized for the aligned pitch, which is at least as large.
     const size_t p0 = (w & 3) ? (size_t)L0.pitch : (size_t)w;
     if (stride == p0 && frame_stride == p0 * h) {
-        PLF_CUDA(ctx, cudaMemcpyAsync(o->lvl_own[0], host_imgs, (size_t)nframes * frame_stride, cudaMemcpyHostToDevice, s));
+        // in pieces of 16 MB, so that transfers queued by other (higher-priority) contexts can slip in between
+        const size_t total = (size_t)nframes * frame_stride, piece = (size_t)16 << 20;
+        for (size_t off = 0; off < total; off += piece)
+            PLF_CUDA(ctx, cudaMemcpyAsync(o->lvl_own[0] + off, host_imgs + off, total - off < piece ? total - off : piece, cudaMemcpyHostToDevice, s));
     } else {
         for (int f = 0; f < nframes; f++)
             PLF_CUDA(ctx, cudaMemcpy2DAsync(o->lvl_own[0] + (size_t)f * p0 * h, p0, host_imgs + (size_t)f * frame_stride,
@@ -330,10 +333,14 @@ extern "C" plf_status plf_orb_extract_batch(plf_orb* o, const uint8_t* host_imgs
     }
     st = orb_run(o, o->lvl_own[0], p0, p0 * h, nframes, o->d_kps, o->d_desc, cap, o->d_nout);
     if (st) return st;
-    PLF_CUDA(ctx, cudaMemcpyAsync(n_out, o->d_nout, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, s));
+    void* pin;   // the counts go through pinned staging (a copy into pageable memory stalls the other contexts' host threads)
+    st = plf_ctx_pinned(ctx, (size_t)nframes * sizeof(int), &pin);
+    if (st) return st;
+    PLF_CUDA(ctx, cudaMemcpyAsync(pin, o->d_nout, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, s));
     PLF_CUDA(ctx, cudaMemcpyAsync(host_kps, o->d_kps, (size_t)nframes * cap * sizeof(plf_keypoint), cudaMemcpyDeviceToHost, s));
     PLF_CUDA(ctx, cudaMemcpyAsync(host_desc, o->d_desc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, s));
     PLF_CUDA(ctx, cudaStreamSynchronize(s));
+    memcpy(n_out, pin, (size_t)nframes * sizeof(int));
     for (int f = 0; f < nframes; f++) {
         if (n_out[f] == -1) return plf_fail(ctx, PLF_ERR_CAPACITY, "frame %d: internal key/node list overflow", f);
         if (n_out[f] == -2) return plf_fail(ctx, PLF_ERR_CAPACITY, "frame %d: output capacity %d too small (use plf_orb_max_keypoints)", f, cap);
