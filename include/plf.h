@@ -216,6 +216,35 @@ plf_status plf_hamming_candidates_device(plf_ctx* ctx, const uint8_t* dev_q, int
                                          const int32_t* dev_cand_off, const int32_t* dev_cand_idx,
                                          int32_t* dev_best_idx, int32_t* dev_best_dist, int32_t* dev_cand_dist);
 
+/* ---- feature grid and area queries: Frame::AssignFeaturesToGrid / AssignFeaturesToGridLines with PosInGrid /
+ * PosInGridLines (src/Frame.cc:365-399, :677-722) and Frame::GetFeaturesInArea / GetFeaturesInAreaLines (:562-676).
+ * The queries return CSR candidate lists in the reference's order (cell column outer, cell row inner, insertion
+ * order inside a cell) -- the input of plf_hamming_candidates[_device].  Reference grids: 64 x 48 for points,
+ * 16 x 12 for lines; inv_w = cols / (mnMaxX - mnMinX), inv_h = rows / (mnMaxY - mnMinY) (src/Frame.cc:139-140). ---- */
+typedef struct {
+    int32_t cols, rows;
+    float min_x, min_y, inv_w, inv_h;
+} plf_grid_params;
+/* one grid per frame of a batch: dev_kps is [frame][cap] (for lines: the mid-point keypoints, and dev_kls [frame][cap]
+ * the keylines whose end points must lie inside the grid too; NULL for points), dev_n [frame]; outputs dev_cell_start
+ * [frame][cols*rows+1] (cell = column * rows + row), dev_cell_items [frame][cap] (feature indices, ascending inside a
+ * cell), dev_feat_cell [frame][cap] (cell of each feature, -1 = outside) */
+plf_status plf_grid_build_device(plf_ctx* ctx, const plf_keypoint* dev_kps, const plf_keyline* dev_kls, const int32_t* dev_n,
+                                 int nframes, int cap, const plf_grid_params* g, int32_t* dev_cell_start,
+                                 int32_t* dev_cell_items, int32_t* dev_feat_cell);
+/* GetFeaturesInArea(x, y, r, minLevel, maxLevel) for nq queries against ONE frame's grid (pass that frame's slices);
+ * dev_qminl / dev_qmaxl may be NULL (= -1, no level check).  dev_cand_off gets nq + 1 offsets, dev_cand_idx the
+ * feature indices; *total = number of candidates (PLF_ERR_CAPACITY if it exceeds cand_cap). */
+plf_status plf_grid_query_device(plf_ctx* ctx, const plf_keypoint* dev_kps, const plf_grid_params* g,
+                                 const int32_t* dev_cell_start, const int32_t* dev_cell_items, const float* dev_qx,
+                                 const float* dev_qy, const float* dev_qr, const int32_t* dev_qminl, const int32_t* dev_qmaxl,
+                                 int nq, int32_t* dev_cand_off, int32_t* dev_cand_idx, int cand_cap, int* total);
+/* host buffers, one frame: build + query in one call */
+plf_status plf_grid_candidates(plf_ctx* ctx, const plf_keypoint* host_kps, const plf_keyline* host_kls, int n,
+                               const plf_grid_params* g, const float* host_qx, const float* host_qy, const float* host_qr,
+                               const int32_t* host_qminl, const int32_t* host_qmaxl, int nq, int32_t* host_cand_off,
+                               int32_t* host_cand_idx, int cand_cap, int* total);
+
 /* ---- stereo: replaces Frame::ComputeStereoMatches (src/Frame.cc:881-1055).  Reads the pyramids the two
  * extractors hold after their last extraction (the reference reads mpORBextractorLeft/Right->mvImagePyramid),
  * so `left` / `right` must have processed the pair's images (the same extractor with two frames of one batch is

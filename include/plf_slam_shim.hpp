@@ -229,6 +229,29 @@ public:
                                           bestIdx.data(), bestDist.data(), candDist ? candDist->data() : nullptr));
     }
 
+    // Frame::AssignFeaturesToGrid + GetFeaturesInArea (src/Frame.cc:365-378, :562-617) for many queries at once: the
+    // candidate lists (CSR, the reference's vIndices order) that candidatesTop2 scans.  grid: 64 x 48 cells over
+    // [mnMinX, mnMaxX) x [mnMinY, mnMaxY), inv_w = cols / (mnMaxX - mnMinX).  minLevel / maxLevel may be empty (= -1).
+    void featuresInArea(const std::vector<cv::KeyPoint>& keysUn, const plf_grid_params& grid, const std::vector<float>& x,
+                        const std::vector<float>& y, const std::vector<float>& r, const std::vector<int>& minLevel,
+                        const std::vector<int>& maxLevel, std::vector<int>& candOff, std::vector<int>& candIdx)
+    {
+        const int nq = (int)x.size();
+        candOff.assign((size_t)nq + 1, 0);
+        if (candIdx.size() < (size_t)nq * 32 + 1) candIdx.resize((size_t)nq * 32 + 1);
+        for (;;) {
+            int total = 0;
+            plf_status st = plf_grid_candidates(ctx_.get(), (const plf_keypoint*)keysUn.data(), nullptr, (int)keysUn.size(), &grid, x.data(),
+                                                y.data(), r.data(), minLevel.empty() ? nullptr : minLevel.data(),
+                                                maxLevel.empty() ? nullptr : maxLevel.data(), nq, candOff.data(), candIdx.data(),
+                                                (int)candIdx.size(), &total);
+            if (st == PLF_ERR_CAPACITY && total > (int)candIdx.size()) { candIdx.resize((size_t)total); continue; }
+            ctx_.check(st);
+            candIdx.resize((size_t)total);
+            return;
+        }
+    }
+
 private:
     PlfContext ctx_;
 };

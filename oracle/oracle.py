@@ -63,6 +63,7 @@ def lib():
         L.orc_orb_level_raw_count.argtypes = [vp, C.c_int]
         L.orc_orb_level_raw.argtypes = [vp, C.c_int, i32p, i32p, i32p]
         L.orc_orb_level_kept_count.argtypes = [vp, C.c_int]
+        L.orc_grid_candidates.argtypes = [vp, vp, C.c_int, vp, f32p, f32p, f32p, i32p, i32p, C.c_int, i32p, i32p, C.c_int]
         L.orc_stereo_match.argtypes = [vp, vp, vp, u8p, C.c_int, vp, u8p, C.c_int, C.c_float, C.c_float, f32p, f32p]
         L.orc_distribute_octree.argtypes = [i32p, i32p, i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_int, i32p, C.c_int]
@@ -246,6 +247,33 @@ def stereo_match(orbL, orbR, kL, dL, kR, dR, mb, mbf):
     u = np.empty(len(kL), np.float32); z = np.empty(len(kL), np.float32)
     lib().orc_stereo_match(orbL._h, orbR._h, _p(kL), _p(dL), len(kL), _p(kR), _p(dR), len(kR), mb, mbf, _p(u), _p(z))
     return u, z
+
+
+class GridParams(C.Structure):
+    _fields_ = [("cols", C.c_int32), ("rows", C.c_int32), ("min_x", C.c_float), ("min_y", C.c_float),
+                ("inv_w", C.c_float), ("inv_h", C.c_float)]
+
+
+def grid_params(cols, rows, min_x, max_x, min_y, max_y):
+    """mfGridElementWidthInv = cols / (mnMaxX - mnMinX) in float (src/Frame.cc:139-140)."""
+    f = np.float32
+    return GridParams(cols, rows, f(min_x), f(min_y), f(cols) / (f(max_x) - f(min_x)), f(rows) / (f(max_y) - f(min_y)))
+
+
+def grid_candidates(kps, g, qx, qy, qr, qminl=None, qmaxl=None, keylines=None):
+    """Frame::AssignFeaturesToGrid[Lines] + GetFeaturesInArea[Lines] (src/Frame.cc:365-399, :562-722) -> (cand_off, cand_idx)."""
+    kps = np.ascontiguousarray(kps, KEYPOINT_DTYPE)
+    kls = None if keylines is None else np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+    qx = np.ascontiguousarray(qx, np.float32); qy = np.ascontiguousarray(qy, np.float32); qr = np.ascontiguousarray(qr, np.float32)
+    mn = None if qminl is None else np.ascontiguousarray(qminl, np.int32)
+    mx = None if qmaxl is None else np.ascontiguousarray(qmaxl, np.int32)
+    nq = len(qx)
+    off = np.zeros(nq + 1, np.int32)
+    cap = max(1, nq * max(len(kps), 1))
+    idx = np.zeros(cap, np.int32)
+    tot = lib().orc_grid_candidates(_p(kps), None if kls is None else _p(kls), len(kps), C.byref(g), _p(qx), _p(qy), _p(qr),
+                                    None if mn is None else _p(mn), None if mx is None else _p(mx), nq, _p(off), _p(idx), cap)
+    return off, idx[:tot].copy()
 
 
 # ---------------- lines ----------------

@@ -588,3 +588,71 @@ void orc_stereo_match(const orc_orb* oL, const orc_orb* oR, const orc_keypoint* 
     }
     free(pairs);
 }
+
+/* ---------------- Frame grid + GetFeaturesInArea, src/Frame.cc:365-399, :562-722 ----------------
+ * cell lists are built by pushing feature indices in ascending order (AssignFeaturesToGrid); the query walks the
+ * cells column-major and keeps the insertion order, like the reference's vector<size_t> code. */
+static int grid_pos(float x, float y, const orc_grid_params* g, int* cx, int* cy)
+{
+    *cx = (int)roundf((x - g->min_x) * g->inv_w);
+    *cy = (int)roundf((y - g->min_y) * g->inv_h);
+    return !(*cx < 0 || *cx >= g->cols || *cy < 0 || *cy >= g->rows);
+}
+
+int orc_grid_candidates(const orc_keypoint* kps, const orc_keyline* kls, int n, const orc_grid_params* g, const float* qx,
+                        const float* qy, const float* qr, const int32_t* qminl, const int32_t* qmaxl, int nq, int32_t* cand_off,
+                        int32_t* cand_idx, int cand_cap)
+{
+    const int ncell = g->cols * g->rows;
+    int* cell = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    int* start = (int*)calloc((size_t)ncell + 2, sizeof(int));
+    int* items = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) {
+        int cx, cy, ax, ay;
+        int ok;
+        if (kls) {   /* PosInGridLines: start point, end point, then mid point */
+            ok = grid_pos(kls[i].startPointX, kls[i].startPointY, g, &ax, &ay) && grid_pos(kls[i].endPointX, kls[i].endPointY, g, &ax, &ay) &&
+                 grid_pos(kps[i].x, kps[i].y, g, &cx, &cy);
+        } else ok = grid_pos(kps[i].x, kps[i].y, g, &cx, &cy);
+        cell[i] = ok ? cx * g->rows + cy : -1;
+        if (ok) start[cell[i] + 1]++;
+    }
+    for (int c = 0; c < ncell; c++) start[c + 1] += start[c];
+    int* fill = (int*)calloc((size_t)ncell + 1, sizeof(int));
+    for (int i = 0; i < n; i++)
+        if (cell[i] >= 0) items[start[cell[i]] + fill[cell[i]]++] = i;
+    int total = 0;
+    for (int q = 0; q < nq; q++) {
+        cand_off[q] = total;
+        const float x = qx[q], y = qy[q], r = qr[q];
+        const int minLevel = qminl ? qminl[q] : -1, maxLevel = qmaxl ? qmaxl[q] : -1;
+        int nMinCellX = (int)floorf((x - g->min_x - r) * g->inv_w); if (nMinCellX < 0) nMinCellX = 0;
+        if (nMinCellX >= g->cols) continue;
+        int nMaxCellX = (int)ceilf((x - g->min_x + r) * g->inv_w); if (nMaxCellX > g->cols - 1) nMaxCellX = g->cols - 1;
+        if (nMaxCellX < 0) continue;
+        int nMinCellY = (int)floorf((y - g->min_y - r) * g->inv_h); if (nMinCellY < 0) nMinCellY = 0;
+        if (nMinCellY >= g->rows) continue;
+        int nMaxCellY = (int)ceilf((y - g->min_y + r) * g->inv_h); if (nMaxCellY > g->rows - 1) nMaxCellY = g->rows - 1;
+        if (nMaxCellY < 0) continue;
+        const int bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+            for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+                const int c = ix * g->rows + iy;
+                for (int j = start[c]; j < start[c + 1]; j++) {
+                    const orc_keypoint* kp = &kps[items[j]];
+                    if (bCheckLevels) {
+                        if (kp->octave < minLevel) continue;
+                        if (maxLevel >= 0 && kp->octave > maxLevel) continue;
+                    }
+                    const float distx = kp->x - x, disty = kp->y - y;
+                    if (fabsf(distx) < r && fabsf(disty) < r) {
+                        if (total < cand_cap) cand_idx[total] = items[j];
+                        total++;
+                    }
+                }
+            }
+    }
+    cand_off[nq] = total;
+    free(cell); free(start); free(items); free(fill);
+    return total;
+}

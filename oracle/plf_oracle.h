@@ -85,6 +85,13 @@ void orc_stereo_match(const orc_orb* oL, const orc_orb* oR, const orc_keypoint* 
                       const orc_keypoint* kR, const uint8_t* dR, int nR, float mb, float mbf,
                       float* uRight, float* depth);
 
+/* Frame::AssignFeaturesToGrid[Lines] + GetFeaturesInArea[Lines] (src/Frame.cc:365-399, :562-722): CSR candidate lists
+ * in the reference's order; kls == NULL for the point grid.  Returns the total candidate count. */
+typedef struct { int32_t cols, rows; float min_x, min_y, inv_w, inv_h; } orc_grid_params;
+int orc_grid_candidates(const orc_keypoint* kps, const orc_keyline* kls, int n, const orc_grid_params* g, const float* qx,
+                        const float* qy, const float* qr, const int32_t* qminl, const int32_t* qmaxl, int nq, int32_t* cand_off,
+                        int32_t* cand_idx, int cand_cap);
+
 /* DistributeOctTree alone (ORBextractor.cc:539-763); keys relative to (minX,minY).
  * out_idx receives indices into the input arrays in final list order; returns count. */
 int  orc_distribute_octree(const int* xs, const int* ys, const int* resp, int n,

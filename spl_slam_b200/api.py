@@ -35,6 +35,17 @@ class PlfError(RuntimeError):
         self.status = status
 
 
+class GridParams(C.Structure):
+    """plf_grid_params: the Frame grid (64 x 48 for points, 16 x 12 for lines in the reference)."""
+    _fields_ = [("cols", C.c_int32), ("rows", C.c_int32), ("min_x", C.c_float), ("min_y", C.c_float),
+                ("inv_w", C.c_float), ("inv_h", C.c_float)]
+
+    @classmethod
+    def for_image(cls, cols, rows, min_x, max_x, min_y, max_y):
+        f = np.float32
+        return cls(cols, rows, f(min_x), f(min_y), f(cols) / (f(max_x) - f(min_x)), f(rows) / (f(max_y) - f(min_y)))
+
+
 class OrbParams(C.Structure):
     _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int),
                 ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int)]
@@ -104,6 +115,9 @@ def load(path=None):
         "plf_match_nnr_mutual": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_float, i32p, P(C.c_int)]),
         "plf_hamming_candidates": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, i32p, i32p, i32p, i32p, i32p]),
         "plf_hamming_candidates_device": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp]),
+        "plf_grid_build_device": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+        "plf_grid_query_device": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, P(C.c_int)]),
+        "plf_grid_candidates": (C.c_int, [vp, vp, vp, C.c_int, vp, f32p, f32p, f32p, i32p, i32p, C.c_int, i32p, i32p, C.c_int, P(C.c_int)]),
         "plf_stereo_match": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_float, f32p, f32p]),
         "plf_stereo_match_batch_device": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
                                                     C.c_int, C.c_float, C.c_float, vp, vp]),
@@ -479,6 +493,28 @@ class Linematcher:
         self.ctx.check(self.lib.plf_hamming_candidates(self.ctx.h, _p(q), len(q), _p(t), len(t), _p(off), _p(flat) if len(flat) else None,
                                                        _p(bi), _p(bd), _p(cd) if want_dist else None))
         return (bi, bd, cd[:len(flat)]) if want_dist else (bi, bd)
+
+
+def features_in_area(ctx, keys, grid, qx, qy, qr, min_level=None, max_level=None, keylines=None, cand_cap=None):
+    """Frame::AssignFeaturesToGrid[Lines] + GetFeaturesInArea[Lines] (src/Frame.cc:365-399, :562-722) for a set of queries:
+    -> (cand_off[nq + 1], cand_idx) CSR candidate lists in the reference's order."""
+    kps = np.ascontiguousarray(keys, KEYPOINT_DTYPE)
+    kls = None if keylines is None else np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+    qx = np.ascontiguousarray(qx, np.float32); qy = np.ascontiguousarray(qy, np.float32); qr = np.ascontiguousarray(qr, np.float32)
+    mn = None if min_level is None else np.ascontiguousarray(min_level, np.int32)
+    mx = None if max_level is None else np.ascontiguousarray(max_level, np.int32)
+    nq = len(qx)
+    cap = cand_cap if cand_cap is not None else max(1, nq * 64)
+    while True:
+        off = np.zeros(nq + 1, np.int32); idx = np.zeros(cap, np.int32)
+        tot = C.c_int()
+        st = ctx.lib.plf_grid_candidates(ctx.h, _p(kps), None if kls is None else _p(kls), len(kps), C.byref(grid), _p(qx), _p(qy), _p(qr),
+                                         None if mn is None else _p(mn), None if mx is None else _p(mx), nq, _p(off), _p(idx), cap, C.byref(tot))
+        if st == PLF_ERR_CAPACITY and cand_cap is None and tot.value > cap:
+            cap = tot.value
+            continue
+        ctx.check(st)
+        return off, idx[:tot.value].copy()
 
 
 ORBmatcher = Linematcher  # ORBmatcher::DescriptorDistance is the same function (src/ORBmatcher.cc:1656-1672)

@@ -163,3 +163,38 @@ def test_emu_candidates(S, oracle, emu_lib):
         bi, bd, cd = m.candidates_top2(q, t, lists, want_dist=True)
         obi, obd, ocd = oracle.candidates_top2(q, t, lists)
         assert np.array_equal(bi, obi) and np.array_equal(bd, obd) and np.array_equal(cd, ocd)
+
+
+def _grid_case(oracle, n, nq, seed, w=752, h=480):
+    rng = np.random.default_rng(seed)
+    k = np.zeros(n, oracle.KEYPOINT_DTYPE)
+    k["x"] = rng.uniform(-6, w + 6, n).astype(np.float32); k["y"] = rng.uniform(-6, h + 6, n).astype(np.float32)   # some fall outside the grid
+    k["octave"] = rng.integers(0, 8, n)
+    qx = rng.uniform(-20, w + 20, nq).astype(np.float32); qy = rng.uniform(-20, h + 20, nq).astype(np.float32)
+    qr = rng.uniform(1, 60, nq).astype(np.float32)
+    qx[:3] = k["x"][:3]; qy[:3] = k["y"][:3]                       # exact hits: |d| < r boundary cases
+    mn = rng.integers(-1, 4, nq).astype(np.int32); mx = rng.integers(-1, 8, nq).astype(np.int32)
+    return k, qx, qy, qr, mn, mx
+
+
+def test_emu_grid_area_queries(S, oracle, emu_lib):
+    ctx = S.Context(0, emu_lib)
+    k, qx, qy, qr, mn, mx = _grid_case(oracle, 700, 300, 11)
+    og = oracle.grid_params(64, 48, 0, 752, 0, 480)
+    g = S.GridParams.for_image(64, 48, 0, 752, 0, 480)
+    for lv in (False, True):
+        off, idx = S.features_in_area(ctx, k, g, qx, qy, qr, mn if lv else None, mx if lv else None)
+        ooff, oidx = oracle.grid_candidates(k, og, qx, qy, qr, mn if lv else None, mx if lv else None)
+        assert np.array_equal(off, ooff) and np.array_equal(idx, oidx) and len(idx) > 1000
+    # line grid: mid-points + end points must be inside (PosInGridLines)
+    kl = np.zeros(len(k), oracle.KEYLINE_DTYPE)
+    rng = np.random.default_rng(3)
+    kl["startPointX"] = k["x"] + rng.uniform(-30, 30, len(k)).astype(np.float32); kl["startPointY"] = k["y"] + rng.uniform(-30, 30, len(k)).astype(np.float32)
+    kl["endPointX"] = 2 * k["x"] - kl["startPointX"]; kl["endPointY"] = 2 * k["y"] - kl["startPointY"]
+    ogl = oracle.grid_params(16, 12, 0, 752, 0, 480); gl = S.GridParams.for_image(16, 12, 0, 752, 0, 480)
+    off, idx = S.features_in_area(ctx, k, gl, qx, qy, qr, keylines=kl)
+    ooff, oidx = oracle.grid_candidates(k, ogl, qx, qy, qr, keylines=kl)
+    assert np.array_equal(off, ooff) and np.array_equal(idx, oidx)
+    # no features / no queries
+    off, idx = S.features_in_area(ctx, k[:0], g, qx, qy, qr)
+    assert (off == 0).all() and len(idx) == 0

@@ -282,3 +282,45 @@ def test_candidate_lists(S, oracle, gpu_ctx):
         assert np.array_equal(bi, obi) and np.array_equal(bd, obd) and np.array_equal(cd, ocd)
     with pytest.raises(S.PlfError):
         m.candidates_top2(q, t, [np.array([nt], np.int32)] + [np.zeros(0, np.int32)] * (nq - 1))
+
+
+def test_grid_area_queries_and_projection_matching(S, oracle, gpu_ctx):
+    """The data path of the tracking matchers (ORBmatcher::SearchByProjection / SearchForInitialization): Frame grid ->
+    GetFeaturesInArea candidate lists -> top-2 over each list, all bit-identical to the sequential reference code."""
+    ox = oracle.ORBextractor(2000, 1.2, 8, 20, 7)
+    ex = S.ORBextractor(2000, 1.2, 8, 20, 7, ctx=gpu_ctx)
+    img1 = oracle.synth_image(1241, 376, 50)
+    img2 = np.roll(img1, (2, -5), axis=(0, 1)).copy()
+    k1, d1 = ex(img1); k2, d2 = ex(img2)
+    g = S.GridParams.for_image(64, 48, 0, 1241, 0, 376); og = oracle.grid_params(64, 48, 0, 1241, 0, 376)
+    # SearchForInitialization (src/ORBmatcher.cc:406-456): level-0 keypoints of frame 1 search a 100-px window in frame 2
+    sel = np.nonzero(k1["octave"] == 0)[0]
+    qx, qy = k1["x"][sel], k1["y"][sel]
+    qr = np.full(len(sel), 100, np.float32); lv = np.zeros(len(sel), np.int32)
+    off, idx = S.features_in_area(gpu_ctx, k2, g, qx, qy, qr, lv, lv)
+    ooff, oidx = oracle.grid_candidates(k2, og, qx, qy, qr, lv, lv)
+    assert np.array_equal(off, ooff) and np.array_equal(idx, oidx) and len(idx) > 10 * len(sel)
+    lists = [idx[off[i]:off[i + 1]] for i in range(len(sel))]
+    m = S.ORBmatcher(0.9, ctx=gpu_ctx)
+    bi, bd, cd = m.candidates_top2(d1[sel], d2, lists, want_dist=True)
+    obi, obd, ocd = oracle.candidates_top2(d1[sel], d2, lists)
+    assert np.array_equal(bi, obi) and np.array_equal(bd, obd) and np.array_equal(cd, ocd)
+    good = (bd[:, 0] <= 50) & (bd[:, 0] < bd[:, 1].astype(np.float32) * np.float32(0.9))
+    assert good.sum() > len(sel) // 4            # the shifted frame is really being matched
+    # random queries with level windows and points outside the grid
+    rng = np.random.default_rng(2)
+    nq = 5000
+    qx = rng.uniform(-30, 1270, nq).astype(np.float32); qy = rng.uniform(-30, 400, nq).astype(np.float32)
+    qr = rng.uniform(1, 40, nq).astype(np.float32)
+    mn = rng.integers(-1, 5, nq).astype(np.int32); mx = rng.integers(-1, 8, nq).astype(np.int32)
+    off, idx = S.features_in_area(gpu_ctx, k2, g, qx, qy, qr, mn, mx)
+    ooff, oidx = oracle.grid_candidates(k2, og, qx, qy, qr, mn, mx)
+    assert np.array_equal(off, ooff) and np.array_equal(idx, oidx)
+    # line grid (16 x 12, PosInGridLines)
+    le, prm = _line_objs(S, oracle, gpu_ctx, 800)
+    K, M, D = le.ComputeLsdWithLbd(img1)
+    gl = S.GridParams.for_image(16, 12, 0, 1241, 0, 376); ogl = oracle.grid_params(16, 12, 0, 1241, 0, 376)
+    qx, qy = M["x"], M["y"]; qr = np.full(len(M), 60, np.float32)
+    off, idx = S.features_in_area(gpu_ctx, M, gl, qx, qy, qr, keylines=K)
+    ooff, oidx = oracle.grid_candidates(M, ogl, qx, qy, qr, keylines=K)
+    assert np.array_equal(off, ooff) and np.array_equal(idx, oidx) and len(idx) > len(M)
