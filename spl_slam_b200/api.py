@@ -10,6 +10,7 @@ memory layouts (28-byte KeyPoint, 68-byte KeyLine, N x 32 CV_8U descriptors).
 There is no CPU fallback: if libplf.so is missing or no CUDA device is usable every call raises.
 """
 import ctypes as C
+import weakref
 import os
 import numpy as np
 
@@ -204,7 +205,16 @@ class Context:
             out[name] = (float(ms), int(n))
         return out
 
+    def _adopt(self, child):
+        """Extractors register here so that the context is never destroyed before the objects that use its stream
+        (garbage collection at interpreter exit finalises objects in no particular order)."""
+        if not hasattr(self, "_children"):
+            self._children = weakref.WeakSet()
+        self._children.add(child)
+
     def close(self):
+        for ch in list(getattr(self, "_children", ())):
+            ch.close()
         if getattr(self, "h", None):
             self.lib.plf_ctx_destroy(self.h)
             self.h = None
@@ -239,6 +249,7 @@ class ORBextractor:
         h = C.c_void_p()
         self.ctx.check(self.lib.plf_orb_create(self.ctx.h, C.byref(self.params), C.byref(h)))
         self.h = h
+        self.ctx._adopt(self)
         self.nlevels = nlevels
         self.scaleFactor = scaleFactor
         n = nlevels
@@ -324,7 +335,9 @@ class ORBextractor:
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.plf_orb_destroy(self.h)
+            # finalisation order at interpreter exit is arbitrary: never touch an extractor whose context is gone
+            if getattr(self.ctx, "h", None):
+                self.lib.plf_orb_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -361,6 +374,7 @@ class Lineextractor:
         h = C.c_void_p()
         self.ctx.check(self.lib.plf_line_create(self.ctx.h, C.byref(self.params), C.byref(h)))
         self.h = h
+        self.ctx._adopt(self)
         self.nlevels = nlevels
         self.scale = scale
         n = nlevels
@@ -424,7 +438,8 @@ class Lineextractor:
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.plf_line_destroy(self.h)
+            if getattr(self.ctx, "h", None):
+                self.lib.plf_line_destroy(self.h)
             self.h = None
 
     def __del__(self):
