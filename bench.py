@@ -163,6 +163,11 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: everything else that libraries print to file descriptor 1 (NCCL's version
+    # banner, for one) goes to stderr until the result line is written
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -504,7 +509,10 @@ def main():
                              "roofline": {"bound": "popc", "achieved": 8 * NQ * NT / (ms_match / 1e3) / world, "peak": popc_peak,
                                           "unit": "popc32/s per GPU", "frac": 8 * NQ * NT / (ms_match / 1e3) / world / popc_peak,
                                           "peak_source": "plf_popc_peak micro-benchmark on this GPU"}}}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
