@@ -216,3 +216,28 @@ __device__ __forceinline__ void plf_blur_strip(const uint8_t* __restrict__ src, 
         }
     }
 }
+
+// Strip scheduling for the 4-px column-strip kernels: strips whose 12-byte (or 16-byte) window stays inside the row take
+// the aligned fast path, the strips at the left / right image edge gather with reflection and are ~3x more expensive.
+// Mixing both in one warp makes the whole warp pay for both, so the interior strips 1 .. F are packed densely into
+// the first `ncx - 1` CTA columns and ONE extra CTA column holds the edge strips (strip 0 and F+1 .. S-1).
+// F = number of interior strips, S = total strips; returns the strip index of (CTA column, lane) or -1.
+__host__ __device__ __forceinline__ int plf_strip_interior(int w, int halo_lo, int halo_hi)
+{
+    // strip s (pixels 4s .. 4s+3) is interior iff 4s - halo_lo >= 0 and 4s + halo_hi <= w, halo_lo a multiple of 4
+    const int first = halo_lo / 4;                 // first interior strip
+    const int last = (w - halo_hi) / 4;            // last interior strip (may be < first)
+    return last >= first ? last - first + 1 : 0;
+}
+__device__ __forceinline__ int plf_strip_of(int bx, int lane, int w, int first, int F, int ncx_int)
+{
+    const int S = (w + 3) >> 2;
+    if (bx < ncx_int) {
+        const int i = bx * 32 + lane;
+        return i < F ? first + i : -1;
+    }
+    // edge column: lanes 0 .. first-1 -> left strips, then the right strips
+    if (lane < first) return lane < S ? lane : -1;
+    const int s = first + F + (lane - first);
+    return s < S ? s : -1;
+}

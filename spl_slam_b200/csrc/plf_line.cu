@@ -375,6 +375,13 @@ static plf_status read_ints(plf_ctx* ctx, const int* dev, int n, int* host)
     return PLF_OK;
 }
 
+// interior output strips of pyrDown for a source of width w: strip s reads source bytes 8s - 4 .. 8s + 11
+static int pyrdown_interior(int w)
+{
+    const int last = (w - 12) / 8;     // 8s + 12 <= w
+    return last >= 1 ? last : 0;       // first interior strip is 1 (8s - 4 >= 0)
+}
+
 // cv::GaussianBlur 8U for a batch: 5 / 7 taps go to the register sliding-window kernel, other sizes to the generic one
 static plf_status gauss_batch(plf_ctx* ctx, const uint8_t* src, uint8_t* dst, int w, int h, int nframes, const GaussQ8& k)
 {
@@ -384,9 +391,10 @@ static plf_status gauss_batch(plf_ctx* ctx, const uint8_t* src, uint8_t* dst, in
         BlurTaps taps;
         memset(&taps, 0, sizeof(taps));
         for (int i = 0; i < k.ksize; i++) taps.k[i] = k.q[i];
-        dim3 grid(plf_div_up(w, 128), plf_div_up(h, 4 * GS_ROWS), nframes), block(32, 4);
-        if (k.ksize == 5) PLF_LAUNCH(k_gauss_strip<2>, grid, block, 0, st, src, frame, w, dst, frame, w, w, h, taps);
-        else PLF_LAUNCH(k_gauss_strip<3>, grid, block, 0, st, src, frame, w, dst, frame, w, w, h, taps);
+        const int F = plf_strip_interior(w, 4, 8), ncx_int = plf_div_up(F, 32);   // interior strips / their CTA columns (+1 edge column)
+        dim3 grid(ncx_int + 1, plf_div_up(h, 4 * GS_ROWS), nframes), block(32, 4);
+        if (k.ksize == 5) PLF_LAUNCH(k_gauss_strip<2>, grid, block, 0, st, src, frame, w, dst, frame, w, w, h, taps, F, ncx_int);
+        else PLF_LAUNCH(k_gauss_strip<3>, grid, block, 0, st, src, frame, w, dst, frame, w, w, h, taps, F, ncx_int);
     } else {
         PLF_LAUNCH(k_gauss_q8, dim3(plf_div_up(w, GB_TW), plf_div_up(h, GB_TH), nframes), dim3(256), 0, st, src, frame, w, dst, frame, w, w, h, k);
     }
@@ -416,8 +424,9 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         PLF_CUDA(ctx, cudaStreamSynchronize(st));
         std::unique_lock<std::mutex> prephase(g_lsd_prephase);
         if (k > 0) {   // computeGaussianPyramid: pyrDown, no pre-blur (LSDDetector_custom.cpp:56-73)
-            PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(ow, 128), plf_div_up(oh, 4 * PD_ROWS), nframes), dim3(32, 4), 0, st, (const uint8_t*)o->d_oct[k - 1],
-                       (size_t)o->ow[k - 1] * o->oh[k - 1], o->ow[k - 1], o->ow[k - 1], o->oh[k - 1], o->d_oct[k], (size_t)ow * oh, ow);
+            const int pdF = pyrdown_interior(o->ow[k - 1]);
+            PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(pdF, 32) + 1, plf_div_up(oh, 4 * PD_ROWS), nframes), dim3(32, 4), 0, st, (const uint8_t*)o->d_oct[k - 1],
+                       (size_t)o->ow[k - 1] * o->oh[k - 1], o->ow[k - 1], o->ow[k - 1], o->oh[k - 1], o->d_oct[k], (size_t)ow * oh, ow, pdF, plf_div_up(pdF, 32));
             PLF_CHECK_LAUNCH(ctx);
         }
         // the image the gradient is taken of: the octave itself (SCALE == 1, pitch = octave width) or its blurred and
@@ -544,12 +553,14 @@ static plf_status lbd_batch(plf_line* o, int nframes, const plf_keyline* d_kl, c
         if (k == 0) {   // computeGaussianPyramid (binary_descriptor_custom.cpp:350-370): blur 5x5 sigma 1, then pyrDown
             { plf_status gs = gauss_batch(ctx, o->d_oct[0], o->d_lbdimg[0], ow, oh, nframes, o->lbd_gauss); if (gs) return gs; }
         } else {
-            PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(ow, 128), plf_div_up(oh, 4 * PD_ROWS), nframes), dim3(32, 4), 0, st, (const uint8_t*)o->d_lbdimg[k - 1],
-                       (size_t)o->ow[k - 1] * o->oh[k - 1], o->ow[k - 1], o->ow[k - 1], o->oh[k - 1], o->d_lbdimg[k], (size_t)ow * oh, ow);
+            const int pdF = pyrdown_interior(o->ow[k - 1]);
+            PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(pdF, 32) + 1, plf_div_up(oh, 4 * PD_ROWS), nframes), dim3(32, 4), 0, st, (const uint8_t*)o->d_lbdimg[k - 1],
+                       (size_t)o->ow[k - 1] * o->oh[k - 1], o->ow[k - 1], o->ow[k - 1], o->oh[k - 1], o->d_lbdimg[k], (size_t)ow * oh, ow, pdF, plf_div_up(pdF, 32));
         }
         PLF_CHECK_LAUNCH(ctx);
-        PLF_LAUNCH(k_sobel3, dim3(plf_div_up(ow, 128), plf_div_up(oh, 4 * SB_ROWS), nframes), dim3(32, 4), 0, st, (const uint8_t*)o->d_lbdimg[k],
-                   (size_t)ow * oh, ow, ow, oh, o->d_dx[k], o->d_dy[k], (size_t)ow * oh);
+        const int sbF = plf_strip_interior(ow, 4, 8);
+        PLF_LAUNCH(k_sobel3, dim3(plf_div_up(sbF, 32) + 1, plf_div_up(oh, 4 * SB_ROWS), nframes), dim3(32, 4), 0, st, (const uint8_t*)o->d_lbdimg[k],
+                   (size_t)ow * oh, ow, ow, oh, o->d_dx[k], o->d_dy[k], (size_t)ow * oh, sbF, plf_div_up(sbF, 32));
         PLF_CHECK_LAUNCH(ctx);
         im.dx[k] = o->d_dx[k]; im.dy[k] = o->d_dy[k]; im.frame[k] = (size_t)ow * oh; im.w[k] = ow; im.h[k] = oh;
     }

@@ -77,11 +77,12 @@ k_gauss_q8(const uint8_t* __restrict__ src, size_t sframe, int spitch, uint8_t* 
 template <int R>
 __global__ void __launch_bounds__(128)
 k_gauss_strip(const uint8_t* __restrict__ src, size_t sframe, int spitch, uint8_t* __restrict__ dst, size_t dframe, int dpitch,
-              int w, int h, BlurTaps taps)
+              int w, int h, BlurTaps taps, int F, int ncx_int)
 {
-    const int x0 = blockIdx.x * 128 + 4 * threadIdx.x, y0 = (blockIdx.y * 4 + threadIdx.y) * GS_ROWS;
-    if (y0 >= h) return;
-    plf_blur_strip<R>(src + (size_t)blockIdx.z * sframe, spitch, dst + (size_t)blockIdx.z * dframe, dpitch, w, h, x0, y0, GS_ROWS, taps);
+    const int strip = plf_strip_of(blockIdx.x, threadIdx.x, w, 1, F, ncx_int);   // interior strips first, edge strips in the last CTA column
+    const int y0 = (blockIdx.y * 4 + threadIdx.y) * GS_ROWS;
+    if (strip < 0 || y0 >= h) return;
+    plf_blur_strip<R>(src + (size_t)blockIdx.z * sframe, spitch, dst + (size_t)blockIdx.z * dframe, dpitch, w, h, 4 * strip, y0, GS_ROWS, taps);
 }
 
 // ---------------- cv::resize INTER_LINEAR_EXACT; tab: .x = offset, .y = c1 (Q8) ----------------
@@ -147,11 +148,12 @@ __device__ __forceinline__ void pyrdown_hrow(const uint8_t* __restrict__ rp, int
 }
 __global__ void __launch_bounds__(128)
 k_pyrdown(const uint8_t* __restrict__ src, size_t sframe, int spitch, int w, int h,
-          uint8_t* __restrict__ dst, size_t dframe, int dpitch)
+          uint8_t* __restrict__ dst, size_t dframe, int dpitch, int F, int ncx_int)
 {
     const int dw = w >> 1, dh = h >> 1;
-    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, y0 = (blockIdx.y * 4 + threadIdx.y) * PD_ROWS;
-    if (x0 >= dw || y0 >= dh) return;
+    const int strip = plf_strip_of(blockIdx.x, threadIdx.x, dw, 1, F, ncx_int);   // interior strips first, edge strips in the last CTA column
+    const int x0 = 4 * strip, y0 = (blockIdx.y * 4 + threadIdx.y) * PD_ROWS;
+    if (strip < 0 || x0 >= dw || y0 >= dh) return;
     const uint8_t* s = src + (size_t)blockIdx.z * sframe;
     uint8_t* d = dst + (size_t)blockIdx.z * dframe;
     const int sx0 = 2 * x0;
@@ -206,10 +208,11 @@ __device__ __forceinline__ void sobel_hrow(const uint8_t* __restrict__ rp, int x
 }
 __global__ void __launch_bounds__(128)
 k_sobel3(const uint8_t* __restrict__ src, size_t sframe, int spitch, int w, int h,
-         short* __restrict__ dx, short* __restrict__ dy, size_t dframe)
+         short* __restrict__ dx, short* __restrict__ dy, size_t dframe, int F, int ncx_int)
 {
-    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, y0 = (blockIdx.y * 4 + threadIdx.y) * SB_ROWS;
-    if (x0 >= w || y0 >= h) return;
+    const int strip = plf_strip_of(blockIdx.x, threadIdx.x, w, 1, F, ncx_int);
+    const int x0 = 4 * strip, y0 = (blockIdx.y * 4 + threadIdx.y) * SB_ROWS;
+    if (strip < 0 || x0 >= w || y0 >= h) return;
     const uint8_t* s = src + (size_t)blockIdx.z * sframe;
     short* ox = dx + (size_t)blockIdx.z * dframe;
     short* oy = dy + (size_t)blockIdx.z * dframe;

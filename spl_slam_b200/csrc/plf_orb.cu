@@ -166,7 +166,8 @@ static plf_status orb_prepare(plf_orb* o, int w, int h, int nframes)
         if (L.wCell + 6 > FAST_MAXC || L.hCell + 6 > FAST_MAXC) return plf_fail(ctx, PLF_ERR_INVALID, "FAST cell too large");
         L.cellBase = g.totalCells;
         g.totalCells += L.nCols * L.nRows;
-        L.blurTilesX = plf_div_up(L.w, BLUR_TW);
+        L.blurF = plf_strip_interior(L.w, 4, 8);
+        L.blurTilesX = plf_div_up(L.blurF, 32) + 1;
         L.blurTileBase = g.totalBlurTiles;
         g.totalBlurTiles += L.blurTilesX * plf_div_up(L.h, BLUR_TH);
         L.nfeat = o->per_level[l];

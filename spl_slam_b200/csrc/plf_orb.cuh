@@ -13,7 +13,8 @@ struct OrbLevelGeom {
     int nCols, nRows, wCell, hCell;
     int cellBase;               // first FAST cell id of this level in the fused grid
     int blurTileBase;           // first blur tile id of this level
-    int blurTilesX;
+    int blurTilesX;             // CTA columns of the blur: interior strip columns + one column of edge strips
+    int blurF;                  // interior 4-px strips of a row (plf_strip_interior)
     int nfeat;                  // mnFeaturesPerLevel[level]
     int rawcap;                 // capacity of the raw key list per frame
     int keptcap;                // capacity of the kept list per frame

@@ -56,7 +56,8 @@ k_resize_linear(const uint8_t* __restrict__ src, size_t srcFrameStride, int spit
 #define BLUR_TW 128
 #define BLUR_TH 35           // a multiple of the 7-row register window
 #define BLUR_WARPS 4
-// one WARP per 128 x 35 tile (lane = 4-px column strip, see plf_blur_strip); tiles of all levels in one launch
+// one WARP per 32 strips x 35 rows (lane = 4-px column strip, see plf_blur_strip; interior strips packed densely,
+// the edge strips of a row band in a warp of their own, see plf_strip_of); tiles of all levels in one launch
 __global__ void __launch_bounds__(32 * BLUR_WARPS, 8)
 k_blur7(OrbGeom g, OrbPtrs p)
 {
@@ -65,12 +66,20 @@ k_blur7(OrbGeom g, OrbPtrs p)
     while (l + 1 < g.nlevels && tileId >= g.lv[l + 1].blurTileBase) l++;
     tileId -= g.lv[l].blurTileBase;
     const OrbLevelGeom& L = g.lv[l];
-    const int tx0 = (tileId % L.blurTilesX) * BLUR_TW, ty0 = (tileId / L.blurTilesX) * BLUR_TH;
+    // tiles of a level: first all interior tiles (row-major), then the edge tiles of all row bands, so that the slow
+    // edge warps share CTAs with each other instead of holding a CTA of fast warps resident
+    const int ncx_int = L.blurTilesX - 1, nInt = ncx_int * ((L.h + BLUR_TH - 1) / BLUR_TH);
+    int tx, ty;
+    if (tileId < nInt) { ty = tileId / ncx_int; tx = tileId - ty * ncx_int; }
+    else { ty = tileId - nInt; tx = ncx_int; }
+    const int ty0 = ty * BLUR_TH;
+    const int strip = plf_strip_of(tx, threadIdx.x & 31, L.w, 1, L.blurF, ncx_int);
+    if (strip < 0) return;
     const uint8_t* src = p.lvl[l] + (size_t)blockIdx.y * p.frameStride[l];
     uint8_t* dst = p.blr[l] + (size_t)blockIdx.y * L.frameBytes;
     BlurTaps taps;
     taps.k[0] = 18; taps.k[1] = 34; taps.k[2] = 48; taps.k[3] = 56; taps.k[4] = 48; taps.k[5] = 34; taps.k[6] = 18; taps.k[7] = 0;
-    plf_blur_strip<3>(src, p.pitch[l], dst, L.pitch, L.w, L.h, tx0 + 4 * (threadIdx.x & 31), ty0, BLUR_TH, taps);
+    plf_blur_strip<3>(src, p.pitch[l], dst, L.pitch, L.w, L.h, 4 * strip, ty0, BLUR_TH, taps);
 }
 
 // ------------------------------------------------------------------------------------------------
