@@ -42,27 +42,35 @@ struct plf_line {
     int keybits[LINE_MAX_OCT];
     int sp[LINE_MAX_OCT];   // working width of the scaled octave: sw rounded up to 4 (row pitch of every per-pixel LSD array; the pad columns are NOTDEF)
     uint8_t* d_base;
-    uint8_t *d_oct[LINE_MAX_OCT], *d_tmp, *d_scaled;       // images (pitch == width)
+    uint8_t *d_oct[LINE_MAX_OCT];                              // octave images (pitch == width)
     uint8_t *d_lbdimg[LINE_MAX_OCT];
     short *d_dx[LINE_MAX_OCT], *d_dy[LINE_MAX_OCT];
-    int2* d_comp;
-    int *d_q, *d_label, *d_regpts, *d_lineidx, *d_lineidx2, *d_cnt, *d_detcount;
-    unsigned* d_mask;       // one bit per scaled pixel: gradient defined
-    int* d_offs;            // inclusive prefix sum of the mask popcounts (+ leading 0)
-    double* d_bincoef;      // per frame
+    // LSD workspace, one set per octave: the octaves of a batch are independent until the line selection, so they run
+    // on two streams and their region-growing chains overlap
+    uint8_t *d_tmp[LINE_MAX_OCT], *d_scaled[LINE_MAX_OCT];
+    int2* d_comp[LINE_MAX_OCT];
+    int *d_q[LINE_MAX_OCT], *d_label[LINE_MAX_OCT], *d_regpts[LINE_MAX_OCT], *d_lineidx[LINE_MAX_OCT], *d_lineidx2[LINE_MAX_OCT], *d_cnt[LINE_MAX_OCT];
+    unsigned* d_mask[LINE_MAX_OCT];       // one bit per scaled pixel: gradient defined
+    int* d_offs[LINE_MAX_OCT];            // inclusive prefix sum of the mask popcounts (+ leading 0)
+    double* d_bincoef[LINE_MAX_OCT];      // per frame
+    float* d_fa[LINE_MAX_OCT];
+    float2* d_cs[LINE_MAX_OCT];
+    unsigned long long *d_keys[LINE_MAX_OCT], *d_keys2[LINE_MAX_OCT], *d_linekey[LINE_MAX_OCT], *d_linekey2[LINE_MAX_OCT];
+    LsdRegion* d_regions[LINE_MAX_OCT];
+    float4* d_lines[LINE_MAX_OCT];
+    void* d_cubtmp[LINE_MAX_OCT];
+    size_t cubtmp_bytes[LINE_MAX_OCT];
+    size_t keycap[LINE_MAX_OCT];
+    size_t maskwords[LINE_MAX_OCT];
+    int regcap;
+    cudaStream_t st2;                      // stream of octave 1 (octave 0 uses the context stream)
+    cudaEvent_t ev_img, ev_join;
+    int* h_pin;                            // pinned host staging for the per-octave counters (64 ints each)
+    int *d_detcount;
     int qthr;               // defined <=> gx^2 + gy^2 > qthr
-    float* d_fa;
-    float2* d_cs;
-    unsigned long long *d_keys, *d_keys2, *d_linekey, *d_linekey2;
-    LsdRegion* d_regions;
-    float4* d_lines;
     plf_keyline* d_det;
     int2* d_tabs;
     const int2 *xtab[LINE_MAX_OCT], *ytab[LINE_MAX_OCT];
-    void* d_cubtmp;
-    size_t cubtmp_bytes;
-    size_t keycap;
-    int regcap;
     // output staging for host entry points
     plf_keyline* d_okl;
     plf_keypoint* d_omid;
@@ -162,8 +170,8 @@ static void line_free_ws(plf_line* o)
 {
     if (o->d_base) cudaFree(o->d_base);
     if (o->d_tabs) cudaFree(o->d_tabs);
-    if (o->d_cubtmp) cudaFree(o->d_cubtmp);
-    o->d_base = nullptr; o->d_tabs = nullptr; o->d_cubtmp = nullptr;
+    for (int k = 0; k < LINE_MAX_OCT; k++) { if (o->d_cubtmp[k]) cudaFree(o->d_cubtmp[k]); o->d_cubtmp[k] = nullptr; }
+    o->d_base = nullptr; o->d_tabs = nullptr;
     o->ws_w = o->ws_h = o->ws_frames = 0;
 }
 
@@ -173,6 +181,10 @@ extern "C" void plf_line_destroy(plf_line* o)
     cudaSetDevice(o->ctx->device);
     cudaStreamSynchronize(o->ctx->stream);
     line_free_ws(o);
+    if (o->st2) cudaStreamDestroy(o->st2);
+    if (o->ev_img) cudaEventDestroy(o->ev_img);
+    if (o->ev_join) cudaEventDestroy(o->ev_join);
+    if (o->h_pin) cudaFreeHost(o->h_pin);
     if (o->d_okl) cudaFree(o->d_okl);
     if (o->d_omid) cudaFree(o->d_omid);
     if (o->d_odesc) cudaFree(o->d_odesc);
@@ -246,54 +258,69 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         tabCount += (size_t)o->sw[k] + o->sh[k];
     }
     const size_t F = (size_t)nframes;
-    o->keycap = F * maxpx;
     o->regcap = nframes * LINE_REGCAP_PER_FRAME;
+    if (!o->st2) {
+#ifndef PLF_EMU
+        int lo = 0, hi = 0, pr = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamGetPriority(ctx->stream, &pr);
+        PLF_CUDA(ctx, cudaStreamCreateWithPriority(&o->st2, cudaStreamNonBlocking, pr));
+#else
+        PLF_CUDA(ctx, cudaStreamCreateWithFlags(&o->st2, cudaStreamNonBlocking));
+#endif
+        PLF_CUDA(ctx, cudaEventCreate(&o->ev_img));
+        PLF_CUDA(ctx, cudaEventCreate(&o->ev_join));
+        PLF_CUDA(ctx, cudaMallocHost((void**)&o->h_pin, LINE_MAX_OCT * 64 * sizeof(int)));
+    }
     size_t bytes = 0;
     auto need = [&](size_t count, size_t elt) { bytes += plf_align_up(count * elt, 256); };
     for (int k = 0; k < noct; k++) {
-        size_t px = (size_t)o->ow[k] * o->oh[k];
-        need(F * px, 1); need(F * px, 1); need(F * px, 2); need(F * px, 2);
+        const size_t px = (size_t)o->ow[k] * o->oh[k], spx = (size_t)o->sp[k] * o->sh[k];
+        o->keycap[k] = F * spx;
+        o->maskwords[k] = F * (spx / 32 + (size_t)o->sh[k] + 64);
+        need(F * px, 1); need(F * px, 1); need(F * px, 2); need(F * px, 2);      // octave, LBD image, dx, dy
+        need(F * px, 1); need(F * spx, 1);                                            // tmp, scaled
+        need(F * spx, 4); need(F * spx, 4); need(F * spx, 4); need(F * spx, 8);   // q, label, fa, cs
+        need(o->keycap[k], 8); need(o->keycap[k], 8); need(o->keycap[k], 4); need(o->keycap[k], 8);    // keys, keys2, regpts, comp
+        need(o->regcap, sizeof(LsdRegion)); need(o->regcap, sizeof(float4));
+        need(o->regcap, 8); need(o->regcap, 8); need(o->regcap, 4); need(o->regcap, 4);
+        need(CNT_MAXQ + F, 4);
+        need(o->maskwords[k], 4); need(o->maskwords[k] + 64, 4); need(F, 8);   // mask, offsets, bin coefficients
     }
-    need(F * (size_t)w * h, 1); need(F * maxpx, 1);
-    need(F * maxpx, 4); need(F * maxpx, 4); need(F * maxpx, 4); need(F * maxpx, 8);   // q, label, fa, cs
-    need(o->keycap, 8); need(o->keycap, 8); need(o->keycap, 4); need(o->keycap, 8);    // keys, keys2, regpts, comp
-    need(o->regcap, sizeof(LsdRegion)); need(o->regcap, sizeof(float4));
-    need(o->regcap, 8); need(o->regcap, 8); need(o->regcap, 4); need(o->regcap, 4);
     need(F * noct * LINE_DETCAP, sizeof(plf_keyline));
-    need(CNT_MAXQ + F, 4); need(F * noct, 4);
-    need(F * (maxpx / 32 + 8192), 4); need(F * (maxpx / 32 + 8192) + 64, 4); need(F, 8);   // mask (rows x ceil(w / 32) words), bin coefficients
+    need(F * noct, 4);
 
     PLF_CUDA(ctx, cudaMalloc((void**)&o->d_base, bytes + 4096));
     uint8_t* p = o->d_base;
     for (int k = 0; k < noct; k++) {
-        size_t px = (size_t)o->ow[k] * o->oh[k];
+        const size_t px = (size_t)o->ow[k] * o->oh[k], spx = (size_t)o->sp[k] * o->sh[k];
         o->d_oct[k] = carve<uint8_t>(p, F * px);
         o->d_lbdimg[k] = carve<uint8_t>(p, F * px);
         o->d_dx[k] = carve<short>(p, F * px);
         o->d_dy[k] = carve<short>(p, F * px);
+        o->d_tmp[k] = carve<uint8_t>(p, F * px);
+        o->d_scaled[k] = carve<uint8_t>(p, F * spx);
+        o->d_q[k] = carve<int>(p, F * spx);
+        o->d_label[k] = carve<int>(p, F * spx);
+        o->d_fa[k] = carve<float>(p, F * spx);
+        o->d_cs[k] = carve<float2>(p, F * spx);
+        o->d_keys[k] = carve<unsigned long long>(p, o->keycap[k]);
+        o->d_keys2[k] = carve<unsigned long long>(p, o->keycap[k]);
+        o->d_regpts[k] = carve<int>(p, o->keycap[k]);
+        o->d_comp[k] = carve<int2>(p, o->keycap[k]);
+        o->d_regions[k] = carve<LsdRegion>(p, o->regcap);
+        o->d_lines[k] = carve<float4>(p, o->regcap);
+        o->d_linekey[k] = carve<unsigned long long>(p, o->regcap);
+        o->d_linekey2[k] = carve<unsigned long long>(p, o->regcap);
+        o->d_lineidx[k] = carve<int>(p, o->regcap);
+        o->d_lineidx2[k] = carve<int>(p, o->regcap);
+        o->d_cnt[k] = carve<int>(p, CNT_MAXQ + F);
+        o->d_mask[k] = carve<unsigned>(p, o->maskwords[k]);
+        o->d_offs[k] = carve<int>(p, o->maskwords[k] + 64);
+        o->d_bincoef[k] = carve<double>(p, F);
     }
-    o->d_tmp = carve<uint8_t>(p, F * (size_t)w * h);
-    o->d_scaled = carve<uint8_t>(p, F * maxpx);
-    o->d_q = carve<int>(p, F * maxpx);
-    o->d_label = carve<int>(p, F * maxpx);
-    o->d_fa = carve<float>(p, F * maxpx);
-    o->d_cs = carve<float2>(p, F * maxpx);
-    o->d_keys = carve<unsigned long long>(p, o->keycap);
-    o->d_keys2 = carve<unsigned long long>(p, o->keycap);
-    o->d_regpts = carve<int>(p, o->keycap);
-    o->d_comp = carve<int2>(p, o->keycap);
-    o->d_regions = carve<LsdRegion>(p, o->regcap);
-    o->d_lines = carve<float4>(p, o->regcap);
-    o->d_linekey = carve<unsigned long long>(p, o->regcap);
-    o->d_linekey2 = carve<unsigned long long>(p, o->regcap);
-    o->d_lineidx = carve<int>(p, o->regcap);
-    o->d_lineidx2 = carve<int>(p, o->regcap);
     o->d_det = carve<plf_keyline>(p, F * noct * LINE_DETCAP);
-    o->d_cnt = carve<int>(p, CNT_MAXQ + F);
     o->d_detcount = carve<int>(p, F * noct);
-    o->d_mask = carve<unsigned>(p, F * (maxpx / 32 + 8192));
-    o->d_offs = carve<int>(p, F * (maxpx / 32 + 8192) + 64);
-    o->d_bincoef = carve<double>(p, F);
     // INTER_LINEAR_EXACT tables
     PLF_CUDA(ctx, cudaMalloc((void**)&o->d_tabs, (tabCount + 1) * sizeof(int2)));
     if (S != 1) {
@@ -306,61 +333,59 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         PLF_CUDA(ctx, cudaMemcpy(o->d_tabs, tabs.data(), tabCount * sizeof(int2), cudaMemcpyHostToDevice));
     }
 #ifndef PLF_EMU
-    size_t t1 = 0, t2 = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, t1, o->d_keys, o->d_keys2, (int)o->keycap, 0, 64, ctx->stream);
-    cub::DeviceRadixSort::SortPairs(nullptr, t2, o->d_linekey, o->d_linekey2, o->d_lineidx, o->d_lineidx2, o->regcap, 0, 48, ctx->stream);
-    size_t t3 = 0;
-    {
-        cub::TransformInputIterator<int, PopcOp, const unsigned*> it(o->d_mask, PopcOp());
-        cub::DeviceScan::InclusiveSum(nullptr, t3, it, o->d_offs + 1, (int)(F * (maxpx / 32 + 8192)), ctx->stream);
+    for (int k = 0; k < noct; k++) {
+        size_t t1 = 0, t2 = 0, t3 = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, t1, o->d_keys[k], o->d_keys2[k], (int)o->keycap[k], 0, 64, ctx->stream);
+        cub::DeviceRadixSort::SortPairs(nullptr, t2, o->d_linekey[k], o->d_linekey2[k], o->d_lineidx[k], o->d_lineidx2[k], o->regcap, 0, 64, ctx->stream);
+        cub::TransformInputIterator<int, PopcOp, const unsigned*> it(o->d_mask[k], PopcOp());
+        cub::DeviceScan::InclusiveSum(nullptr, t3, it, o->d_offs[k] + 1, (int)o->maskwords[k], ctx->stream);
+        o->cubtmp_bytes[k] = t1 > t2 ? t1 : t2;
+        if (t3 > o->cubtmp_bytes[k]) o->cubtmp_bytes[k] = t3;
+        PLF_CUDA(ctx, cudaMalloc(&o->d_cubtmp[k], o->cubtmp_bytes[k] + 256));
     }
-    o->cubtmp_bytes = t1 > t2 ? t1 : t2;
-    if (t3 > o->cubtmp_bytes) o->cubtmp_bytes = t3;
-    PLF_CUDA(ctx, cudaMalloc(&o->d_cubtmp, o->cubtmp_bytes + 256));
 #endif
-    PLF_CUDA(ctx, cudaMemset(o->d_offs, 0, sizeof(int)));
+    for (int k = 0; k < noct; k++) PLF_CUDA(ctx, cudaMemset(o->d_offs[k], 0, sizeof(int)));
     o->ws_w = w; o->ws_h = h; o->ws_frames = nframes;
     return PLF_OK;
 }
 
-static plf_status sort_keys(plf_line* o, int n, int end_bit)
+static plf_status sort_keys(plf_line* o, int k, int n, int end_bit, cudaStream_t st)
 {
     plf_ctx* ctx = o->ctx;
 #ifdef PLF_EMU
-    std::sort(o->d_keys, o->d_keys + n);
-    memcpy(o->d_keys2, o->d_keys, (size_t)n * 8);
+    std::sort(o->d_keys[k], o->d_keys[k] + n);
+    memcpy(o->d_keys2[k], o->d_keys[k], (size_t)n * 8);
 #else
-    size_t tb = o->cubtmp_bytes;
+    size_t tb = o->cubtmp_bytes[k];
     plf_prof_begin(ctx, "cub_radix_sort_keys");
-    cudaError_t e = cub::DeviceRadixSort::SortKeys(o->d_cubtmp, tb, o->d_keys, o->d_keys2, n, 0, end_bit, ctx->stream);
+    cudaError_t e = cub::DeviceRadixSort::SortKeys(o->d_cubtmp[k], tb, o->d_keys[k], o->d_keys2[k], n, 0, end_bit, st);
     plf_prof_end(ctx);
     PLF_CUDA(ctx, e);
 #endif
     return PLF_OK;
 }
 
-static plf_status sort_lines(plf_line* o, int nframes)
+static plf_status sort_lines(plf_line* o, int k, int nframes, cudaStream_t st)
 {
     plf_ctx* ctx = o->ctx;
 #ifdef PLF_EMU
     std::vector<std::pair<unsigned long long, int>> v(o->regcap);
-    for (int i = 0; i < o->regcap; i++) v[i] = std::make_pair(o->d_linekey[i], o->d_lineidx[i]);
+    for (int i = 0; i < o->regcap; i++) v[i] = std::make_pair(o->d_linekey[k][i], o->d_lineidx[k][i]);
     std::stable_sort(v.begin(), v.end(), [](const std::pair<unsigned long long, int>& a, const std::pair<unsigned long long, int>& b) { return a.first < b.first; });
-    for (int i = 0; i < o->regcap; i++) { o->d_linekey2[i] = v[i].first; o->d_lineidx2[i] = v[i].second; }
+    for (int i = 0; i < o->regcap; i++) { o->d_linekey2[k][i] = v[i].first; o->d_lineidx2[k][i] = v[i].second; }
 #else
-    size_t tb = o->cubtmp_bytes;
+    size_t tb = o->cubtmp_bytes[k];
     // line keys use bits [0, 40 + frame bits); padding keys are ~0, i.e. all ones in that range too (one past the last frame),
     // so sorting just those bits still puts them at the end
     int fbits = 1;
     while ((1 << fbits) < nframes + 1) fbits++;
     plf_prof_begin(ctx, "cub_radix_sort_lines");
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(o->d_cubtmp, tb, o->d_linekey, o->d_linekey2, o->d_lineidx, o->d_lineidx2, o->regcap, 0, 40 + fbits, ctx->stream);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(o->d_cubtmp[k], tb, o->d_linekey[k], o->d_linekey2[k], o->d_lineidx[k], o->d_lineidx2[k], o->regcap, 0, 40 + fbits, st);
     plf_prof_end(ctx);
     PLF_CUDA(ctx, e);
 #endif
     return PLF_OK;
 }
-
 
 // small device -> host reads go through pinned staging: a copy into pageable memory makes the driver wait for the stream
 // inside the call (holding its lock), which stalls the launches of every other context's host thread
@@ -383,9 +408,8 @@ static int pyrdown_interior(int w)
 }
 
 // cv::GaussianBlur 8U for a batch: 5 / 7 taps go to the register sliding-window kernel, other sizes to the generic one
-static plf_status gauss_batch(plf_ctx* ctx, const uint8_t* src, uint8_t* dst, int w, int h, int nframes, const GaussQ8& k)
+static plf_status gauss_batch(plf_ctx* ctx, cudaStream_t st, const uint8_t* src, uint8_t* dst, int w, int h, int nframes, const GaussQ8& k)
 {
-    cudaStream_t st = ctx->stream;
     const size_t frame = (size_t)w * h;
     if (k.ksize == 5 || k.ksize == 7) {
         BlurTaps taps;
@@ -408,92 +432,119 @@ static plf_status gauss_batch(plf_ctx* ctx, const uint8_t* src, uint8_t* dst, in
 // the other contexts' first phases instead of marching in lockstep.
 static std::mutex g_lsd_prephase;
 
-// LSDDetectorC::detect for a batch resident in d_oct[0]: fills d_det / d_detcount
+// LSDDetectorC::detect for a batch resident in d_oct[0]: fills d_det / d_detcount.
+// The octaves are independent until the line selection: each has its own workspace and (when there are two) its own
+// stream, the host walks both through the same phases, so the two region-growing chains run side by side.
+// With profiling on, everything stays on the context stream (the per-kernel event times must not overlap).
 static plf_status lsd_detect_batch(plf_line* o, int nframes)
 {
     plf_ctx* ctx = o->ctx;
-    cudaStream_t st = ctx->stream;
     const int noct = o->prm.nlevels;
     const double S = o->prm.scale;
-    PLF_CUDA(ctx, cudaMemsetAsync(o->d_detcount, 0, (size_t)nframes * noct * sizeof(int), st));
-    PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt + CNT_ERR, 0, sizeof(int), st));
+    cudaStream_t st0 = ctx->stream;
+    cudaStream_t stk[LINE_MAX_OCT];
+    for (int k = 0; k < noct; k++) stk[k] = (k == 0 || ctx->prof_on) ? st0 : o->st2;
+    PLF_CUDA(ctx, cudaMemsetAsync(o->d_detcount, 0, (size_t)nframes * noct * sizeof(int), st0));
+    // whatever is still queued on this stream (the image upload of a host-buffer call) finishes before the turn is
+    // taken: the lock must not be held across a PCIe transfer
+    PLF_CUDA(ctx, cudaStreamSynchronize(st0));
+    std::unique_lock<std::mutex> prephase(g_lsd_prephase);
+    // computeGaussianPyramid: pyrDown, no pre-blur (LSDDetector_custom.cpp:56-73)
+    for (int k = 1; k < noct; k++) {
+        const int pdF = pyrdown_interior(o->ow[k - 1]);
+        PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(pdF, 32) + 1, plf_div_up(o->oh[k], 4 * PD_ROWS), nframes), dim3(32, 4), 0, st0, (const uint8_t*)o->d_oct[k - 1],
+                   (size_t)o->ow[k - 1] * o->oh[k - 1], o->ow[k - 1], o->ow[k - 1], o->oh[k - 1], o->d_oct[k], (size_t)o->ow[k] * o->oh[k], o->ow[k], pdF,
+                   plf_div_up(pdF, 32));
+        PLF_CHECK_LAUNCH(ctx);
+    }
+    if (noct > 1 && stk[1] != st0) {
+        PLF_CUDA(ctx, cudaEventRecord(o->ev_img, st0));
+        PLF_CUDA(ctx, cudaStreamWaitEvent(stk[1], o->ev_img, 0));
+    }
+    int nwords[LINE_MAX_OCT], nkeys[LINE_MAX_OCT], mwk[LINE_MAX_OCT];
+    // ---- phase 1: scaled image, gradient, mask, components, keys ----
     for (int k = 0; k < noct; k++) {
         const int ow = o->ow[k], oh = o->oh[k], sw = o->sw[k], sh = o->sh[k], sp = o->sp[k];
-        // whatever is still queued on this stream (the image upload of a host-buffer call, the previous octave's tail)
-        // finishes before the turn is taken: the lock must not be held across a PCIe transfer
-        PLF_CUDA(ctx, cudaStreamSynchronize(st));
-        std::unique_lock<std::mutex> prephase(g_lsd_prephase);
-        if (k > 0) {   // computeGaussianPyramid: pyrDown, no pre-blur (LSDDetector_custom.cpp:56-73)
-            const int pdF = pyrdown_interior(o->ow[k - 1]);
-            PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(pdF, 32) + 1, plf_div_up(oh, 4 * PD_ROWS), nframes), dim3(32, 4), 0, st, (const uint8_t*)o->d_oct[k - 1],
-                       (size_t)o->ow[k - 1] * o->oh[k - 1], o->ow[k - 1], o->ow[k - 1], o->oh[k - 1], o->d_oct[k], (size_t)ow * oh, ow, pdF, plf_div_up(pdF, 32));
-            PLF_CHECK_LAUNCH(ctx);
-        }
+        cudaStream_t st = stk[k];
         // the image the gradient is taken of: the octave itself (SCALE == 1, pitch = octave width) or its blurred and
         // resized copy (pitch = sp)
         const uint8_t* scaled = o->d_oct[k];
         int spitch = ow;
         size_t sframe = (size_t)ow * oh;
         if (S != 1) {
-            { plf_status gs = gauss_batch(ctx, o->d_oct[k], o->d_tmp, ow, oh, nframes, o->lsd_gauss); if (gs) return gs; }
-            PLF_LAUNCH(k_resize_exact, dim3(plf_div_up(sw, 32), plf_div_up(sh, 8), nframes), dim3(32, 8), 0, st, (const uint8_t*)o->d_tmp,
-                       (size_t)ow * oh, ow, ow, oh, o->d_scaled, (size_t)sp * sh, sp, sw, sh, o->xtab[k], o->ytab[k]);
+            { plf_status gs = gauss_batch(ctx, st, o->d_oct[k], o->d_tmp[k], ow, oh, nframes, o->lsd_gauss); if (gs) return gs; }
+            PLF_LAUNCH(k_resize_exact, dim3(plf_div_up(sw, 32), plf_div_up(sh, 8), nframes), dim3(32, 8), 0, st, (const uint8_t*)o->d_tmp[k],
+                       (size_t)ow * oh, ow, ow, oh, o->d_scaled[k], (size_t)sp * sh, sp, sw, sh, o->xtab[k], o->ytab[k]);
             PLF_CHECK_LAUNCH(ctx);
-            scaled = o->d_scaled; spitch = sp; sframe = (size_t)sp * sh;
+            scaled = o->d_scaled[k]; spitch = sp; sframe = (size_t)sp * sh;
         }
-        PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt, 0, 4 * sizeof(int), st));
-        PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt + CNT_BCOUNT, 0, (CNT_MAXQ - CNT_BCOUNT) * sizeof(int), st));
-        PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt + CNT_MAXQ, 0xff, (size_t)nframes * sizeof(int), st));   // maxq = -1
+        PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt[k], 0, 8 * sizeof(int), st));
+        PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt[k] + CNT_BCOUNT, 0, (CNT_MAXQ - CNT_BCOUNT) * sizeof(int), st));
+        PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt[k] + CNT_MAXQ, 0xff, (size_t)nframes * sizeof(int), st));   // maxq = -1
         // from here on every per-pixel array has sp columns per row (sw real ones + NOTDEF padding)
         const int mw = plf_div_up(sp, 32);
+        mwk[k] = mw;
         dim3 g2(mw, plf_div_up(sh, 8), nframes), b2(32, 8);
         PLF_LAUNCH(k_lsd_grad, dim3(plf_div_up(sp, 128), plf_div_up(sh, 4), nframes), dim3(32, 4), 0, st, scaled, sframe, spitch, sw, sp, sh, o->qthr,
-                   o->d_q, o->d_fa, o->d_label, o->d_mask, mw, o->d_cnt + CNT_MAXQ);
+                   o->d_q[k], o->d_fa[k], o->d_label[k], o->d_mask[k], mw, o->d_cnt[k] + CNT_MAXQ);
         PLF_CHECK_LAUNCH(ctx);
-        PLF_LAUNCH(k_lsd_bincoef, dim3(plf_div_up(nframes, 128)), dim3(128), 0, st, (const int*)(o->d_cnt + CNT_MAXQ), nframes, o->prm.n_bins,
-                   o->d_bincoef);
+        PLF_LAUNCH(k_lsd_bincoef, dim3(plf_div_up(nframes, 128)), dim3(128), 0, st, (const int*)(o->d_cnt[k] + CNT_MAXQ), nframes, o->prm.n_bins,
+                   o->d_bincoef[k]);
         PLF_CHECK_LAUNCH(ctx);
-        PLF_LAUNCH(k_ccl_merge, g2, b2, 0, st, o->d_label, (const unsigned*)o->d_mask, mw, sp, sh);
+        PLF_LAUNCH(k_ccl_merge, g2, b2, 0, st, o->d_label[k], (const unsigned*)o->d_mask[k], mw, sp, sh);
         PLF_CHECK_LAUNCH(ctx);
         // key positions: inclusive scan of the mask popcounts (d_offs[0] = 0 is set once per workspace)
-        const int nwords = nframes * sh * mw;
+        nwords[k] = nframes * sh * mw;
 #ifdef PLF_EMU
-        { int acc = 0; o->d_offs[0] = 0; for (int i = 0; i < nwords; i++) { acc += __builtin_popcount(o->d_mask[i]); o->d_offs[i + 1] = acc; } }
+        { int acc = 0; o->d_offs[k][0] = 0; for (int i = 0; i < nwords[k]; i++) { acc += __builtin_popcount(o->d_mask[k][i]); o->d_offs[k][i + 1] = acc; } }
 #else
         {
-            size_t tb = o->cubtmp_bytes;
-            cub::TransformInputIterator<int, PopcOp, const unsigned*> it(o->d_mask, PopcOp());
+            size_t tb = o->cubtmp_bytes[k];
+            cub::TransformInputIterator<int, PopcOp, const unsigned*> it(o->d_mask[k], PopcOp());
             plf_prof_begin(ctx, "cub_scan_mask");
-            cudaError_t e = cub::DeviceScan::InclusiveSum(o->d_cubtmp, tb, it, o->d_offs + 1, nwords, st);
+            cudaError_t e = cub::DeviceScan::InclusiveSum(o->d_cubtmp[k], tb, it, o->d_offs[k] + 1, nwords[k], st);
             plf_prof_end(ctx);
             PLF_CUDA(ctx, e);
         }
 #endif
-        PLF_LAUNCH(k_lsd_keys, g2, b2, 0, st, (const int*)o->d_label, (const int*)o->d_q, (const unsigned*)o->d_mask, mw, (const int*)o->d_offs,
-                   (const double*)o->d_bincoef, sp, sh, o->prm.n_bins, o->d_keys, (int)o->keycap, o->kbits[k]);
+        PLF_LAUNCH(k_lsd_keys, g2, b2, 0, st, (const int*)o->d_label[k], (const int*)o->d_q[k], (const unsigned*)o->d_mask[k], mw, (const int*)o->d_offs[k],
+                   (const double*)o->d_bincoef[k], sp, sh, o->prm.n_bins, o->d_keys[k], (int)o->keycap[k], o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
-        int nkeys = 0;
-        { plf_status rs = read_ints(ctx, o->d_offs + nwords, 1, &nkeys); if (rs) return rs; }
-        if (nkeys > (int)o->keycap) return plf_fail(ctx, PLF_ERR_CAPACITY, "LSD key buffer overflow");
-        if (nkeys > 0) {
-            int fbits = 1;
-            while ((1 << fbits) < nframes) fbits++;
-            plf_status s = sort_keys(o, nkeys, o->keybits[k] + fbits > 64 ? 64 : o->keybits[k] + fbits);
-            if (s) return s;
-            for (int pass = 0; pass < 2; pass++) {
-                PLF_LAUNCH(k_lsd_heads, dim3(plf_div_up(nkeys, 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2, nkeys, o->d_comp,
-                           o->d_cnt + CNT_BCOUNT, o->d_cnt + CNT_BFILL, pass, o->kbits[k]);
-                PLF_CHECK_LAUNCH(ctx);
-            }
-            // the sorted position of every defined pixel (compact component index), then the big components with
-            // warp-cooperative ordered growth (one warp each) and everything else with one thread per component
-            PLF_LAUNCH(k_lsd_cid, dim3(plf_div_up(nkeys, 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2, nkeys, o->d_label,
-                       (const float*)o->d_fa, o->d_cs, (size_t)sp * sh, o->kbits[k]);
+        PLF_CUDA(ctx, cudaMemcpyAsync(o->h_pin + 64 * k, o->d_offs[k] + nwords[k], sizeof(int), cudaMemcpyDeviceToHost, st));   // pinned staging
+    }
+    // ---- phase 2: sort, component heads, sorted positions ----
+    for (int k = 0; k < noct; k++) {
+        cudaStream_t st = stk[k];
+        PLF_CUDA(ctx, cudaStreamSynchronize(st));
+        nkeys[k] = o->h_pin[64 * k];
+        if (nkeys[k] > (int)o->keycap[k]) return plf_fail(ctx, PLF_ERR_CAPACITY, "LSD key buffer overflow");
+        if (nkeys[k] <= 0) continue;
+        int fbits = 1;
+        while ((1 << fbits) < nframes) fbits++;
+        plf_status s = sort_keys(o, k, nkeys[k], o->keybits[k] + fbits > 64 ? 64 : o->keybits[k] + fbits, st);
+        if (s) return s;
+        for (int pass = 0; pass < 2; pass++) {
+            PLF_LAUNCH(k_lsd_heads, dim3(plf_div_up(nkeys[k], 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2[k], nkeys[k], o->d_comp[k],
+                       o->d_cnt[k] + CNT_BCOUNT, o->d_cnt[k] + CNT_BFILL, pass, o->kbits[k]);
             PLF_CHECK_LAUNCH(ctx);
-            // size the used-bitmap of the warp kernel from the largest component present (bucket counts)
-            int bc[LSD_NBUCKET];
-            { plf_status rs = read_ints(ctx, o->d_cnt + CNT_BCOUNT, LSD_NBUCKET, bc); if (rs) return rs; }
-            prephase.unlock();   // everything up to here has finished on the GPU; growing may overlap other contexts
+        }
+        // the sorted position of every defined pixel (compact component index) and its cos / sin
+        PLF_LAUNCH(k_lsd_cid, dim3(plf_div_up(nkeys[k], 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2[k], nkeys[k], o->d_label[k],
+                   (const float*)o->d_fa[k], o->d_cs[k], (size_t)o->sp[k] * o->sh[k], o->kbits[k]);
+        PLF_CHECK_LAUNCH(ctx);
+        PLF_CUDA(ctx, cudaMemcpyAsync(o->h_pin + 64 * k + 8, o->d_cnt[k] + CNT_BCOUNT, LSD_NBUCKET * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    for (int k = 0; k < noct; k++)
+        if (nkeys[k] > 0) PLF_CUDA(ctx, cudaStreamSynchronize(stk[k]));
+    prephase.unlock();   // everything up to here has finished on the GPU; growing may overlap other contexts
+    // ---- phase 3: region growing (the latency-bound chains of both octaves side by side), rectangles, keylines ----
+    for (int k = 0; k < noct; k++) {
+        cudaStream_t st = stk[k];
+        const int sp = o->sp[k], sh = o->sh[k];
+        if (nkeys[k] > 0) {
+            // the big components with warp-cooperative ordered growth (one warp each), everything else with one thread per
+            // component; the used-bitmap of the warp kernel is sized from the largest component present (bucket counts)
+            const int* bc = o->h_pin + 64 * k + 8;
             int topb = 0, nbig = 0;
             for (int b = 0; b < LSD_NBUCKET; b++) { if (bc[b]) topb = b; if (b >= LSD_BIG_BUCKET) nbig += bc[b]; }
             int wg_maxc = 1 << (topb + 1);
@@ -501,28 +552,33 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             if (wg_maxc < 1024) wg_maxc = 1024;
             const int wg_smem = WG_WARPS * (wg_maxc / 8);
 #ifndef PLF_EMU
-            PLF_CUDA(ctx, cudaFuncSetAttribute(k_lsd_grow_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem));
+            PLF_CUDA(ctx, cudaFuncSetAttribute(k_lsd_grow_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_WARPS * (WARPGROW_MAXC / 8)));
 #endif
             const int wg_ctas = plf_div_up(nbig, WG_WARPS) < 148 * 4 ? plf_div_up(nbig, WG_WARPS) : 148 * 4;
-            if (nbig > 0) PLF_LAUNCH(k_lsd_grow_warp, dim3(wg_ctas), dim3(32 * WG_WARPS), wg_smem, st, (const unsigned long long*)o->d_keys2,
-                       (const int2*)o->d_comp, (const int*)(o->d_cnt + CNT_BCOUNT), (const float*)o->d_fa, (const float2*)o->d_cs,
-                       (const int*)o->d_label, sp, sh, o->prec, o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap, o->kbits[k], wg_maxc);
+            if (nbig > 0) PLF_LAUNCH(k_lsd_grow_warp, dim3(wg_ctas), dim3(32 * WG_WARPS), wg_smem, st, (const unsigned long long*)o->d_keys2[k],
+                       (const int2*)o->d_comp[k], (const int*)(o->d_cnt[k] + CNT_BCOUNT), (const float*)o->d_fa[k], (const float2*)o->d_cs[k],
+                       (const int*)o->d_label[k], sp, sh, o->prec, o->min_reg[k], o->d_regpts[k], o->d_regions[k], o->d_cnt[k] + CNT_NREG, o->regcap, o->kbits[k], wg_maxc);
             PLF_CHECK_LAUNCH(ctx);
-            PLF_LAUNCH(k_lsd_grow, dim3(148 * 4), dim3(128), 0, st, (const unsigned long long*)o->d_keys2, nkeys, (const int2*)o->d_comp,
-                       (const int*)(o->d_cnt + CNT_BCOUNT), o->d_cnt + CNT_NEXT, o->d_fa, (const float2*)o->d_cs, sp, sh, o->prec,
-                       o->min_reg[k], o->d_regpts, o->d_regions, o->d_cnt + CNT_NREG, o->regcap, 1, wg_maxc, o->kbits[k]);
+            PLF_LAUNCH(k_lsd_grow, dim3(148 * 4), dim3(128), 0, st, (const unsigned long long*)o->d_keys2[k], nkeys[k], (const int2*)o->d_comp[k],
+                       (const int*)(o->d_cnt[k] + CNT_BCOUNT), o->d_cnt[k] + CNT_NEXT, o->d_fa[k], (const float2*)o->d_cs[k], sp, sh, o->prec,
+                       o->min_reg[k], o->d_regpts[k], o->d_regions[k], o->d_cnt[k] + CNT_NREG, o->regcap, 1, wg_maxc, o->kbits[k]);
             PLF_CHECK_LAUNCH(ctx);
         }
-        PLF_LAUNCH(k_lsd_rect, dim3(plf_div_up(o->regcap, RECT_WARPS)), dim3(32 * RECT_WARPS), 0, st, (const LsdRegion*)o->d_regions,
-                   (const int*)(o->d_cnt + CNT_NREG), o->regcap, (const int*)o->d_regpts, (const int*)o->d_q, sp, sh, o->prec, S, o->d_lines,
-                   o->d_linekey, o->d_lineidx, o->d_cnt + CNT_ERR, o->kbits[k]);
+        PLF_LAUNCH(k_lsd_rect, dim3(plf_div_up(o->regcap, RECT_WARPS)), dim3(32 * RECT_WARPS), 0, st, (const LsdRegion*)o->d_regions[k],
+                   (const int*)(o->d_cnt[k] + CNT_NREG), o->regcap, (const int*)o->d_regpts[k], (const int*)o->d_q[k], sp, sh, o->prec, S, o->d_lines[k],
+                   o->d_linekey[k], o->d_lineidx[k], o->d_cnt[k] + CNT_ERR, o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
-        plf_status s = sort_lines(o, nframes);
+        plf_status s = sort_lines(o, k, nframes, st);
         if (s) return s;
-        PLF_LAUNCH(k_lsd_keylines, dim3(plf_div_up(o->regcap, 128)), dim3(128), 0, st, (const unsigned long long*)o->d_linekey2,
-                   (const int*)o->d_lineidx2, o->regcap, (const float4*)o->d_lines, nframes, k, noct, ow, oh, o->prm.min_line_length,
+        PLF_LAUNCH(k_lsd_keylines, dim3(plf_div_up(o->regcap, 128)), dim3(128), 0, st, (const unsigned long long*)o->d_linekey2[k],
+                   (const int*)o->d_lineidx2[k], o->regcap, (const float4*)o->d_lines[k], nframes, k, noct, o->ow[k], o->oh[k], o->prm.min_line_length,
                    o->d_det, o->d_detcount, LINE_DETCAP);
         PLF_CHECK_LAUNCH(ctx);
+    }
+    // the selection / LBD that follow run on the context stream: join octave 1
+    if (noct > 1 && stk[1] != st0) {
+        PLF_CUDA(ctx, cudaEventRecord(o->ev_join, stk[1]));
+        PLF_CUDA(ctx, cudaStreamWaitEvent(st0, o->ev_join, 0));
     }
     return PLF_OK;
 }
@@ -551,7 +607,7 @@ static plf_status lbd_batch(plf_line* o, int nframes, const plf_keyline* d_kl, c
     for (int k = 0; k < noct; k++) {
         const int ow = o->ow[k], oh = o->oh[k];
         if (k == 0) {   // computeGaussianPyramid (binary_descriptor_custom.cpp:350-370): blur 5x5 sigma 1, then pyrDown
-            { plf_status gs = gauss_batch(ctx, o->d_oct[0], o->d_lbdimg[0], ow, oh, nframes, o->lbd_gauss); if (gs) return gs; }
+            { plf_status gs = gauss_batch(ctx, st, o->d_oct[0], o->d_lbdimg[0], ow, oh, nframes, o->lbd_gauss); if (gs) return gs; }
         } else {
             const int pdF = pyrdown_interior(o->ow[k - 1]);
             PLF_LAUNCH(k_pyrdown, dim3(plf_div_up(pdF, 32) + 1, plf_div_up(oh, 4 * PD_ROWS), nframes), dim3(32, 4), 0, st, (const uint8_t*)o->d_lbdimg[k - 1],
@@ -642,9 +698,11 @@ static plf_status check_counts(plf_ctx* ctx, const int32_t* n_out, int nframes)
 static plf_status check_regions(plf_line* o)
 {
     plf_ctx* ctx = o->ctx;
-    int err = 0;
-    { plf_status rs = read_ints(ctx, o->d_cnt + CNT_ERR, 1, &err); if (rs) return rs; }
-    if (err) return plf_fail(ctx, PLF_ERR_CAPACITY, "LSD region buffer overflow (more than %d regions in the batch)", o->regcap);
+    for (int k = 0; k < o->prm.nlevels; k++) {
+        int err = 0;
+        { plf_status rs = read_ints(ctx, o->d_cnt[k] + CNT_ERR, 1, &err); if (rs) return rs; }
+        if (err) return plf_fail(ctx, PLF_ERR_CAPACITY, "LSD region buffer overflow (more than %d regions in the batch)", o->regcap);
+    }
     return PLF_OK;
 }
 
