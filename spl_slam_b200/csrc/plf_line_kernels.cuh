@@ -608,24 +608,13 @@ __device__ __forceinline__ WgCand wg_load(int q, int arena, const int* ring, con
         // the entries accepted from here will look one pixel further: pull the 5x5 ring towards L1 now
         const int x2 = c.xx + gdx, y2 = c.yy + gdy;
         if (x2 >= 0 && y2 >= 0 && x2 < w && y2 < h) {
-            const int q2 = y2 * w + x2;
+            const int q2 = qi + gdy * w + gdx;
             PLF_PREFETCH_L1(&CID[q2]);
             PLF_PREFETCH_L1(&F[q2]);
             PLF_PREFETCH_L1(&CS[q2]);
         }
     }
     return c;
-}
-
-// lanes (of earlier queue entries) that test the same pixel as lane (grp, nbr) of entry pp: the pixel is a
-// neighbour of entry e' = pp_other iff it lies within one pixel of it
-__device__ __forceinline__ unsigned wg_dupmask(int xx, int yy, int grp, int pp_other, int g_other)
-{
-    if (g_other >= grp) return 0u;
-    const int dx = xx - (pp_other & 0xffff), dy = yy - (pp_other >> 16);
-    if (dx < -1 || dx > 1 || dy < -1 || dy > 1 || (dx == 0 && dy == 0)) return 0u;
-    const int nb = (dy + 1) * 3 + dx + 1;
-    return 1u << (g_other * 8 + (nb < 4 ? nb : nb - 1));
 }
 
 __device__ __forceinline__ double wg_ntheta(double reg_angle, double a)
@@ -729,10 +718,6 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
                         cd.inb = false; cd.ci = -1; cd.pp = -(4 << 16);   // far outside: never adjacent to a pixel
                         if (grp < ng) cd = wg_load(r + grp, arena, ring, regpts, gdx, gdy, w, h, CID, F, CS);
                     }
-                    // lanes of earlier entries looking at the same pixel (off the critical path: entries are known here)
-                    unsigned dupmask = 0u;
-#pragma unroll
-                    for (int g2 = 0; g2 < WG_E - 1; g2++) dupmask |= wg_dupmask(cd.xx, cd.yy, grp, __shfl_sync(FULL, cd.pp, g2 * 8), g2);
                     const int rn = r + ng;
                     npf = min(WG_E, arena - rn);
                     if (grp < npf) pf = wg_load(rn + grp, arena, ring, regpts, gdx, gdy, w, h, CID, F, CS);
@@ -753,14 +738,19 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
                             const float L2 = sumdx * sumdx + sumdy * sumdy;
                             if (L2 >= 16.f) {
                                 const float D = (float)__popc(m) * sphi * rsqrtf(L2) + 1e-3f;
-                                double margin = n_theta - prec;
-                                if (margin < 0) margin = -margin;
-                                const bool risky = cand && (float)margin <= D * 1.0001f;
+                                const double Dd = (double)D;
+                                const bool risky = cand && fabs(n_theta - prec) <= Dd;
                                 fast = D <= 0.09f && !__any_sync(FULL, risky);
                             }
                         }
                         if (fast) {
-                            const bool win = pass && !(m & dupmask);     // first lane per pixel
+                            // first lane per pixel: two queue entries can have the same neighbour (needed only when
+                            // more than one lane passes)
+                            bool win = pass;
+                            if (__popc(m) > 1) {
+                                const unsigned same = __match_any_sync(FULL, cc);     // non-candidates hold unique negative values
+                                win = pass && (__ffs((int)same) - 1 == lane);
+                            }
                             const unsigned mw = __ballot_sync(FULL, win);
                             const int nw = __popc(mw);
                             if (win) {
@@ -790,10 +780,11 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
                                     ring[arena & (WG_RING - 1)] = cd.xx | (cd.yy << 16);
                                 }
                                 arena++;
+                                const int cc0 = __shfl_sync(FULL, cc, k0);
                                 sumdx += __shfl_sync(FULL, cd.cv.x, k0);
                                 sumdy += __shfl_sync(FULL, cd.cv.y, k0);
                                 reg_angle = (double)plf_fast_atan2(sumdy, sumdx) * LSD_D2R;
-                                cand = cand && lane > k0 && !((dupmask >> k0) & 1u);   // earlier tests stand; the same pixel seen from another entry is now used
+                                cand = cand && lane > k0 && cc != cc0;             // earlier tests stand; the same pixel seen from another entry is now used
                                 pass = cand && wg_ntheta(reg_angle, a) <= prec;
                                 m = __ballot_sync(FULL, pass);
                                 if (!m) break;
