@@ -324,3 +324,29 @@ def test_grid_area_queries_and_projection_matching(S, oracle, gpu_ctx):
     off, idx = S.features_in_area(gpu_ctx, M, gl, qx, qy, qr, keylines=K)
     ooff, oidx = oracle.grid_candidates(M, ogl, qx, qy, qr, keylines=K)
     assert np.array_equal(off, ooff) and np.array_equal(idx, oidx) and len(idx) > len(M)
+
+
+def test_1080p_batch_equals_single_and_frame_sharding(S, oracle, gpu_ctx):
+    """BASELINE config 4 (1920x1080 frames, frame i -> GPU i mod G) through its size-independent property: a frame's
+    result does not depend on the batch it travels in, so any frame sharding reproduces the single-frame results."""
+    from spl_slam_b200 import sharded
+    ex = S.ORBextractor(2000, 1.2, 8, 20, 7, ctx=gpu_ctx)
+    le, prm = _line_objs(S, oracle, gpu_ctx, 800)
+    imgs = np.stack([oracle.synth_image(1920, 1080, 60 + i) for i in range(6)])
+    ks, ds = ex.extract_batch(imgs)
+    Ks, Ms, Ds = le.extract_batch(imgs)
+    ox = oracle.ORBextractor(2000, 1.2, 8, 20, 7)
+    for b in (0, 5):                                           # two frames against the oracle (1080p LSD is ~0.5 s each on the CPU)
+        ok, od = ox(imgs[b])
+        assert np.array_equal(ks[b].view(np.uint8), ok.view(np.uint8)) and np.array_equal(ds[b], od)
+        oK, oM, oD = oracle.line_extract(prm, imgs[b])
+        assert np.array_equal(Ks[b].view(np.uint8), oK.view(np.uint8)) and np.array_equal(Ds[b], oD)
+    for world in (2, 4):                                       # every shard of every world size gives the same per-frame output
+        for rank in range(world):
+            mine = list(sharded.frame_shard(len(imgs), rank, world))
+            assert mine == [i for i in range(len(imgs)) if i % world == rank]
+            k2, d2 = ex.extract_batch(imgs[mine])
+            K2, M2, D2 = le.extract_batch(imgs[mine])
+            for j, i in enumerate(mine):
+                assert np.array_equal(k2[j].view(np.uint8), ks[i].view(np.uint8)) and np.array_equal(d2[j], ds[i])
+                assert np.array_equal(K2[j].view(np.uint8), Ks[i].view(np.uint8)) and np.array_equal(D2[j], Ds[i])
