@@ -53,6 +53,7 @@ typedef struct {
 typedef struct plf_ctx plf_ctx;
 typedef struct plf_orb plf_orb;
 typedef struct plf_line plf_line;
+typedef struct plf_vocab plf_vocab;
 
 /* ---- context: one per host thread / GPU stream.  The reference calls its extractors and
  * matchNNR from concurrent std::threads (src/Frame.cc:116-119, :301-304;
@@ -244,6 +245,25 @@ plf_status plf_grid_candidates(plf_ctx* ctx, const plf_keypoint* host_kps, const
                                const plf_grid_params* g, const float* host_qx, const float* host_qy, const float* host_qr,
                                const int32_t* host_qminl, const int32_t* host_qmaxl, int nq, int32_t* host_cand_off,
                                int32_t* host_cand_idx, int cand_cap, int* total);
+
+/* ---- bag of words: the per-feature vocabulary-tree descent of DBoW2's TemplatedVocabulary::transform(features, BowVector&,
+ * FeatureVector&, levelsup) (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1124-1190, :1218-1258) as called from
+ * Frame::ComputeBoW (src/Frame.cc:724-731), FORB::distance = 256-bit Hamming.  For feature i: word[i] = leaf word id,
+ * weight[i] = its weight (0 = stopped word), node[i] = ancestor at level L - levelsup (0 when that level is <= 0 or the
+ * leaf is shallower -- the reference leaves it uninitialised then).  The ordered BowVector / FeatureVector insertions
+ * (addWeight, addFeature, normalize) are replayed on the host from these arrays (plf_slam_shim.hpp). ---- */
+/* vocabulary from flat arrays: node 0 is the root, parent[i] < i, children keep node-id order and words are numbered in
+ * leaf order, exactly as loadFromTextFile builds them (:1377-1418); desc is nnodes x 32 bytes */
+plf_status plf_vocab_create(plf_ctx* ctx, int k, int L, int scoring, int weighting, int nnodes, const int32_t* parent,
+                            const uint8_t* desc, const double* weight, const uint8_t* is_leaf, plf_vocab** out);
+/* the ORBvoc.txt text format of TemplatedVocabulary::loadFromTextFile (:1338-1424) */
+plf_status plf_vocab_load_text(plf_ctx* ctx, const char* path, plf_vocab** out);
+void plf_vocab_destroy(plf_vocab* v);
+plf_status plf_vocab_info(const plf_vocab* v, int* k, int* L, int* nnodes, int* nwords, int* scoring, int* weighting);
+plf_status plf_bow_transform(plf_vocab* v, const uint8_t* host_desc, int n, int levelsup, int32_t* host_word,
+                             double* host_weight, int32_t* host_node);
+plf_status plf_bow_transform_device(plf_vocab* v, const uint8_t* dev_desc, int n, int levelsup, int32_t* dev_word,
+                                    double* dev_weight, int32_t* dev_node);
 
 /* ---- stereo: replaces Frame::ComputeStereoMatches (src/Frame.cc:881-1055).  Reads the pyramids the two
  * extractors hold after their last extraction (the reference reads mpORBextractorLeft/Right->mvImagePyramid),

@@ -17,6 +17,8 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <map>
+#include <cmath>
 #include <cstring>
 #include "plf.h"
 #ifndef PLF_SHIM_MOCK_OPENCV
@@ -254,6 +256,48 @@ public:
 
 private:
     PlfContext ctx_;
+};
+
+// ORBVocabulary::transform(features, BowVector&, FeatureVector&, levelsup) as used by Frame::ComputeBoW
+// (src/Frame.cc:724-731; Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1124-1190): the tree descent of every descriptor
+// runs on the GPU, the ordered map insertions (BowVector::addWeight, FeatureVector::addFeature) and the L1
+// normalisation are replayed here in feature order, so the two maps equal DBoW2's (TF_IDF / TF weighting, L1 scoring,
+// what ORBvoc.txt uses).  BowVec / FeatVec are any std::map-like types: DBoW2::BowVector / DBoW2::FeatureVector fit.
+class PlfVocabulary {
+public:
+    explicit PlfVocabulary(const std::string& orbvoc_txt, int device = 0) : ctx_(device), voc_(nullptr)
+    {
+        ctx_.check(plf_vocab_load_text(ctx_.get(), orbvoc_txt.c_str(), &voc_));
+    }
+    ~PlfVocabulary() { plf_vocab_destroy(voc_); }
+    PlfVocabulary(const PlfVocabulary&) = delete;
+    PlfVocabulary& operator=(const PlfVocabulary&) = delete;
+
+    template <class BowVec, class FeatVec>
+    void transform(const cv::Mat& descriptors, BowVec& v, FeatVec& fv, int levelsup)
+    {
+        v.clear();
+        fv.clear();
+        const int n = descriptors.rows;
+        if (n == 0) return;
+        word_.resize(n); weight_.resize(n); node_.resize(n);
+        ctx_.check(plf_bow_transform(voc_, descriptors.data, n, levelsup, word_.data(), weight_.data(), node_.data()));
+        for (int i = 0; i < n; i++)
+            if (weight_[i] > 0) {                           // not stopped
+                v[(unsigned)word_[i]] += weight_[i];        // BowVector::addWeight
+                fv[(unsigned)node_[i]].push_back((unsigned)i);   // FeatureVector::addFeature
+            }
+        double norm = 0.0;                                  // BowVector::normalize(L1)
+        for (typename BowVec::iterator it = v.begin(); it != v.end(); ++it) norm += std::fabs(it->second);
+        if (norm > 0.0)
+            for (typename BowVec::iterator it = v.begin(); it != v.end(); ++it) it->second /= norm;
+    }
+
+private:
+    PlfContext ctx_;
+    plf_vocab* voc_;
+    std::vector<int> word_, node_;
+    std::vector<double> weight_;
 };
 
 // Frame::ComputeStereoMatches (src/Frame.cc:881-1055) for the pair the two extractors processed last: fills mvuRight

@@ -64,6 +64,7 @@ def lib():
         L.orc_orb_level_raw.argtypes = [vp, C.c_int, i32p, i32p, i32p]
         L.orc_orb_level_kept_count.argtypes = [vp, C.c_int]
         L.orc_grid_candidates.argtypes = [vp, vp, C.c_int, vp, f32p, f32p, f32p, i32p, i32p, C.c_int, i32p, i32p, C.c_int]
+        L.orc_bow_transform.argtypes = [C.c_int, C.c_int, i32p, u8p, vp, u8p, u8p, C.c_int, C.c_int, i32p, vp, i32p]
         L.orc_stereo_match.argtypes = [vp, vp, vp, u8p, C.c_int, vp, u8p, C.c_int, C.c_float, C.c_float, f32p, f32p]
         L.orc_distribute_octree.argtypes = [i32p, i32p, i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_int, i32p, C.c_int]
@@ -247,6 +248,57 @@ def stereo_match(orbL, orbR, kL, dL, kR, dR, mb, mbf):
     u = np.empty(len(kL), np.float32); z = np.empty(len(kL), np.float32)
     lib().orc_stereo_match(orbL._h, orbR._h, _p(kL), _p(dL), len(kL), _p(kR), _p(dR), len(kR), mb, mbf, _p(u), _p(z))
     return u, z
+
+
+def synth_vocabulary(k, L, seed, dup=True):
+    """A random k-ary vocabulary tree of depth L in loadFromTextFile node order (breadth first): parent, descriptors,
+    weights (some zero = stopped words), leaf flags.  With dup, some siblings share a descriptor (first-minimum ties)."""
+    rng = np.random.default_rng(seed)
+    parent, leaf = [0], [0]
+    level_nodes = [0]
+    for lv in range(1, L + 1):
+        nxt = []
+        for p in level_nodes:
+            for _ in range(k):
+                parent.append(p); leaf.append(1 if lv == L else 0); nxt.append(len(parent) - 1)
+        level_nodes = nxt
+    n = len(parent)
+    desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    if dup:
+        for i in range(2, n, 7):
+            if parent[i] == parent[i - 1]:
+                desc[i] = desc[i - 1]
+    weight = rng.uniform(0.0, 9.0, n)
+    weight[rng.random(n) < 0.05] = 0.0
+    weight[np.array(leaf) == 0] = 0.0
+    return (np.array(parent, np.int32), np.ascontiguousarray(desc), np.ascontiguousarray(weight, np.float64), np.array(leaf, np.uint8))
+
+
+def bow_transform(vocab, L, feats, levelsup):
+    """Per-feature tree descent (TemplatedVocabulary.h:1218-1258) -> (word, weight, node)."""
+    parent, desc, weight, leaf = vocab
+    feats = np.ascontiguousarray(feats, np.uint8)
+    n = len(feats)
+    w = np.zeros(n, np.int32); wt = np.zeros(n, np.float64); nd = np.zeros(n, np.int32)
+    lib().orc_bow_transform(L, len(parent), _p(parent), _p(desc), _p(weight), _p(leaf), _p(feats), n, levelsup, _p(w), _p(wt), _p(nd))
+    return w, wt, nd
+
+
+def bow_vectors(word, weight, node):
+    """The BowVector / FeatureVector maps of transform(features, v, fv, levelsup) for TF_IDF + L1 (TemplatedVocabulary.h:1145-1190,
+    BowVector.cpp:34-46, :62-84, FeatureVector.cpp:31-45): ordered dicts word -> value and node -> feature indices."""
+    v, fv = {}, {}
+    for i in range(len(word)):
+        if weight[i] > 0:
+            v[int(word[i])] = v.get(int(word[i]), 0.0) + float(weight[i])
+            fv.setdefault(int(node[i]), []).append(i)
+    norm = 0.0
+    for k in sorted(v):
+        norm += abs(v[k])
+    if norm > 0.0:
+        for k in v:
+            v[k] /= norm
+    return dict(sorted(v.items())), dict(sorted(fv.items()))
 
 
 class GridParams(C.Structure):

@@ -92,6 +92,10 @@ int orc_grid_candidates(const orc_keypoint* kps, const orc_keyline* kls, int n, 
                         const float* qy, const float* qr, const int32_t* qminl, const int32_t* qmaxl, int nq, int32_t* cand_off,
                         int32_t* cand_idx, int cand_cap);
 
+/* DBoW2 tree descent per feature (TemplatedVocabulary.h:1218-1258): word id, weight, node at level L - levelsup */
+void orc_bow_transform(int L, int nnodes, const int32_t* parent, const uint8_t* ndesc, const double* nweight, const uint8_t* is_leaf,
+                       const uint8_t* feat, int n, int levelsup, int32_t* word, double* weight, int32_t* node);
+
 /* DistributeOctTree alone (ORBextractor.cc:539-763); keys relative to (minX,minY).
  * out_idx receives indices into the input arrays in final list order; returns count. */
 int  orc_distribute_octree(const int* xs, const int* ys, const int* resp, int n,

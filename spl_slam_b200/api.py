@@ -119,6 +119,12 @@ def load(path=None):
         "plf_grid_build_device": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
         "plf_grid_query_device": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, P(C.c_int)]),
         "plf_grid_candidates": (C.c_int, [vp, vp, vp, C.c_int, vp, f32p, f32p, f32p, i32p, i32p, C.c_int, i32p, i32p, C.c_int, P(C.c_int)]),
+        "plf_vocab_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, vp, vp, vp, P(vp)]),
+        "plf_vocab_load_text": (C.c_int, [vp, C.c_char_p, P(vp)]),
+        "plf_vocab_destroy": (None, [vp]),
+        "plf_vocab_info": (C.c_int, [vp, P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int)]),
+        "plf_bow_transform": (C.c_int, [vp, vp, C.c_int, C.c_int, i32p, vp, i32p]),
+        "plf_bow_transform_device": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp]),
         "plf_stereo_match": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_float, f32p, f32p]),
         "plf_stereo_match_batch_device": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
                                                     C.c_int, C.c_float, C.c_float, vp, vp]),
@@ -508,6 +514,64 @@ class Linematcher:
         self.ctx.check(self.lib.plf_hamming_candidates(self.ctx.h, _p(q), len(q), _p(t), len(t), _p(off), _p(flat) if len(flat) else None,
                                                        _p(bi), _p(bd), _p(cd) if want_dist else None))
         return (bi, bd, cd[:len(flat)]) if want_dist else (bi, bd)
+
+
+class ORBVocabulary:
+    """The device-resident DBoW2 vocabulary tree (ORBVocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB>,
+    include/ORBVocabulary.h) and its transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1124-1258)."""
+
+    def __init__(self, ctx, k=None, L=None, parent=None, desc=None, weight=None, is_leaf=None, path=None, scoring=0, weighting=0):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        h = C.c_void_p()
+        if path is not None:
+            ctx.check(self.lib.plf_vocab_load_text(ctx.h, os.fsencode(path), C.byref(h)))
+        else:
+            parent = np.ascontiguousarray(parent, np.int32); desc = np.ascontiguousarray(desc, np.uint8)
+            weight = np.ascontiguousarray(weight, np.float64); is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+            ctx.check(self.lib.plf_vocab_create(ctx.h, k, L, scoring, weighting, len(parent), _p(parent), _p(desc), _p(weight), _p(is_leaf), C.byref(h)))
+        self.h = h
+        ctx._adopt(self)
+        vals = [C.c_int() for _ in range(6)]
+        self.lib.plf_vocab_info(self.h, *[C.byref(v) for v in vals])
+        self.k, self.L, self.nnodes, self.nwords, self.scoring, self.weighting = [v.value for v in vals]
+
+    def transform_features(self, descriptors, levelsup=4):
+        """Per-feature (word id, weight, node id at level L - levelsup)."""
+        d = _desc(descriptors)
+        n = len(d)
+        w = np.zeros(n, np.int32); wt = np.zeros(n, np.float64); nd = np.zeros(n, np.int32)
+        self.ctx.check(self.lib.plf_bow_transform(self.h, _p(d), n, levelsup, _p(w), _p(wt), _p(nd)))
+        return w, wt, nd
+
+    def transform(self, descriptors, levelsup=4):
+        """transform(features, BowVector, FeatureVector, levelsup) for TF_IDF / TF weighting + L1 norm: the ordered
+        insertions (BowVector::addWeight, FeatureVector::addFeature, BowVector::normalize) replayed on the host."""
+        w, wt, nd = self.transform_features(descriptors, levelsup)
+        v, fv = {}, {}
+        for i in range(len(w)):
+            if wt[i] > 0:
+                v[int(w[i])] = v.get(int(w[i]), 0.0) + float(wt[i])
+                fv.setdefault(int(nd[i]), []).append(i)
+        norm = 0.0
+        for k in sorted(v):
+            norm += abs(v[k])
+        if norm > 0.0:
+            for k in v:
+                v[k] /= norm
+        return dict(sorted(v.items())), dict(sorted(fv.items()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            if getattr(self.ctx, "h", None):
+                self.lib.plf_vocab_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def features_in_area(ctx, keys, grid, qx, qy, qr, min_level=None, max_level=None, keylines=None, cand_cap=None):

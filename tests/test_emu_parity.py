@@ -198,3 +198,35 @@ def test_emu_grid_area_queries(S, oracle, emu_lib):
     # no features / no queries
     off, idx = S.features_in_area(ctx, k[:0], g, qx, qy, qr)
     assert (off == 0).all() and len(idx) == 0
+
+
+def _write_vocab_text(path, k, L, vocab):
+    parent, desc, weight, leaf = vocab
+    with open(path, "w") as f:
+        f.write("%d %d  0 0\n" % (k, L))                      # "k L scoring weighting" (saveToTextFile writes two spaces)
+        for i in range(1, len(parent)):
+            f.write("%d %d %s %r\n" % (parent[i], leaf[i], " ".join(str(int(b)) for b in desc[i]), float(weight[i])))
+
+
+def test_emu_bow_transform(S, oracle, emu_lib, tmp_path):
+    ctx = S.Context(0, emu_lib)
+    rng = np.random.default_rng(8)
+    for (k, L, levelsup) in [(10, 3, 1), (4, 5, 4), (3, 4, 9)]:
+        vocab = oracle.synth_vocabulary(k, L, seed=k * 10 + L)
+        voc = S.ORBVocabulary(ctx, k, L, *vocab)
+        assert voc.nwords == k ** L and voc.nnodes == len(vocab[0])
+        feats = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+        feats[:40] = vocab[1][rng.integers(1, len(vocab[0]), 40)]          # exact node descriptors: distance 0, sibling ties
+        w, wt, nd = voc.transform_features(feats, levelsup)
+        ow, owt, ond = oracle.bow_transform(vocab, L, feats, levelsup)
+        assert np.array_equal(w, ow) and np.array_equal(wt.view(np.uint64), owt.view(np.uint64)) and np.array_equal(nd, ond)
+        v, fv = voc.transform(feats, levelsup)
+        ov, ofv = oracle.bow_vectors(ow, owt, ond)
+        assert v == ov and fv == ofv and abs(sum(v.values()) - 1.0) < 1e-12
+        # the same tree through the ORBvoc.txt text format
+        path = str(tmp_path / ("voc_%d_%d.txt" % (k, L)))
+        _write_vocab_text(path, k, L, vocab)
+        voc2 = S.ORBVocabulary(ctx, path=path)
+        w2, wt2, nd2 = voc2.transform_features(feats, levelsup)
+        assert np.array_equal(w2, ow) and np.array_equal(wt2.view(np.uint64), owt.view(np.uint64)) and np.array_equal(nd2, ond)
+    assert len(voc.transform_features(feats[:0])[0]) == 0

@@ -350,3 +350,23 @@ def test_1080p_batch_equals_single_and_frame_sharding(S, oracle, gpu_ctx):
             for j, i in enumerate(mine):
                 assert np.array_equal(k2[j].view(np.uint8), ks[i].view(np.uint8)) and np.array_equal(d2[j], ds[i])
                 assert np.array_equal(K2[j].view(np.uint8), Ks[i].view(np.uint8)) and np.array_equal(D2[j], Ds[i])
+
+
+@pytest.mark.parametrize("k,L,levelsup", [(10, 5, 4), (10, 3, 1), (6, 4, 7)])
+def test_bow_transform(S, oracle, gpu_ctx, k, L, levelsup):
+    """Frame::ComputeBoW (src/Frame.cc:724-731): DBoW2 tree descent for every ORB descriptor of a frame, then the ordered
+    BowVector / FeatureVector maps, against the sequential restatement (bit-exact word ids, weights, node ids, values)."""
+    vocab = oracle.synth_vocabulary(k, L, seed=100 + k + L)
+    voc = S.ORBVocabulary(gpu_ctx, k, L, *vocab)
+    ex = S.ORBextractor(2000, 1.2, 8, 20, 7, ctx=gpu_ctx)
+    kp, d = ex(oracle.synth_image(1241, 376, 70))
+    rng = np.random.default_rng(0)
+    d = d.copy()
+    d[:100] = vocab[1][rng.integers(1, len(vocab[0]), 100)]       # exact node descriptors: zero distances and sibling ties
+    w, wt, nd = voc.transform_features(d, levelsup)
+    ow, owt, ond = oracle.bow_transform(vocab, L, d, levelsup)
+    assert np.array_equal(w, ow) and np.array_equal(wt.view(np.uint64), owt.view(np.uint64)) and np.array_equal(nd, ond)
+    v, fv = voc.transform(d, levelsup)
+    ov, ofv = oracle.bow_vectors(ow, owt, ond)
+    assert v == ov and fv == ofv and len(v) > 100
+    assert sum(len(x) for x in fv.values()) == int((owt > 0).sum())
