@@ -246,6 +246,22 @@ plf_status plf_grid_candidates(plf_ctx* ctx, const plf_keypoint* host_kps, const
                                const int32_t* host_qminl, const int32_t* host_qmaxl, int nq, int32_t* host_cand_off,
                                int32_t* host_cand_idx, int cand_cap, int* total);
 
+/* ---- undistortion: Frame::UndistortKeyPoints / UndistortKeyLines (src/Frame.cc:733-826) =
+ * cv::undistortPoints(pts, pts, mK, mDistCoef, Mat(), mK) on the key point positions, the line mid-points and both
+ * line end points; everything else of the records is copied.  k[0] == 0 -> plain copy, as in the reference.
+ * k = (k1, k2, p1, p2[, k3]) as in the settings files (Camera.k1 ... Camera.k3). ---- */
+typedef struct {
+    float fx, fy, cx, cy;
+    float k[5];
+    int32_t nk; /* 4 or 5 */
+} plf_camera;
+plf_status plf_undistort_keypoints(plf_ctx* ctx, const plf_camera* cam, const plf_keypoint* host_in, int n, plf_keypoint* host_out);
+plf_status plf_undistort_keypoints_device(plf_ctx* ctx, const plf_camera* cam, const plf_keypoint* dev_in, int n, plf_keypoint* dev_out);
+plf_status plf_undistort_keylines(plf_ctx* ctx, const plf_camera* cam, const plf_keyline* host_kl, const plf_keypoint* host_mid, int n,
+                                  plf_keyline* host_kl_out, plf_keypoint* host_mid_out);
+plf_status plf_undistort_keylines_device(plf_ctx* ctx, const plf_camera* cam, const plf_keyline* dev_kl, const plf_keypoint* dev_mid,
+                                         int n, plf_keyline* dev_kl_out, plf_keypoint* dev_mid_out);
+
 /* ---- bag of words: the per-feature vocabulary-tree descent of DBoW2's TemplatedVocabulary::transform(features, BowVector&,
  * FeatureVector&, levelsup) (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1124-1190, :1218-1258) as called from
  * Frame::ComputeBoW (src/Frame.cc:724-731), FORB::distance = 256-bit Hamming.  For feature i: word[i] = leaf word id,

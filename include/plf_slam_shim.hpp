@@ -258,6 +258,38 @@ private:
     PlfContext ctx_;
 };
 
+// Frame::UndistortKeyPoints / UndistortKeyLines (src/Frame.cc:733-826): cv::undistortPoints(pts, pts, mK, mDistCoef, Mat(), mK)
+// on the key point positions, the line mid-points and both line end points; mDistCoef(0) == 0 -> plain copy.
+// mK is the 3x3 CV_32F camera matrix, mDistCoef the 4x1 or 5x1 CV_32F coefficient vector of the Frame.
+inline plf_camera MakeCamera(const cv::Mat& mK, const cv::Mat& mDistCoef)
+{
+    plf_camera c;
+    std::memset(&c, 0, sizeof(c));
+    c.fx = mK.at<float>(0, 0); c.fy = mK.at<float>(1, 1); c.cx = mK.at<float>(0, 2); c.cy = mK.at<float>(1, 2);
+    c.nk = mDistCoef.rows * mDistCoef.cols > 4 ? 5 : 4;
+    for (int i = 0; i < c.nk; i++) c.k[i] = mDistCoef.at<float>(i);
+    return c;
+}
+inline void UndistortKeyPoints(PlfContext& ctx, const cv::Mat& mK, const cv::Mat& mDistCoef, const std::vector<cv::KeyPoint>& mvKeys,
+                               std::vector<cv::KeyPoint>& mvKeysUn)
+{
+    mvKeysUn.resize(mvKeys.size());
+    if (mvKeys.empty()) return;
+    const plf_camera c = MakeCamera(mK, mDistCoef);
+    ctx.check(plf_undistort_keypoints(ctx.get(), &c, (const plf_keypoint*)mvKeys.data(), (int)mvKeys.size(), (plf_keypoint*)mvKeysUn.data()));
+}
+inline void UndistortKeyLines(PlfContext& ctx, const cv::Mat& mK, const cv::Mat& mDistCoef, const std::vector<KeyLine>& mvLines,
+                              const std::vector<cv::KeyPoint>& mvMidPoints, std::vector<KeyLine>& mvLinesUn,
+                              std::vector<cv::KeyPoint>& mvMidPointsUn)
+{
+    mvLinesUn.resize(mvLines.size());
+    mvMidPointsUn.resize(mvMidPoints.size());
+    if (mvLines.empty()) return;
+    const plf_camera c = MakeCamera(mK, mDistCoef);
+    ctx.check(plf_undistort_keylines(ctx.get(), &c, (const plf_keyline*)mvLines.data(), (const plf_keypoint*)mvMidPoints.data(),
+                                     (int)mvLines.size(), (plf_keyline*)mvLinesUn.data(), (plf_keypoint*)mvMidPointsUn.data()));
+}
+
 // ORBVocabulary::transform(features, BowVector&, FeatureVector&, levelsup) as used by Frame::ComputeBoW
 // (src/Frame.cc:724-731; Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1124-1190): the tree descent of every descriptor
 // runs on the GPU, the ordered map insertions (BowVector::addWeight, FeatureVector::addFeature) and the L1

@@ -65,6 +65,7 @@ def lib():
         L.orc_orb_level_kept_count.argtypes = [vp, C.c_int]
         L.orc_grid_candidates.argtypes = [vp, vp, C.c_int, vp, f32p, f32p, f32p, i32p, i32p, C.c_int, i32p, i32p, C.c_int]
         L.orc_bow_transform.argtypes = [C.c_int, C.c_int, i32p, u8p, vp, u8p, u8p, C.c_int, C.c_int, i32p, vp, i32p]
+        L.orc_undistort_points.argtypes = [f32p, f32p, C.c_int, f32p, C.c_int, f32p]
         L.orc_stereo_match.argtypes = [vp, vp, vp, u8p, C.c_int, vp, u8p, C.c_int, C.c_float, C.c_float, f32p, f32p]
         L.orc_distribute_octree.argtypes = [i32p, i32p, i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_int, i32p, C.c_int]
@@ -299,6 +300,35 @@ def bow_vectors(word, weight, node):
         for k in v:
             v[k] /= norm
     return dict(sorted(v.items())), dict(sorted(fv.items()))
+
+
+def undistort_points(pts, fx, fy, cx, cy, dist):
+    """cv::undistortPoints(pts, pts, K, D, Mat(), K) on N x 2 float points (src/Frame.cc:750, :785, :814-815)."""
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    cam = np.array([fx, fy, cx, cy], np.float32); kd = np.ascontiguousarray(dist, np.float32)
+    out = np.empty_like(pts)
+    lib().orc_undistort_points(_p(cam), _p(kd), len(kd), _p(pts), len(pts), _p(out))
+    return out
+
+
+def undistort_keypoints(kps, fx, fy, cx, cy, dist):
+    """Frame::UndistortKeyPoints (src/Frame.cc:733-763)."""
+    out = np.ascontiguousarray(kps, KEYPOINT_DTYPE).copy()
+    if np.float32(dist[0]) != 0:
+        p = undistort_points(np.stack([out["x"], out["y"]], 1), fx, fy, cx, cy, dist)
+        out["x"], out["y"] = p[:, 0], p[:, 1]
+    return out
+
+
+def undistort_keylines(kls, mids, fx, fy, cx, cy, dist):
+    """Frame::UndistortKeyLines (src/Frame.cc:766-826): mid-points, start points, end points."""
+    ok = np.ascontiguousarray(kls, KEYLINE_DTYPE).copy()
+    om = undistort_keypoints(mids, fx, fy, cx, cy, dist)
+    if np.float32(dist[0]) != 0:
+        a = undistort_points(np.stack([ok["startPointX"], ok["startPointY"]], 1), fx, fy, cx, cy, dist)
+        b = undistort_points(np.stack([ok["endPointX"], ok["endPointY"]], 1), fx, fy, cx, cy, dist)
+        ok["startPointX"], ok["startPointY"], ok["endPointX"], ok["endPointY"] = a[:, 0], a[:, 1], b[:, 0], b[:, 1]
+    return ok, om
 
 
 class GridParams(C.Structure):

@@ -656,3 +656,29 @@ int orc_grid_candidates(const orc_keypoint* kps, const orc_keyline* kls, int n, 
     free(cell); free(start); free(items); free(fill);
     return total;
 }
+
+/* ---------------- Frame::UndistortKeyPoints / UndistortKeyLines, src/Frame.cc:733-826 ----------------
+ * cv::undistortPoints(pts, pts, K, D, Mat(), K) (OpenCV cvUndistortPointsInternal, default criteria = 5 iterations):
+ * pinned bit-for-bit against cv2 4.13 in tests/test_oracle_vs_cv2.py.  k = k1, k2, p1, p2[, k3]. */
+void orc_undistort_points(const float* cam /* fx fy cx cy */, const float* kd, int nk, const float* in, int n, float* out)
+{
+    const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
+    const double k1 = kd[0], k2 = kd[1], p1 = kd[2], p2 = kd[3], k3 = nk > 4 ? kd[4] : 0.0;
+    const double ifx = 1.0 / fx, ify = 1.0 / fy;
+    for (int i = 0; i < n; i++) {
+        const double u = in[2 * i], v = in[2 * i + 1];
+        double x = (u - cx) * ifx, y = (v - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; j++) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((0.0 * r2 + 0.0) * r2 + 0.0) * r2) / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);
+            if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+            const double deltaX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x);
+            const double deltaY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        out[2 * i] = (float)(fx * x + cx);
+        out[2 * i + 1] = (float)(fy * y + cy);
+    }
+}

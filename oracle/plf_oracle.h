@@ -96,6 +96,9 @@ int orc_grid_candidates(const orc_keypoint* kps, const orc_keyline* kls, int n, 
 void orc_bow_transform(int L, int nnodes, const int32_t* parent, const uint8_t* ndesc, const double* nweight, const uint8_t* is_leaf,
                        const uint8_t* feat, int n, int levelsup, int32_t* word, double* weight, int32_t* node);
 
+/* cv::undistortPoints(pts, pts, K, D, Mat(), K) as used by Frame::UndistortKeyPoints / UndistortKeyLines (src/Frame.cc:733-826) */
+void orc_undistort_points(const float* cam, const float* kd, int nk, const float* in, int n, float* out);
+
 /* DistributeOctTree alone (ORBextractor.cc:539-763); keys relative to (minX,minY).
  * out_idx receives indices into the input arrays in final list order; returns count. */
 int  orc_distribute_octree(const int* xs, const int* ys, const int* resp, int n,

@@ -119,6 +119,10 @@ def load(path=None):
         "plf_grid_build_device": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
         "plf_grid_query_device": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, P(C.c_int)]),
         "plf_grid_candidates": (C.c_int, [vp, vp, vp, C.c_int, vp, f32p, f32p, f32p, i32p, i32p, C.c_int, i32p, i32p, C.c_int, P(C.c_int)]),
+        "plf_undistort_keypoints": (C.c_int, [vp, vp, vp, C.c_int, vp]),
+        "plf_undistort_keypoints_device": (C.c_int, [vp, vp, vp, C.c_int, vp]),
+        "plf_undistort_keylines": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp]),
+        "plf_undistort_keylines_device": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp]),
         "plf_vocab_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, vp, vp, vp, P(vp)]),
         "plf_vocab_load_text": (C.c_int, [vp, C.c_char_p, P(vp)]),
         "plf_vocab_destroy": (None, [vp]),
@@ -514,6 +518,32 @@ class Linematcher:
         self.ctx.check(self.lib.plf_hamming_candidates(self.ctx.h, _p(q), len(q), _p(t), len(t), _p(off), _p(flat) if len(flat) else None,
                                                        _p(bi), _p(bd), _p(cd) if want_dist else None))
         return (bi, bd, cd[:len(flat)]) if want_dist else (bi, bd)
+
+
+class Camera(C.Structure):
+    """plf_camera: mK (fx, fy, cx, cy) and mDistCoef (k1, k2, p1, p2[, k3]) of a Frame."""
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("k", C.c_float * 5), ("nk", C.c_int32)]
+
+    @classmethod
+    def make(cls, fx, fy, cx, cy, dist):
+        k = (C.c_float * 5)(*([float(np.float32(v)) for v in dist] + [0.0] * (5 - len(dist))))
+        return cls(fx, fy, cx, cy, k, len(dist))
+
+
+def undistort_keypoints(ctx, cam, keys):
+    """Frame::UndistortKeyPoints (src/Frame.cc:733-763)."""
+    k = np.ascontiguousarray(keys, KEYPOINT_DTYPE)
+    out = np.empty_like(k)
+    ctx.check(ctx.lib.plf_undistort_keypoints(ctx.h, C.byref(cam), _p(k), len(k), _p(out)))
+    return out
+
+
+def undistort_keylines(ctx, cam, keylines, midpoints):
+    """Frame::UndistortKeyLines (src/Frame.cc:766-826) -> (mvLinesUn, mvMidPointsUn)."""
+    kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE); mid = np.ascontiguousarray(midpoints, KEYPOINT_DTYPE)
+    okl = np.empty_like(kl); om = np.empty_like(mid)
+    ctx.check(ctx.lib.plf_undistort_keylines(ctx.h, C.byref(cam), _p(kl), _p(mid), len(kl), _p(okl), _p(om)))
+    return okl, om
 
 
 class ORBVocabulary:

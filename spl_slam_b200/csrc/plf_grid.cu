@@ -233,3 +233,130 @@ extern "C" plf_status plf_grid_candidates(plf_ctx* ctx, const plf_keypoint* host
     cudaFree(base);
     return st;
 }
+
+// ---------------- Frame::UndistortKeyPoints / UndistortKeyLines (src/Frame.cc:733-826) ----------------
+// cv::undistortPoints(pts, pts, K, distCoef, Mat(), K) on float points: normalise, five fixed-point iterations of the
+// radial (k1, k2, k3) + tangential (p1, p2) model in double, re-project with K, round to float.  Same operation
+// order as OpenCV's cvUndistortPointsInternal (verified bit-for-bit against cv2 4.13 through the oracle).
+__device__ __forceinline__ void undistort_point(const plf_camera& c, float px, float py, float& ox, float& oy)
+{
+    const double fx = (double)c.fx, fy = (double)c.fy, cx = (double)c.cx, cy = (double)c.cy;
+    const double k1 = (double)c.k[0], k2 = (double)c.k[1], p1 = (double)c.k[2], p2 = (double)c.k[3], k3 = c.nk > 4 ? (double)c.k[4] : 0.0;
+    const double ifx = 1.0 / fx, ify = 1.0 / fy;
+    const double u = (double)px, v = (double)py;
+    double x = (u - cx) * ifx, y = (v - cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; j++) {
+        const double r2 = x * x + y * y;
+        const double icdist = (1 + ((0.0 * r2 + 0.0) * r2 + 0.0) * r2) / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);
+        if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+        const double deltaX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x);
+        const double deltaY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    ox = (float)(fx * x + cx);
+    oy = (float)(fy * y + cy);
+}
+
+__global__ void k_undistort_keypoints(plf_camera c, const plf_keypoint* __restrict__ in, int n, plf_keypoint* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    plf_keypoint k = in[i];
+    if (c.k[0] != 0.0f) undistort_point(c, k.x, k.y, k.x, k.y);     // mDistCoef.at<float>(0) == 0 -> plain copy (:735-739)
+    out[i] = k;
+}
+
+__global__ void k_undistort_keylines(plf_camera c, const plf_keyline* __restrict__ in, int n, plf_keyline* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    plf_keyline k = in[i];
+    if (c.k[0] != 0.0f) {
+        undistort_point(c, k.startPointX, k.startPointY, k.startPointX, k.startPointY);
+        undistort_point(c, k.endPointX, k.endPointY, k.endPointX, k.endPointY);
+    }
+    out[i] = k;
+}
+
+static plf_status cam_check(plf_ctx* ctx, const plf_camera* c)
+{
+    if (!c || !(c->fx != 0) || !(c->fy != 0) || c->nk < 4 || c->nk > 5) return plf_fail(ctx, PLF_ERR_INVALID, "bad camera parameters (4 or 5 distortion coefficients)");
+    return PLF_OK;
+}
+
+extern "C" plf_status plf_undistort_keypoints_device(plf_ctx* ctx, const plf_camera* cam, const plf_keypoint* dev_in, int n, plf_keypoint* dev_out)
+{
+    if (!ctx) return PLF_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!dev_in || !dev_out))) return plf_fail(ctx, PLF_ERR_INVALID, "plf_undistort_keypoints_device: bad arguments");
+    plf_status st = cam_check(ctx, cam);
+    if (st || n == 0) return st;
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    PLF_LAUNCH(k_undistort_keypoints, dim3(plf_div_up(n, 128)), dim3(128), 0, ctx->stream, *cam, dev_in, n, dev_out);
+    PLF_CHECK_LAUNCH(ctx);
+    return PLF_OK;
+}
+
+extern "C" plf_status plf_undistort_keylines_device(plf_ctx* ctx, const plf_camera* cam, const plf_keyline* dev_kl, const plf_keypoint* dev_mid, int n,
+                                                    plf_keyline* dev_kl_out, plf_keypoint* dev_mid_out)
+{
+    if (!ctx) return PLF_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!dev_kl || !dev_mid || !dev_kl_out || !dev_mid_out))) return plf_fail(ctx, PLF_ERR_INVALID, "plf_undistort_keylines_device: bad arguments");
+    plf_status st = cam_check(ctx, cam);
+    if (st || n == 0) return st;
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    PLF_LAUNCH(k_undistort_keypoints, dim3(plf_div_up(n, 128)), dim3(128), 0, ctx->stream, *cam, dev_mid, n, dev_mid_out);
+    PLF_CHECK_LAUNCH(ctx);
+    PLF_LAUNCH(k_undistort_keylines, dim3(plf_div_up(n, 128)), dim3(128), 0, ctx->stream, *cam, dev_kl, n, dev_kl_out);
+    PLF_CHECK_LAUNCH(ctx);
+    return PLF_OK;
+}
+
+extern "C" plf_status plf_undistort_keypoints(plf_ctx* ctx, const plf_camera* cam, const plf_keypoint* host_in, int n, plf_keypoint* host_out)
+{
+    if (!ctx) return PLF_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!host_in || !host_out))) return plf_fail(ctx, PLF_ERR_INVALID, "plf_undistort_keypoints: bad arguments");
+    plf_status st = cam_check(ctx, cam);
+    if (st || n == 0) return st;
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    void* s;
+    const size_t kb = plf_align_up((size_t)n * sizeof(plf_keypoint), 256);
+    st = plf_ctx_scratch(ctx, 2 * kb, &s);
+    if (st) return st;
+    plf_keypoint* din = (plf_keypoint*)s;
+    plf_keypoint* dout = (plf_keypoint*)((uint8_t*)s + kb);
+    PLF_CUDA(ctx, cudaMemcpyAsync(din, host_in, (size_t)n * sizeof(plf_keypoint), cudaMemcpyHostToDevice, ctx->stream));
+    st = plf_undistort_keypoints_device(ctx, cam, din, n, dout);
+    if (st) return st;
+    PLF_CUDA(ctx, cudaMemcpyAsync(host_out, dout, (size_t)n * sizeof(plf_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PLF_OK;
+}
+
+extern "C" plf_status plf_undistort_keylines(plf_ctx* ctx, const plf_camera* cam, const plf_keyline* host_kl, const plf_keypoint* host_mid, int n,
+                                             plf_keyline* host_kl_out, plf_keypoint* host_mid_out)
+{
+    if (!ctx) return PLF_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!host_kl || !host_mid || !host_kl_out || !host_mid_out))) return plf_fail(ctx, PLF_ERR_INVALID, "plf_undistort_keylines: bad arguments");
+    plf_status st = cam_check(ctx, cam);
+    if (st || n == 0) return st;
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    void* s;
+    const size_t kb = plf_align_up((size_t)n * sizeof(plf_keypoint), 256), lb = plf_align_up((size_t)n * sizeof(plf_keyline), 256);
+    st = plf_ctx_scratch(ctx, 2 * kb + 2 * lb, &s);
+    if (st) return st;
+    uint8_t* p = (uint8_t*)s;
+    plf_keypoint* dmi = (plf_keypoint*)p; p += kb;
+    plf_keypoint* dmo = (plf_keypoint*)p; p += kb;
+    plf_keyline* dli = (plf_keyline*)p; p += lb;
+    plf_keyline* dlo = (plf_keyline*)p;
+    PLF_CUDA(ctx, cudaMemcpyAsync(dmi, host_mid, (size_t)n * sizeof(plf_keypoint), cudaMemcpyHostToDevice, ctx->stream));
+    PLF_CUDA(ctx, cudaMemcpyAsync(dli, host_kl, (size_t)n * sizeof(plf_keyline), cudaMemcpyHostToDevice, ctx->stream));
+    st = plf_undistort_keylines_device(ctx, cam, dli, dmi, n, dlo, dmo);
+    if (st) return st;
+    PLF_CUDA(ctx, cudaMemcpyAsync(host_mid_out, dmo, (size_t)n * sizeof(plf_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaMemcpyAsync(host_kl_out, dlo, (size_t)n * sizeof(plf_keyline), cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PLF_OK;
+}

@@ -31,6 +31,9 @@ public:
     unsigned char* ptr(int r = 0) { return data + (size_t)r * step; }
     const unsigned char* ptr(int r = 0) const { return data + (size_t)r * step; }
     template <class T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step); }
+    // float element access for the 3x3 camera matrix / the distortion vector (the mock stores them as rows x cols floats, step in bytes)
+    template <class T> const T& at(int r, int c) const { return ((const T*)(data + (size_t)r * step))[c]; }
+    template <class T> const T& at(int i) const { return ((const T*)data)[i]; }
     Mat getMat() const { return *this; }
 };
 typedef const Mat& InputArray;

@@ -230,3 +230,28 @@ def test_emu_bow_transform(S, oracle, emu_lib, tmp_path):
         w2, wt2, nd2 = voc2.transform_features(feats, levelsup)
         assert np.array_equal(w2, ow) and np.array_equal(wt2.view(np.uint64), owt.view(np.uint64)) and np.array_equal(nd2, ond)
     assert len(voc.transform_features(feats[:0])[0]) == 0
+
+
+def test_emu_undistort(S, oracle, emu_lib):
+    ctx = S.Context(0, emu_lib)
+    rng = np.random.default_rng(4)
+    n = 500
+    k = np.zeros(n, oracle.KEYPOINT_DTYPE)
+    k["x"] = rng.uniform(0, 752, n).astype(np.float32); k["y"] = rng.uniform(0, 480, n).astype(np.float32)
+    k["octave"] = rng.integers(0, 8, n); k["response"] = rng.uniform(7, 90, n).astype(np.float32); k["class_id"] = -1
+    kl = np.zeros(n, oracle.KEYLINE_DTYPE)
+    for f in ("startPointX", "endPointX"): kl[f] = rng.uniform(0, 752, n).astype(np.float32)
+    for f in ("startPointY", "endPointY"): kl[f] = rng.uniform(0, 480, n).astype(np.float32)
+    kl["lineLength"] = 33.0; kl["octave"] = 1
+    for (fx, fy, cx, cy), dist in [((458.654, 457.296, 367.215, 248.375), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)),
+                                   ((517.3, 516.5, 318.6, 255.3), (0.2624, -0.9531, -0.0054, 0.0026, 1.1633)),
+                                   ((435.2, 435.2, 367.4, 252.2), (0.0, 0.0, 0.0, 0.0))]:      # k1 == 0: plain copy
+        cam = S.Camera.make(fx, fy, cx, cy, dist)
+        out = S.undistort_keypoints(ctx, cam, k)
+        ref = oracle.undistort_keypoints(k, np.float32(fx), np.float32(fy), np.float32(cx), np.float32(cy), dist)
+        assert np.array_equal(out.view(np.uint8), ref.view(np.uint8))
+        okl, om = S.undistort_keylines(ctx, cam, kl, k)
+        rkl, rm = oracle.undistort_keylines(kl, k, np.float32(fx), np.float32(fy), np.float32(cx), np.float32(cy), dist)
+        assert np.array_equal(okl.view(np.uint8), rkl.view(np.uint8)) and np.array_equal(om.view(np.uint8), rm.view(np.uint8))
+        if dist[0] != 0:
+            assert not np.array_equal(out["x"], k["x"])

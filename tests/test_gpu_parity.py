@@ -370,3 +370,43 @@ def test_bow_transform(S, oracle, gpu_ctx, k, L, levelsup):
     ov, ofv = oracle.bow_vectors(ow, owt, ond)
     assert v == ov and fv == ofv and len(v) > 100
     assert sum(len(x) for x in fv.values()) == int((owt > 0).sum())
+
+
+def test_frame_pipeline_after_extraction(S, oracle, gpu_ctx):
+    """What Frame::Frame does after the extractors (src/Frame.cc:296-362): UndistortKeyPoints / UndistortKeyLines,
+    ComputeImageBounds, AssignFeaturesToGrid[Lines] -- then a tracking-style GetFeaturesInArea sweep.  Every stage
+    bit-identical to the CPU restatement (cv::undistortPoints itself is pinned against cv2 in test_oracle_vs_cv2)."""
+    (fx, fy, cx, cy), dist = (458.654, 457.296, 367.215, 248.375), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)   # EuRoC cam0
+    f32 = np.float32
+    cam = S.Camera.make(fx, fy, cx, cy, dist)
+    img = oracle.synth_image(752, 480, 80)
+    ex = S.ORBextractor(1200, 1.2, 8, 20, 7, ctx=gpu_ctx)
+    le, prm = _line_objs(S, oracle, gpu_ctx, 200, sigma_scale=0.8, density_th=0.8)
+    k, d = ex(img)
+    K, M, D = le.ComputeLsdWithLbd(img)
+    ku = S.undistort_keypoints(gpu_ctx, cam, k)
+    oku = oracle.undistort_keypoints(k, f32(fx), f32(fy), f32(cx), f32(cy), dist)
+    assert np.array_equal(ku.view(np.uint8), oku.view(np.uint8)) and not np.array_equal(ku["x"], k["x"])
+    Ku, Mu = S.undistort_keylines(gpu_ctx, cam, K, M)
+    oKu, oMu = oracle.undistort_keylines(K, M, f32(fx), f32(fy), f32(cx), f32(cy), dist)
+    assert np.array_equal(Ku.view(np.uint8), oKu.view(np.uint8)) and np.array_equal(Mu.view(np.uint8), oMu.view(np.uint8))
+    # ComputeImageBounds (src/Frame.cc:851-878): undistorted image corners
+    corners = np.zeros(4, oracle.KEYPOINT_DTYPE)
+    corners["x"] = [0, 752, 0, 752]; corners["y"] = [0, 0, 480, 480]
+    cu = S.undistort_keypoints(gpu_ctx, cam, corners)
+    ocu = oracle.undistort_keypoints(corners, f32(fx), f32(fy), f32(cx), f32(cy), dist)
+    assert np.array_equal(cu.view(np.uint8), ocu.view(np.uint8))
+    minx, maxx = min(cu["x"][0], cu["x"][2]), max(cu["x"][1], cu["x"][3])
+    miny, maxy = min(cu["y"][0], cu["y"][1]), max(cu["y"][2], cu["y"][3])
+    g = S.GridParams.for_image(64, 48, minx, maxx, miny, maxy); og = oracle.grid_params(64, 48, minx, maxx, miny, maxy)
+    gl = S.GridParams.for_image(16, 12, minx, maxx, miny, maxy); ogl = oracle.grid_params(16, 12, minx, maxx, miny, maxy)
+    rng = np.random.default_rng(6)
+    qx = (ku["x"] + rng.uniform(-3, 3, len(ku))).astype(f32); qy = (ku["y"] + rng.uniform(-3, 3, len(ku))).astype(f32)
+    qr = (15 * np.power(f32(1.2), ku["octave"])).astype(f32)
+    mn = (ku["octave"] - 1).astype(np.int32); mx = ku["octave"].astype(np.int32)
+    off, idx = S.features_in_area(gpu_ctx, ku, g, qx, qy, qr, mn, mx)
+    ooff, oidx = oracle.grid_candidates(oku, og, qx, qy, qr, mn, mx)
+    assert np.array_equal(off, ooff) and np.array_equal(idx, oidx) and len(idx) >= len(ku)
+    off, idx = S.features_in_area(gpu_ctx, Mu, gl, Mu["x"], Mu["y"], np.full(len(Mu), 40, f32), keylines=Ku)
+    ooff, oidx = oracle.grid_candidates(oMu, ogl, oMu["x"], oMu["y"], np.full(len(Mu), 40, f32), keylines=oKu)
+    assert np.array_equal(off, ooff) and np.array_equal(idx, oidx)

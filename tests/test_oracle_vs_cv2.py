@@ -111,3 +111,24 @@ def test_knn2_vs_bfmatcher(oracle):
             assert np.array_equal(a, b)
     for a, b in zip(oracle.knn2(q[:3], t[:1]), P.knn2(q[:3], t[:1])):
         assert np.array_equal(a, b)
+
+
+CAMERAS = [   # (fx, fy, cx, cy), (k1, k2, p1, p2[, k3]): EuRoC cam0, TUM1, a mild 4-coefficient set
+    ((458.654, 457.296, 367.215, 248.375), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)),
+    ((517.306408, 516.469215, 318.643040, 255.313989), (0.262383, -0.953104, -0.005358, 0.002628, 1.163314)),
+    ((718.856, 718.856, 607.1928, 185.2157), (0.1, -0.05, 0.001, -0.002)),
+]
+
+
+def test_undistort_points_vs_cv2(oracle):
+    """Frame::UndistortKeyPoints / UndistortKeyLines call cv::undistortPoints(pts, pts, mK, mDistCoef, Mat(), mK)
+    (src/Frame.cc:750, :785, :814-815): the restatement is bit-identical to cv2 4.13 on float points."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for (fx, fy, cx, cy), dist in CAMERAS:
+        K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+        D = np.array(dist, np.float32)
+        pts = np.stack([rng.uniform(-20, 1260, 20000), rng.uniform(-20, 500, 20000)], 1).astype(np.float32)
+        ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
+        got = oracle.undistort_points(pts, K[0, 0], K[1, 1], K[0, 2], K[1, 2], D)
+        assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
