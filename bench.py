@@ -39,17 +39,63 @@ ORB_CONTEXTS = 2              # ORB extractor instances, same idea (uploads of o
 WORKLOAD = "EuRoC-style stereo 752x480 pairs, 1200 ORB (8 lv x1.2, FAST 20/7) + LSD/LBD 200 lines per image"
 
 
+def _gauss_kernel_q8(ksize, sigma):
+    """cv::GaussianBlur's 8-bit kernel: Q8, error-diffused, sums to 256 (SURVEY.md appendix A2)."""
+    import math
+    n2 = ksize // 2
+    scale2x = -0.125 / (sigma * sigma)
+    w = [math.exp(float(x * x) * scale2x) for x in range(1 - ksize, 0, 2)]
+    tot = 1.0 / (sum(w) * 2 + 1)
+    q, err, acc = [0] * ksize, 0.0, 0
+    for i in range(n2):
+        v = w[i] * tot * 256.0 + err
+        v0 = int(np.rint(v))
+        err = v - v0
+        q[i] = q[ksize - 1 - i] = v0
+        acc += v0
+    q[n2] = 256 - 2 * acc
+    return q
+
+
+def _gauss_blur_u8(img, ksize, sigma):
+    """Separable Q8 Gaussian with BORDER_REFLECT_101, (v + 32768) >> 16 -- numpy, bit-identical to cv::GaussianBlur on 8U."""
+    q, r = _gauss_kernel_q8(ksize, sigma), ksize // 2
+    a = np.pad(img.astype(np.int64), ((0, 0), (r, r)), mode="reflect")
+    h = sum(q[i] * a[:, i:i + img.shape[1]] for i in range(ksize))
+    b = np.pad(h, ((r, r), (0, 0)), mode="reflect")
+    v = sum(q[i] * b[i:i + img.shape[0], :] for i in range(ksize))
+    return ((v + 32768) >> 16).astype(np.uint8)
+
+
+def synth_image(w, h, seed):
+    """The synthetic test image of SURVEY.md 8d (uniform u8 noise -> Gaussian s=2 -> K filled rectangles -> 3x3 s=0.8 blur).
+    Input generation only -- numpy, nothing of oracle/ is involved (tests/test_bench_inputs.py checks that it equals the
+    generator the parity tests use)."""
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+    img = _gauss_blur_u8(img, 13, 2.0)
+    K = int(round(60.0 * (w * h) / (640.0 * 480.0)))
+    for _ in range(K):
+        x0 = int(rng.integers(0, w - 8)); y0 = int(rng.integers(0, h - 8))
+        rw = int(rng.integers(8, max(9, w // 4))); rh = int(rng.integers(8, max(9, h // 4)))
+        g = int(rng.integers(0, 256))
+        img[y0:min(h, y0 + rh), x0:min(w, x0 + rw)] = g
+    return _gauss_blur_u8(img, 3, 0.8)
+
+
 def make_frames(n_pairs, seed0):
     """Synthetic stereo pairs: right = left shifted by a disparity + small noise."""
-    from oracle import oracle as O   # synthetic image generator only (inputs, not the measured path)
-    frames = []
-    for p in range(n_pairs):
-        left = O.synth_image(W, H, seed0 + p)
+    from concurrent.futures import ThreadPoolExecutor
+
+    def pair(p):
+        left = synth_image(W, H, seed0 + p)
         rng = np.random.default_rng(10_000 + seed0 + p)
         right = np.roll(left, -int(rng.integers(4, 24)), axis=1).astype(np.int16) + rng.integers(-2, 3, left.shape)
-        frames.append(left)
-        frames.append(np.clip(right, 0, 255).astype(np.uint8))
-    return np.stack(frames)
+        return left, np.clip(right, 0, 255).astype(np.uint8)
+
+    with ThreadPoolExecutor(min(16, os.cpu_count() or 1)) as ex:
+        pairs = list(ex.map(pair, range(n_pairs)))
+    return np.stack([im for lr in pairs for im in lr])
 
 
 def peaks():

@@ -2,8 +2,8 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import spl_slam_b200 as S
-from oracle import oracle as O
-img = O.synth_image(752, 480, 0)
+import bench
+img = bench.synth_image(752, 480, 0)
 cl = S.Context(0, priority=1)
 le = S.Lineextractor(200, 2, 0, 1.1, 0.8, 2.2, 12.5, 1.0, 0.8, 1024, 0.0, ctx=cl)
 for _ in range(5): le.ComputeLsdWithLbd(img)
