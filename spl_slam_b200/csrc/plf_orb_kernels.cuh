@@ -226,27 +226,27 @@ k_fast_cells(OrbGeom g, OrbPtrs p, int tp, int rows, int lcap)
             const int rpi = 32 / nwl;                            // rows per step
             const int lr = lane / nwl, wq = w0 + lane - lr * nwl;
             const unsigned* T = (const unsigned*)tile;
+            const unsigned th4 = (unsigned)th * 0x01010101u;
+            unsigned vmask = 0;       // bytes of this lane's word that are interior pixels
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (4 * wq + b >= c0 && 4 * wq + b < c1) vmask |= 0xffu << (8 * b);
             for (int rb = 3; rb < ch - 3; rb += rpi) {
                 const int ry = rb + lr;
-                unsigned go = 0;
+                unsigned go = 0;          // byte mask: 0xff where the pixel survives the compass test
                 if (lr < rpi && ry < ch - 3) {
                     const unsigned C = T[ry * tpw + wq], Lw = T[ry * tpw + wq - 1], Rw = T[ry * tpw + wq + 1];
                     const unsigned U = T[(ry - 3) * tpw + wq], D = T[(ry + 3) * tpw + wq];
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const int col = 4 * wq + b;
-                        const int v = (int)((C >> (8 * b)) & 0xffu);
-                        const int pu = (int)((U >> (8 * b)) & 0xffu), pd = (int)((D >> (8 * b)) & 0xffu);
-                        const int pl = b < 3 ? (int)((Lw >> (8 * (b + 1))) & 0xffu) : (int)(C & 0xffu);
-                        const int pr = b > 0 ? (int)((Rw >> (8 * (b - 1))) & 0xffu) : (int)(C >> 24);
-                        const int d0 = v - pd, d8 = v - pu, d4 = v - pr, d12 = v - pl;
-                        const bool g1 = (d0 > th || d8 > th || d0 < -th || d8 < -th) && (d4 > th || d12 > th || d4 < -th || d12 < -th);
-                        if (g1 && col >= c0 && col < c1) go |= 1u << b;
-                    }
+                    // four pixels at once with byte SIMD: |centre - ring pixel| > th for the four compass points
+                    const unsigned Lf = __funnelshift_r(Lw, C, 8);      // the pixels three columns to the left of C's four
+                    const unsigned Rt = __funnelshift_r(C, Rw, 24);     // ... three columns to the right
+                    const unsigned gv = __vcmpgtu4(__vabsdiffu4(C, U), th4) | __vcmpgtu4(__vabsdiffu4(C, D), th4);
+                    const unsigned gh = __vcmpgtu4(__vabsdiffu4(C, Lf), th4) | __vcmpgtu4(__vabsdiffu4(C, Rt), th4);
+                    go = gv & gh & vmask;
                 }
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
-                    const bool g1 = (go >> b) & 1u;
+                    const bool g1 = (go >> (8 * b)) & 1u;
                     const unsigned m = __ballot_sync(FULL, g1);
                     if (g1) list[n1 + __popc(m & LT)] = (unsigned short)(ry * tp + 4 * wq + b);
                     n1 += __popc(m);

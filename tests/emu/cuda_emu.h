@@ -210,6 +210,22 @@ static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline unsigned __vabsdiffu4(unsigned a, unsigned b)
+{
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        int x = (a >> (8 * i)) & 0xff, y = (b >> (8 * i)) & 0xff;
+        r |= (unsigned)(x > y ? x - y : y - x) << (8 * i);
+    }
+    return r;
+}
+static inline unsigned __vcmpgtu4(unsigned a, unsigned b)
+{
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++)
+        if (((a >> (8 * i)) & 0xff) > ((b >> (8 * i)) & 0xff)) r |= 0xffu << (8 * i);
+    return r;
+}
 static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
 {
     unsigned long long v = ((unsigned long long)b << 32) | a;
