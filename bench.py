@@ -83,8 +83,9 @@ def synth_image(w, h, seed):
     return _gauss_blur_u8(img, 3, 0.8)
 
 
-def make_frames(n_pairs, seed0):
-    """Synthetic stereo pairs: right = left shifted by a disparity + small noise."""
+def make_frames(n_pairs, seed0, pair_ids=None):
+    """Synthetic stereo pairs: right = left shifted by a disparity + small noise.
+    Returns [L0, R0, L1, R1, ...] for pairs seed0 .. seed0 + n_pairs - 1 (or for `pair_ids`)."""
     from concurrent.futures import ThreadPoolExecutor
 
     def pair(p):
@@ -94,7 +95,7 @@ def make_frames(n_pairs, seed0):
         return left, np.clip(right, 0, 255).astype(np.uint8)
 
     with ThreadPoolExecutor(min(16, os.cpu_count() or 1)) as ex:
-        pairs = list(ex.map(pair, range(n_pairs)))
+        pairs = list(ex.map(pair, pair_ids if pair_ids is not None else range(n_pairs)))
     return np.stack([im for lr in pairs for im in lr])
 
 
@@ -241,14 +242,10 @@ def main():
     if world > 1:
         mine = [i for i in range(B * world) if i % world == rank]
         # generate only the pairs this rank touches
-        cache = {}
-        frames = []
-        for i in mine:
-            p = i // 2
-            if p not in cache:
-                cache[p] = make_frames(1, p)
-            frames.append(cache[p][i % 2])
-        frames = np.stack(frames)
+        pids = sorted(set(i // 2 for i in mine))
+        gen = make_frames(len(pids), 0, pair_ids=pids)
+        pos = {p: j for j, p in enumerate(pids)}
+        frames = np.stack([gen[2 * pos[i // 2] + (i % 2)] for i in mine])
     else:
         frames = allf
     dev = local_rank
