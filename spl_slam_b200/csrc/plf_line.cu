@@ -448,7 +448,8 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
     // whatever is still queued on this stream (the image upload of a host-buffer call) finishes before the turn is
     // taken: the lock must not be held across a PCIe transfer
     PLF_CUDA(ctx, cudaStreamSynchronize(st0));
-    std::unique_lock<std::mutex> prephase(g_lsd_prephase);
+    std::unique_lock<std::mutex> prephase(g_lsd_prephase, std::defer_lock);
+    if (!getenv("PLF_NO_PREPHASE_LOCK")) prephase.lock();
     // computeGaussianPyramid: pyrDown, no pre-blur (LSDDetector_custom.cpp:56-73)
     for (int k = 1; k < noct; k++) {
         const int pdF = pyrdown_interior(o->ow[k - 1]);
@@ -536,7 +537,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
     }
     for (int k = 0; k < noct; k++)
         if (nkeys[k] > 0) PLF_CUDA(ctx, cudaStreamSynchronize(stk[k]));
-    prephase.unlock();   // everything up to here has finished on the GPU; growing may overlap other contexts
+    if (prephase.owns_lock()) prephase.unlock();   // everything up to here has finished on the GPU; growing may overlap other contexts
     // ---- phase 3: region growing (the latency-bound chains of both octaves side by side), rectangles, keylines ----
     for (int k = 0; k < noct; k++) {
         cudaStream_t st = stk[k];
