@@ -526,7 +526,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         if (s) return s;
         for (int pass = 0; pass < 2; pass++) {
             PLF_LAUNCH(k_lsd_heads, dim3(plf_div_up(nkeys[k], 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2[k], nkeys[k], o->d_comp[k],
-                       o->d_cnt[k] + CNT_BCOUNT, o->d_cnt[k] + CNT_BFILL, pass, o->kbits[k]);
+                       o->d_cnt[k] + CNT_BCOUNT, o->d_cnt[k] + CNT_BFILL, o->d_cnt[k] + CNT_NCOMP, pass, o->kbits[k]);
             PLF_CHECK_LAUNCH(ctx);
         }
         // the sorted position of every defined pixel (compact component index) and its cos / sin
@@ -534,6 +534,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
                    (const float*)o->d_fa[k], o->d_cs[k], (size_t)o->sp[k] * o->sh[k], o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
         PLF_CUDA(ctx, cudaMemcpyAsync(o->h_pin + 64 * k + 8, o->d_cnt[k] + CNT_BCOUNT, LSD_NBUCKET * sizeof(int), cudaMemcpyDeviceToHost, st));
+        PLF_CUDA(ctx, cudaMemcpyAsync(o->h_pin + 64 * k + 1, o->d_cnt[k] + CNT_NCOMP, sizeof(int), cudaMemcpyDeviceToHost, st));   // largest component
     }
     for (int k = 0; k < noct; k++)
         if (nkeys[k] > 0) PLF_CUDA(ctx, cudaStreamSynchronize(stk[k]));
@@ -548,7 +549,8 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             const int* bc = o->h_pin + 64 * k + 8;
             int topb = 0, nbig = 0;
             for (int b = 0; b < LSD_NBUCKET; b++) { if (bc[b]) topb = b; if (b >= LSD_BIG_BUCKET) nbig += bc[b]; }
-            int wg_maxc = 1 << (topb + 1);
+            (void)topb;
+            int wg_maxc = (o->h_pin[64 * k + 1] + 1023) & ~1023;     // used-bitmap bits per warp: the largest component, rounded up
             if (wg_maxc > WARPGROW_MAXC) wg_maxc = WARPGROW_MAXC;
             if (wg_maxc < 1024) wg_maxc = 1024;
             const int wg_smem = WG_WARPS * (wg_maxc / 8);

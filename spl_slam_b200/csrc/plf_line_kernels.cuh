@@ -445,7 +445,7 @@ k_lsd_keys(const int* __restrict__ label, const int* __restrict__ q, const unsig
 #endif
 __global__ void __launch_bounds__(256)
 k_lsd_heads(const unsigned long long* __restrict__ keys, int n, int2* __restrict__ comp, int* __restrict__ bcount,
-            int* __restrict__ bfill, int pass, int kb)
+            int* __restrict__ bfill, int* __restrict__ maxsize, int pass, int kb)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
@@ -459,7 +459,7 @@ k_lsd_heads(const unsigned long long* __restrict__ keys, int n, int2* __restrict
     const int size = lo - i;
     int b = 31 - __clz(size);
     if (b >= LSD_NBUCKET) b = LSD_NBUCKET - 1;
-    if (pass == 0) { atomicAdd(&bcount[b], 1); return; }
+    if (pass == 0) { atomicAdd(&bcount[b], 1); atomicMax(maxsize, size); return; }
     int base = 0;
     for (int k = LSD_NBUCKET - 1; k > b; k--) base += bcount[k];
     comp[base + atomicAdd(&bfill[b], 1)] = make_int2(i, size);
@@ -570,7 +570,7 @@ k_lsd_grow(const unsigned long long* __restrict__ keys, int n, const int2* __res
 // into the label array after the sort), so the angle / cos-sin arrays stay read-only and L1-resident.
 // ------------------------------------------------------------------------------------------------
 #define WARPGROW_MAXC (256 * 1024)          // component pixels one warp can track (32 KB of used bits; four warps per CTA)
-#define WG_RING 1024                        // queue entries kept in shared memory
+#define WG_RING 128                         // queue entries kept in shared memory (the frontier is a handful of entries; older ones come from the global arena)
 
 // after the sort: the sorted position of every defined pixel (its compact index inside the component), and -- one
 // thread per defined pixel, no divergence -- cs = float cos / sin of the float-cast radian angle, which is what
