@@ -34,7 +34,7 @@ ORB = dict(nfeatures=1200, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7
 LINE = dict(nfeatures=200, nlevels=2, refine=0, scale=1.1, sigma_scale=0.8, quant=2.2, ang_th=12.5, log_eps=1.0,
             density_th=0.8, n_bins=1024, min_line_length=0.0)   # Examples/Monocular/EuRoC.yaml (Camera.width absent -> 0)
 FRAMES_PER_GPU = 1024         # 512 stereo pairs per GPU per step (~35 GB of HBM workspace)
-LINE_CONTEXTS = 4             # line extractor instances (own context/stream + host thread each), frames split evenly
+LINE_CONTEXTS = 2             # line extractor instances (own context + host thread each; every instance runs its two octaves on two streams)
 ORB_CONTEXTS = 2              # ORB extractor instances, same idea (uploads of one overlap kernels of the other)
 WORKLOAD = "EuRoC-style stereo 752x480 pairs, 1200 ORB (8 lv x1.2, FAST 20/7) + LSD/LBD 200 lines per image"
 
