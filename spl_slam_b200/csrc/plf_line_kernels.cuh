@@ -86,22 +86,36 @@ k_gauss_strip(const uint8_t* __restrict__ src, size_t sframe, int spitch, uint8_
 }
 
 // ---------------- cv::resize INTER_LINEAR_EXACT; tab: .x = offset, .y = c1 (Q8) ----------------
+// block = (32, 8): a thread produces four adjacent pixels of one row (one packed 32-bit store)
 __global__ void __launch_bounds__(256)
 k_resize_exact(const uint8_t* __restrict__ src, size_t sframe, int spitch, int sw, int sh,
                uint8_t* __restrict__ dst, size_t dframe, int dpitch, int dw, int dh,
                const int2* __restrict__ xtab, const int2* __restrict__ ytab)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= dw || y >= dh) return;
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y;
+    if (x0 >= dw || y >= dh) return;
     const uint8_t* s = src + (size_t)blockIdx.z * sframe;
-    const int2 ty = ytab[y], tx = xtab[x];
-    const int sy0 = ty.x, sy1 = min(sy0 + 1, sh - 1), sx0 = tx.x, sx1 = min(sx0 + 1, sw - 1);
-    const int cy1 = ty.y, cy0 = 256 - cy1, cx1 = tx.y, cx0 = 256 - cx1;
+    const int2 ty = ytab[y];
+    const int sy0 = ty.x, sy1 = min(sy0 + 1, sh - 1);
+    const int cy1 = ty.y, cy0 = 256 - cy1;
     const uint8_t* r0 = s + (size_t)sy0 * spitch;
     const uint8_t* r1 = s + (size_t)sy1 * spitch;
-    int h0 = cx0 * r0[sx0] + cx1 * r0[sx1];
-    int h1 = cx0 * r1[sx0] + cx1 * r1[sx1];
-    dst[(size_t)blockIdx.z * dframe + (size_t)y * dpitch + x] = (uint8_t)((cy0 * h0 + cy1 * h1 + 32768) >> 16);
+    unsigned out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (x0 + k < dw) {
+            const int2 tx = xtab[x0 + k];
+            const int sx0 = tx.x, sx1 = min(sx0 + 1, sw - 1);
+            const int cx1 = tx.y, cx0 = 256 - cx1;
+            const int h0 = cx0 * r0[sx0] + cx1 * r0[sx1];
+            const int h1 = cx0 * r1[sx0] + cx1 * r1[sx1];
+            out |= (unsigned)((cy0 * h0 + cy1 * h1 + 32768) >> 16) << (8 * k);
+        }
+    }
+    uint8_t* d = dst + (size_t)blockIdx.z * dframe + (size_t)y * dpitch + x0;
+    if (x0 + 3 < dw && ((((size_t)dst) | (size_t)dpitch | dframe) & 3) == 0) *(unsigned*)d = out;
+    else
+        for (int k = 0; k < 4 && x0 + k < dw; k++) d[k] = (uint8_t)(out >> (8 * k));
 }
 
 // 12 bytes x0-4 .. x0+7 of an image row as three words (aligned fast path, or gathered with REFLECT_101)

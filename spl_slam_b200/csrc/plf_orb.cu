@@ -243,7 +243,7 @@ static plf_status orb_run(plf_orb* o, const uint8_t* lvl0, size_t stride0, size_
     for (int l = 1; l < g.nlevels; l++) {
         const OrbLevelGeom &S = g.lv[l - 1], &D = g.lv[l];
         // (a shared-memory tiled variant measured slower than these L1-served gathers: 2.3 vs 1.8 ms per 1024 frames)
-        dim3 grid(plf_div_up(D.w, 128), plf_div_up(D.h, 8), nframes);
+        dim3 grid(plf_div_up(D.w, 128), plf_div_up(D.h, 8 * RL_ROWS), nframes);
         PLF_LAUNCH(k_resize_linear, grid, dim3(32, 8), 0, st, P.lvl[l - 1], P.frameStride[l - 1], P.pitch[l - 1], S.w, S.h,
                    o->lvl_own[l], D.frameBytes, D.pitch, D.w, D.h, o->xtab[l], o->ytab[l]);
         PLF_CHECK_LAUNCH(ctx);

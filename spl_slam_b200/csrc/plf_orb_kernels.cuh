@@ -11,41 +11,48 @@ __device__ __align__(16) const signed char d_orb_pattern[1024] = {
 // ------------------------------------------------------------------------------------------------
 // ComputePyramid: cv::resize INTER_LINEAR 8U, level l from level l-1 (src/ORBextractor.cc:1120).
 // tab entries: .x = source offset, .y = coef0 | coef1 << 16 (11-bit fixed point).
-// block = (32, 8): each thread produces 4 adjacent pixels of one row.
+// block = (32, 8): each thread produces 4 adjacent pixels of RL_ROWS rows.
 // ------------------------------------------------------------------------------------------------
+#define RL_ROWS 2
 __global__ void __launch_bounds__(256)
 k_resize_linear(const uint8_t* __restrict__ src, size_t srcFrameStride, int spitch, int sw, int sh,
                 uint8_t* __restrict__ dst, size_t dstFrameStride, int dpitch, int dw, int dh,
                 const int2* __restrict__ xtab, const int2* __restrict__ ytab)
 {
+    // a thread produces 4 adjacent pixels of RL_ROWS rows (8 apart): the column table entries are loaded once
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    if (x0 >= dw || y >= dh) return;
+    if (x0 >= dw) return;
     const uint8_t* s = src + (size_t)blockIdx.z * srcFrameStride;
-    uint8_t* d = dst + (size_t)blockIdx.z * dstFrameStride + (size_t)y * dpitch;
-    const int2 ty = ytab[y];
-    const int sy0 = ty.x, sy1 = min(sy0 + 1, sh - 1);
-    const int b0 = (short)(ty.y & 0xffff), b1 = (short)(ty.y >> 16);
-    const uint8_t* r0 = s + (size_t)sy0 * spitch;
-    const uint8_t* r1 = s + (size_t)sy1 * spitch;
-    unsigned out = 0;
+    int sx[4], sx1[4], a0[4], a1[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        int x = x0 + k;
-        if (x < dw) {
-            const int2 tx = xtab[x];
-            const int sx = tx.x, sx1 = min(sx + 1, sw - 1);
-            const int a0 = (short)(tx.y & 0xffff), a1 = (short)(tx.y >> 16);
-            int h0 = r0[sx] * a0 + r0[sx1] * a1;
-            int h1 = r1[sx] * a0 + r1[sx1] * a1;
-            int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        const int2 tx = xtab[min(x0 + k, dw - 1)];
+        sx[k] = tx.x; sx1[k] = min(tx.x + 1, sw - 1);
+        a0[k] = (short)(tx.y & 0xffff); a1[k] = (short)(tx.y >> 16);
+    }
+#pragma unroll
+    for (int rr = 0; rr < RL_ROWS; rr++) {
+        const int y = (blockIdx.y * RL_ROWS + rr) * 8 + threadIdx.y;
+        if (y >= dh) break;
+        uint8_t* d = dst + (size_t)blockIdx.z * dstFrameStride + (size_t)y * dpitch;
+        const int2 ty = ytab[y];
+        const int sy0 = ty.x, sy1 = min(sy0 + 1, sh - 1);
+        const int b0 = (short)(ty.y & 0xffff), b1 = (short)(ty.y >> 16);
+        const uint8_t* r0 = s + (size_t)sy0 * spitch;
+        const uint8_t* r1 = s + (size_t)sy1 * spitch;
+        unsigned out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int h0 = r0[sx[k]] * a0[k] + r0[sx1[k]] * a1[k];
+            const int h1 = r1[sx[k]] * a0[k] + r1[sx1[k]] * a1[k];
+            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
             out |= (unsigned)(v & 0xff) << (8 * k);
         }
-    }
-    if (x0 + 3 < dw) {
-        *(unsigned*)(d + x0) = out;  // dpitch and x0 are multiples of 4
-    } else {
-        for (int k = 0; k < 4 && x0 + k < dw; k++) d[x0 + k] = (uint8_t)(out >> (8 * k));
+        if (x0 + 3 < dw) {
+            *(unsigned*)(d + x0) = out;  // dpitch and x0 are multiples of 4
+        } else {
+            for (int k = 0; k < 4 && x0 + k < dw; k++) d[x0 + k] = (uint8_t)(out >> (8 * k));
+        }
     }
 }
 
