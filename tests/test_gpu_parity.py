@@ -410,3 +410,42 @@ def test_frame_pipeline_after_extraction(S, oracle, gpu_ctx):
     off, idx = S.features_in_area(gpu_ctx, Mu, gl, Mu["x"], Mu["y"], np.full(len(Mu), 40, f32), keylines=Ku)
     ooff, oidx = oracle.grid_candidates(oMu, ogl, oMu["x"], oMu["y"], np.full(len(Mu), 40, f32), keylines=oKu)
     assert np.array_equal(off, ooff) and np.array_equal(idx, oidx)
+
+
+def test_error_conventions(S, oracle, gpu_ctx):
+    """The ABI never truncates silently and never throws across the boundary: capacity / argument problems come back as
+    status codes with a message (translated to PlfError by the Python mirror, to std::runtime_error by the C++ shim)."""
+    import ctypes as C
+    lib, h = gpu_ctx.lib, gpu_ctx.h
+    img = oracle.synth_image(640, 480, 2)
+    ex = S.ORBextractor(1000, 1.2, 8, 20, 7, ctx=gpu_ctx)
+    kps = np.zeros(100, S.KEYPOINT_DTYPE); desc = np.zeros((100, 32), np.uint8); n = C.c_int()
+    st = lib.plf_orb_extract(ex.h, img.ctypes.data, 640, 480, 640, kps.ctypes.data, desc.ctypes.data, 100, C.byref(n))
+    assert st == S.api.PLF_ERR_CAPACITY and b"capacity" in lib.plf_last_error(h)          # 1000 keypoints do not fit 100 slots
+    st = lib.plf_orb_extract(ex.h, img.ctypes.data, 640, 480, 100, kps.ctypes.data, desc.ctypes.data, 100, C.byref(n))
+    assert st == S.api.PLF_ERR_INVALID                                                     # stride < width
+    k, d = ex(img)                                                                         # the extractor is still usable
+    assert len(k) > 900
+    # stereo before any extraction on the right extractor: call-order error, not a crash
+    ex2 = S.ORBextractor(1000, 1.2, 8, 20, 7, ctx=gpu_ctx)
+    with pytest.raises(S.PlfError) as e:
+        ex.ComputeStereoMatches(ex2, k, d, k, d, 0.1, 40.0)
+    assert e.value.status == S.api.PLF_ERR_STATE
+    # lines: unsupported parameters are rejected at construction (refine != 0, > 2 octaves)
+    with pytest.raises(S.PlfError):
+        S.Lineextractor(200, 2, 1, 1.1, 0.6, 2.2, 12.5, 1.0, 0.6, 1024, 0.0, ctx=gpu_ctx)
+    with pytest.raises(S.PlfError):
+        S.Lineextractor(200, 3, 0, 1.1, 0.6, 2.2, 12.5, 1.0, 0.6, 1024, 0.0, ctx=gpu_ctx)
+    # keyline capacity too small for the per-octave quota
+    le, prm = _line_objs(S, oracle, gpu_ctx, 200)
+    kl = np.zeros(10, S.KEYLINE_DTYPE); mid = np.zeros(10, S.KEYPOINT_DTYPE); ld = np.zeros((10, 32), np.uint8)
+    st = lib.plf_line_extract(le.h, img.ctypes.data, 640, 480, 640, kl.ctypes.data, mid.ctypes.data, ld.ctypes.data, 10, C.byref(n))
+    assert st == S.api.PLF_ERR_CAPACITY
+    K, M, D = le.ComputeLsdWithLbd(img)
+    assert len(K) == 200
+    # candidate lists with an out-of-range train index, grid with a bad geometry
+    m = S.ORBmatcher(0.9, ctx=gpu_ctx)
+    with pytest.raises(S.PlfError):
+        m.candidates_top2(d[:2], d[:5], [np.array([5], np.int32), np.zeros(0, np.int32)])
+    with pytest.raises(S.PlfError):
+        S.features_in_area(gpu_ctx, k, S.GridParams(0, 48, 0, 0, 1, 1), k["x"], k["y"], np.ones(len(k), np.float32))
