@@ -508,7 +508,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             PLF_CUDA(ctx, e);
         }
 #endif
-        PLF_LAUNCH(k_lsd_keys, g2, b2, 0, st, (const int*)o->d_label[k], (const int*)o->d_q[k], (const unsigned*)o->d_mask[k], mw, (const int*)o->d_offs[k],
+        PLF_LAUNCH(k_lsd_keys, g2, b2, 0, st, o->d_label[k], (const int*)o->d_q[k], (const unsigned*)o->d_mask[k], mw, (const int*)o->d_offs[k],
                    (const double*)o->d_bincoef[k], sp, sh, o->prm.n_bins, o->d_keys[k], (int)o->keycap[k], o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
         PLF_CUDA(ctx, cudaMemcpyAsync(o->h_pin + 64 * k, o->d_offs[k] + nwords[k], sizeof(int), cudaMemcpyDeviceToHost, st));   // pinned staging

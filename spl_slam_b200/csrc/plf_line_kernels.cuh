@@ -421,7 +421,7 @@ k_ccl_merge(int* __restrict__ label, const unsigned* __restrict__ mask, int mw, 
 // emit one sort key per defined pixel (root label, bin, raster index).  Positions come from an inclusive prefix sum of
 // the mask popcounts (offs[i + 1] = number of defined pixels in mask words 0 .. i): no atomics, keys in raster order.
 __global__ void __launch_bounds__(256)
-k_lsd_keys(const int* __restrict__ label, const int* __restrict__ q, const unsigned* __restrict__ mask, int mw,
+k_lsd_keys(int* __restrict__ label, const int* __restrict__ q, const unsigned* __restrict__ mask, int mw,
            const int* __restrict__ offs, const double* __restrict__ coef, int w, int h, int n_bins,
            unsigned long long* __restrict__ keys, int keycap, int kb)
 {
@@ -436,7 +436,12 @@ k_lsd_keys(const int* __restrict__ label, const int* __restrict__ q, const unsig
     const unsigned below = ~m & ((1u << lane) - 1u);
     const int head = below ? 32 - __clz((int)below) : 0;
     int root = -1;
-    if (have && head == lane) root = ccl_find(label + (size_t)f * w * h, y * w + blockIdx.x * 32 + lane);
+    if (have && head == lane) {
+        int* Lf = label + (size_t)f * w * h;
+        const int hp = y * w + blockIdx.x * 32 + lane;
+        root = ccl_find(Lf, hp);
+        if (Lf[hp] != root) Lf[hp] = root;     // shorten the chain for the run heads that hang below this one
+    }
     root = __shfl_sync(0xffffffffu, root, head);
     if (have) {
         const int p = y * w + blockIdx.x * 32 + lane;
