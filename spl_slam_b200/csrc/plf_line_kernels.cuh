@@ -388,33 +388,46 @@ __device__ __forceinline__ void ccl_union(int* L, int a, int b)
 //   N  : first pixel of the overlap with a run above (skipped when the W neighbour made the same link via its N),
 //   NE : N undefined, NE defined (a run above starting one to the right),
 //   NW : N and W undefined, NW defined.
+// One WARP per image row (block = (32, 8) = 8 rows): the lanes fetch the row's mask words and those of the row above
+// with two coalesced loads, then the warp walks only the non-empty 32-px segments (the others cost nothing).
 __global__ void __launch_bounds__(256)
 k_ccl_merge(int* __restrict__ label, const unsigned* __restrict__ mask, int mw, int w, int h)
 {
-    const int seg = blockIdx.x, lane = threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const int lane = threadIdx.x, y = blockIdx.x * 8 + threadIdx.y;
     if (y >= h) return;
+    const unsigned FULL = 0xffffffffu;
     const unsigned* M = mask + ((size_t)blockIdx.z * h + y) * mw;
-    const unsigned m1 = M[seg];
-    if (!m1) return;
-    const unsigned m1l = seg > 0 ? M[seg - 1] : 0u;
-    unsigned m0 = 0u, m0l = 0u, m0r = 0u;
-    if (y > 0) {
-        m0 = M[seg - mw];
-        m0l = seg > 0 ? M[seg - mw - 1] : 0u;
-        m0r = seg + 1 < mw ? M[seg - mw + 1] : 0u;
-    }
-    if (!((m1 >> lane) & 1u)) return;
-    const bool dW = lane > 0 ? (m1 >> (lane - 1)) & 1u : (m1l >> 31) & 1u;
-    const bool dN = (m0 >> lane) & 1u;
-    const bool dNW = lane > 0 ? (m0 >> (lane - 1)) & 1u : (m0l >> 31) & 1u;
-    const bool dNE = lane < 31 ? (m0 >> (lane + 1)) & 1u : m0r & 1u;
     int* L = label + (size_t)blockIdx.z * w * h;
-    const int p = y * w + seg * 32 + lane;
-    if (lane == 0 && dW) ccl_union(L, p, p - 1);
-    if (dN) { if (!(dW && dNW)) ccl_union(L, p, p - w); }
-    else {
-        if (dNE) ccl_union(L, p, p - w + 1);
-        if (!dW && dNW) ccl_union(L, p, p - w - 1);
+    for (int s0 = 0; s0 < mw; s0 += 32) {
+        // words s0-1 .. s0+32 of this row and the row above, held one per lane (+ the two neighbours of the chunk)
+        const int sg = s0 + lane;
+        const unsigned cur = sg < mw ? M[sg] : 0u;
+        const unsigned up = (y > 0 && sg < mw) ? M[sg - mw] : 0u;
+        const unsigned curPrev = s0 > 0 ? M[s0 - 1] : 0u;                       // word left of the chunk (warp-uniform)
+        const unsigned upPrev = (y > 0 && s0 > 0) ? M[s0 - 1 - mw] : 0u;
+        const unsigned upNext = (y > 0 && s0 + 32 < mw) ? M[s0 + 32 - mw] : 0u;  // word right of the chunk in the row above
+        unsigned todo = __ballot_sync(FULL, cur != 0u);
+        while (todo) {
+            const int s = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            const unsigned m1 = __shfl_sync(FULL, cur, s);
+            const unsigned m0 = __shfl_sync(FULL, up, s);
+            const unsigned m1l = s > 0 ? __shfl_sync(FULL, cur, s - 1) : curPrev;
+            const unsigned m0l = s > 0 ? __shfl_sync(FULL, up, s - 1) : upPrev;
+            const unsigned m0r = s < 31 ? __shfl_sync(FULL, up, s + 1) : upNext;
+            if (!((m1 >> lane) & 1u)) continue;
+            const bool dW = lane > 0 ? (m1 >> (lane - 1)) & 1u : (m1l >> 31) & 1u;
+            const bool dN = (m0 >> lane) & 1u;
+            const bool dNW = lane > 0 ? (m0 >> (lane - 1)) & 1u : (m0l >> 31) & 1u;
+            const bool dNE = lane < 31 ? (m0 >> (lane + 1)) & 1u : m0r & 1u;
+            const int p = y * w + (s0 + s) * 32 + lane;
+            if (lane == 0 && dW) ccl_union(L, p, p - 1);
+            if (dN) { if (!(dW && dNW)) ccl_union(L, p, p - w); }
+            else {
+                if (dNE) ccl_union(L, p, p - w + 1);
+                if (!dW && dNW) ccl_union(L, p, p - w - 1);
+            }
+        }
     }
 }
 
@@ -425,34 +438,46 @@ k_lsd_keys(int* __restrict__ label, const int* __restrict__ q, const unsigned* _
            const int* __restrict__ offs, const double* __restrict__ coef, int w, int h, int n_bins,
            unsigned long long* __restrict__ keys, int keycap, int kb)
 {
-    const int lane = threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    // one WARP per image row (block = (32, 8)): the mask words of the row are fetched with one coalesced load and only
+    // the non-empty segments are walked
+    const int lane = threadIdx.x, y = blockIdx.x * 8 + threadIdx.y;
     const int f = blockIdx.z;
     if (y >= h) return;
-    const size_t widx = ((size_t)f * h + y) * mw + blockIdx.x;
-    const unsigned m = mask[widx];
-    if (!m) return;
-    const bool have = (m >> lane) & 1u;
-    // pixels of one run share a label (k_lsd_grad): only the head of each run chases its root, the others take it by shuffle
-    const unsigned below = ~m & ((1u << lane) - 1u);
-    const int head = below ? 32 - __clz((int)below) : 0;
-    int root = -1;
-    if (have && head == lane) {
-        int* Lf = label + (size_t)f * w * h;
-        const int hp = y * w + blockIdx.x * 32 + lane;
-        root = ccl_find(Lf, hp);
-        if (Lf[hp] != root) Lf[hp] = root;     // shorten the chain for the run heads that hang below this one
-    }
-    root = __shfl_sync(0xffffffffu, root, head);
-    if (have) {
-        const int p = y * w + blockIdx.x * 32 + lane;
-        const size_t o = (size_t)f * w * h + p;
-        int bin = (int)(sqrt((double)q[o] / 4.0) * coef[f]);
-        if (bin < 0) bin = 0;
-        if (bin > n_bins - 1) bin = n_bins - 1;
-        const unsigned long long key = ((unsigned long long)f << (2 * LSD_KB + LSD_BB)) | ((unsigned long long)root << (LSD_KB + LSD_BB)) |
-                                       ((unsigned long long)(n_bins - 1 - bin) << LSD_KB) | (unsigned long long)p;
-        const int oo = offs[widx] + __popc(m & ((1u << lane) - 1));
-        if (oo < keycap) keys[oo] = key;
+    const unsigned FULL = 0xffffffffu;
+    const size_t rowbase = ((size_t)f * h + y) * mw;
+    int* Lf = label + (size_t)f * w * h;
+    const double bin_coef = coef[f];
+    for (int s0 = 0; s0 < mw; s0 += 32) {
+        const int sg = s0 + lane;
+        const unsigned cur = sg < mw ? mask[rowbase + sg] : 0u;
+        const int myoff = sg < mw ? offs[rowbase + sg] : 0;
+        unsigned todo = __ballot_sync(FULL, cur != 0u);
+        while (todo) {
+            const int s = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            const unsigned m = __shfl_sync(FULL, cur, s);
+            const int base = __shfl_sync(FULL, myoff, s);
+            const bool have = (m >> lane) & 1u;
+            // pixels of one run share a label (k_lsd_grad): only the head of each run chases its root, the others take it by shuffle
+            const unsigned below = ~m & ((1u << lane) - 1u);
+            const int head = below ? 32 - __clz((int)below) : 0;
+            const int p = y * w + (s0 + s) * 32 + lane;
+            int root = -1;
+            if (have && head == lane) {
+                root = ccl_find(Lf, p);
+                if (Lf[p] != root) Lf[p] = root;     // shorten the chain for the run heads that hang below this one
+            }
+            root = __shfl_sync(FULL, root, head);
+            if (have) {
+                int bin = (int)(sqrt((double)q[(size_t)f * w * h + p] / 4.0) * bin_coef);
+                if (bin < 0) bin = 0;
+                if (bin > n_bins - 1) bin = n_bins - 1;
+                const unsigned long long key = ((unsigned long long)f << (2 * LSD_KB + LSD_BB)) | ((unsigned long long)root << (LSD_KB + LSD_BB)) |
+                                               ((unsigned long long)(n_bins - 1 - bin) << LSD_KB) | (unsigned long long)p;
+                const int oo = base + __popc(m & ((1u << lane) - 1));
+                if (oo < keycap) keys[oo] = key;
+            }
+        }
     }
 }
 
