@@ -1130,9 +1130,10 @@ k_lbd(const plf_keyline* __restrict__ kl, const int* __restrict__ nlines, int ca
         float sCorX = sCorX0, sCorY = sCorY0;
         float pgdL = 0, ngdL = 0, pgdO = 0, ngdO = 0;
         for (int wID = 0; wID < lengthOfLSP; wID++) {
-            short tc = (short)(int)round((double)sCorX);
+            // round() of the reference (double, half away from zero) == roundf(): float -> double is exact and so is the rounding
+            short tc = (short)(int)roundf(sCorX);
             const int xCor = tc < 0 ? 0 : (tc > imageWidth ? imageWidth : tc);
-            tc = (short)(int)round((double)sCorY);
+            tc = (short)(int)roundf(sCorY);
             const int yCor = tc < 0 ? 0 : (tc > imageHeight ? imageHeight : tc);
             const float dxv = (float)pdx[yCor * realWidth + xCor], dyv = (float)pdy[yCor * realWidth + xCor];
             float a0 = dxv * dL0, a1 = dyv * dL1;
