@@ -430,7 +430,7 @@ static plf_status gauss_batch(plf_ctx* ctx, cudaStream_t st, const uint8_t* src,
 // bandwidth-bound and fills the GPU; region growing is a latency-bound dependent chain that leaves it mostly
 // idle.  Contexts therefore take turns for the first phase (this mutex) and overlap their growing phases with
 // the other contexts' first phases instead of marching in lockstep.
-static std::mutex g_lsd_prephase;
+static std::mutex g_lsd_prephase[64];   // one per device: contexts of different GPUs in one process never wait for each other
 
 // LSDDetectorC::detect for a batch resident in d_oct[0]: fills d_det / d_detcount.
 // The octaves are independent until the line selection: each has its own workspace and (when there are two) its own
@@ -448,7 +448,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
     // whatever is still queued on this stream (the image upload of a host-buffer call) finishes before the turn is
     // taken: the lock must not be held across a PCIe transfer
     PLF_CUDA(ctx, cudaStreamSynchronize(st0));
-    std::unique_lock<std::mutex> prephase(g_lsd_prephase, std::defer_lock);
+    std::unique_lock<std::mutex> prephase(g_lsd_prephase[ctx->device & 63], std::defer_lock);
     if (!getenv("PLF_NO_PREPHASE_LOCK")) prephase.lock();
     // computeGaussianPyramid: pyrDown, no pre-blur (LSDDetector_custom.cpp:56-73)
     for (int k = 1; k < noct; k++) {
