@@ -49,13 +49,13 @@ struct plf_line {
     // on two streams and their region-growing chains overlap
     uint8_t *d_tmp[LINE_MAX_OCT], *d_scaled[LINE_MAX_OCT];
     int2* d_comp[LINE_MAX_OCT];
-    int *d_q[LINE_MAX_OCT], *d_label[LINE_MAX_OCT], *d_regpts[LINE_MAX_OCT], *d_lineidx[LINE_MAX_OCT], *d_lineidx2[LINE_MAX_OCT], *d_cnt[LINE_MAX_OCT];
+    int *d_q[LINE_MAX_OCT], *d_label[LINE_MAX_OCT], *d_regpts[LINE_MAX_OCT], *d_cnt[LINE_MAX_OCT];
     unsigned* d_mask[LINE_MAX_OCT];       // one bit per scaled pixel: gradient defined
     int* d_offs[LINE_MAX_OCT];            // inclusive prefix sum of the mask popcounts (+ leading 0)
     double* d_bincoef[LINE_MAX_OCT];      // per frame
     float* d_fa[LINE_MAX_OCT];
     float2* d_cs[LINE_MAX_OCT];
-    unsigned long long *d_keys[LINE_MAX_OCT], *d_keys2[LINE_MAX_OCT], *d_linekey[LINE_MAX_OCT], *d_linekey2[LINE_MAX_OCT];
+    unsigned long long *d_keys[LINE_MAX_OCT], *d_keys2[LINE_MAX_OCT], *d_linekey[LINE_MAX_OCT];
     LsdRegion* d_regions[LINE_MAX_OCT];
     float4* d_lines[LINE_MAX_OCT];
     void* d_cubtmp[LINE_MAX_OCT];
@@ -80,7 +80,7 @@ struct plf_line {
     int out_frames, out_cap;
 };
 
-// d_cnt layout (ints): [0]=nkeys [1]=ncomp [2]=next [3]=nregions [4]=sticky overflow flag [8..32) bucket counts [32..56) bucket fill [64..64+frames) = maxq
+// d_cnt layout (ints): [0]=nkeys [1]=ncomp [2]=next [4]=sticky overflow flag [8..32) bucket counts [32..56) bucket fill [96..96+F) = maxq, then F region counts (one per frame)
 enum { CNT_NKEYS = 0, CNT_NCOMP = 1, CNT_NEXT = 2, CNT_NREG = 3, CNT_ERR = 4, CNT_BCOUNT = 8, CNT_BFILL = 32, CNT_STATS = 64, CNT_MAXQ = 96 };
 
 static int gauss_kernel_q8(int ksize, double sigma, int* q)
@@ -283,8 +283,8 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         need(F * spx, 4); need(F * spx, 4); need(F * spx, 4); need(F * spx, 8);   // q, label, fa, cs
         need(o->keycap[k], 8); need(o->keycap[k], 8); need(o->keycap[k], 4); need(o->keycap[k], 8);    // keys, keys2, regpts, comp
         need(o->regcap, sizeof(LsdRegion)); need(o->regcap, sizeof(float4));
-        need(o->regcap, 8); need(o->regcap, 8); need(o->regcap, 4); need(o->regcap, 4);
-        need(CNT_MAXQ + F, 4);
+        need(o->regcap, 8);
+        need(CNT_MAXQ + 2 * F, 4);
         need(o->maskwords[k], 4); need(o->maskwords[k] + 64, 4); need(F, 8);   // mask, offsets, bin coefficients
     }
     need(F * noct * LINE_DETCAP, sizeof(plf_keyline));
@@ -311,10 +311,7 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         o->d_regions[k] = carve<LsdRegion>(p, o->regcap);
         o->d_lines[k] = carve<float4>(p, o->regcap);
         o->d_linekey[k] = carve<unsigned long long>(p, o->regcap);
-        o->d_linekey2[k] = carve<unsigned long long>(p, o->regcap);
-        o->d_lineidx[k] = carve<int>(p, o->regcap);
-        o->d_lineidx2[k] = carve<int>(p, o->regcap);
-        o->d_cnt[k] = carve<int>(p, CNT_MAXQ + F);
+        o->d_cnt[k] = carve<int>(p, CNT_MAXQ + 2 * F);     // counters, maxq[F], regions per frame[F]
         o->d_mask[k] = carve<unsigned>(p, o->maskwords[k]);
         o->d_offs[k] = carve<int>(p, o->maskwords[k] + 64);
         o->d_bincoef[k] = carve<double>(p, F);
@@ -334,13 +331,11 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
     }
 #ifndef PLF_EMU
     for (int k = 0; k < noct; k++) {
-        size_t t1 = 0, t2 = 0, t3 = 0;
+        size_t t1 = 0, t3 = 0;
         cub::DeviceRadixSort::SortKeys(nullptr, t1, o->d_keys[k], o->d_keys2[k], (int)o->keycap[k], 0, 64, ctx->stream);
-        cub::DeviceRadixSort::SortPairs(nullptr, t2, o->d_linekey[k], o->d_linekey2[k], o->d_lineidx[k], o->d_lineidx2[k], o->regcap, 0, 64, ctx->stream);
         cub::TransformInputIterator<int, PopcOp, const unsigned*> it(o->d_mask[k], PopcOp());
         cub::DeviceScan::InclusiveSum(nullptr, t3, it, o->d_offs[k] + 1, (int)o->maskwords[k], ctx->stream);
-        o->cubtmp_bytes[k] = t1 > t2 ? t1 : t2;
-        if (t3 > o->cubtmp_bytes[k]) o->cubtmp_bytes[k] = t3;
+        o->cubtmp_bytes[k] = t1 > t3 ? t1 : t3;
         PLF_CUDA(ctx, cudaMalloc(&o->d_cubtmp[k], o->cubtmp_bytes[k] + 256));
     }
 #endif
@@ -359,28 +354,6 @@ static plf_status sort_keys(plf_line* o, int k, int n, int end_bit, cudaStream_t
     size_t tb = o->cubtmp_bytes[k];
     plf_prof_begin(ctx, "cub_radix_sort_keys");
     cudaError_t e = cub::DeviceRadixSort::SortKeys(o->d_cubtmp[k], tb, o->d_keys[k], o->d_keys2[k], n, 0, end_bit, st);
-    plf_prof_end(ctx);
-    PLF_CUDA(ctx, e);
-#endif
-    return PLF_OK;
-}
-
-static plf_status sort_lines(plf_line* o, int k, int nframes, cudaStream_t st)
-{
-    plf_ctx* ctx = o->ctx;
-#ifdef PLF_EMU
-    std::vector<std::pair<unsigned long long, int>> v(o->regcap);
-    for (int i = 0; i < o->regcap; i++) v[i] = std::make_pair(o->d_linekey[k][i], o->d_lineidx[k][i]);
-    std::stable_sort(v.begin(), v.end(), [](const std::pair<unsigned long long, int>& a, const std::pair<unsigned long long, int>& b) { return a.first < b.first; });
-    for (int i = 0; i < o->regcap; i++) { o->d_linekey2[k][i] = v[i].first; o->d_lineidx2[k][i] = v[i].second; }
-#else
-    size_t tb = o->cubtmp_bytes[k];
-    // line keys use bits [0, 40 + frame bits); padding keys are ~0, i.e. all ones in that range too (one past the last frame),
-    // so sorting just those bits still puts them at the end
-    int fbits = 1;
-    while ((1 << fbits) < nframes + 1) fbits++;
-    plf_prof_begin(ctx, "cub_radix_sort_lines");
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(o->d_cubtmp[k], tb, o->d_linekey[k], o->d_linekey2[k], o->d_lineidx[k], o->d_lineidx2[k], o->regcap, 0, 40 + fbits, st);
     plf_prof_end(ctx);
     PLF_CUDA(ctx, e);
 #endif
@@ -482,6 +455,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt[k], 0, 8 * sizeof(int), st));
         PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt[k] + CNT_BCOUNT, 0, (CNT_MAXQ - CNT_BCOUNT) * sizeof(int), st));
         PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt[k] + CNT_MAXQ, 0xff, (size_t)nframes * sizeof(int), st));   // maxq = -1
+        PLF_CUDA(ctx, cudaMemsetAsync(o->d_cnt[k] + CNT_MAXQ + nframes, 0, (size_t)nframes * sizeof(int), st));   // regions per frame
         // from here on every per-pixel array has sp columns per row (sw real ones + NOTDEF padding)
         const int mw = plf_div_up(sp, 32);
         mwk[k] = mw;
@@ -560,22 +534,23 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             const int wg_ctas = plf_div_up(nbig, WG_WARPS) < 148 * 4 ? plf_div_up(nbig, WG_WARPS) : 148 * 4;
             if (nbig > 0) PLF_LAUNCH(k_lsd_grow_warp, dim3(wg_ctas), dim3(32 * WG_WARPS), wg_smem, st, (const unsigned long long*)o->d_keys2[k],
                        (const int2*)o->d_comp[k], (const int*)(o->d_cnt[k] + CNT_BCOUNT), (const float*)o->d_fa[k], (const float2*)o->d_cs[k],
-                       (const int*)o->d_label[k], sp, sh, o->prec, o->min_reg[k], o->d_regpts[k], o->d_regions[k], o->d_cnt[k] + CNT_NREG, o->regcap, o->kbits[k], wg_maxc);
+                       (const int*)o->d_label[k], sp, sh, o->prec, o->min_reg[k], o->d_regpts[k], o->d_regions[k], o->d_cnt[k] + CNT_MAXQ + nframes, LINE_REGCAP_PER_FRAME, o->kbits[k], wg_maxc);
             PLF_CHECK_LAUNCH(ctx);
             PLF_LAUNCH(k_lsd_grow, dim3(148 * 4), dim3(128), 0, st, (const unsigned long long*)o->d_keys2[k], nkeys[k], (const int2*)o->d_comp[k],
                        (const int*)(o->d_cnt[k] + CNT_BCOUNT), o->d_cnt[k] + CNT_NEXT, o->d_fa[k], (const float2*)o->d_cs[k], sp, sh, o->prec,
-                       o->min_reg[k], o->d_regpts[k], o->d_regions[k], o->d_cnt[k] + CNT_NREG, o->regcap, 1, wg_maxc, o->kbits[k]);
+                       o->min_reg[k], o->d_regpts[k], o->d_regions[k], o->d_cnt[k] + CNT_MAXQ + nframes, LINE_REGCAP_PER_FRAME, 1, wg_maxc, o->kbits[k]);
             PLF_CHECK_LAUNCH(ctx);
         }
-        PLF_LAUNCH(k_lsd_rect, dim3(plf_div_up(o->regcap, RECT_WARPS)), dim3(32 * RECT_WARPS), 0, st, (const LsdRegion*)o->d_regions[k],
-                   (const int*)(o->d_cnt[k] + CNT_NREG), o->regcap, (const int*)o->d_regpts[k], (const int*)o->d_q[k], sp, sh, o->prec, S, o->d_lines[k],
-                   o->d_linekey[k], o->d_lineidx[k], o->d_cnt[k] + CNT_ERR, o->kbits[k]);
+        // enough CTAs per frame to fill the GPU for small batches, one or two for large ones
+        int rsplit = plf_div_up(148 * 8, nframes);
+        if (rsplit > LINE_REGCAP_PER_FRAME / RECT_WARPS) rsplit = LINE_REGCAP_PER_FRAME / RECT_WARPS;
+        PLF_LAUNCH(k_lsd_rect, dim3(rsplit, nframes), dim3(32 * RECT_WARPS), 0, st, (const LsdRegion*)o->d_regions[k],
+                   (const int*)(o->d_cnt[k] + CNT_MAXQ + nframes), LINE_REGCAP_PER_FRAME, (const int*)o->d_regpts[k], (const int*)o->d_q[k], sp, sh,
+                   o->prec, S, o->d_lines[k], o->d_linekey[k], o->d_cnt[k] + CNT_ERR, o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
-        plf_status s = sort_lines(o, k, nframes, st);
-        if (s) return s;
-        PLF_LAUNCH(k_lsd_keylines, dim3(plf_div_up(o->regcap, 128)), dim3(128), 0, st, (const unsigned long long*)o->d_linekey2[k],
-                   (const int*)o->d_lineidx2[k], o->regcap, (const float4*)o->d_lines[k], nframes, k, noct, o->ow[k], o->oh[k], o->prm.min_line_length,
-                   o->d_det, o->d_detcount, LINE_DETCAP);
+        PLF_LAUNCH(k_lsd_keylines, dim3(nframes), dim3(KL_T), 0, st, (const unsigned long long*)o->d_linekey[k],
+                   (const int*)(o->d_cnt[k] + CNT_MAXQ + nframes), LINE_REGCAP_PER_FRAME, (const float4*)o->d_lines[k], k, noct, o->ow[k], o->oh[k],
+                   o->prm.min_line_length, o->d_det, o->d_detcount, LINE_DETCAP);
         PLF_CHECK_LAUNCH(ctx);
     }
     // the selection / LBD that follow run on the context stream: join octave 1
@@ -704,7 +679,7 @@ static plf_status check_regions(plf_line* o)
     for (int k = 0; k < o->prm.nlevels; k++) {
         int err = 0;
         { plf_status rs = read_ints(ctx, o->d_cnt[k] + CNT_ERR, 1, &err); if (rs) return rs; }
-        if (err) return plf_fail(ctx, PLF_ERR_CAPACITY, "LSD region buffer overflow (more than %d regions in the batch)", o->regcap);
+        if (err) return plf_fail(ctx, PLF_ERR_CAPACITY, "LSD region buffer overflow (more than %d regions in one frame)", LINE_REGCAP_PER_FRAME);
     }
     return PLF_OK;
 }

@@ -592,11 +592,12 @@ k_lsd_grow(const unsigned long long* __restrict__ keys, int n, const int2* __res
             }
             const int nreg = arena - r0;
             if (nreg >= min_reg_size) {
-                const int rr = atomicAdd(nregions, 1);
+                const int rf = LSD_KEY_FRAME(key);
+                const int rr = atomicAdd(nregions + rf, 1);      // slot inside the frame's block of `regcap` regions
                 if (rr < regcap) {
                     LsdRegion R;
                     R.start = r0; R.n = nreg; R.reg_angle = reg_angle; R.seedkey = key;
-                    regions[rr] = R;
+                    regions[(size_t)rf * regcap + rr] = R;
                 }
             }
         }
@@ -840,11 +841,12 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
                 }
                 const int nreg = arena - r0;
                 if (lane == 0 && nreg >= min_reg_size) {
-                    const int rr = atomicAdd(nregions, 1);
+                    const int rf = LSD_KEY_FRAME(key);
+                    const int rr = atomicAdd(nregions + rf, 1);
                     if (rr < regcap) {
                         LsdRegion R;
                         R.start = r0; R.n = nreg; R.reg_angle = reg_angle; R.seedkey = key;
-                        regions[rr] = R;
+                        regions[(size_t)rf * regcap + rr] = R;
                     }
                 }
                 __syncwarp();
@@ -862,20 +864,19 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
 __global__ void __launch_bounds__(32 * RECT_WARPS)
 k_lsd_rect(const LsdRegion* __restrict__ regions, const int* __restrict__ nregions, int regcap, const int* __restrict__ regpts,
            const int* __restrict__ q, int w, int h, double prec, double scale, float4* __restrict__ lines,
-           unsigned long long* __restrict__ linekey, int* __restrict__ lineidx, int* __restrict__ errflag, int kb)
+           unsigned long long* __restrict__ linekey, int* __restrict__ errflag, int kb)
 {
+    // grid (split, frames): the warps of a frame's CTAs stride over the frame's region slots
     __shared__ double s_buf[RECT_WARPS][32][3];
-    const int rr = blockIdx.x * RECT_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
     double (*buf)[3] = s_buf[threadIdx.x >> 5];
     const unsigned FULL = 0xffffffffu;
-    if (rr >= regcap) return;
-    int nr = *nregions;
-    if (nr > regcap) { nr = regcap; if (rr == 0 && lane == 0) *errflag = 1; }
-    if (lane == 0) lineidx[rr] = rr;
-    if (rr >= nr) { if (lane == 0) linekey[rr] = ~0ull; return; }
-    const LsdRegion R = regions[rr];
-    const int f = LSD_KEY_FRAME(R.seedkey);
+    int nr = nregions[f];
+    if (nr > regcap) { nr = regcap; if (blockIdx.x == 0 && threadIdx.x == 0) *errflag = 1; }
     const int* Q = q + (size_t)f * w * h;
+    for (int slot = blockIdx.x * RECT_WARPS + (threadIdx.x >> 5); slot < nr; slot += gridDim.x * RECT_WARPS) {
+    const size_t rr = (size_t)f * regcap + slot;
+    const LsdRegion R = regions[rr];
     const int* pts = regpts + R.start;
     double x = 0, y = 0, sum = 0;
     for (int i0 = 0; i0 < R.n; i0 += 32) {
@@ -946,48 +947,44 @@ k_lsd_rect(const LsdRegion* __restrict__ regions, const int* __restrict__ nregio
         if (a > l_max) l_max = a;
         if (b < l_min) l_min = b;
     }
-    if (lane != 0) return;
+    __syncwarp();
+    if (lane != 0) continue;
     double x1 = x + l_min * dx, y1 = y + l_min * dy, x2 = x + l_max * dx, y2 = y + l_max * dy;
     x1 += 0.5; y1 += 0.5; x2 += 0.5; y2 += 0.5;
     if (scale != 1) { x1 /= scale; y1 /= scale; x2 /= scale; y2 /= scale; }
     float4 L;
     L.x = (float)x1; L.y = (float)y1; L.z = (float)x2; L.w = (float)y2;
     lines[rr] = L;
-    linekey[rr] = ((unsigned long long)f << 40) | ((unsigned long long)LSD_KEY_BIN(R.seedkey) << 22) | (unsigned long long)LSD_KEY_IDX(R.seedkey);
+    linekey[rr] = R.seedkey & ((1ull << (LSD_KB + LSD_BB)) - 1);     // (bin descending, raster) order inside the frame
+    }
 }
 
-// KeyLine assembly for one octave (LSDDetector_custom.cpp:266-308): one thread per sorted line.
+// KeyLine assembly for one octave (LSDDetector_custom.cpp:266-308): one CTA per frame.  The frame's regions sit in its own
+// block of slots in arrival order; their order keys are unique, so the position of a line in the reference's seed order is
+// the number of keys of the frame below its own (counted against a shared-memory copy).
 // det layout: [frame][octave][detcap] keylines in seed order, with a per (frame, octave) count.
-__global__ void __launch_bounds__(128)
-k_lsd_keylines(const unsigned long long* __restrict__ skeys, const int* __restrict__ sidx, int nsorted,
-               const float4* __restrict__ lines, int nframes, int octave, int noct, int ow, int oh, double min_length,
+#define KL_T 256
+#define KL_MAXREG 4096
+__global__ void __launch_bounds__(KL_T)
+k_lsd_keylines(const unsigned long long* __restrict__ linekey, const int* __restrict__ nregions, int regcap,
+               const float4* __restrict__ lines, int octave, int noct, int ow, int oh, double min_length,
                plf_keyline* __restrict__ det, int* __restrict__ detcount, int detcap)
 {
-    const int i = blockIdx.x * 128 + threadIdx.x;
-    if (i >= nsorted) return;
-    const unsigned long long key = skeys[i];
-    if (key == ~0ull) return;
-    const int f = (int)(key >> 40);
-    if (f >= nframes) return;
-    // position inside the frame = i - first index of the frame (binary search on the sorted keys)
-    int lo = 0, hi = i;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if ((int)(skeys[mid] >> 40) < f) lo = mid + 1; else hi = mid;
-    }
-    const int pos = i - lo;
+    __shared__ unsigned long long s_key[KL_MAXREG];
+    const int f = blockIdx.x;
+    int n = nregions[f];
+    if (n > regcap) n = regcap;
+    const size_t base = (size_t)f * regcap;
+    for (int i = threadIdx.x; i < n; i += KL_T) s_key[i] = linekey[base + i];
+    if (threadIdx.x == 0) detcount[f * noct + octave] = n;
+    __syncthreads();
     plf_keyline* out = det + ((size_t)f * noct + octave) * detcap;
-    if (pos == 0) {
-        // the last line of the frame publishes the count: find the end of the frame's run
-        int l2 = i, h2 = nsorted;
-        while (l2 < h2) {
-            int mid = (l2 + h2) >> 1;
-            if (skeys[mid] != ~0ull && (int)(skeys[mid] >> 40) <= f) l2 = mid + 1; else h2 = mid;
-        }
-        detcount[f * noct + octave] = l2 - lo;
-    }
-    if (pos >= detcap) return;
-    const float4 L = lines[sidx[i]];
+    for (int i = threadIdx.x; i < n; i += KL_T) {
+    const unsigned long long key = s_key[i];
+    int pos = 0;
+    for (int j = 0; j < n; j++) pos += s_key[j] < key;
+    if (pos >= detcap) continue;
+    const float4 L = lines[base + i];
     float e0 = L.x, e1 = L.y, e2 = L.z, e3 = L.w;
     // checkLineExtremes (:76-102)
     if (e0 < 0) e0 = 0;
@@ -1016,6 +1013,7 @@ k_lsd_keylines(const unsigned long long* __restrict__ skeys, const int* __restri
     K.pt_x = (K.endPointX + K.startPointX) / 2;
     K.pt_y = (K.endPointY + K.startPointY) / 2;
     out[pos] = K;
+    }
 }
 
 // min_length filter + class ids (detectImpl) and, when `select`, the per-octave response quota with
