@@ -344,16 +344,20 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
     return PLF_OK;
 }
 
-static plf_status sort_keys(plf_line* o, int k, int n, int end_bit, cudaStream_t st)
+// k_lsd_keys emits the keys in (frame, raster index) order, so a STABLE sort of the bits above the raster index
+// [begin_bit, end_bit) = (frame, root, bin) yields the fully sorted array with two radix passes fewer
+static plf_status sort_keys(plf_line* o, int k, int n, int begin_bit, int end_bit, cudaStream_t st)
 {
     plf_ctx* ctx = o->ctx;
 #ifdef PLF_EMU
-    std::sort(o->d_keys[k], o->d_keys[k] + n);
+    std::stable_sort(o->d_keys[k], o->d_keys[k] + n, [begin_bit](unsigned long long a, unsigned long long b) { return (a >> begin_bit) < (b >> begin_bit); });
     memcpy(o->d_keys2[k], o->d_keys[k], (size_t)n * 8);
+    for (int i = 1; i < n; i++)
+        if (o->d_keys2[k][i - 1] >= o->d_keys2[k][i]) return plf_fail(ctx, PLF_ERR_STATE, "LSD keys not in raster order before the sort");
 #else
     size_t tb = o->cubtmp_bytes[k];
     plf_prof_begin(ctx, "cub_radix_sort_keys");
-    cudaError_t e = cub::DeviceRadixSort::SortKeys(o->d_cubtmp[k], tb, o->d_keys[k], o->d_keys2[k], n, 0, end_bit, st);
+    cudaError_t e = cub::DeviceRadixSort::SortKeys(o->d_cubtmp[k], tb, o->d_keys[k], o->d_keys2[k], n, begin_bit, end_bit, st);
     plf_prof_end(ctx);
     PLF_CUDA(ctx, e);
 #endif
@@ -496,7 +500,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         if (nkeys[k] <= 0) continue;
         int fbits = 1;
         while ((1 << fbits) < nframes) fbits++;
-        plf_status s = sort_keys(o, k, nkeys[k], o->keybits[k] + fbits > 64 ? 64 : o->keybits[k] + fbits, st);
+        plf_status s = sort_keys(o, k, nkeys[k], o->kbits[k] & 0xff, o->keybits[k] + fbits > 64 ? 64 : o->keybits[k] + fbits, st);
         if (s) return s;
         for (int pass = 0; pass < 2; pass++) {
             PLF_LAUNCH(k_lsd_heads, dim3(plf_div_up(nkeys[k], 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2[k], nkeys[k], o->d_comp[k],
