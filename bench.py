@@ -513,6 +513,17 @@ def main():
                 traffic_src = tj.get("note")
             except Exception:
                 pass
+        # per-kernel DRAM traffic and SM throughput from the committed ncu section capture (one 256-frame batch per path)
+        ncu_k = {}
+        kp = os.path.join(ROOT, "profiles", "r1_kernels_ncu.json")
+        if os.path.exists(kp):
+            try:
+                for o in json.load(open(kp))["kernels"]:
+                    nm = o["kernel"].replace("void ", "")
+                    nm = "cub_radix_sort_keys" if "RadixSortOnesweep" in nm else nm
+                    ncu_k[nm] = {"traffic_bytes_per_frame": int(o["dram_bytes"] / 256), "sm_pct": o["sm_pct"], "dram_pct": o["dram_pct"]}
+            except Exception:
+                ncu_k = {}
         roof = None
         if top[0]:
             name, (ms_k, n_k_l) = top
@@ -524,9 +535,10 @@ def main():
                     "note": "k_lsd_grow_warp is the ordered (as-if-sequential) LSD region growing: a dependent chain per connected component, "
                             "latency-bound by construction, so its HBM fraction is tiny; it runs on high-priority streams and is overlapped by "
                             "the bandwidth kernels listed in `kernels` (their times are measured one stream at a time)",
-                    "kernels": [{"kernel": k, "ms_per_step": round(v[0], 4), "launches_per_step": v[1], "algorithmic_bytes_per_frame": alg.get(k),
-                                 "achieved_gbs": round(kernel_roof(k, v[0], v[1]), 1) if alg.get(k) else None,
-                                 "frac": round(kernel_roof(k, v[0], v[1]) / peak, 4) if alg.get(k) else None}
+                    "kernels_ncu_source": "profiles/r1_kernels_ncu.json (traffic_bytes_per_frame, sm_pct, dram_pct)" if ncu_k else None,
+                    "kernels": [dict({"kernel": k, "ms_per_step": round(v[0], 4), "launches_per_step": v[1], "algorithmic_bytes_per_frame": alg.get(k),
+                                      "achieved_gbs": round(kernel_roof(k, v[0], v[1]), 1) if alg.get(k) else None,
+                                      "frac": round(kernel_roof(k, v[0], v[1]) / peak, 4) if alg.get(k) else None}, **ncu_k.get(k, {}))
                                 for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])]}
         cpu = None
         if not args.no_cpu_baseline:
