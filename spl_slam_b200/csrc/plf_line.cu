@@ -545,8 +545,9 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
                        o->min_reg[k], o->d_regpts[k], o->d_regions[k], o->d_cnt[k] + CNT_MAXQ + nframes, LINE_REGCAP_PER_FRAME, 1, wg_maxc, o->kbits[k]);
             PLF_CHECK_LAUNCH(ctx);
         }
-        // enough CTAs per frame to fill the GPU for small batches, one or two for large ones
+        // enough CTAs per frame to fill the GPU for small batches
         int rsplit = plf_div_up(148 * 8, nframes);
+        if (rsplit < 8) rsplit = 8;      // region sizes vary a lot: shorter per-warp loops even out the tails
         if (rsplit > LINE_REGCAP_PER_FRAME / RECT_WARPS) rsplit = LINE_REGCAP_PER_FRAME / RECT_WARPS;
         PLF_LAUNCH(k_lsd_rect, dim3(rsplit, nframes), dim3(32 * RECT_WARPS), 0, st, (const LsdRegion*)o->d_regions[k],
                    (const int*)(o->d_cnt[k] + CNT_MAXQ + nframes), LINE_REGCAP_PER_FRAME, (const int*)o->d_regpts[k], (const int*)o->d_q[k], sp, sh,
