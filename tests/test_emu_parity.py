@@ -121,6 +121,19 @@ def test_emu_lines_empty_and_flat(S, oracle, emu_lib):
     assert len(K) == 0
 
 
+def test_emu_lines_batch_with_flat_frame(S, oracle, emu_lib):
+    """Regions live in per-frame slot blocks: a batch whose middle frame has no region at all."""
+    ctx = S.Context(0, emu_lib)
+    le = S.Lineextractor(40, 2, 0, 1.1, 0.6, 2.2, 12.5, 1.0, 0.6, 1024, 0.0, ctx=ctx)
+    prm = oracle.line_params(40, 2, 0, 1.1, 0.6, 2.2, 12.5, 1.0, 0.6, 1024, 0.0)
+    imgs = np.stack([oracle.synth_image(160, 120, 5), np.full((120, 160), 90, np.uint8), oracle.synth_image(160, 120, 6)])
+    Ks, Ms, Ds = le.extract_batch(imgs)
+    for b in range(3):
+        oK, oM, oD = oracle.line_extract(prm, imgs[b])
+        assert len(Ks[b]) == len(oK) and np.array_equal(Ks[b].view(np.uint8), oK.view(np.uint8)) and np.array_equal(Ds[b], oD)
+    assert len(Ks[1]) == 0 and len(Ks[0]) > 5 and len(Ks[2]) > 5
+
+
 def _stereo_pair(oracle, w, h, seed, shift):
     left = oracle.synth_image(w, h, seed)
     rng = np.random.default_rng(seed + 1000)

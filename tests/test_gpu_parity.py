@@ -205,6 +205,11 @@ def test_line_min_length_batch_and_edges(S, oracle, gpu_ctx):
     assert len(K) == 0
     K, M, D = le.ComputeLsdWithLbd(np.full((480, 752), 200, np.uint8))
     assert len(K) == 0
+    # a frame without any region between two ordinary ones: its block of region slots stays empty
+    mixed = np.stack([imgs[0], np.full((480, 752), 200, np.uint8), imgs[1]])
+    Ks2, Ms2, Ds2 = le.extract_batch(mixed)
+    assert len(Ks2[1]) == 0 and np.array_equal(Ds2[0], Ds[0]) and np.array_equal(Ds2[2], Ds[1])
+    assert np.array_equal(Ks2[0].view(np.uint8), Ks[0].view(np.uint8)) and np.array_equal(Ks2[2].view(np.uint8), Ks[1].view(np.uint8))
     rng = np.random.default_rng(0)
     noise = rng.integers(0, 256, (240, 320), dtype=np.uint8)   # every pixel has a defined gradient
     oK, oM, oD = oracle.line_extract(prm, noise)
