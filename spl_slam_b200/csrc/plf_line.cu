@@ -464,7 +464,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         const int mw = plf_div_up(sp, 32);
         mwk[k] = mw;
         dim3 g2(plf_div_up(sh, 8), 1, nframes), b2(32, 8);      // one warp per image row (ccl, keys)
-        PLF_LAUNCH(k_lsd_grad, dim3(plf_div_up(sp, 128), plf_div_up(sh, 4), nframes), dim3(32, 4), 0, st, scaled, sframe, spitch, sw, sp, sh, o->qthr,
+        PLF_LAUNCH(k_lsd_grad, dim3(plf_div_up(sp, 128), plf_div_up(sh, 4 * GRAD_ROWS), nframes), dim3(32, 4), 0, st, scaled, sframe, spitch, sw, sp, sh, o->qthr,
                    o->d_q[k], o->d_fa[k], o->d_label[k], o->d_mask[k], mw, o->d_cnt[k] + CNT_MAXQ);
         PLF_CHECK_LAUNCH(ctx);
         PLF_LAUNCH(k_lsd_bincoef, dim3(plf_div_up(nframes, 128)), dim3(128), 0, st, (const int*)(o->d_cnt[k] + CNT_MAXQ), nframes, o->prm.n_bins,

@@ -275,78 +275,95 @@ k_sobel3(const uint8_t* __restrict__ src, size_t sframe, int spitch, int w, int 
 // kernels test, so they skip empty segments without touching the per-pixel arrays.
 // Layout: every per-pixel array has P = w rounded up to 4 columns per row (the pad columns are NOTDEF), so a thread
 // handles four adjacent pixels with one 32-bit load per image row and one 16-byte store of the angles.
-// block = (32, 4): a warp covers 128 pixels (four mask words) of one row.
+// block = (32, 4): a warp covers 128 pixels (four mask words) of a row.
+// A warp walks GRAD_ROWS consecutive rows: the GRAD_ROWS + 1 image words it needs are requested up front (one memory
+// round trip per thread instead of one per row, and every image row is fetched 1.25 instead of 2 times).
+#define GRAD_ROWS 4
 __global__ void __launch_bounds__(128)
 k_lsd_grad(const uint8_t* __restrict__ img, size_t iframe, int ipitch, int w, int P, int h, int qthr,
            int* __restrict__ q, float* __restrict__ fa, int* __restrict__ label,
            unsigned* __restrict__ mask, int mw, int* __restrict__ maxq)
 {
     const int lane = threadIdx.x;
-    const int x0 = (blockIdx.x * 32 + lane) * 4, y = blockIdx.y * 4 + threadIdx.y;
+    const int x0 = (blockIdx.x * 32 + lane) * 4, y0 = (blockIdx.y * 4 + threadIdx.y) * GRAD_ROWS;
     const int f = blockIdx.z;
     const unsigned FULL = 0xffffffffu;
-    if (y >= h) return;                                   // warp-uniform
-    const uint8_t* r0 = img + (size_t)f * iframe + (size_t)y * ipitch;
-    const uint8_t* r1 = r0 + ipitch;
-    // five pixels of both rows: x0 .. x0 + 4 (the fifth comes from the next lane's word)
-    unsigned a = 0, b = 0, a4 = 0, b4 = 0;
-    const bool rows_ok = y < h - 1;
-    if (rows_ok && x0 < w) {
-        if (((((size_t)img) | (size_t)ipitch | iframe) & 3) == 0 && x0 + 4 <= ipitch) {
-            a = *(const unsigned*)(r0 + x0);
-            b = *(const unsigned*)(r1 + x0);
-        } else {
+    if (y0 >= h) return;                                  // warp-uniform
+    const uint8_t* fr = img + (size_t)f * iframe;
+    const bool aligned = ((((size_t)img) | (size_t)ipitch | iframe) & 3) == 0 && x0 + 4 <= ipitch;
+    // five pixels of every row: x0 .. x0 + 4 (the fifth comes from the next lane's word)
+    unsigned rw[GRAD_ROWS + 1], r4[GRAD_ROWS + 1];
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (x0 + j < w) { a |= (unsigned)r0[x0 + j] << (8 * j); b |= (unsigned)r1[x0 + j] << (8 * j); }
+    for (int k = 0; k <= GRAD_ROWS; k++) {
+        rw[k] = 0; r4[k] = 0;
+        const uint8_t* r = fr + (size_t)(y0 + k) * ipitch;
+        if (y0 + k < h && x0 < w) {
+            if (aligned) rw[k] = *(const unsigned*)(r + x0);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (x0 + j < w) rw[k] |= (unsigned)r[x0 + j] << (8 * j);
+            }
+            if (lane == 31 && x0 + 4 < w) r4[k] = r[x0 + 4];
         }
     }
-    a4 = __shfl_down_sync(FULL, a, 1) & 0xffu;
-    b4 = __shfl_down_sync(FULL, b, 1) & 0xffu;
-    if (lane == 31 && rows_ok && x0 + 4 < w) { a4 = r0[x0 + 4]; b4 = r1[x0 + 4]; }
-    int pa[5], pb[5];
 #pragma unroll
-    for (int j = 0; j < 4; j++) { pa[j] = (int)((a >> (8 * j)) & 0xffu); pb[j] = (int)((b >> (8 * j)) & 0xffu); }
-    pa[4] = (int)a4; pb[4] = (int)b4;
-    int gx[4], gy[4], qq[4];
-    unsigned nib = 0;
+    for (int k = 0; k <= GRAD_ROWS; k++) {
+        const unsigned nx = __shfl_down_sync(FULL, rw[k], 1) & 0xffu;
+        if (lane != 31) r4[k] = nx;
+    }
     int myq = -1;
+    bool anydef = false;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int DA = pb[j + 1] - pa[j], BC = pa[j + 1] - pb[j];
-        gx[j] = DA + BC; gy[j] = DA - BC;
-        qq[j] = gx[j] * gx[j] + gy[j] * gy[j];
-        const bool def = rows_ok && x0 + j < w - 1 && qq[j] > qthr;
-        if (def) { nib |= 1u << j; myq = max(myq, qq[j]); }
-    }
-    // the mask word of this lane's 32-px segment: nibbles of its eight lanes
-    unsigned m = nib << (4 * (lane & 7));
-    m |= __shfl_xor_sync(FULL, m, 1);
-    m |= __shfl_xor_sync(FULL, m, 2);
-    m |= __shfl_xor_sync(FULL, m, 4);
-    const int seg = blockIdx.x * 4 + (lane >> 3);
-    if ((lane & 7) == 0 && seg < mw) mask[((size_t)f * h + y) * mw + seg] = m;
-    if (x0 < P) {
-        const size_t o = (size_t)f * P * h + (size_t)y * P + x0;
-        float4 ang = make_float4(LSD_NOTDEF, LSD_NOTDEF, LSD_NOTDEF, LSD_NOTDEF);
-        if (nib) {
-            float* av = &ang.x;
+    for (int k = 0; k < GRAD_ROWS; k++) {
+        const int y = y0 + k;
+        if (y >= h) break;                                // warp-uniform
+        const bool rows_ok = y < h - 1;
+        const unsigned a = rw[k], b = rw[k + 1];
+        int pa[5], pb[5];
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if ((nib >> j) & 1u) {
-                    av[j] = plf_fast_atan2((float)gx[j], (float)(-gy[j]));
-                    q[o + j] = qq[j];     // (cos / sin of the angle are filled in densely by k_lsd_cid after the sort)
-                    // head of the run of defined pixels this pixel belongs to (inside its 32-px segment)
-                    const int bit = 4 * (lane & 7) + j;
-                    const unsigned below = ~m & ((1u << bit) - 1u);
-                    const int head = below ? 32 - __clz((int)below) : 0;
-                    label[o + j] = y * P + seg * 32 + head;
-                }
+        for (int j = 0; j < 4; j++) { pa[j] = (int)((a >> (8 * j)) & 0xffu); pb[j] = (int)((b >> (8 * j)) & 0xffu); }
+        pa[4] = (int)r4[k]; pb[4] = (int)r4[k + 1];
+        int gx[4], gy[4], qq[4];
+        unsigned nib = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int DA = pb[j + 1] - pa[j], BC = pa[j + 1] - pb[j];
+            gx[j] = DA + BC; gy[j] = DA - BC;
+            qq[j] = gx[j] * gx[j] + gy[j] * gy[j];
+            const bool def = rows_ok && x0 + j < w - 1 && qq[j] > qthr;
+            if (def) { nib |= 1u << j; myq = max(myq, qq[j]); }
         }
-        *(float4*)(fa + o) = ang;
+        anydef |= nib != 0;
+        // the mask word of this lane's 32-px segment: nibbles of its eight lanes
+        unsigned m = nib << (4 * (lane & 7));
+        m |= __shfl_xor_sync(FULL, m, 1);
+        m |= __shfl_xor_sync(FULL, m, 2);
+        m |= __shfl_xor_sync(FULL, m, 4);
+        const int seg = blockIdx.x * 4 + (lane >> 3);
+        if ((lane & 7) == 0 && seg < mw) mask[((size_t)f * h + y) * mw + seg] = m;
+        if (x0 < P) {
+            const size_t o = (size_t)f * P * h + (size_t)y * P + x0;
+            float4 ang = make_float4(LSD_NOTDEF, LSD_NOTDEF, LSD_NOTDEF, LSD_NOTDEF);
+            if (nib) {
+                float* av = &ang.x;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if ((nib >> j) & 1u) {
+                        av[j] = plf_fast_atan2((float)gx[j], (float)(-gy[j]));
+                        q[o + j] = qq[j];     // (cos / sin of the angle are filled in densely by k_lsd_cid after the sort)
+                        // head of the run of defined pixels this pixel belongs to (inside its 32-px segment)
+                        const int bit = 4 * (lane & 7) + j;
+                        const unsigned below = ~m & ((1u << bit) - 1u);
+                        const int head = below ? 32 - __clz((int)below) : 0;
+                        label[o + j] = y * P + seg * 32 + head;
+                    }
+            }
+            *(float4*)(fa + o) = ang;
+        }
     }
     // frame maximum of q over defined pixels -> one atomic per warp that has any
-    if (__any_sync(FULL, nib != 0)) {
+    if (__any_sync(FULL, anydef)) {
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) myq = max(myq, __shfl_xor_sync(FULL, myq, s));
         if (lane == 0) atomicMax(&maxq[f], myq);
