@@ -10,6 +10,29 @@ import math
 import numpy as np
 import cv2
 
+
+# the float overloads the reference's C++ picks (libm through ctypes: numpy may route float32 trig through SVML)
+import ctypes as _C
+_libm = _C.CDLL("libm.so.6")
+for _n in ("cosf", "sinf"):
+    getattr(_libm, _n).restype = _C.c_float
+    getattr(_libm, _n).argtypes = [_C.c_float]
+_libm.atan2f.restype = _C.c_float
+_libm.atan2f.argtypes = [_C.c_float, _C.c_float]
+
+
+def _cosf(x):
+    return np.float32(_libm.cosf(float(x)))
+
+
+def _sinf(x):
+    return np.float32(_libm.sinf(float(x)))
+
+
+def _atan2f(y, x):
+    return np.float32(_libm.atan2f(float(y), float(x)))
+
+
 EDGE = 19
 HALF = 15
 f32 = np.float32
@@ -221,7 +244,7 @@ def ic_angle(img, x, y, umax):
 def orb_descriptor(blur, x, y, angle_deg, pattern):
     factorPI = f32(math.pi / 180.0)
     ang = f32(angle_deg) * factorPI
-    a, b = f32(math.cos(float(ang))), f32(math.sin(float(ang)))
+    a, b = _cosf(ang), _sinf(ang)    # cos(float) under `using namespace std` = cosf (observed by compiling the reference)
     px = pattern[:, 0].astype(f32)
     py = pattern[:, 1].astype(f32)
     yy = np.rint((px * b).astype(f32) + (py * a).astype(f32)).astype(np.int64)
@@ -298,7 +321,7 @@ def lsd_keylines(image, nlevels, opts, min_length):
             cid += 1
             sx, sy, ex, ey = e[0] * osc, e[1] * osc, e[2] * osc, e[3] * osc
             ax, ay, bx, by = (int(np.rint(v)) for v in e)
-            out.append((f32(math.atan2(float(ey - sy), float(ex - sx))), cid, o, (ex + sx) / f32(2), (ey + sy) / f32(2),
+            out.append((_atan2f(ey - sy, ex - sx), cid, o, (ex + sx) / f32(2), (ey + sy) / f32(2),
                         f32(length) / f32(max(w, h)), (ex - sx) * (ey - sy), sx, sy, ex, ey,
                         e[0], e[1], e[2], e[3], f32(length), max(abs(bx - ax), abs(by - ay)) + 1))
     return np.array(out, dtype=KEYLINE_DTYPE) if out else np.zeros(0, KEYLINE_DTYPE)

@@ -33,7 +33,7 @@ class LineParams(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("orc_prims.c", "orc_orb.c", "orc_lsd.c", "orc_lbd.c", "plf_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("orc_prims.c", "orc_orb.c", "orc_lsd.c", "orc_lbd.c", "orc_bow.c", "orc_fld.c", "plf_oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "liboracle.so"])
     return so
@@ -86,6 +86,7 @@ def lib():
         L.orc_lsd_detect_keylines.argtypes = [C.POINTER(LineParams), u8p, C.c_int, C.c_int, C.c_size_t, vp, C.c_int]
         L.orc_lbd_compute.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, u8p, f32p]
         L.orc_line_extract.argtypes = [C.POINTER(LineParams), u8p, C.c_int, C.c_int, C.c_size_t, vp, vp, u8p, C.c_int]
+        L.orc_std_sort_desc.argtypes = [f32p, C.c_int, i32p]
         L.orc_descriptor_distance.argtypes = [u8p, u8p]
         L.orc_knn2.argtypes = [u8p, C.c_int, u8p, C.c_long, i32p, i32p]
         L.orc_match_nnr.argtypes = [u8p, C.c_int, u8p, C.c_long, C.c_float, i32p]
@@ -407,6 +408,14 @@ def line_extract(params, img):
 
 def features_per_level_lines(params):
     return [lib().orc_line_features_per_level(C.byref(params), l) for l in range(params.nlevels)]
+
+
+def std_sort_desc(keys):
+    """libstdc++ std::sort with comparator k[a] > k[b] (unstable) as a permutation."""
+    k = np.ascontiguousarray(keys, np.float32)
+    p = np.zeros(max(len(k), 1), np.int32)
+    lib().orc_std_sort_desc(_p(k), len(k), _p(p))
+    return p[:len(k)]
 
 
 # ---------------- matching ----------------

@@ -5,12 +5,15 @@
  * (src/Lineextractor.cc:112-212) and of the brute-force matcher pieces
  * (src/Linematcher.cc:50-66, :520-541).  TEST INFRASTRUCTURE ONLY (see plf_oracle.h).
  *
- * Documented float choices (toolchain dependent in the reference):
- * unqualified cos/sin/sqrt/round resolve to the C double functions; results are
- * rounded to float where the reference stores to float; no FMA contraction;
- * the std::sort by response (Lineextractor.cc:175) is taken as stable.
- * There is no compiled LBD anywhere in this container (cv2 has no line_descriptor),
- * so LBD parity is "bit-exact vs this restatement of the source".
+ * Float semantics, as the reference's code resolves under g++ / libstdc++ (observed by compiling it: oracle/_ref):
+ * unqualified cos / sin / sqrt / round / atan2 on float arguments pick the FLOAT overloads (cosf, sinf, sqrtf, roundf,
+ * atan2f: libstdc++'s <math.h> puts std::cos(float) etc. into the global namespace and cvstd.hpp has `using std::sqrt`
+ * inside namespace cv), `1 / sqrt(x)` is an int / float division; no FMA contraction.
+ * Pinned against the reference's own binary_descriptor_custom.cpp compiled into oracle/_ref: the 72-float
+ * descriptor is bit-identical to the -O3 build; the reference's CMake flags (-O3 -march=native) let GCC contract
+ * multiply-adds into FMAs, which moves 45 % of the floats by one ulp and none of the binary descriptors on the test images
+ * (tests/test_oracle_vs_ref.py asserts both).
+ * The std::sort by response (Lineextractor.cc:175) is checked against the compiled reference as well.
  */
 #include "plf_oracle.h"
 #include <math.h>
@@ -40,8 +43,8 @@ static void lbd_one(const orc_keyline* K, const int16_t* pdx, const int16_t* pdy
     float lineMiddlePointX = (float)(0.5 * (K->sPointInOctaveX + K->ePointInOctaveX));
     float lineMiddlePointY = (float)(0.5 * (K->sPointInOctaveY + K->ePointInOctaveY));
     float dL[2], dO[2];
-    dL[0] = (float)cos((double)K->angle);
-    dL[1] = (float)sin((double)K->angle);
+    dL[0] = cosf(K->angle); /* cos(float) resolves to std::cos(float) = cosf (libstdc++ <math.h> overloads) */
+    dL[1] = sinf(K->angle);
     dO[0] = -dL[1];
     dO[1] = dL[0];
     float t0 = -dL[0] * halfWidth, t1 = dL[1] * halfHeight;
@@ -53,9 +56,9 @@ static void lbd_one(const orc_keyline* K, const int16_t* pdx, const int16_t* pdy
         float sCorX = sCorX0, sCorY = sCorY0;
         float pgdLRowSum = 0, ngdLRowSum = 0, pgdORowSum = 0, ngdORowSum = 0;
         for (short wID = 0; wID < lengthOfLSP; wID++) {
-            short tempCor = (short)round((double)sCorX);
+            short tempCor = (short)roundf(sCorX);
             short xCor = (tempCor < 0) ? 0 : (tempCor > imageWidth) ? imageWidth : tempCor;
-            tempCor = (short)round((double)sCorY);
+            tempCor = (short)roundf(sCorY);
             short yCor = (tempCor < 0) ? 0 : (tempCor > imageHeight) ? imageHeight : tempCor;
             short dx = pdx[yCor * realWidth + xCor];
             short dy = pdy[yCor * realWidth + xCor];
@@ -105,21 +108,21 @@ static void lbd_one(const orc_keyline* K, const int16_t* pdx, const int16_t* pdy
         int desID = bandID * 8;
         float temp, u, v;
         temp = pgdLBandSum[bandID] * invN; desVec[desID] = temp;
-        u = pgdL2BandSum[bandID] * invN; v = temp * temp; desVec[desID + 4] = (float)sqrt((double)(u - v));
+        u = pgdL2BandSum[bandID] * invN; v = temp * temp; desVec[desID + 4] = sqrtf(u - v);
         temp = ngdLBandSum[bandID] * invN; desVec[desID + 1] = temp;
-        u = ngdL2BandSum[bandID] * invN; v = temp * temp; desVec[desID + 5] = (float)sqrt((double)(u - v));
+        u = ngdL2BandSum[bandID] * invN; v = temp * temp; desVec[desID + 5] = sqrtf(u - v);
         temp = pgdOBandSum[bandID] * invN; desVec[desID + 2] = temp;
-        u = pgdO2BandSum[bandID] * invN; v = temp * temp; desVec[desID + 6] = (float)sqrt((double)(u - v));
+        u = pgdO2BandSum[bandID] * invN; v = temp * temp; desVec[desID + 6] = sqrtf(u - v);
         temp = ngdOBandSum[bandID] * invN; desVec[desID + 3] = temp;
-        u = ngdO2BandSum[bandID] * invN; v = temp * temp; desVec[desID + 7] = (float)sqrt((double)(u - v));
+        u = ngdO2BandSum[bandID] * invN; v = temp * temp; desVec[desID + 7] = sqrtf(u - v);
     }
     float tempM = 0, tempS = 0, m;
     for (int i = 0; i < NUM_OF_BANDS * 8; i += 8) {
         for (int k = 0; k < 4; k++) { m = desVec[i + k] * desVec[i + k]; tempM += m; }
         for (int k = 4; k < 8; k++) { m = desVec[i + k] * desVec[i + k]; tempS += m; }
     }
-    tempM = (float)(1 / sqrt((double)tempM));
-    tempS = (float)(1 / sqrt((double)tempS));
+    tempM = 1 / sqrtf(tempM); /* namespace cv: using std::sqrt -> sqrt(float), then int / float */
+    tempS = 1 / sqrtf(tempS);
     for (int i = 0; i < NUM_OF_BANDS * 8; i += 8) {
         for (int k = 0; k < 4; k++) desVec[i + k] = desVec[i + k] * tempM;
         for (int k = 4; k < 8; k++) desVec[i + k] = desVec[i + k] * tempS;
@@ -128,7 +131,7 @@ static void lbd_one(const orc_keyline* K, const int16_t* pdx, const int16_t* pdy
         if ((double)desVec[i] > 0.4) desVec[i] = (float)0.4;
     float temp = 0;
     for (int i = 0; i < NUM_OF_BANDS * 8; i++) { m = desVec[i] * desVec[i]; temp += m; }
-    temp = (float)(1 / sqrt((double)temp));
+    temp = 1 / sqrtf(temp);
     for (int i = 0; i < NUM_OF_BANDS * 8; i++) desVec[i] = desVec[i] * temp;
 }
 
@@ -190,16 +193,111 @@ void orc_lbd_compute(const uint8_t* img, int w, int h, size_t stride,
     free(dxs); free(dys); free(ws); free(hs);
 }
 
-/* Lineextractor::ComputeLsdWithLbd, src/Lineextractor.cc:112-212 */
-typedef struct { float resp; int idx; } ridx;
-static int ridx_cmp(const void* a, const void* b)
+/* ---- std::sort as libstdc++ runs it (bits/stl_algo.h: introsort with median-of-3 to first, unguarded partition, threshold
+ * 16, heapsort past depth 2 * floor(log2 n), final insertion sort).  Lineextractor.cc:175 sorts the lines of an octave by
+ * `a.response > b.response` with std::sort, which is NOT stable: lines of equal response come out in an order that only
+ * this exact sequence of comparisons and moves defines.  Restated on a permutation p[] of indices with keys k[] (the
+ * algorithm only ever compares and moves elements); checked against the real std::sort inside oracle/_ref
+ * (ref_std_sort_desc) on tie-heavy and adversarial inputs by tests/test_oracle_vs_ref.py. */
+#define SS_LT(a, b) (k[a] > k[b]) /* comp(a, b) of sort_lines_by_response */
+static void ss_unguarded_linear_insert(const float* k, int* p, int last)
 {
-    const ridx* x = (const ridx*)a; const ridx* y = (const ridx*)b;
-    if (x->resp > y->resp) return -1;
-    if (x->resp < y->resp) return 1;
-    return x->idx < y->idx ? -1 : (x->idx > y->idx);
+    int val = p[last], next = last - 1;
+    while (SS_LT(val, p[next])) { p[last] = p[next]; last = next; --next; }
+    p[last] = val;
+}
+static void ss_insertion_sort(const float* k, int* p, int first, int last)
+{
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        if (SS_LT(p[i], p[first])) {
+            int val = p[i];
+            memmove(p + first + 1, p + first, sizeof(int) * (size_t)(i - first));
+            p[first] = val;
+        } else
+            ss_unguarded_linear_insert(k, p, i);
+    }
+}
+static void ss_push_heap(const float* k, int* p, int first, int hole, int top, int value)
+{
+    int parent = (hole - 1) / 2;
+    while (hole > top && SS_LT(p[first + parent], value)) { p[first + hole] = p[first + parent]; hole = parent; parent = (hole - 1) / 2; }
+    p[first + hole] = value;
+}
+static void ss_adjust_heap(const float* k, int* p, int first, int hole, int len, int value)
+{
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (SS_LT(p[first + child], p[first + child - 1])) child--;
+        p[first + hole] = p[first + child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        p[first + hole] = p[first + child - 1];
+        hole = child - 1;
+    }
+    ss_push_heap(k, p, first, hole, top, value);
+}
+static int ss_heap_calls = 0; /* test hook: how often the depth limit sent a range to heapsort */
+int orc_std_sort_heap_calls(void) { return ss_heap_calls; }
+static void ss_heap_sort(const float* k, int* p, int first, int last) /* __partial_sort(first, last, last) */
+{
+    int len = last - first;
+    ss_heap_calls++;
+    if (len >= 2)
+        for (int parent = (len - 2) / 2;; parent--) {
+            ss_adjust_heap(k, p, first, parent, len, p[first + parent]);
+            if (parent == 0) break;
+        }
+    while (last - first > 1) {
+        --last;
+        int value = p[last];
+        p[last] = p[first];
+        ss_adjust_heap(k, p, first, 0, last - first, value);
+    }
+}
+static void ss_introsort_loop(const float* k, int* p, int first, int last, int depth)
+{
+    while (last - first > 16) {
+        if (depth == 0) { ss_heap_sort(k, p, first, last); return; }
+        --depth;
+        /* __move_median_to_first(first, first + 1, mid, last - 1) */
+        int a = first + 1, b = first + (last - first) / 2, c = last - 1, t, m;
+        if (SS_LT(p[a], p[b])) m = SS_LT(p[b], p[c]) ? b : SS_LT(p[a], p[c]) ? c : a;
+        else m = SS_LT(p[a], p[c]) ? a : SS_LT(p[b], p[c]) ? c : b;
+        t = p[first]; p[first] = p[m]; p[m] = t;
+        /* __unguarded_partition(first + 1, last, pivot = first) */
+        int lo = first + 1, hi = last;
+        for (;;) {
+            while (SS_LT(p[lo], p[first])) ++lo;
+            --hi;
+            while (SS_LT(p[first], p[hi])) --hi;
+            if (!(lo < hi)) break;
+            t = p[lo]; p[lo] = p[hi]; p[hi] = t;
+            ++lo;
+        }
+        ss_introsort_loop(k, p, lo, last, depth);
+        last = lo;
+    }
+}
+void orc_std_sort_desc(const float* k, int n, int* p)
+{
+    for (int i = 0; i < n; i++) p[i] = i;
+    if (n == 0) return;
+    int lg = 0;
+    for (int v = n; v > 1; v >>= 1) lg++;
+    ss_introsort_loop(k, p, 0, n, 2 * lg);
+    if (n > 16) {
+        ss_insertion_sort(k, p, 0, 16);
+        for (int i = 16; i != n; ++i) ss_unguarded_linear_insert(k, p, i);
+    } else
+        ss_insertion_sort(k, p, 0, n);
 }
 
+/* Lineextractor::ComputeLsdWithLbd, src/Lineextractor.cc:112-212 */
 int orc_line_extract(const orc_line_params* P, const uint8_t* img, int w, int h, size_t stride,
                      orc_keyline* kl, orc_keypoint* mid, uint8_t* desc, int cap)
 {
@@ -217,19 +315,20 @@ int orc_line_extract(const orc_line_params* P, const uint8_t* img, int w, int h,
     }
     bstart[++nb] = nd;
     int n = 0;
-    ridx* tmp = (ridx*)malloc(sizeof(ridx) * (size_t)(nd > 0 ? nd : 1));
+    float* keys = (float*)malloc(sizeof(float) * (size_t)(nd > 0 ? nd : 1));
+    int* perm = (int*)malloc(sizeof(int) * (size_t)(nd > 0 ? nd : 1));
     for (int b = 0; b < nb; b++) {
         int cnt = bstart[b + 1] - bstart[b];
         int quota = b < P->nlevels ? orc_line_features_per_level(P, b) : 0;
         if (cnt <= quota) {
             for (int k = 0; k < cnt; k++) { if (n < cap) kl[n] = det[bstart[b] + k]; n++; }
         } else {
-            for (int k = 0; k < cnt; k++) { tmp[k].resp = det[bstart[b] + k].response; tmp[k].idx = k; }
-            qsort(tmp, (size_t)cnt, sizeof(ridx), ridx_cmp);
-            for (int k = 0; k < quota; k++) { if (n < cap) kl[n] = det[bstart[b] + tmp[k].idx]; n++; }
+            for (int k = 0; k < cnt; k++) keys[k] = det[bstart[b] + k].response;
+            orc_std_sort_desc(keys, cnt, perm); /* std::sort(..., sort_lines_by_response()), :175 */
+            for (int k = 0; k < quota; k++) { if (n < cap) kl[n] = det[bstart[b] + perm[k]]; n++; }
         }
     }
-    free(tmp); free(bstart); free(det);
+    free(keys); free(perm); free(bstart); free(det);
     if (n > cap) return -1;
     for (int k = 0; k < n; k++) {
         kl[k].class_id = k;

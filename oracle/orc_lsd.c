@@ -268,7 +268,7 @@ int orc_lsd_detect_keylines(const orc_line_params* P, const uint8_t* img, int w,
             int ax = (int)lrintf(e[0]), ay = (int)lrintf(e[1]), bx = (int)lrintf(e[2]), by = (int)lrintf(e[3]);
             int adx = abs(bx - ax), ady = abs(by - ay);
             K.numOfPixels = (adx > ady ? adx : ady) + 1;
-            K.angle = (float)atan2((double)(K.endPointY - K.startPointY), (double)(K.endPointX - K.startPointX));
+            K.angle = atan2f(K.endPointY - K.startPointY, K.endPointX - K.startPointX); /* atan2(float, float) = atan2f */
             K.class_id = ++class_counter;
             K.octave = oct;
             K.size = (K.endPointX - K.startPointX) * (K.endPointY - K.startPointY);

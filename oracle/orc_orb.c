@@ -6,10 +6,14 @@
  * (SURVEY.md section 7 "hard parts"):
  *  - DistributeOctTree refinement sort (ORBextractor.cc:684) orders equal-size nodes by
  *    heap address; the oracle orders them by creation index (ascending), iterated from
- *    the back, i.e. "later-created first".
- *  - rBRIEF rotation (ORBextractor.cc:112-120): a,b = correctly rounded float of
- *    cos/sin computed in double; products and sum in IEEE single without FMA;
- *    cvRound = round-half-even.
+ *    the back, i.e. "later-created first".  This IS the reference's order when heap addresses
+ *    grow with allocation order (oracle/_ref heap mode 1: identical keypoint lists, order included);
+ *    under glibc malloc the reference itself returns different sets for the same input
+ *    (tests/test_oracle_vs_ref.py).
+ *  - rBRIEF rotation (ORBextractor.cc:112-120): `cos(angle)` on a float under `using namespace std`
+ *    is cosf; products and sum in IEEE single without FMA; cvRound = round-half-even.
+ * Pinned bit for bit (keypoints, order, angles, descriptors) against the reference's own
+ * ORBextractor.cc compiled into oracle/_ref/libref.so.
  */
 #include "plf_oracle.h"
 #include <math.h>
@@ -323,7 +327,7 @@ static void orb_descriptor(float angle_deg, const uint8_t* center, int step, uin
 {
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     float angle = angle_deg * factorPI;
-    float a = (float)cos((double)angle), b = (float)sin((double)angle);
+    float a = cosf(angle), b = sinf(angle); /* cos(float) under `using namespace std` = std::cos(float) = cosf */
     const int8_t* p = bit_pattern_31;
     for (int i = 0; i < 32; i++) {
         int val = 0;

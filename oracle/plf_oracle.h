@@ -61,6 +61,10 @@ float orc_fast_atan2(float y, float x);
 int  orc_fast9(const uint8_t* img, int w, int h, size_t stride, int th,
                int* xs, int* ys, int* score, int cap);
 
+/* FLD branch primitives (orc_fld.c): cv::Canny (aperture 3, L1 gradient) -> dense w*h 255/0; cv::fitLine DIST_L2 on int points */
+void orc_canny_u8(const uint8_t* src, int w, int h, size_t stride, double th1, double th2, uint8_t* edges);
+void orc_fit_line_l2(const int32_t* pts, int count, float* line /* vx, vy, x0, y0 */);
+
 /* ---- ORB extractor (src/ORBextractor.cc) ---- */
 typedef struct orc_orb orc_orb;
 orc_orb* orc_orb_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh);
@@ -127,6 +131,9 @@ void orc_lbd_compute(const uint8_t* img, int w, int h, size_t stride,
 /* ComputeLsdWithLbd: returns number of lines kept */
 int  orc_line_extract(const orc_line_params* p, const uint8_t* img, int w, int h, size_t stride,
                       orc_keyline* kl, orc_keypoint* mid, uint8_t* desc, int cap);
+
+/* libstdc++'s std::sort with comparator k[a] > k[b], as a permutation of 0..n-1 (unstable: the exact introsort sequence) */
+void orc_std_sort_desc(const float* k, int n, int* p);
 
 /* ---- matching (src/Linematcher.cc:50-66, 520-541; src/ORBmatcher.cc:1656-1672) ---- */
 int  orc_descriptor_distance(const uint8_t* a, const uint8_t* b);

@@ -27,6 +27,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include "plf.h"
+#include "plf_libm.cuh"
 
 struct plf_ctx {
     int device;

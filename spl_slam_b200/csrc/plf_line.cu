@@ -571,7 +571,7 @@ static plf_status line_select(plf_line* o, int nframes, bool select, plf_keyline
 {
     plf_ctx* ctx = o->ctx;
     const int noct = o->prm.nlevels;
-    PLF_LAUNCH(k_line_select, dim3(nframes), dim3(SEL_T), LINE_DETCAP * sizeof(int), ctx->stream, (const plf_keyline*)o->d_det,
+    PLF_LAUNCH(k_line_select, dim3(nframes), dim3(SEL_T), SEL_SMEM_BYTES(LINE_DETCAP), ctx->stream, (const plf_keyline*)o->d_det,
                (const int*)o->d_detcount, LINE_DETCAP, noct, select ? 1 : 0, o->per_level[0], noct > 1 ? o->per_level[1] : 0, d_kl, d_mid,
                cap, d_nout);
     PLF_CHECK_LAUNCH(ctx);

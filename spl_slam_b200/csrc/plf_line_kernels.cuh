@@ -9,6 +9,7 @@
 // reproduces the reference's regions exactly while thousands of components (x frames) run in parallel.
 #pragma once
 #include "plf_common.cuh"
+#include "plf_stdsort.cuh"
 
 #define LSD_NOTDEF (-1024.0f)
 #define LSD_USED (-2048.0f)
@@ -1022,7 +1023,7 @@ k_lsd_keylines(const unsigned long long* __restrict__ linekey, const int* __rest
     const int ax = __float2int_rn(e0), ay = __float2int_rn(e1), bx = __float2int_rn(e2), by = __float2int_rn(e3);
     const int adx = ax > bx ? ax - bx : bx - ax, ady = ay > by ? ay - by : by - ay;
     K.numOfPixels = (adx > ady ? adx : ady) + 1;
-    K.angle = (float)atan2((double)(K.endPointY - K.startPointY), (double)(K.endPointX - K.startPointX));
+    K.angle = plf_libm::atan2f_glibc(K.endPointY - K.startPointY, K.endPointX - K.startPointX);   // atan2(float, float) = atan2f (:298)
     K.class_id = (length > min_length) ? 0 : -1;   // -1 marks "dropped by the min_length filter" for the next stage
     K.octave = octave;
     K.size = (K.endPointX - K.startPointX) * (K.endPointY - K.startPointY);
@@ -1036,15 +1037,18 @@ k_lsd_keylines(const unsigned long long* __restrict__ linekey, const int* __rest
 // min_length filter + class ids (detectImpl) and, when `select`, the per-octave response quota with
 // mid-point keypoints (Lineextractor::ComputeLsdWithLbd, src/Lineextractor.cc:138-207).  One CTA per frame.
 #define SEL_T 256
+#define SEL_SMEM_BYTES(detcap) ((size_t)(detcap) * (sizeof(int) + sizeof(float) + sizeof(unsigned short)))
 __global__ void __launch_bounds__(SEL_T)
 k_line_select(const plf_keyline* __restrict__ det, const int* __restrict__ detcount, int detcap, int noct,
               int select, int quota0, int quota1, plf_keyline* __restrict__ out_kl, plf_keypoint* __restrict__ out_mid,
               int cap, int* __restrict__ n_out)
 {
     __shared__ int s_pos[2][2];   // [octave]: {valid count, kept count}
-    __shared__ int s_err;
+    __shared__ int s_err, s_tie;
     PLF_DYN_SMEM(smem);
-    int* vidx = (int*)smem;               // valid line indices of the current octave (order preserved)
+    int* vidx = (int*)smem;                                   // valid line indices of the current octave (order preserved)
+    float* skey = (float*)(vidx + detcap);                    // their responses
+    unsigned short* sperm = (unsigned short*)(skey + detcap); // sorted position -> index into vidx
     const int f = blockIdx.x, tid = threadIdx.x;
     int outbase = 0;
     if (tid == 0) s_err = 0;
@@ -1058,38 +1062,52 @@ k_line_select(const plf_keyline* __restrict__ det, const int* __restrict__ detco
             int m = 0;
             for (int i = 0; i < cnt; i++) if (D[i].class_id == 0) vidx[m++] = i;
             s_pos[o][0] = m;
+            s_tie = 0;
         }
         __syncthreads();
         const int m = s_pos[o][0];
         const int quota = o == 0 ? quota0 : quota1;
-        const int keep = (select && m > quota) ? quota : m;
-        for (int i = tid; i < m; i += SEL_T) {
-            int pos = i;
-            if (select && m > quota) {
-                // rank in the stable descending-response order (Lineextractor.cc:175, ties by index)
-                const float r = D[vidx[i]].response;
-                int rank = 0;
+        const bool sorted = select && m > quota;
+        const int keep = sorted ? quota : m;
+        if (sorted) {
+            for (int i = tid; i < m; i += SEL_T) skey[i] = D[vidx[i]].response;
+            __syncthreads();
+            // Lineextractor.cc:175: std::sort by descending response.  With all responses distinct the order is unique:
+            // a line's place is the number of larger responses.  Equal responses make the result depend on libstdc++'s
+            // introsort itself (std::sort is unstable), which one thread then replays exactly (plf_stdsort.cuh).
+            for (int i = tid; i < m; i += SEL_T) {
+                const float r = skey[i];
+                int rank = 0, tie = 0;
                 for (int j = 0; j < m; j++) {
-                    const float rj = D[vidx[j]].response;
-                    if (rj > r || (rj == r && j < i)) rank++;
+                    const float rj = skey[j];
+                    rank += (rj > r || (rj == r && j < i)) ? 1 : 0;
+                    tie |= (rj == r && j != i) ? 1 : 0;
                 }
-                pos = rank < quota ? rank : -1;
+                sperm[rank] = (unsigned short)i;
+                if (tie) s_tie = 1;
             }
-            if (pos >= 0) {
-                const int op = outbase + pos;
-                if (op < cap) {
-                    plf_keyline K = D[vidx[i]];
-                    K.class_id = op;
-                    out_kl[(size_t)f * cap + op] = K;
-                    if (out_mid) {
-                        plf_keypoint P;
-                        P.x = (K.startPointX + K.endPointX) / 2;
-                        P.y = (K.startPointY + K.endPointY) / 2;
-                        P.size = 0; P.angle = -1; P.response = 0; P.octave = K.octave; P.class_id = -1;
-                        out_mid[(size_t)f * cap + op] = P;
-                    }
-                } else s_err = 2;
+            __syncthreads();
+            if (s_tie && tid == 0) {
+                for (int i = 0; i < m; i++) sperm[i] = (unsigned short)i;
+                plf_stdsort::sort_desc(skey, m, sperm);
             }
+            __syncthreads();
+        }
+        for (int pos = tid; pos < keep; pos += SEL_T) {
+            const int i = sorted ? (int)sperm[pos] : pos;
+            const int op = outbase + pos;
+            if (op < cap) {
+                plf_keyline K = D[vidx[i]];
+                K.class_id = op;
+                out_kl[(size_t)f * cap + op] = K;
+                if (out_mid) {
+                    plf_keypoint P;
+                    P.x = (K.startPointX + K.endPointX) / 2;
+                    P.y = (K.startPointY + K.endPointY) / 2;
+                    P.size = 0; P.angle = -1; P.response = 0; P.octave = K.octave; P.class_id = -1;
+                    out_mid[(size_t)f * cap + op] = P;
+                }
+            } else s_err = 2;
         }
         outbase += keep;
         __syncthreads();
@@ -1134,7 +1152,7 @@ k_lbd(const plf_keyline* __restrict__ kl, const int* __restrict__ nlines, int ca
     const short halfHeight = 31;
     const float midX = (float)(0.5 * (double)(K.sPointInOctaveX + K.ePointInOctaveX));
     const float midY = (float)(0.5 * (double)(K.sPointInOctaveY + K.ePointInOctaveY));
-    const float dL0 = (float)cos((double)K.angle), dL1 = (float)sin((double)K.angle);
+    const float dL0 = plf_libm::cosf_glibc(K.angle), dL1 = plf_libm::sinf_glibc(K.angle);   // cos(float) = cosf (:1130-1131)
     const float dO0 = -dL1, dO1 = dL0;
     if (tid < 63) {
         float t0 = -dL0 * (float)halfWidth, t1 = dL1 * (float)halfHeight;
@@ -1194,21 +1212,21 @@ k_lbd(const plf_keyline* __restrict__ kl, const int* __restrict__ nlines, int ca
             const float invN = (b == 0 || b == 8) ? invN2 : invN3;
             float temp, u, v;
             temp = band[b][0] * invN; dv[b * 8] = temp;
-            u = band[b][2] * invN; v = temp * temp; dv[b * 8 + 4] = (float)sqrt((double)(u - v));
+            u = band[b][2] * invN; v = temp * temp; dv[b * 8 + 4] = sqrtf(u - v);
             temp = band[b][1] * invN; dv[b * 8 + 1] = temp;
-            u = band[b][3] * invN; v = temp * temp; dv[b * 8 + 5] = (float)sqrt((double)(u - v));
+            u = band[b][3] * invN; v = temp * temp; dv[b * 8 + 5] = sqrtf(u - v);
             temp = band[b][4] * invN; dv[b * 8 + 2] = temp;
-            u = band[b][6] * invN; v = temp * temp; dv[b * 8 + 6] = (float)sqrt((double)(u - v));
+            u = band[b][6] * invN; v = temp * temp; dv[b * 8 + 6] = sqrtf(u - v);
             temp = band[b][5] * invN; dv[b * 8 + 3] = temp;
-            u = band[b][7] * invN; v = temp * temp; dv[b * 8 + 7] = (float)sqrt((double)(u - v));
+            u = band[b][7] * invN; v = temp * temp; dv[b * 8 + 7] = sqrtf(u - v);
         }
         float tempM = 0, tempS = 0, m;
         for (int i = 0; i < 72; i += 8) {
             for (int k = 0; k < 4; k++) { m = dv[i + k] * dv[i + k]; tempM += m; }
             for (int k = 4; k < 8; k++) { m = dv[i + k] * dv[i + k]; tempS += m; }
         }
-        tempM = (float)(1 / sqrt((double)tempM));
-        tempS = (float)(1 / sqrt((double)tempS));
+        tempM = 1.0f / sqrtf(tempM);   // namespace cv: using std::sqrt -> sqrt(float); int / float (:1302-1303)
+        tempS = 1.0f / sqrtf(tempS);
         for (int i = 0; i < 72; i += 8) {
             for (int k = 0; k < 4; k++) dv[i + k] = dv[i + k] * tempM;
             for (int k = 4; k < 8; k++) dv[i + k] = dv[i + k] * tempS;
@@ -1216,7 +1234,7 @@ k_lbd(const plf_keyline* __restrict__ kl, const int* __restrict__ nlines, int ca
         for (int i = 0; i < 72; i++) if ((double)dv[i] > 0.4) dv[i] = (float)0.4;
         float temp = 0;
         for (int i = 0; i < 72; i++) { m = dv[i] * dv[i]; temp += m; }
-        temp = (float)(1 / sqrt((double)temp));
+        temp = 1.0f / sqrtf(temp);
         for (int i = 0; i < 72; i++) dv[i] = dv[i] * temp;
     }
     __syncthreads();

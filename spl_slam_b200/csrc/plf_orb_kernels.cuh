@@ -663,7 +663,8 @@ k_describe(OrbGeom g, OrbPtrs p, plf_keypoint* __restrict__ kps, uint8_t* __rest
     // steered BRIEF on the blurred level; lane i produces descriptor byte i
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     const float ang = angle * factorPI;
-    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+    // cos(float) under `using namespace std` is cosf (src/ORBextractor.cc:114): glibc's cosf / sinf, bit for bit (plf_libm.cuh)
+    const float a = plf_libm::cosf_glibc(ang), b = plf_libm::sinf_glibc(ang);
     const uint8_t* center = p.blr[l] + (size_t)f * L.frameBytes + (size_t)Y * L.pitch + X;
     // the lane's 16 point pairs (32 signed bytes) as two 16-byte loads
     signed char pat[32];
