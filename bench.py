@@ -1,22 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- frames/s of ORB + LSD/LBD extraction (BASELINE.json metric) on N B200.
+"""bench.py -- frames/s of ORB + LSD/LBD extraction (BASELINE.json metric) on N B200, and Hamming matches/s.
 
-Workload (BASELINE.json configs[1]): EuRoC-style stereo 752x480 pairs, 1200 ORB points
-(8 levels x1.2, FAST 20/7) + LSD/LBD lines (EuRoC line settings: 200 lines, 2 octaves, LSD scale 1.1,
-sigma_scale 0.8, quant 2.2, ang_th 12.5, n_bins 1024) per image.  A "frame" is one image; a stereo pair is
-two frames (left -> rank 2k, right -> rank 2k+1 when N > 1; both on the one GPU when N = 1).
-A step = one batch of FRAMES_PER_GPU frames per GPU through the whole hot path.
-
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c3|c4|c5]
   (N > 1: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...)
 
-Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM (device-timed, max over
-ranks); `e2e` = the same through the C-ABI host-buffer calls (pinned host memory, H2D + D2H inside the
-timed region); `roofline` = the dominant kernel against the measured HBM peak; `cpu_baseline` = the oracle
-(CPU port of the reference algorithm) on the box's host cores on a bounded sample.
+Configurations = BASELINE.json `configs`:
+  c4 (default, the headline): batched sequence extraction, 1920x1080 frames, 2000 ORB (8 lv x1.2, FAST 20/7) + LSD/LBD 800 lines
+      (TUM LSD options, min length 0.02 * 1080), 1024 frames per GPU per step in sub-batches, frame i -> rank i mod N.
+  c2: EuRoC-style stereo 752x480 pairs, 1200 ORB + 200 lines per image (round 1's headline).
+  c3: KITTI-style stereo 1241x376 pairs, 2000 ORB + 800 lines, plus stereo point matching and L<->R line matchNNR.
+  c1: one 640x480 frame, ORB 1000 + TUM lines through the drop-in calls (ORB thread || line thread): latency.
+  c5: brute-force Hamming top-2 sweep, 1e4 queries x 1e4..1e7 train rows, train-sharded with an NCCL merge.
+A default run prints the c4 line and attaches short measurements of the others under `other_configs`.
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM (device-timed, max over ranks); `e2e` = the
+same through the C-ABI host-buffer calls (pinned host memory, H2D + D2H inside the timed region); `roofline` = the kernel
+that takes the largest share of the step measured while all streams run together, against the measured HBM peak, plus the
+whole step's algorithmic bytes / step time; `cpu_baseline` = the reference's own CPU code (oracle/_ref, compiled from the
+reference's unmodified sources) on the box's host cores on a bounded sample.
 """
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -29,14 +32,27 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H = 752, 480
-ORB = dict(nfeatures=1200, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7)
-LINE = dict(nfeatures=200, nlevels=2, refine=0, scale=1.1, sigma_scale=0.8, quant=2.2, ang_th=12.5, log_eps=1.0,
-            density_th=0.8, n_bins=1024, min_line_length=0.0)   # Examples/Monocular/EuRoC.yaml (Camera.width absent -> 0)
-FRAMES_PER_GPU = 1024         # 512 stereo pairs per GPU per step (~35 GB of HBM workspace)
+ORB_TUM = dict(nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7)
+LSD_TUM = dict(nlevels=2, refine=0, scale=1.1, sigma_scale=0.6, quant=2.2, ang_th=12.5, log_eps=1.0, density_th=0.6, n_bins=1024)
+CONFIGS = {
+    # Examples/Monocular/TUM1.yaml: ORB 1000, Lineextractor 600 lines, min_line_length_ratio 0.02 (src/Tracking.cc:168-169)
+    "c1": dict(W=640, H=480, stereo=False, frames=2, sub=1, orb=dict(ORB_TUM),
+               line=dict(LSD_TUM, nfeatures=600, min_line_length=0.02 * 480),
+               workload="single 640x480 frame, ORB 1000 (8 lv x1.2, FAST 20/7) + LSD/LBD 600 lines (TUM settings), drop-in calls"),
+    # Examples/Monocular/EuRoC.yaml line settings (Camera.width absent -> min length 0)
+    "c2": dict(W=752, H=480, stereo=True, frames=1024, sub=512, orb=dict(ORB_TUM, nfeatures=1200),
+               line=dict(LSD_TUM, nfeatures=200, sigma_scale=0.8, density_th=0.8, min_line_length=0.0),
+               workload="EuRoC-style stereo 752x480 pairs, 1200 ORB (8 lv x1.2, FAST 20/7) + LSD/LBD 200 lines per image"),
+    "c3": dict(W=1241, H=376, stereo=True, frames=512, sub=256, orb=dict(ORB_TUM, nfeatures=2000),
+               line=dict(LSD_TUM, nfeatures=800, min_line_length=0.02 * 376),
+               workload="KITTI-style stereo 1241x376 pairs, 2000 ORB + LSD/LBD 800 lines per image, stereo point matching + L<->R line matchNNR"),
+    "c4": dict(W=1920, H=1080, stereo=False, frames=1024, sub=128, orb=dict(ORB_TUM, nfeatures=2000),
+               line=dict(LSD_TUM, nfeatures=800, min_line_length=0.02 * 1080),
+               workload="batched sequence extraction: 1920x1080 frames, 2000 ORB (8 lv x1.2, FAST 20/7) + LSD/LBD 800 lines (TUM LSD options), frame-sharded"),
+}
 LINE_CONTEXTS = 2             # line extractor instances (own context + host thread each; every instance runs its two octaves on two streams)
 ORB_CONTEXTS = 2              # ORB extractor instances, same idea (uploads of one overlap kernels of the other)
-WORKLOAD = "EuRoC-style stereo 752x480 pairs, 1200 ORB (8 lv x1.2, FAST 20/7) + LSD/LBD 200 lines per image"
+NSETS = 2                     # distinct frame sets per GPU; step k works on set k % NSETS
 
 
 def _gauss_kernel_q8(ksize, sigma):
@@ -58,19 +74,19 @@ def _gauss_kernel_q8(ksize, sigma):
 
 
 def _gauss_blur_u8(img, ksize, sigma):
-    """Separable Q8 Gaussian with BORDER_REFLECT_101, (v + 32768) >> 16 -- numpy, bit-identical to cv::GaussianBlur on 8U."""
-    q, r = _gauss_kernel_q8(ksize, sigma), ksize // 2
-    a = np.pad(img.astype(np.int64), ((0, 0), (r, r)), mode="reflect")
-    h = sum(q[i] * a[:, i:i + img.shape[1]] for i in range(ksize))
-    b = np.pad(h, ((r, r), (0, 0)), mode="reflect")
-    v = sum(q[i] * b[i:i + img.shape[0], :] for i in range(ksize))
+    """Separable Q8 Gaussian with BORDER_REFLECT_101, (v + 32768) >> 16 -- integer arithmetic, bit-identical to
+    cv::GaussianBlur on 8U (scipy's correlate1d in int32 with mode 'mirror' = reflect-101)."""
+    from scipy.ndimage import correlate1d
+    q = np.array(_gauss_kernel_q8(ksize, sigma), np.int32)
+    h = correlate1d(img.astype(np.int32), q, axis=1, mode="mirror")
+    v = correlate1d(h, q, axis=0, mode="mirror")
     return ((v + 32768) >> 16).astype(np.uint8)
 
 
 def synth_image(w, h, seed):
     """The synthetic test image of SURVEY.md 8d (uniform u8 noise -> Gaussian s=2 -> K filled rectangles -> 3x3 s=0.8 blur).
-    Input generation only -- numpy, nothing of oracle/ is involved (tests/test_bench_inputs.py checks that it equals the
-    generator the parity tests use)."""
+    Input generation only -- numpy / scipy, nothing of oracle/ is involved (tests/test_bench_inputs.py checks that it equals
+    the generator the parity tests use)."""
     rng = np.random.default_rng(seed)
     img = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
     img = _gauss_blur_u8(img, 13, 2.0)
@@ -83,26 +99,31 @@ def synth_image(w, h, seed):
     return _gauss_blur_u8(img, 3, 0.8)
 
 
-def make_frames(n_pairs, seed0, pair_ids=None):
-    """Synthetic stereo pairs: right = left shifted by a disparity + small noise.
-    Returns [L0, R0, L1, R1, ...] for pairs seed0 .. seed0 + n_pairs - 1 (or for `pair_ids`)."""
+def make_frames(cfg, ids):
+    """Frames with the given global ids.  Mono: frame i = synth_image(seed i).  Stereo: frames 2p, 2p+1 = left, right of pair p
+    (right = left shifted by a disparity + small noise)."""
     from concurrent.futures import ThreadPoolExecutor
+    W, H = cfg["W"], cfg["H"]
 
-    def pair(p):
-        left = synth_image(W, H, seed0 + p)
-        rng = np.random.default_rng(10_000 + seed0 + p)
+    def one(i):
+        if not cfg["stereo"]:
+            return synth_image(W, H, i)
+        p = i // 2
+        left = synth_image(W, H, p)
+        if i % 2 == 0:
+            return left
+        rng = np.random.default_rng(10_000 + p)
         right = np.roll(left, -int(rng.integers(4, 24)), axis=1).astype(np.int16) + rng.integers(-2, 3, left.shape)
-        return left, np.clip(right, 0, 255).astype(np.uint8)
+        return np.clip(right, 0, 255).astype(np.uint8)
 
     with ThreadPoolExecutor(min(16, os.cpu_count() or 1)) as ex:
-        pairs = list(ex.map(pair, pair_ids if pair_ids is not None else range(n_pairs)))
-    return np.stack([im for lr in pairs for im in lr])
+        return np.stack(list(ex.map(one, ids)))
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return json.load(open(p)).get("hbm_gbs", 6650.0), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "MEASURED_PEAKS.json hbm_gbs (measured copy, burst)"
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
@@ -142,53 +163,525 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_throughput(frames, nthreads):
-    """Oracle (CPU restatement of the reference algorithm) on `frames`, one frame per worker thread.
-    Mirrors the reference's per-frame work: ORBextractor::operator() + Lineextractor::ComputeLsdWithLbd."""
+# ------------------------------------------------------------------------------------------------ CPU reference legs
+def cpu_reference_throughput(cfg, frames, nthreads, what="both"):
+    """The reference's own CPU code on `frames`, one frame per worker thread: ORBextractor::operator() +
+    Lineextractor::ComputeLsdWithLbd compiled from the reference's unmodified sources (oracle/_ref, kind "reference");
+    falls back to the C restatement (oracle/, kind "port") only if libref.so is absent.  Returns (frames/s, seconds, kind)."""
     from concurrent.futures import ThreadPoolExecutor
-    from oracle import oracle as O
+    from oracle import oracle as O, ref as R
     O.build()
-    prm = O.line_params(**LINE)
+    kind = "reference" if (R.available() or R.build()) else "port"
+    M = R if kind == "reference" else O
+    if kind == "reference":
+        R.set_heap_mode(0)          # the reference as it runs (glibc malloc)
+    prm = O.line_params(**cfg["line"])
+    orb = cfg["orb"]
     local = threading.local()
 
     def work(i):
-        if not hasattr(local, "orb"):
-            local.orb = O.ORBextractor(ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"])
-        k, d = local.orb(frames[i])
-        kl, mid, ld = O.line_extract(prm, frames[i])
-        return len(k) + len(kl)
+        n = 0
+        if what in ("both", "orb"):
+            if not hasattr(local, "orb"):
+                local.orb = M.ORBextractor(orb["nfeatures"], orb["scaleFactor"], orb["nlevels"], orb["iniThFAST"], orb["minThFAST"])
+            n += len(local.orb(frames[i])[0])
+        if what in ("both", "line"):
+            n += len(M.line_extract(prm, frames[i])[0])
+        return n
 
     with ThreadPoolExecutor(nthreads) as ex:
         list(ex.map(work, range(min(len(frames), nthreads))))   # warm-up (ctypes releases the GIL)
         t0 = time.perf_counter()
         list(ex.map(work, range(len(frames))))
         dt = time.perf_counter() - t0
-    return len(frames) / dt, dt
+    return len(frames) / dt, dt, kind
+
+
+def cpu_knn2(q, t, nthreads):
+    """Brute-force Hamming top-2 on the host: cv2.BFMatcher.knnMatch(k=2) -- what Linematcher::matchNNR calls
+    (src/Linematcher.cc:526-527) -- with `nthreads` OpenCV threads; seconds."""
+    import cv2
+    cv2.setNumThreads(nthreads)
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING, False)
+    t0 = time.perf_counter()
+    bf.knnMatch(q, t, 2)
+    return time.perf_counter() - t0
+
+
+def config_dict(name, cfg, B, world, extra=None):
+    d = {"workload": cfg["workload"], "config": name, "frames_per_gpu_per_step": B, "frame": "one %dx%d image" % (cfg["W"], cfg["H"]) +
+         ("; a stereo pair is 2 frames" if cfg["stereo"] else ""),
+         "sharding": "frame i -> rank i mod N" + (" (left/right of a pair on separate GPUs for N > 1)" if cfg["stereo"] else "") + ", no collective"}
+    if extra:
+        d.update(extra)
+    return d
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port: the reference itself cannot be compiled
-    here -- no OpenCV C++/Eigen/Pangolin) on the host cores, all threads, bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, all threads, each step a
+    bounded sample of the same workload (same config dict as our arm)."""
     if rank != 0:
         return
+    name = args.config
+    cfg = CONFIGS[name if name != "c5" else "c4"]
     cores = os.cpu_count() or 1
-    nfr = 256
-    frames = make_frames(nfr // 2, 0)
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_oracle_throughput(frames[:cores], cores)
+    if name == "c5":
+        return run_reference_c5(args, cores)
+    B = args.frames or cfg["frames"]
+    # sample sized for ~10-20 s of CPU work per step
+    per_frame_s = 1.1e-6 * cfg["W"] * cfg["H"] * 0.25      # ~0.5 s at 1080p, ~0.09 s at 752x480 (one thread, -O3)
+    nfr = max(cores, min(B, int(12.0 * cores / per_frame_s)))
+    nfr -= nfr % 2
+    frames = make_frames(cfg, list(range(nfr)))
+    kind = "reference"
+    for _ in range(1 if args.warmup else 0):
+        cpu_reference_throughput(cfg, frames[:cores], cores)
     tot_t, tot_f = 0.0, 0
     for _ in range(args.steps):
-        fps, dt = cpu_oracle_throughput(frames, cores)
+        fps, dt, kind = cpu_reference_throughput(cfg, frames, cores)
         tot_t += dt; tot_f += len(frames)
     value = tot_f / tot_t
     line = {"impl": "reference", "metric": "frames/s ORB+LSD/LBD extraction", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": len(frames)},
-            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": "%d frames per step, one frame per thread on %d threads (C oracle, -O3)" % (len(frames), cores)},
+            "config": config_dict(name, cfg, B, world),
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
+                             "sample": "%d of the step's %d frames per step, one frame per thread on %d threads (%s)" %
+                                       (len(frames), B, cores, "oracle/_ref: the reference's own sources, -O3 -march=native" if kind == "reference" else "C oracle, -O3")},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def run_reference_c5(args, cores):
+    NQ, NT = 10000, 1000000
+    rng = np.random.default_rng(1234)
+    q = rng.integers(0, 256, (NQ, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (NT // 10, 32), dtype=np.uint8)     # bounded sample: a tenth of the train rows, same queries
+    tot = 0.0
+    for _ in range(args.steps):
+        tot += cpu_knn2(q, t, cores)
+    pairs = NQ * (NT // 10) * args.steps / tot
+    value = pairs / NT            # queries/s at 1e6 train rows
+    line = {"impl": "reference", "metric": "Hamming matches/s", "value": value, "unit": "queries/s at 1e6 train rows", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": c5_config(1, NT),
+            "cpu_baseline": {"value": value, "unit": "queries/s at 1e6 train rows", "cores": cores, "kind": "reference",
+                             "sample": "cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2), 1e4 queries x 1e5 train rows per step on %d threads, scaled by pairs" % cores},
+            "e2e": {"value": value, "unit": "queries/s at 1e6 train rows", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def c5_config(world, nt):
+    return {"workload": "brute-force Hamming top-2 + ratio 0.75, 256-bit descriptors, 1e4 queries x %.0e train rows" % nt, "config": "c5",
+            "sharding": "train rows sharded over %d GPU(s)%s" % (world, ", NCCL all-gather of the per-shard top-2 + merge" if world > 1 else "")}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class Extraction:
+    """One configuration's extraction workload on this rank's GPU: device-resident and end-to-end runs."""
+
+    def __init__(self, S, torch, cfg, B, rank, world, dev, args, nsets=NSETS):
+        self.S, self.torch, self.cfg, self.B, self.dev = S, torch, cfg, B, dev
+        W, H = cfg["W"], cfg["H"]
+        self.W, self.H = W, H
+        orb, line = cfg["orb"], cfg["line"]
+        # global frame i -> rank i mod world; set s holds global frames [s * B * world, (s + 1) * B * world)
+        self.nsets = nsets
+        sets = []
+        for s in range(nsets):
+            ids = [s * B * world + i for i in range(B * world) if i % world == rank]
+            sets.append(make_frames(cfg, ids))
+        self.frames = sets
+        NO = args.orb_contexts if B % (2 * args.orb_contexts) == 0 else 1
+        NL = args.line_contexts if B % (2 * args.line_contexts) == 0 else 1
+        self.NO, self.NL = NO, NL
+        self.ctx_os = [S.Context(dev, priority=-1) for _ in range(NO)]    # ORB streams: filler priority, run one step ahead of the lines
+        self.ctx_ls = [S.Context(dev, priority=1) for _ in range(NL)]     # line streams: their region-growing chains set the step time
+        self.ctx_o = self.ctx_os[0]
+        self.lib = self.ctx_o.lib
+        self.orbs = [S.ORBextractor(orb["nfeatures"], orb["scaleFactor"], orb["nlevels"], orb["iniThFAST"], orb["minThFAST"], ctx=c) for c in self.ctx_os]
+        self.les = [S.Lineextractor(line["nfeatures"], line["nlevels"], line["refine"], line["scale"], line["sigma_scale"], line["quant"],
+                                    line["ang_th"], line["log_eps"], line["density_th"], line["n_bins"], line["min_line_length"], ctx=c) for c in self.ctx_ls]
+        self.capk, self.capl = self.orbs[0].max_keypoints, self.les[0].max_keylines
+        capk, capl = self.capk, self.capl
+        self.BL, self.BO = B // NL, B // NO
+        sub = args.line_sub or cfg["sub"]
+        self.SUB = sub if sub and self.BL % sub == 0 else self.BL
+        osub = args.orb_sub or min(self.BO, 256)
+        self.OSUB = osub if self.BO % osub == 0 else self.BO
+        from concurrent.futures import ThreadPoolExecutor
+        self.pool = ThreadPoolExecutor(NL + NO)
+        self.d_img = [torch.from_numpy(f).cuda() for f in sets]
+        self.d_kps = torch.empty((B, capk, 28), dtype=torch.uint8, device="cuda"); self.d_desc = torch.empty((B, capk, 32), dtype=torch.uint8, device="cuda")
+        self.d_nk = torch.empty(B, dtype=torch.int32, device="cuda")
+        self.d_kl = torch.empty((B, capl, 68), dtype=torch.uint8, device="cuda"); self.d_mid = torch.empty((B, capl, 28), dtype=torch.uint8, device="cuda")
+        self.d_ld = torch.empty((B, capl, 32), dtype=torch.uint8, device="cuda"); self.d_nl = torch.empty(B, dtype=torch.int32, device="cuda")
+        self.h_img = None
+
+    def close(self):
+        self.pool.shutdown()
+        for o in self.orbs + self.les:
+            o.close()
+        for c in self.ctx_os + self.ctx_ls:
+            c.close()
+        self.d_img = self.h_img = None
+        self.torch.cuda.empty_cache()
+
+    def contexts(self):
+        return self.ctx_os + self.ctx_ls
+
+    # ---- device-resident ----
+    def dev_orb_i(self, i, k):
+        W, H = self.W, self.H
+        img = self.d_img[k % self.nsets]
+        for j in range(i * self.BO, (i + 1) * self.BO, self.OSUB):
+            s = slice(j, j + self.OSUB)
+            self.ctx_os[i].check(self.lib.plf_orb_extract_batch_device(self.orbs[i].h, img[s].data_ptr(), self.OSUB, W, H, W, W * H, self.d_kps[s].data_ptr(),
+                                                                       self.d_desc[s].data_ptr(), self.capk, self.d_nk[s].data_ptr()))
+
+    def dev_orb(self, k):
+        for i in range(self.NO):   # asynchronous launches, one stream per ORB context
+            self.dev_orb_i(i, k)
+
+    def dev_line(self, i, k):
+        W, H = self.W, self.H
+        img = self.d_img[k % self.nsets]
+        for j in range(i * self.BL, (i + 1) * self.BL, self.SUB):     # sub-batches bound the workspace and keep the contexts out of lockstep
+            s = slice(j, j + self.SUB)
+            self.ctx_ls[i].check(self.lib.plf_line_extract_batch_device(self.les[i].h, img[s].data_ptr(), self.SUB, W, H, W, W * H, self.d_kl[s].data_ptr(),
+                                                                        self.d_mid[s].data_ptr(), self.d_ld[s].data_ptr(), self.capl, self.d_nl[s].data_ptr()))
+
+    def _line_steps(self, i, nsteps, with_orb):
+        for k in range(nsteps):
+            if with_orb and i == 0 and k + 1 < nsteps:
+                self.dev_orb(k + 1)      # ORB launches of step k + 1 (low-priority streams): filler for the gaps the line path leaves
+            self.dev_line(i, k)
+
+    def run_device(self, nsteps, what="both"):
+        """nsteps steps back to back: every extractor instance (own stream + host thread) walks through its share of each
+        step's batch without a global barrier between steps, so the tail of one step overlaps the start of the next, as it
+        does in a running system.  Returns the device time in ms."""
+        self.torch.cuda.synchronize()
+        self.ctx_o.timer_start()
+        if what == "orb":
+            for k in range(nsteps):
+                self.dev_orb(k)
+        else:
+            if what == "both":
+                self.dev_orb(0)
+            futs = [self.pool.submit(self._line_steps, i, nsteps, what == "both") for i in range(self.NL)]   # line calls contain stream syncs: one host thread each
+            for f in futs:
+                f.result()
+        for c in self.ctx_os[1:] + self.ctx_ls:
+            self.ctx_o.wait(c)                  # the first ORB stream's stop event waits for every other stream
+        return self.ctx_o.timer_stop()
+
+    # ---- end to end ----
+    def prepare_e2e(self):
+        torch, B, capk, capl = self.torch, self.B, self.capk, self.capl
+        self.h_img = [torch.from_numpy(f).pin_memory() for f in self.frames]
+        self.h_kps = torch.empty((B, capk, 28), dtype=torch.uint8).pin_memory(); self.h_desc = torch.empty((B, capk, 32), dtype=torch.uint8).pin_memory()
+        self.h_kl = torch.empty((B, capl, 68), dtype=torch.uint8).pin_memory(); self.h_mid = torch.empty((B, capl, 28), dtype=torch.uint8).pin_memory()
+        self.h_ld = torch.empty((B, capl, 32), dtype=torch.uint8).pin_memory()
+        self.n_k = np.zeros(B, np.int32); self.n_l = np.zeros(B, np.int32)
+
+    def e2e_orb(self, i, k):
+        W, H = self.W, self.H
+        img = self.h_img[k % self.nsets]
+        for j in range(i * self.BO, (i + 1) * self.BO, self.OSUB):
+            s = slice(j, j + self.OSUB)
+            self.ctx_os[i].check(self.lib.plf_orb_extract_batch(self.orbs[i].h, img[s].data_ptr(), self.OSUB, W, H, W, W * H, self.h_kps[s].data_ptr(),
+                                                                self.h_desc[s].data_ptr(), self.capk, self.n_k[s].ctypes.data))
+
+    def e2e_line(self, i, k):
+        W, H = self.W, self.H
+        img = self.h_img[k % self.nsets]
+        for j in range(i * self.BL, (i + 1) * self.BL, self.SUB):
+            s = slice(j, j + self.SUB)
+            self.ctx_ls[i].check(self.lib.plf_line_extract_batch(self.les[i].h, img[s].data_ptr(), self.SUB, W, H, W, W * H, self.h_kl[s].data_ptr(),
+                                                                 self.h_mid[s].data_ptr(), self.h_ld[s].data_ptr(), self.capl, self.n_l[s].ctypes.data))
+
+    def run_e2e(self, nsteps):
+        """The same through the host-buffer C-ABI calls: every call uploads its images from pinned host memory and
+        downloads its results (H2D + D2H inside the timed region); one host thread per extractor instance, the
+        reference's ORB thread and line thread (Frame.cc:301-304)."""
+        self.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        gates = [threading.Semaphore(1) for _ in range(self.NO)]   # step 0 is free to start
+
+        def orb_steps(i):
+            for k in range(nsteps):
+                gates[i].acquire()     # paced by the first line instance: ORB and line work of a step stay interleaved
+                self.e2e_orb(i, k)
+
+        def line_steps(i):
+            for k in range(nsteps):
+                if i == 0 and k + 1 < nsteps:
+                    for g_ in gates:
+                        g_.release()   # ORB instances may start step k + 1 (they run one step ahead, as in run_device)
+                self.e2e_line(i, k)
+
+        futs = [self.pool.submit(orb_steps, i) for i in range(self.NO)] + [self.pool.submit(line_steps, i) for i in range(self.NL)]
+        for f in futs:
+            f.result()
+        self.torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3
+
+    def e2e_bytes(self):
+        B = self.B
+        return 2 * B * self.W * self.H, B * (self.capk * 60 + 4 + self.capl * (68 + 28 + 32) + 4)
+
+    def check_outputs(self):
+        nk = self.d_nk.cpu().numpy(); nl = self.d_nl.cpu().numpy()
+        assert (nk > 0).all() and (nl >= 0).all(), "extraction reported an overflow (n_out < 0)"
+        return nk, nl
+
+    def checksum(self):
+        """Order-sensitive checksum of the step's results on the device: keypoint / keyline records and both descriptor sets
+        of every frame (valid rows only)."""
+        torch = self.torch
+        nk, nl = self.d_nk.long(), self.d_nl.long()
+        mk = (torch.arange(self.capk, device="cuda")[None, :] < nk[:, None])
+        ml = (torch.arange(self.capl, device="cuda")[None, :] < nl[:, None])
+        tot = 0
+        for t, m in ((self.d_kps, mk), (self.d_desc, mk), (self.d_kl, ml), (self.d_ld, ml)):
+            v = t.to(torch.int64) * m[:, :, None]
+            wgt = (torch.arange(v.shape[1] * v.shape[2], device="cuda", dtype=torch.int64) % 65521 + 1).view(1, v.shape[1], v.shape[2])
+            tot += int((v * wgt).sum().item())
+        return tot & 0xFFFFFFFFFFFF
+
+
+def algorithmic_bytes(cfg):
+    """Algorithmic bytes per frame per kernel: px0 = input pixels, spx = scaled LSD pixels of both
+    octaves, sumpx = ORB pyramid pixels; `dens` = fraction of LSD pixels with a defined gradient on this workload."""
+    W, H, line, orb = cfg["W"], cfg["H"], cfg["line"], cfg["orb"]
+    sw, sh = int(round(W * line["scale"])), int(round(H * line["scale"]))
+    spx = sw * sh + (int(round((W // 2) * line["scale"])) * int(round((H // 2) * line["scale"])))
+    lv = [(int(np.rint(np.float32(W) / np.float32(orb["scaleFactor"]) ** l)), int(np.rint(np.float32(H) / np.float32(orb["scaleFactor"]) ** l))) for l in range(orb["nlevels"])]
+    sumpx = sum(a * b for a, b in lv)
+    px0 = W * H
+    p01 = px0 + px0 // 4
+    dens = 0.07
+    alg = {
+        "k_lsd_grow_warp": 6 * spx, "k_lsd_grow": 6 * spx,
+        "k_lsd_grad": int((1 + 4 + 1 / 8 + dens * 8) * spx), "k_ccl_merge": int((1 / 8 + dens * 8) * spx),
+        "k_lsd_keys": int((1 / 8 + dens * 16) * spx), "k_lsd_cid": int(dens * (8 + 4 + 4 + 8) * spx),
+        "k_lsd_rect": int(dens * 2 * (4 + 4) * spx),
+        "k_fast_cells": sumpx, "k_blur7": 2 * sumpx, "k_resize_linear": 2 * sumpx - 2 * px0 + (px0 - lv[-1][0] * lv[-1][1]),
+        "k_gauss_strip<3>": 2 * p01, "k_gauss_strip<2>": 2 * px0, "k_resize_exact": p01 + spx,
+        "k_pyrdown": 2 * (px0 + px0 // 4), "k_sobel3": 5 * p01,
+        "cub_radix_sort_keys": int(2 * 8 * 8 * dens * spx), "k_describe": 2 * 1024 * orb["nfeatures"], "k_lbd": 63 * 4 * 60 * line["nfeatures"],
+    }
+    # SURVEY.md 8d: B_orb + the per-octave line figures (LSD-pre, gradient, sort, grow, LBD-prep, LBD gathers)
+    b_orb = px0 + sumpx + (sumpx - lv[-1][0] * lv[-1][1]) + sumpx + 2 * sumpx + 60 * orb["nfeatures"]
+    b_line = 0
+    for p in (px0, px0 // 4):
+        s2p = line["scale"] ** 2 * p
+        b_line += (2 * p + p + s2p) + 9 * s2p + 2 * 8 * s2p * dens + 6 * s2p + (2 * p + (p + p / 4) + 5 * p)
+    b_line += 63 * 4 * 60 * line["nfeatures"]
+    return alg, int(b_orb), int(b_line), spx, sumpx
+
+
+def concurrent_profile(ex, nst):
+    """Per-kernel time while ALL streams run together, as in the timed region: CUDA-event brackets around every launch
+    (plf_profile_enable), each kernel's busy time = the union of its launch intervals over `nst` steps."""
+    for c in ex.contexts():
+        c.profile_enable(True)
+    t = ex.run_device(nst) / nst
+    per = {}
+    for c in ex.contexts():
+        for name, t0, t1 in c.profile_timeline(ex.ctx_o):
+            per.setdefault(name, []).append((t0, t1))
+        c.profile_enable(False)
+
+    def union(iv):
+        tot, c0, c1 = 0.0, None, None
+        for a, b in sorted(iv):
+            if c1 is None or a > c1:
+                if c1 is not None:
+                    tot += c1 - c0
+                c0, c1 = a, b
+            else:
+                c1 = max(c1, b)
+        return tot + ((c1 - c0) if c1 is not None else 0.0)
+
+    out = {k: {"busy_ms": union(v) / nst, "sum_ms": sum(b - a for a, b in v) / nst, "launches": len(v) // nst} for k, v in per.items()}
+    allk = union([iv for v in per.values() for iv in v]) / nst
+    return t, out, allk
+
+
+def measure_extraction(S, torch, dist, name, cfg, args, rank, world, dev, barrier, maxr, headline):
+    """Device-resident value, e2e, ORB-only, roofline for one extraction config.  Returns the pieces of the JSON line."""
+    B = args.frames or cfg["frames"]
+    if not headline:
+        B = min(B, 256)
+    steps, warm = (args.steps, max(args.warmup, 3)) if headline else (3, 3)
+    ex = Extraction(S, torch, cfg, B, rank, world, dev, args)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    ex.run_device(warm)
+    flush.zero_()
+    barrier()
+    sampler = ClockSampler(dev) if (rank == 0 and headline) else None
+    l0 = sum(c.launch_count() for c in ex.contexts())
+    ms_dev = ex.run_device(steps)
+    barrier()
+    launches = sum(c.launch_count() for c in ex.contexts()) - l0
+    clocks = sampler.stop() if sampler else None
+    nk, nl = ex.check_outputs()
+    csum = ex.checksum()
+    # ORB only
+    ex.run_device(2, "orb"); flush.zero_(); barrier()
+    ms_orb = ex.run_device(steps, "orb")
+    barrier()
+    ms_line = None
+    if headline:
+        ex.run_device(1, "line"); flush.zero_(); barrier()
+        ms_line = ex.run_device(steps, "line")
+        barrier()
+    prof = None
+    if rank == 0 and headline:
+        prof = concurrent_profile(ex, 3)
+    barrier()
+    # end to end
+    ex.prepare_e2e()
+    ex.run_e2e(warm if headline else 1)
+    flush.zero_()
+    barrier()
+    ms_e2e = ex.run_e2e(steps)
+    barrier()
+    h2d, d2h = ex.e2e_bytes()
+    ms_dev, ms_e2e, ms_orb = maxr(ms_dev), maxr(ms_e2e), maxr(ms_orb)
+    if ms_line is not None:
+        ms_line = maxr(ms_line)
+    res = dict(B=B, steps=steps, warm=warm, ms_dev=ms_dev, ms_e2e=ms_e2e, ms_orb=ms_orb, ms_line=ms_line, launches=int(launches), clocks=clocks,
+               nk=float(nk.mean()), nl=float(nl.mean()), checksum=csum, h2d=h2d, d2h=d2h, prof=prof, NO=ex.NO, NL=ex.NL, SUB=ex.SUB, OSUB=ex.OSUB,
+               sample=ex.frames[0][:min(B, 512)].copy() if rank == 0 else None)
+    ex.close()
+    del flush
+    torch.cuda.empty_cache()
+    return res
+
+
+def latency_c1(S, cfg, dev, nrep=60):
+    """BASELINE config 1 / the drop-in use: one frame through plf_orb_extract || plf_line_extract from host buffers, the
+    reference's two threads (src/Frame.cc:301-304).  Returns median / p90 milliseconds per frame."""
+    W, H, orb, line = cfg["W"], cfg["H"], cfg["orb"], cfg["line"]
+    imgs = [synth_image(W, H, s) for s in range(4)]
+    co, cl = S.Context(dev), S.Context(dev, priority=1)
+    eo = S.ORBextractor(orb["nfeatures"], orb["scaleFactor"], orb["nlevels"], orb["iniThFAST"], orb["minThFAST"], ctx=co)
+    el = S.Lineextractor(line["nfeatures"], line["nlevels"], line["refine"], line["scale"], line["sigma_scale"], line["quant"], line["ang_th"],
+                         line["log_eps"], line["density_th"], line["n_bins"], line["min_line_length"], ctx=cl)
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(2)
+    ts, to, tl = [], [], []
+
+    def timed(fn, img):
+        t0 = time.perf_counter(); fn(img); return (time.perf_counter() - t0) * 1e3
+
+    for r in range(nrep + 5):
+        img = imgs[r % len(imgs)]
+        t0 = time.perf_counter()
+        fo = pool.submit(timed, eo, img); fl = pool.submit(timed, el.ComputeLsdWithLbd, img)
+        a, b = fo.result(), fl.result()
+        dt = (time.perf_counter() - t0) * 1e3
+        if r >= 5:
+            ts.append(dt); to.append(a); tl.append(b)
+    pool.shutdown(); eo.close(); el.close(); co.close(); cl.close()
+    return {"frame_ms_median": float(np.median(ts)), "frame_ms_p90": float(np.percentile(ts, 90)), "orb_ms_median": float(np.median(to)),
+            "line_ms_median": float(np.median(tl)), "frames_per_s": 1e3 / float(np.median(ts)), "reps": nrep,
+            "how": "plf_orb_extract || plf_line_extract on two host threads, host buffers, wall clock per frame"}
+
+
+def stereo_c3(S, torch, cfg, dev, npairs=128, reps=5):
+    """BASELINE config 3's matching half on device-resident extraction results: Frame::ComputeStereoMatches for `npairs` pairs in
+    one call (plf_stereo_match_batch_device) and the L<->R line matchNNR of every pair (knn2 + ratio test, nnr 0.75)."""
+    W, H, orb, line = cfg["W"], cfg["H"], cfg["orb"], cfg["line"]
+    frames = make_frames(cfg, list(range(2 * npairs)))
+    ctx = S.Context(dev)
+    lib = ctx.lib
+    ex = S.ORBextractor(orb["nfeatures"], orb["scaleFactor"], orb["nlevels"], orb["iniThFAST"], orb["minThFAST"], ctx=ctx)
+    le = S.Lineextractor(line["nfeatures"], line["nlevels"], line["refine"], line["scale"], line["sigma_scale"], line["quant"], line["ang_th"],
+                         line["log_eps"], line["density_th"], line["n_bins"], line["min_line_length"], ctx=ctx)
+    capk, capl, nfr = ex.max_keypoints, le.max_keylines, 2 * npairs
+    d_img = torch.from_numpy(frames).cuda()
+    dk = torch.empty((nfr, capk, 28), dtype=torch.uint8, device="cuda"); dd = torch.empty((nfr, capk, 32), dtype=torch.uint8, device="cuda")
+    dn = torch.empty(nfr, dtype=torch.int32, device="cuda")
+    du = torch.empty((npairs, capk), dtype=torch.float32, device="cuda"); dz = torch.empty((npairs, capk), dtype=torch.float32, device="cuda")
+    kl = torch.empty((nfr, capl, 68), dtype=torch.uint8, device="cuda"); mid = torch.empty((nfr, capl, 28), dtype=torch.uint8, device="cuda")
+    ld = torch.empty((nfr, capl, 32), dtype=torch.uint8, device="cuda"); nl = torch.empty(nfr, dtype=torch.int32, device="cuda")
+    ctx.check(lib.plf_orb_extract_batch_device(ex.h, d_img.data_ptr(), nfr, W, H, W, W * H, dk.data_ptr(), dd.data_ptr(), capk, dn.data_ptr()))
+    ctx.check(lib.plf_line_extract_batch_device(le.h, d_img.data_ptr(), nfr, W, H, W, W * H, kl.data_ptr(), mid.data_ptr(), ld.data_ptr(), capl, nl.data_ptr()))
+    ctx.synchronize()
+    nlh = nl.cpu().numpy()
+    mb, mbf = 0.54, 0.54 * 718.856
+    idx = torch.empty((capl, 2), dtype=torch.int32, device="cuda"); dst = torch.empty((capl, 2), dtype=torch.int32, device="cuda")
+    m12 = torch.empty(capl, dtype=torch.int32, device="cuda"); nm = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ts, tl = [], []
+    for r in range(reps + 1):
+        ctx.timer_start()
+        ctx.check(lib.plf_stereo_match_batch_device(ex.h, ex.h, npairs, 0, 2, 1, 2, dk.data_ptr(), dd.data_ptr(), dn.data_ptr(), dk.data_ptr(),
+                                                    dd.data_ptr(), dn.data_ptr(), capk, mb, mbf, du.data_ptr(), dz.data_ptr()))
+        a = ctx.timer_stop()
+        ctx.timer_start()
+        for p_ in range(npairs):
+            nq, nt = int(nlh[2 * p_]), int(nlh[2 * p_ + 1])
+            if nq == 0 or nt < 2:
+                continue
+            ctx.check(lib.plf_hamming_knn2_device(ctx.h, ld[2 * p_].data_ptr(), nq, ld[2 * p_ + 1].data_ptr(), nt, 0, idx.data_ptr(), dst.data_ptr()))
+            ctx.check(lib.plf_nnr_from_knn2_device(ctx.h, idx.data_ptr(), dst.data_ptr(), nq, 0.75, m12.data_ptr(), nm.data_ptr()))
+        b = ctx.timer_stop()
+        if r:
+            ts.append(a); tl.append(b)
+    matched = float((du[:, :] >= 0).sum().item()) / npairs
+    ex.close(); le.close(); ctx.close()
+    return {"pairs": npairs, "stereo_points_ms": float(np.median(ts)), "stereo_pairs_per_s": npairs / (float(np.median(ts)) / 1e3),
+            "line_nnr_ms": float(np.median(tl)), "line_nnr_pairs_per_s": npairs / (float(np.median(tl)) / 1e3), "mean_stereo_matches": matched,
+            "what": "plf_stereo_match_batch_device over all pairs in one call; per pair plf_hamming_knn2_device + plf_nnr_from_knn2_device on the line descriptors"}
+
+
+def measure_matching(S, torch, dist, args, rank, world, dev, barrier, maxr, sizes, cpu=True):
+    """BASELINE config 5: 1e4 queries x T train rows, train-sharded across ranks with the NCCL merge; every size is also
+    checked against the unsharded result through a checksum of the merged table (N > 1)."""
+    from spl_slam_b200 import sharded
+    NQ = 10000
+    ctx_m = S.Context(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    gq = torch.Generator(device="cuda"); gq.manual_seed(1234)
+    dq = torch.randint(0, 256, (NQ, 32), dtype=torch.uint8, device="cuda", generator=gq)
+    out = []
+    popc_peak = ctx_m.popc_peak()
+    for NT in sizes:
+        # the SAME global train set on every world size: generated in fixed chunks of 1e5 rows seeded by the chunk number
+        tb, te = sharded.train_shard(NT, rank, world)
+        CH = 100000
+        parts = []
+        for c in range(tb // CH, (te + CH - 1) // CH):
+            g = torch.Generator(device="cuda"); g.manual_seed(4321 + c)
+            blk = torch.randint(0, 256, (CH, 32), dtype=torch.uint8, device="cuda", generator=g)
+            lo, hi = max(tb, c * CH), min(te, (c + 1) * CH)
+            parts.append(blk[lo - c * CH:hi - c * CH])
+        dt = torch.cat(parts) if parts else torch.empty((0, 32), dtype=torch.uint8, device="cuda")
+        for _ in range(2):
+            idx, dst = sharded.knn2_sharded(ctx_m, dq, dt, tb)
+        barrier()
+        reps = []
+        for _ in range(5 if NT >= 10 ** 7 else 7):
+            flush.zero_(); torch.cuda.synchronize()
+            ctx_m.timer_start()
+            idx, dst = sharded.knn2_sharded(ctx_m, dq, dt, tb)       # local top-2 + NCCL all-gather + merge (world > 1)
+            m12, nm = sharded.nnr_from_knn2(ctx_m, idx, dst, 0.75)
+            reps.append(ctx_m.timer_stop())
+        barrier()
+        ms = maxr(float(np.median(reps)))
+        # checksum of the merged top-2 + matches: equal for every world size (same global train set), reported per N
+        wq = (torch.arange(NQ, device="cuda", dtype=torch.int64) % 65521 + 1)
+        csum = int(((idx.to(torch.int64) * 3 + dst.to(torch.int64)).sum(1) * wq).sum().item() + (m12.to(torch.int64) * wq).sum().item()) & 0xFFFFFFFFFFFF
+        ent = {"train_rows": NT, "ms": ms, "queries_per_s": NQ / (ms / 1e3), "pairs_per_s": NQ * NT / (ms / 1e3), "matches": nm, "checksum": csum,
+               "popc_frac": 8 * NQ * NT / (ms / 1e3) / world / popc_peak}
+        out.append(ent)
+        del dt, parts
+    ctx_m.close()
+    return out, popc_peak
 
 
 def main():
@@ -197,11 +690,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU)
+    ap.add_argument("--config", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (0 = the configuration's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline configuration only")
     ap.add_argument("--line-contexts", type=int, default=LINE_CONTEXTS)
     ap.add_argument("--orb-contexts", type=int, default=ORB_CONTEXTS)
-    ap.add_argument("--line-sub", type=int, default=0, help="frames per line call (0 = one call per context)")
+    ap.add_argument("--line-sub", type=int, default=0, help="frames per line call (0 = the configuration's)")
+    ap.add_argument("--orb-sub", type=int, default=0, help="frames per ORB call (0 = min(share, 256))")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -234,230 +730,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    B = args.frames
-    assert B % 2 == 0 and B <= 4096
-    # global frame i -> rank i mod world; this rank's frames: pairs p where frame index = 2p (+1)
-    n_pairs_global = B * world // 2
-    allf = make_frames(n_pairs_global, 0) if world == 1 else None
-    if world > 1:
-        mine = [i for i in range(B * world) if i % world == rank]
-        # generate only the pairs this rank touches
-        pids = sorted(set(i // 2 for i in mine))
-        gen = make_frames(len(pids), 0, pair_ids=pids)
-        pos = {p: j for j, p in enumerate(pids)}
-        frames = np.stack([gen[2 * pos[i // 2] + (i % 2)] for i in mine])
-    else:
-        frames = allf
-    dev = local_rank
-    from concurrent.futures import ThreadPoolExecutor
-    NO = args.orb_contexts if B % (2 * args.orb_contexts) == 0 else 1
-    ctx_os = [S.Context(dev, priority=-1) for _ in range(NO)]    # ORB streams: filler priority, run one step ahead of the lines
-    ctx_o = ctx_os[0]
-    NL = args.line_contexts if B % (2 * args.line_contexts) == 0 else 1
-    ctx_ls = [S.Context(dev, priority=1) for _ in range(NL)]   # line streams (their chains set the step time): the region-growing chain of one sub-batch overlaps
-    lib = ctx_o.lib                                 # the bandwidth-bound kernels of the others
-    orbs = [S.ORBextractor(ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"], ctx=c) for c in ctx_os]
-    orb = orbs[0]
-    les = [S.Lineextractor(LINE["nfeatures"], LINE["nlevels"], LINE["refine"], LINE["scale"], LINE["sigma_scale"], LINE["quant"],
-                           LINE["ang_th"], LINE["log_eps"], LINE["density_th"], LINE["n_bins"], LINE["min_line_length"], ctx=c) for c in ctx_ls]
-    capk, capl = orb.max_keypoints, les[0].max_keylines
-    BL = B // NL
-    BO = B // NO
-    pool = ThreadPoolExecutor(NL + NO)
-    # device-resident inputs / outputs (torch only provides the memory)
-    d_img = torch.from_numpy(frames).cuda()
-    d_kps = torch.empty((B, capk, 28), dtype=torch.uint8, device="cuda"); d_desc = torch.empty((B, capk, 32), dtype=torch.uint8, device="cuda")
-    d_nk = torch.empty(B, dtype=torch.int32, device="cuda")
-    d_kl = torch.empty((B, capl, 68), dtype=torch.uint8, device="cuda"); d_mid = torch.empty((B, capl, 28), dtype=torch.uint8, device="cuda")
-    d_ld = torch.empty((B, capl, 32), dtype=torch.uint8, device="cuda"); d_nl = torch.empty(B, dtype=torch.int32, device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-    # pinned host buffers for the end-to-end path
-    h_img = torch.from_numpy(frames).pin_memory()
-    h_kps = torch.empty((B, capk, 28), dtype=torch.uint8).pin_memory(); h_desc = torch.empty((B, capk, 32), dtype=torch.uint8).pin_memory()
-    h_kl = torch.empty((B, capl, 68), dtype=torch.uint8).pin_memory(); h_mid = torch.empty((B, capl, 28), dtype=torch.uint8).pin_memory()
-    h_ld = torch.empty((B, capl, 32), dtype=torch.uint8).pin_memory()
-    n_k = np.zeros(B, np.int32); n_l = np.zeros(B, np.int32)
-
-    def dev_orb_i(i):
-        s = slice(i * BO, (i + 1) * BO)
-        ctx_os[i].check(lib.plf_orb_extract_batch_device(orbs[i].h, d_img[s].data_ptr(), BO, W, H, W, W * H, d_kps[s].data_ptr(),
-                                                         d_desc[s].data_ptr(), capk, d_nk[s].data_ptr()))
-
-    def dev_orb():
-        for i in range(NO):   # asynchronous launches, one stream per ORB context
-            dev_orb_i(i)
-
-    SUB = args.line_sub if args.line_sub and BL % args.line_sub == 0 else BL
-
-    def dev_line(i):
-        for j in range(i * BL, (i + 1) * BL, SUB):     # sub-batches keep the contexts out of lockstep: one context's
-            s = slice(j, j + SUB)                      # region-growing chain overlaps the others' bandwidth kernels
-            ctx_ls[i].check(lib.plf_line_extract_batch_device(les[i].h, d_img[s].data_ptr(), SUB, W, H, W, W * H, d_kl[s].data_ptr(),
-                                                              d_mid[s].data_ptr(), d_ld[s].data_ptr(), capl, d_nl[s].data_ptr()))
-
-    def dev_line_steps(i, nsteps):
-        for k in range(nsteps):
-            if i == 0 and k + 1 < nsteps:
-                dev_orb()      # ORB launches of step k + 1 (low-priority streams): filler for the gaps the line path leaves
-            dev_line(i)        # (host syncs, phases where only region-growing chains are running)
-
-    def run_device(nsteps):
-        """nsteps steps back to back: every extractor instance (own stream + host thread) walks through its share of each
-        step's batch without a global barrier between steps, so the tail of one step (the last region-growing chain,
-        LBD) overlaps the start of the next, as it does in a running system.  Returns the device time in ms."""
-        torch.cuda.synchronize()
-        ctx_o.timer_start()
-        dev_orb()                                                            # ORB of step 0
-        futs = [pool.submit(dev_line_steps, i, nsteps) for i in range(NL)]   # line calls contain stream syncs: one host thread each
-        for f in futs:
-            f.result()
-        for c in ctx_os[1:] + ctx_ls:
-            ctx_o.wait(c)                  # the first ORB stream's stop event waits for every other stream
-        return ctx_o.timer_stop()
-
-    def e2e_orb(i):
-        s = slice(i * BO, (i + 1) * BO)
-        ctx_os[i].check(lib.plf_orb_extract_batch(orbs[i].h, h_img[s].data_ptr(), BO, W, H, W, W * H, h_kps[s].data_ptr(), h_desc[s].data_ptr(),
-                                                  capk, n_k[s].ctypes.data))
-
-    def e2e_line(i):
-        for j in range(i * BL, (i + 1) * BL, SUB):
-            s = slice(j, j + SUB)
-            ctx_ls[i].check(lib.plf_line_extract_batch(les[i].h, h_img[s].data_ptr(), SUB, W, H, W, W * H, h_kl[s].data_ptr(), h_mid[s].data_ptr(),
-                                                       h_ld[s].data_ptr(), capl, n_l[s].ctypes.data))
-
-    def e2e_orb_steps(i, nsteps, gate):
-        for _ in range(nsteps):
-            gate.acquire()     # paced by the first line instance: ORB and line work of a step stay interleaved
-            e2e_orb(i)
-
-    def e2e_line_steps(i, nsteps, gates):
-        for k in range(nsteps):
-            if i == 0 and k + 1 < nsteps:
-                for g_ in gates:
-                    g_.release()   # ORB instances may start step k + 1 (they run one step ahead, as in run_device)
-            e2e_line(i)
-
-    def run_e2e(nsteps):
-        """The same through the host-buffer C-ABI calls: every call uploads its images from pinned host memory and
-        downloads its results (H2D + D2H inside the timed region); one host thread per extractor instance, the
-        reference's ORB thread and line thread (Frame.cc:301-304)."""
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        gates = [threading.Semaphore(1) for _ in range(NO)]   # step 0 is free to start
-        futs = [pool.submit(e2e_orb_steps, i, nsteps, gates[i]) for i in range(NO)] + [pool.submit(e2e_line_steps, i, nsteps, gates) for i in range(NL)]
-        for f in futs:
-            f.result()
-        torch.cuda.synchronize()
-        return (time.perf_counter() - t0) * 1e3
-
-    # ---- device-resident throughput ----
-    run_device(args.warmup)
-    flush.zero_()                          # leave nothing of the warm-up in L2; the per-step working set (GBs) exceeds L2 anyway
-    barrier()
-    sampler = ClockSampler(dev) if rank == 0 else None
-    l0 = sum(c.launch_count() for c in ctx_os + ctx_ls)
-    ms_dev = run_device(args.steps)
-    barrier()
-    launches = sum(c.launch_count() for c in ctx_os + ctx_ls) - l0
-    clocks = sampler.stop() if sampler else None
-    nk = d_nk.cpu().numpy(); nl = d_nl.cpu().numpy()
-    assert (nk > 0).all() and (nl >= 0).all(), "extraction reported an overflow"
-
-    if os.environ.get("PLF_PROF_CONCURRENT"):   # diagnostic: kernel timeline while all streams run together
-        for c in ctx_os + ctx_ls:
-            c.profile_enable(True)
-        nst = 3
-        t_conc = run_device(nst) / nst
-        ivs = []
-        for ci, c in enumerate(ctx_os + ctx_ls):
-            for name, t0, t1 in c.profile_timeline(ctx_o):
-                ivs.append((t0, t1, name, ci))
-            c.profile_enable(False)
-
-        def union(iv):
-            tot, cur0, cur1 = 0.0, None, None
-            for a, b in sorted(iv):
-                if cur1 is None or a > cur1:
-                    if cur1 is not None:
-                        tot += cur1 - cur0
-                    cur0, cur1 = a, b
-                else:
-                    cur1 = max(cur1, b)
-            return tot + ((cur1 - cur0) if cur1 is not None else 0.0)
-        thr = [(a, b) for a, b, n, ci in ivs if n != "k_lsd_grow_warp"]
-        allk = [(a, b) for a, b, n, ci in ivs]
-        print("concurrent: %.1f ms/step; busy with any kernel %.1f ms/step; busy with a kernel other than grow_warp %.1f ms/step" %
-              (t_conc, union(allk) / nst, union(thr) / nst), file=sys.stderr)
-        with open(os.path.join(ROOT, "gpurun_out", "timeline.txt"), "w") as fh:
-            for a, b, n, ci in sorted(ivs):
-                fh.write("%.3f %.3f %d %s\n" % (a, b, ci, n))
-    if os.environ.get("PLF_PROF_E2E"):   # diagnostic: kernel timeline of the host-buffer path
-        run_e2e(2)
-        for c in ctx_os + ctx_ls:
-            c.profile_enable(True)
-        ctx_o.timer_start()
-        nst = 3
-        t_conc = run_e2e(nst) / nst
-        ivs = []
-        for ci, c in enumerate(ctx_os + ctx_ls):
-            for name, t0, t1 in c.profile_timeline(ctx_o):
-                ivs.append((t0, t1, name, ci))
-            c.profile_enable(False)
-        with open(os.path.join(ROOT, "gpurun_out", "timeline_e2e.txt"), "w") as fh:
-            for a, b, n, ci in sorted(ivs):
-                fh.write("%.3f %.3f %d %s\n" % (a, b, ci, n))
-        print("e2e profiled: %.1f ms/step" % t_conc, file=sys.stderr)
-    # ---- per-kernel times for the roofline (separate profiled steps, CUDA events per launch) ----
-    for c in ctx_os + ctx_ls:
-        c.profile_enable(True)
-    PROF_STEPS = 3
-    for _ in range(PROF_STEPS):   # one stream at a time here, so that kernel times are not mixed
-        flush.zero_(); torch.cuda.synchronize()
-        for i in range(NO):
-            dev_orb_i(i)
-            ctx_os[i].synchronize()
-        for i in range(NL):
-            dev_line(i)
-            ctx_ls[i].synchronize()
-    prof = {}
-    for c in ctx_os + ctx_ls:
-        for k, v in c.profile_report().items():
-            a = prof.get(k, (0.0, 0))
-            prof[k] = (a[0] + v[0] / PROF_STEPS, a[1] + v[1] // PROF_STEPS)
-        c.profile_enable(False)
-
-    # ---- end to end ----
-    run_e2e(args.warmup)
-    flush.zero_()
-    barrier()
-    ms_e2e = run_e2e(args.steps)
-    barrier()
-
-    # ---- matching (BASELINE config 5): 1e4 queries x 1e6 train rows, train-sharded across ranks ----
-    from spl_slam_b200 import sharded
-    NQ, NT = 10000, 1000000
-    gq = torch.Generator(device="cuda"); gq.manual_seed(1234)
-    dq = torch.randint(0, 256, (NQ, 32), dtype=torch.uint8, device="cuda", generator=gq)
-    tb, te = sharded.train_shard(NT, rank, world)
-    gt = torch.Generator(device="cuda"); gt.manual_seed(4321 + rank)
-    dt = torch.randint(0, 256, (te - tb, 32), dtype=torch.uint8, device="cuda", generator=gt)
-    ctx_m = S.Context(dev)
-    for _ in range(2):
-        idx, dst = sharded.knn2_sharded(ctx_m, dq, dt, tb)
-    barrier()
-    ms_match_all = []
-    MREP = 7
-    for _ in range(MREP):
-        flush.zero_(); torch.cuda.synchronize()
-        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-        ctx_m.timer_start()
-        idx, dst = sharded.knn2_sharded(ctx_m, dq, dt, tb)       # local top-2 + NCCL all-gather + merge (world > 1)
-        m12, nm = sharded.nnr_from_knn2(ctx_m, idx, dst, 0.75)
-        ms_match_all.append(ctx_m.timer_stop())
-    barrier()
-    popc_peak = ctx_m.popc_peak()
-
     def maxr(v):
         if world == 1:
             return v
@@ -465,109 +737,135 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    print("matching reps (ms): %s" % [round(v, 2) for v in ms_match_all], file=sys.stderr)
-    ms_dev = maxr(ms_dev); ms_e2e = maxr(ms_e2e); ms_match = maxr(float(np.median(ms_match_all)))   # median of MREP runs
-    total_frames = B * world * args.steps
-    value = total_frames / (ms_dev / 1e3)
-    e2e_value = total_frames / (ms_e2e / 1e3)
-    h2d = 2 * B * W * H                                              # each extractor uploads the batch once
-    d2h = B * (capk * 60 + 4 + capl * (68 + 28 + 32) + 4)
+    dev = local_rank
+    name = args.config
+    t_start = time.time()
+
+    def emit(line):
+        if rank == 0:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            print(json.dumps(line), flush=True)
+            os.dup2(2, 1)
+
+    if name == "c5":
+        sweep, popc_peak = measure_matching(S, torch, dist, args, rank, world, dev, barrier, maxr, [10 ** 4, 10 ** 5, 10 ** 6, 10 ** 7])
+        e6 = [e for e in sweep if e["train_rows"] == 10 ** 6][0]
+        line = {"metric": "Hamming matches/s", "value": e6["queries_per_s"], "unit": "queries/s at 1e6 train rows", "n_gpus": world, "steps": 7,
+                "warmup": 2, "ms_per_step": e6["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic", "config": c5_config(world, 10 ** 6), "sweep": sweep,
+                "roofline": {"bound": "popc", "achieved": 8 * e6["pairs_per_s"] / world, "peak": popc_peak, "unit": "popc32/s per GPU",
+                             "frac": e6["popc_frac"], "peak_source": "plf_popc_peak micro-benchmark on this GPU"}}
+        emit(line)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cfg = CONFIGS[name]
+    if name == "c1":
+        lat = latency_c1(S, cfg, dev, nrep=max(args.steps, 20) * 5)
+        line = {"metric": "frames/s ORB+LSD/LBD extraction", "value": lat["frames_per_s"], "unit": "frames/s", "n_gpus": 1, "steps": lat["reps"],
+                "warmup": 5, "ms_per_step": lat["frame_ms_median"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic", "config": config_dict(name, cfg, 1, 1), "latency": lat}
+        emit(line)
+        return
+
+    r = measure_extraction(S, torch, dist, name, cfg, args, rank, world, dev, barrier, maxr, True)
+    B = r["B"]
+    total_frames = B * world * r["steps"]
+    value = total_frames / (r["ms_dev"] / 1e3)
+    e2e_value = total_frames / (r["ms_e2e"] / 1e3)
+
+    others = {}
+    if not args.no_extras and name == "c4":
+        # short measurements of the other BASELINE configurations (extra keys; the headline stays c4)
+        for oname in ("c2", "c3"):
+            o = measure_extraction(S, torch, dist, oname, CONFIGS[oname], args, rank, world, dev, barrier, maxr, False)
+            tf = o["B"] * world * o["steps"]
+            others[oname] = {"workload": CONFIGS[oname]["workload"], "frames_per_gpu_per_step": o["B"], "steps": o["steps"],
+                             "frames_per_s": tf / (o["ms_dev"] / 1e3), "ms_per_step": o["ms_dev"] / o["steps"],
+                             "e2e_frames_per_s": tf / (o["ms_e2e"] / 1e3), "orb_only_frames_per_s": tf / (o["ms_orb"] / 1e3),
+                             "mean_keypoints": o["nk"], "mean_lines": o["nl"], "checksum": o["checksum"]}
+        if rank == 0:
+            others["c1"] = dict(latency_c1(S, CONFIGS["c1"], dev), workload=CONFIGS["c1"]["workload"])
+            c3 = CONFIGS["c3"]
+            others["c3_single_image"] = dict(latency_c1(S, c3, dev, nrep=30), workload="one 1241x376 image through the drop-in calls (per image)")
+            others["c3"]["stereo_matching"] = stereo_c3(S, torch, c3, dev)
+        barrier()
+        sweep, popc_peak = measure_matching(S, torch, dist, args, rank, world, dev, barrier, maxr, [10 ** 4, 10 ** 5, 10 ** 6, 10 ** 7])
+        others["c5"] = {"workload": c5_config(world, 10 ** 6)["workload"].replace("1e+06", "1e4..1e7"), "sweep": sweep, "popc_peak": popc_peak,
+                        "popc_peak_source": "plf_popc_peak micro-benchmark on this GPU"}
 
     if rank == 0:
-        # roofline of the dominant kernel (by measured time share)
         peak, peak_src = peaks()
-        sw, sh = int(round(W * LINE["scale"])), int(round(H * LINE["scale"]))
-        spx = sw * sh + (int(round((W // 2) * LINE["scale"])) * int(round((H // 2) * LINE["scale"])))   # scaled px, both octaves
-        lv = [(int(np.rint(np.float32(W) / np.float32(1.2) ** l)), int(np.rint(np.float32(H) / np.float32(1.2) ** l))) for l in range(8)]
-        sumpx = sum(a * b for a, b in lv)
-        # algorithmic bytes per frame per kernel; px0 = input pixels, spx = scaled LSD pixels of both
-        # octaves, sumpx = ORB pyramid pixels; `dens` = fraction of LSD pixels with a defined gradient on this workload
-        px0 = W * H
-        p01 = px0 + px0 // 4
-        dens = 0.07
-        alg = {
-            "k_lsd_grow_warp": 6 * spx, "k_lsd_grow": 6 * spx,
-            "k_lsd_grad": int((1 + 4 + 1 / 8 + dens * 8) * spx), "k_ccl_merge": int((1 / 8 + dens * 8) * spx),
-            "k_lsd_keys": int((1 / 8 + dens * 16) * spx), "k_lsd_cid": int(dens * (8 + 4 + 4 + 8) * spx),
-            "k_lsd_rect": int(dens * 2 * (4 + 4) * spx),
-            "k_fast_cells": sumpx, "k_blur7": 2 * sumpx, "k_resize_linear": 2 * sumpx - 2 * px0 + (px0 - lv[-1][0] * lv[-1][1]),
-            "k_gauss_strip<3>": 2 * p01, "k_gauss_strip<2>": 2 * px0, "k_resize_exact": p01 + spx,
-            "k_pyrdown": 2 * (px0 + px0 // 4), "k_sobel3": 5 * p01,
-            "cub_radix_sort_keys": int(2 * 8 * 8 * dens * spx), "k_describe": 2 * 1024 * ORB["nfeatures"], "k_lbd": 63 * 4 * 60 * LINE["nfeatures"],
-        }
-        top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, (0, 0))
-        step_kernel_ms = sum(v[0] for v in prof.values())
-
-        def kernel_roof(name, ms_k, n_k_l):
-            bytes_launch = alg.get(name, 0) * B / max(n_k_l, 1)
-            ach = bytes_launch / (ms_k / max(n_k_l, 1) / 1e3) / 1e9 if ms_k > 0 else 0.0
-            return ach
-
-        # ncu `--set full` DRAM traffic of the dominant kernel, if a capture of this round is committed (profiles/)
-        traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r1_dominant_kernel_ncu.json")
-        if os.path.exists(tp):
-            try:
-                tj = json.load(open(tp))
-                traffic = tj.get("dram_bytes_per_launch")
-                traffic_src = tj.get("note")
-            except Exception:
-                pass
-        # per-kernel DRAM traffic and SM throughput from the committed ncu section capture (one 256-frame batch per path)
-        ncu_k = {}
-        kp = os.path.join(ROOT, "profiles", "r1_kernels_ncu.json")
-        if os.path.exists(kp):
-            try:
-                for o in json.load(open(kp))["kernels"]:
-                    nm = o["kernel"].replace("void ", "")
-                    nm = "cub_radix_sort_keys" if "RadixSortOnesweep" in nm else nm
-                    ncu_k[nm] = {"traffic_bytes_per_frame": int(o["dram_bytes"] / 256), "sm_pct": o["sm_pct"], "dram_pct": o["dram_pct"]}
-            except Exception:
-                ncu_k = {}
+        alg, b_orb, b_line, spx, sumpx = algorithmic_bytes(cfg)
+        ms_step = r["ms_dev"] / r["steps"]
+        t_conc, prof, busy_any = r["prof"] if r["prof"] else (None, {}, None)
         roof = None
-        if top[0]:
-            name, (ms_k, n_k_l) = top
-            achieved = kernel_roof(name, ms_k, n_k_l)
-            roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches_per_step": n_k_l, "ms_per_step": ms_k,
-                    "share_of_kernel_time": ms_k / step_kernel_ms if step_kernel_ms else None,
-                    "algorithmic_bytes_per_frame": alg.get(name, 0),
-                    "note": "k_lsd_grow_warp is the ordered (as-if-sequential) LSD region growing: a dependent chain per connected component, "
-                            "latency-bound by construction, so its HBM fraction is tiny; it runs on high-priority streams and is overlapped by "
-                            "the bandwidth kernels listed in `kernels` (their times are measured one stream at a time)",
-                    "kernels_ncu_source": "profiles/r1_kernels_ncu.json (traffic_bytes_per_frame, sm_pct, dram_pct)" if ncu_k else None,
-                    "kernels": [dict({"kernel": k, "ms_per_step": round(v[0], 4), "launches_per_step": v[1], "algorithmic_bytes_per_frame": alg.get(k),
-                                      "achieved_gbs": round(kernel_roof(k, v[0], v[1]), 1) if alg.get(k) else None,
-                                      "frac": round(kernel_roof(k, v[0], v[1]) / peak, 4) if alg.get(k) else None}, **ncu_k.get(k, {}))
-                                for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])]}
+        if prof:
+            # the dominant kernel = the one whose launches cover the largest part of the step while everything runs together
+            name_k, pk = max(prof.items(), key=lambda kv: kv[1]["busy_ms"])
+            nl_ = max(pk["launches"], 1)
+            ach = alg.get(name_k, 0) * B / nl_ / (pk["sum_ms"] / nl_ / 1e3) / 1e9 if pk["sum_ms"] > 0 else 0.0
+            traffic, traffic_src = None, None
+            tp = os.path.join(ROOT, "profiles", "r2_dominant_kernel_ncu.json")
+            if os.path.exists(tp):
+                try:
+                    tj = json.load(open(tp))
+                    if tj.get("kernel") == name_k:
+                        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("note")
+                except Exception:
+                    pass
+            roof = {"bound": "hbm", "kernel": name_k, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "traffic_source": traffic_src, "peak_source": peak_src, "launches_per_step": pk["launches"],
+                    "avg_launch_ms": pk["sum_ms"] / nl_, "busy_ms_per_step": pk["busy_ms"], "share_of_step": pk["busy_ms"] / t_conc,
+                    "algorithmic_bytes_per_frame": alg.get(name_k, 0),
+                    "how": "CUDA-event brackets around every launch while all streams run together (the timed configuration, %.1f ms/step "
+                           "with the brackets on); busy = union of the kernel's launch intervals, so no kernel exceeds the step" % t_conc,
+                    "whole_step": {"algorithmic_bytes_per_frame": b_orb + b_line, "orb_bytes_per_frame": b_orb, "line_bytes_per_frame": b_line,
+                                   "achieved_gbs": (b_orb + b_line) * B / (ms_step / 1e3) / 1e9, "frac": (b_orb + b_line) * B / (ms_step / 1e3) / 1e9 / peak,
+                                   "orb_only_gbs": b_orb * B * r["steps"] / (r["ms_orb"] / 1e3) / 1e9,
+                                   "orb_only_frac": b_orb * B * r["steps"] / (r["ms_orb"] / 1e3) / 1e9 / peak,
+                                   "note": "SURVEY.md 8d byte counts (B_orb + per-octave line figures) x frames / device step time"},
+                    "busy_any_kernel_ms_per_step": busy_any,
+                    "kernels": [{"kernel": k, "busy_ms_per_step": round(v["busy_ms"], 4), "sum_ms_per_step": round(v["sum_ms"], 4),
+                                 "launches_per_step": v["launches"], "algorithmic_bytes_per_frame": alg.get(k),
+                                 "achieved_gbs": round(alg[k] * B / (v["sum_ms"] / 1e3) / 1e9, 1) if alg.get(k) and v["sum_ms"] > 0 else None,
+                                 "frac": round(alg[k] * B / (v["sum_ms"] / 1e3) / 1e9 / peak, 4) if alg.get(k) and v["sum_ms"] > 0 else None}
+                                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["busy_ms"])]}
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            sample = frames[:min(len(frames), 512)]
-            fps, dt = cpu_oracle_throughput(sample, cores)
-            cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                   "sample": "%d of the step's frames, one frame per thread on %d threads, %.1f s (C oracle of the reference algorithm)" % (len(sample), cores, dt)}
-        line = {"metric": "frames/s ORB+LSD/LBD extraction", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            per_frame_s = 1.1e-6 * cfg["W"] * cfg["H"] * 0.25
+            ns = max(cores, min(len(r["sample"]), int(15.0 * cores / per_frame_s)))
+            sample = r["sample"][:ns]
+            fps, dt, kind = cpu_reference_throughput(cfg, sample, cores)
+            cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+                   "sample": "%d of the step's frames, one frame per thread on %d threads, %.1f s (%s)" %
+                             (len(sample), cores, dt, "oracle/_ref: the reference's own sources compiled unmodified" if kind == "reference" else "C oracle")}
+            if others.get("c5"):
+                rng = np.random.default_rng(1234)
+                q = rng.integers(0, 256, (10000, 32), dtype=np.uint8); t = rng.integers(0, 256, (100000, 32), dtype=np.uint8)
+                t1 = cpu_knn2(q[:2000], t, 1); tn = cpu_knn2(q, t, cores)
+                others["c5"]["cpu_baseline"] = {"kind": "reference", "what": "cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2) (src/Linematcher.cc:526-527)",
+                                                "pairs_per_s_1_thread": 2000 * 100000 / t1, "pairs_per_s_all_threads": 10000 * 100000 / tn, "cores": cores,
+                                                "sample": "1e4 (2e3 for one thread) queries x 1e5 train rows"}
+        line = {"metric": "frames/s ORB+LSD/LBD extraction", "value": value, "unit": "frames/s", "n_gpus": world, "steps": r["steps"],
+                "warmup": r["warm"], "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "orb_contexts": NO, "line_contexts": NL, "frames_per_line_call": SUB, "frame": "one 752x480 image; a stereo pair is 2 frames",
-                           "sharding": "frame i -> rank i mod N (left/right of a pair on separate GPUs for N > 1), no collective",
-                           "l2": "inputs larger than L2: per-step working set ~%.1f GB vs 126 MB (256 MiB flush before the timed region); the K steps run back to back, no barrier between steps" % (B * (45 * spx + 3 * sumpx) / 1e9)},
-                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "outputs": {"mean_keypoints": float(nk.mean()), "mean_lines": float(nl.mean())},
-                "matching": {"metric": "Hamming matches/s", "value": NQ / (ms_match / 1e3), "unit": "queries/s at 1e6 train rows",
-                             "pairs_per_s": NQ * NT / (ms_match / 1e3), "ms": ms_match,
-                             "config": "1e4 queries x 1e6 train, 256-bit, top-2 + ratio 0.75, train rows sharded over %d GPU(s)%s" %
-                                       (world, " + NCCL all-gather + merge" if world > 1 else ""),
-                             "roofline": {"bound": "popc", "achieved": 8 * NQ * NT / (ms_match / 1e3) / world, "peak": popc_peak,
-                                          "unit": "popc32/s per GPU", "frac": 8 * NQ * NT / (ms_match / 1e3) / world / popc_peak,
-                                          "peak_source": "plf_popc_peak micro-benchmark on this GPU"}}}
-        sys.stdout.flush()
-        os.dup2(saved_stdout, 1)
-        print(json.dumps(line), flush=True)
-        os.dup2(2, 1)
+                "config": config_dict(name, cfg, B, world),
+                "run": {"orb_contexts": r["NO"], "line_contexts": r["NL"], "frames_per_line_call": r["SUB"], "frames_per_orb_call": r["OSUB"],
+                        "distinct_frame_sets": NSETS,
+                        "l2": "inputs larger than L2: %d distinct frames (%.1f GB) per GPU, step k works on set k %% %d; 256 MiB flush before the timed "
+                              "region; the K steps run back to back, no barrier between steps" % (NSETS * B, NSETS * B * cfg["W"] * cfg["H"] / 1e9, NSETS)},
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                        "ms_per_step": r["ms_e2e"] / r["steps"]},
+                "orb_only": {"value": total_frames / (r["ms_orb"] / 1e3), "unit": "frames/s", "ms_per_step": r["ms_orb"] / r["steps"]},
+                "lines_only": {"value": total_frames / (r["ms_line"] / 1e3), "unit": "frames/s", "ms_per_step": r["ms_line"] / r["steps"]} if r["ms_line"] else None,
+                "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": roof, "cpu_baseline": cpu,
+                "outputs": {"mean_keypoints": r["nk"], "mean_lines": r["nl"], "checksum_rank0": r["checksum"]},
+                "other_configs": others or None, "bench_wall_s": round(time.time() - t_start, 1)}
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -73,6 +73,31 @@ static inline plf_status plf_fail(plf_ctx* ctx, plf_status st, const char* fmt, 
                             __FILE__, __LINE__);                                                        \
     } while (0)
 
+#ifndef PLF_EMU
+// Opt a kernel in to the device's MAXIMUM dynamic shared memory, once per (kernel, device).  The attribute is per-function
+// state shared by every extractor and host thread of the process: setting it to one caller's requirement would LOWER it
+// for another (two ORB extractors with different nfeatures), so it is only ever set to the maximum.
+#include <mutex>
+#include <map>
+static inline cudaError_t plf_smem_optin(const void* kernel, int device)
+{
+    static std::mutex mu;
+    static std::map<const void*, unsigned long long> done;   // kernel -> bit per device
+    std::lock_guard<std::mutex> lk(mu);
+    const unsigned long long bit = 1ull << (device & 63);
+    if (done[kernel] & bit) return cudaSuccess;
+    int mx = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&mx, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e == cudaSuccess) done[kernel] |= bit;
+    return e;
+}
+#define PLF_SMEM_OPTIN(ctx, kernel) PLF_CUDA(ctx, plf_smem_optin((const void*)(kernel), (ctx)->device))
+#else
+#define PLF_SMEM_OPTIN(ctx, kernel) do { } while (0)
+#endif
+
 #define PLF_CHECK_LAUNCH(ctx)                                                                     \
     do {                                                                                          \
         (ctx)->launches++;                                                                        \

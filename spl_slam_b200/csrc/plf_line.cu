@@ -532,9 +532,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             if (wg_maxc > WARPGROW_MAXC) wg_maxc = WARPGROW_MAXC;
             if (wg_maxc < 1024) wg_maxc = 1024;
             const int wg_smem = WG_WARPS * (wg_maxc / 8);
-#ifndef PLF_EMU
-            PLF_CUDA(ctx, cudaFuncSetAttribute(k_lsd_grow_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_WARPS * (WARPGROW_MAXC / 8)));
-#endif
+            PLF_SMEM_OPTIN(ctx, k_lsd_grow_warp);
             const int wg_ctas = plf_div_up(nbig, WG_WARPS) < 148 * 4 ? plf_div_up(nbig, WG_WARPS) : 148 * 4;
             if (nbig > 0) PLF_LAUNCH(k_lsd_grow_warp, dim3(wg_ctas), dim3(32 * WG_WARPS), wg_smem, st, (const unsigned long long*)o->d_keys2[k],
                        (const int2*)o->d_comp[k], (const int*)(o->d_cnt[k] + CNT_BCOUNT), (const float*)o->d_fa[k], (const float2*)o->d_cs[k],

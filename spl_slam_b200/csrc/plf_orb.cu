@@ -189,9 +189,7 @@ static plf_status orb_prepare(plf_orb* o, int w, int h, int nframes)
     o->oct_cap = maxnode;
     o->oct_smem = oct_smem_bytes(maxnode);
     if (o->oct_smem > 200 * 1024) return plf_fail(ctx, PLF_ERR_INVALID, "nfeatures too large for the octree kernel");
-#ifndef PLF_EMU
-    PLF_CUDA(ctx, cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->oct_smem));
-#endif
+    PLF_SMEM_OPTIN(ctx, k_octree);
     // device buffers
     PLF_CUDA(ctx, cudaMalloc((void**)&o->d_levels, lvlBytes * nframes));
     size_t listBytes = (size_t)nframes * (g.rawPerFrame * (sizeof(unsigned) + sizeof(unsigned short)) +
@@ -253,9 +251,7 @@ static plf_status orb_run(plf_orb* o, const uint8_t* lvl0, size_t stride0, size_
     const int ftp = (fw + 3 + 3) & ~3;
     const int flcap = ((fw - 6) * (fh - 6) + 1) & ~1;   // work-list entries: one per interior pixel
     const size_t fsmem = (size_t)FAST_WARPS * (2 * ftp * fh + 2 * flcap);
-#ifndef PLF_EMU
-    if (fsmem > 48 * 1024) PLF_CUDA(ctx, cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-#endif
+    PLF_SMEM_OPTIN(ctx, k_fast_cells);
     PLF_LAUNCH(k_fast_cells, dim3(plf_div_up(g.totalCells, FAST_WARPS), nframes), dim3(32 * FAST_WARPS), fsmem, st, g, P, ftp, fh, flcap);
     PLF_CHECK_LAUNCH(ctx);
     PLF_LAUNCH(k_blur7, dim3(plf_div_up(g.totalBlurTiles, BLUR_WARPS), nframes), dim3(32 * BLUR_WARPS), 0, st, g, P);
@@ -441,9 +437,7 @@ extern "C" plf_status plf_orb_distribute_octree(plf_ctx* ctx, const int32_t* xs,
     int nodecap = orb_nodecap(N);
     size_t smem = oct_smem_bytes(nodecap);
     if (smem > 200 * 1024) return plf_fail(ctx, PLF_ERR_INVALID, "N too large");
-#ifndef PLF_EMU
-    PLF_CUDA(ctx, cudaFuncSetAttribute(k_octree_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-#endif
+    PLF_SMEM_OPTIN(ctx, k_octree_single);
     size_t bytes = (size_t)n * 4 + (size_t)n * 2 + 16 + (size_t)nodecap * 4 + 16;
     void* s;
     plf_status st = plf_ctx_scratch(ctx, bytes + 64, &s);
@@ -525,9 +519,7 @@ extern "C" plf_status plf_stereo_match_batch_device(plf_orb* left, plf_orb* righ
         right_first >= right->last_frames || lastR >= right->last_frames)
         return plf_fail(ctx, PLF_ERR_INVALID, "stereo pair frames outside the extractors' last batch");
     PLF_CUDA(ctx, cudaSetDevice(ctx->device));
-#ifndef PLF_EMU
-    PLF_CUDA(ctx, cudaFuncSetAttribute(k_stereo_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)cap * sizeof(int))));
-#endif
+    PLF_SMEM_OPTIN(ctx, k_stereo_filter);
     void* s;
     st = plf_ctx_scratch(ctx, (size_t)npairs * cap * sizeof(int), &s);
     if (st) return st;
@@ -553,9 +545,7 @@ extern "C" plf_status plf_stereo_match(plf_orb* left, int frame_l, plf_orb* righ
     if (frame_l < 0 || frame_l >= left->last_frames || frame_r < 0 || frame_r >= right->last_frames)
         return plf_fail(ctx, PLF_ERR_INVALID, "stereo frames outside the extractors' last batch");
     PLF_CUDA(ctx, cudaSetDevice(ctx->device));
-#ifndef PLF_EMU
-    PLF_CUDA(ctx, cudaFuncSetAttribute(k_stereo_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)cap * sizeof(int))));
-#endif
+    PLF_SMEM_OPTIN(ctx, k_stereo_filter);
     // scratch layout: kps L, kps R, desc L, desc R, n[2], uright, depth, sad
     const size_t kb = plf_align_up((size_t)cap * sizeof(plf_keypoint), 256), db = plf_align_up((size_t)cap * 32, 256), fb = plf_align_up((size_t)cap * 4, 256);
     void* s;

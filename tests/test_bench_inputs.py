@@ -1,4 +1,4 @@
-"""bench.py generates its synthetic inputs with numpy only (nothing under oracle/ may run outside the cpu_baseline /
+"""bench.py generates its synthetic inputs with numpy / scipy only (nothing under oracle/ may run outside the cpu_baseline /
 reference legs); the generator must produce exactly the images the parity tests use."""
 import numpy as np
 
@@ -14,7 +14,7 @@ def test_bench_generator_equals_oracle_generator(oracle):
 def test_bench_has_no_oracle_import_outside_baseline_legs():
     import os, re
     src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
-    # the only places that touch oracle/: cpu_oracle_throughput (cpu_baseline / --impl reference)
+    # the only place that touches oracle/: cpu_reference_throughput (the cpu_baseline / --impl reference legs)
     uses = [m.start() for m in re.finditer(r"from oracle import", src)]
-    body = src[src.index("def cpu_oracle_throughput"):src.index("def run_reference")]
+    body = src[src.index("def cpu_reference_throughput"):src.index("def cpu_knn2")]
     assert len(uses) == 1 and "from oracle import" in body
