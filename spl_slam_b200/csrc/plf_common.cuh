@@ -89,7 +89,10 @@ static inline cudaError_t plf_smem_optin(const void* kernel, int device)
     int mx = 0;
     cudaError_t e = cudaDeviceGetAttribute(&mx, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx - (int)fa.sharedSizeBytes);   // dynamic + static <= opt-in maximum
     if (e == cudaSuccess) done[kernel] |= bit;
     return e;
 }

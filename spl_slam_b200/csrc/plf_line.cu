@@ -64,6 +64,10 @@ struct plf_line {
     size_t maskwords[LINE_MAX_OCT];
     int regcap;
     cudaStream_t st2;                      // stream of octave 1 (octave 0 uses the context stream)
+    unsigned char* d_likely[LINE_MAX_OCT];  // per sorted seed: may start a region (k_lsd_likely)
+    int2* d_gcscr[LINE_MAX_OCT];            // scratch of k_lsd_grow_cta (speculative regions)
+    int gc_grid;                            // speculator warps the scratch is sized for
+    unsigned long long* d_gcdbg;            // PLF_GC_DEBUG=1: counters of k_lsd_grow_cta (diagnosis only)
     cudaEvent_t ev_img, ev_join;
     int* h_pin;                            // pinned host staging for the per-octave counters (64 ints each)
     int *d_detcount;
@@ -272,6 +276,7 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         PLF_CUDA(ctx, cudaEventCreate(&o->ev_join));
         PLF_CUDA(ctx, cudaMallocHost((void**)&o->h_pin, LINE_MAX_OCT * 64 * sizeof(int)));
     }
+    o->gc_grid = (int)((8 * F + 8) * (GC_MAXWARPS - 1) < 148 * 24 ? (8 * F + 8) * (GC_MAXWARPS - 1) : 148 * 24);   // most SPECULATOR WARPS of one k_lsd_grow_cta launch (its scratch is sized for them)
     size_t bytes = 0;
     auto need = [&](size_t count, size_t elt) { bytes += plf_align_up(count * elt, 256); };
     for (int k = 0; k < noct; k++) {
@@ -286,6 +291,7 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         need(o->regcap, 8);
         need(CNT_MAXQ + 2 * F, 4);
         need(o->maskwords[k], 4); need(o->maskwords[k] + 64, 4); need(F, 8);   // mask, offsets, bin coefficients
+        need(o->keycap[k], 1); need((size_t)o->gc_grid * GC_BUF * GC_RMAX, sizeof(int2));   // likely flags, speculation scratch
     }
     need(F * noct * LINE_DETCAP, sizeof(plf_keyline));
     need(F * noct, 4);
@@ -315,6 +321,8 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         o->d_mask[k] = carve<unsigned>(p, o->maskwords[k]);
         o->d_offs[k] = carve<int>(p, o->maskwords[k] + 64);
         o->d_bincoef[k] = carve<double>(p, F);
+        o->d_likely[k] = carve<unsigned char>(p, o->keycap[k]);
+        o->d_gcscr[k] = carve<int2>(p, (size_t)o->gc_grid * GC_BUF * GC_RMAX);
     }
     o->d_det = carve<plf_keyline>(p, F * noct * LINE_DETCAP);
     o->d_detcount = carve<int>(p, F * noct);
@@ -511,6 +519,10 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         PLF_LAUNCH(k_lsd_cid, dim3(plf_div_up(nkeys[k], 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2[k], nkeys[k], o->d_label[k],
                    (const float*)o->d_fa[k], o->d_cs[k], (size_t)o->sp[k] * o->sh[k], o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
+        // which seeds are worth growing ahead of their turn (k_lsd_grow_cta)
+        PLF_LAUNCH(k_lsd_likely, dim3(plf_div_up(nkeys[k], 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2[k], nkeys[k], (const int*)o->d_label[k],
+                   (const float*)o->d_fa[k], o->sp[k], o->sh[k], o->prec, o->d_likely[k], o->kbits[k]);
+        PLF_CHECK_LAUNCH(ctx);
         PLF_CUDA(ctx, cudaMemcpyAsync(o->h_pin + 64 * k + 8, o->d_cnt[k] + CNT_BCOUNT, LSD_NBUCKET * sizeof(int), cudaMemcpyDeviceToHost, st));
         PLF_CUDA(ctx, cudaMemcpyAsync(o->h_pin + 64 * k + 1, o->d_cnt[k] + CNT_NCOMP, sizeof(int), cudaMemcpyDeviceToHost, st));   // largest component
     }
@@ -532,11 +544,53 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             if (wg_maxc > WARPGROW_MAXC) wg_maxc = WARPGROW_MAXC;
             if (wg_maxc < 1024) wg_maxc = 1024;
             const int wg_smem = WG_WARPS * (wg_maxc / 8);
+            // giant components: one CTA each, in-order commit with speculative growth ahead of it (plf_lsd_grow_cta.cuh)
+            // Which components get a CTA (speculators + committer), and how many speculators each: few components in the launch
+            // -> everything from 1024 seeds up with as many speculators as the bitmaps allow (latency); many -> only the largest
+            // size classes and fewer speculators, so that every CTA is resident at once and other kernels still find shared
+            // memory (throughput).  The rest goes to k_lsd_grow_warp.
+            const int bm = wg_maxc / 8;
+            // CTAs of g warps that fit at once: by shared memory (160 KB per SM, the rest stays for other kernels), by warps (24 per SM)
+            // and by the speculation scratch
+            auto resident = [&](int g) {
+                int per_sm = (int)((160 * 1024) / ((size_t)g * bm + sizeof(GcShared)));
+                if (per_sm > 24 / g) per_sm = 24 / g;
+                const int by_scratch = o->gc_grid / (g - 1);
+                return 148 * per_sm < by_scratch ? 148 * per_sm : by_scratch;
+            };
+            int gthr = LSD_GIANT_BUCKET, ngiant = 0;
+            for (;; gthr += 2) {
+                ngiant = 0;
+                for (int b = gthr; b < LSD_NBUCKET; b++) ngiant += bc[b];
+                if (ngiant <= resident(4) || gthr + 2 >= LSD_NBUCKET) break;
+            }
+            // Speculation buys latency with extra work and shared memory.  A launch with hundreds of giant components has enough
+            // independent chains to fill the GPU with one warp per component (measured: 752x480 x 512 frames per call is 40 % faster
+            // without it, 1080p x 128 frames per call 15-25 % faster with it), so it is used only below that.
+            if (ngiant > resident(4) || ngiant > 300) { ngiant = 0; gthr = LSD_NBUCKET; }
+#ifndef PLF_EMU
+            if (!o->d_gcdbg && getenv("PLF_GC_DEBUG")) { PLF_CUDA(ctx, cudaMalloc((void**)&o->d_gcdbg, 16 * 8)); PLF_CUDA(ctx, cudaMemset(o->d_gcdbg, 0, 16 * 8)); }
+#endif
+            if (ngiant > 0) {
+                int gc_warps = GC_SMEM_BUDGET / bm;
+                if (gc_warps > GC_MAXWARPS) gc_warps = GC_MAXWARPS;
+                while (gc_warps > 2 && ngiant > resident(gc_warps)) gc_warps--;
+                if (getenv("PLF_GC_WARPS") && atoi(getenv("PLF_GC_WARPS")) < gc_warps) gc_warps = atoi(getenv("PLF_GC_WARPS"));   // diagnosis
+                if (gc_warps < 2) gc_warps = 2;
+                PLF_SMEM_OPTIN(ctx, k_lsd_grow_cta);
+                PLF_LAUNCH(k_lsd_grow_cta, dim3(ngiant), dim3(32 * gc_warps), (size_t)gc_warps * (wg_maxc / 8), st,
+                           (const unsigned long long*)o->d_keys2[k], (const int2*)o->d_comp[k], (const int*)(o->d_cnt[k] + CNT_BCOUNT),
+                           (const unsigned char*)o->d_likely[k], (const float*)o->d_fa[k], (const float2*)o->d_cs[k], (const int*)o->d_label[k], sp, sh,
+                           o->prec, o->min_reg[k], o->d_regpts[k], o->d_regions[k], o->d_cnt[k] + CNT_MAXQ + nframes, LINE_REGCAP_PER_FRAME, o->kbits[k],
+                           wg_maxc, o->d_gcscr[k], gthr, o->d_gcdbg);
+                PLF_CHECK_LAUNCH(ctx);
+            }
             PLF_SMEM_OPTIN(ctx, k_lsd_grow_warp);
-            const int wg_ctas = plf_div_up(nbig, WG_WARPS) < 148 * 4 ? plf_div_up(nbig, WG_WARPS) : 148 * 4;
-            if (nbig > 0) PLF_LAUNCH(k_lsd_grow_warp, dim3(wg_ctas), dim3(32 * WG_WARPS), wg_smem, st, (const unsigned long long*)o->d_keys2[k],
+            const int nmid = nbig - ngiant;
+            const int wg_ctas = plf_div_up(nmid, WG_WARPS) < 148 * 4 ? plf_div_up(nmid, WG_WARPS) : 148 * 4;
+            if (nmid > 0) PLF_LAUNCH(k_lsd_grow_warp, dim3(wg_ctas), dim3(32 * WG_WARPS), wg_smem, st, (const unsigned long long*)o->d_keys2[k],
                        (const int2*)o->d_comp[k], (const int*)(o->d_cnt[k] + CNT_BCOUNT), (const float*)o->d_fa[k], (const float2*)o->d_cs[k],
-                       (const int*)o->d_label[k], sp, sh, o->prec, o->min_reg[k], o->d_regpts[k], o->d_regions[k], o->d_cnt[k] + CNT_MAXQ + nframes, LINE_REGCAP_PER_FRAME, o->kbits[k], wg_maxc);
+                       (const int*)o->d_label[k], sp, sh, o->prec, o->min_reg[k], o->d_regpts[k], o->d_regions[k], o->d_cnt[k] + CNT_MAXQ + nframes, LINE_REGCAP_PER_FRAME, o->kbits[k], wg_maxc, gthr);
             PLF_CHECK_LAUNCH(ctx);
             PLF_LAUNCH(k_lsd_grow, dim3(148 * 4), dim3(128), 0, st, (const unsigned long long*)o->d_keys2[k], nkeys[k], (const int2*)o->d_comp[k],
                        (const int*)(o->d_cnt[k] + CNT_BCOUNT), o->d_cnt[k] + CNT_NEXT, o->d_fa[k], (const float2*)o->d_cs[k], sp, sh, o->prec,
@@ -556,6 +610,16 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
                    o->prm.min_line_length, o->d_det, o->d_detcount, LINE_DETCAP);
         PLF_CHECK_LAUNCH(ctx);
     }
+#ifndef PLF_EMU
+    if (o->d_gcdbg) {
+        unsigned long long hd[16];
+        cudaDeviceSynchronize();
+        cudaMemcpy(hd, o->d_gcdbg, sizeof hd, cudaMemcpyDeviceToHost);
+        cudaMemset(o->d_gcdbg, 0, sizeof hd);
+        fprintf(stderr, "[gc] frames %d: spec-consumed %llu regions / %llu px, failed validations %llu, committer-grown %llu regions / %llu px, wait polls %llu, speculated %llu regions / %llu px, aborted %llu\n",
+                nframes, hd[0], hd[1], hd[2], hd[3], hd[4], hd[5], hd[6], hd[7], hd[8]);
+    }
+#endif
     // the selection / LBD that follow run on the context stream: join octave 1
     if (noct > 1 && stk[1] != st0) {
         PLF_CUDA(ctx, cudaEventRecord(o->ev_join, stk[1]));

@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(32 * WG_WARPS)
 k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restrict__ comp, const int* __restrict__ bcount,
                 const float* __restrict__ fa, const float2* __restrict__ cs, const int* __restrict__ cid, int w, int h,
                 double prec, int min_reg_size, int* __restrict__ regpts, LsdRegion* __restrict__ regions,
-                int* __restrict__ nregions, int regcap, int kb, int maxc)
+                int* __restrict__ nregions, int regcap, int kb, int maxc, int giant_bucket)
 {
     PLF_DYN_SMEM(smem);
     __shared__ int s_ring[WG_WARPS][WG_RING];
@@ -731,7 +731,9 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
     const int gdx = (nbr % 3) - 1, gdy = (nbr / 3) - 1;
     const bool fast_ok = prec < 1.4;
     const float sphi = (float)sin(prec + 0.1) * 1.05f;   // 1.05 covers the float rounding of this product and of rsqrtf below
-    for (int c = blockIdx.x * WG_WARPS + wid; c < nbig; c += gridDim.x * WG_WARPS) {
+    int ngiant = 0;      // the first components of the list (largest first) belong to k_lsd_grow_cta
+    for (int k = giant_bucket; k < LSD_NBUCKET; k++) ngiant += bcount[k];
+    for (int c = ngiant + blockIdx.x * WG_WARPS + wid; c < nbig; c += gridDim.x * WG_WARPS) {
         const int start = comp[c].x, C = comp[c].y, end = start + C;
         if (C > maxc) continue;   // handled by k_lsd_grow
         const size_t foff = (size_t)LSD_KEY_FRAME(keys[start]) * px;
@@ -872,6 +874,8 @@ k_lsd_grow_warp(const unsigned long long* __restrict__ keys, const int2* __restr
         }
     }
 }
+
+#include "plf_lsd_grow_cta.cuh"
 
 // region2rect + get_theta (OpenCV lsd.cpp, refine = 0): one WARP per region.  The double sums are order dependent,
 // so they are accumulated strictly in region order -- but the per-point work (gather, double sqrt, products) is done

@@ -18,7 +18,7 @@ def build_emu(force=False):
         return LIB
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    flags = ["-std=c++17", "-O2", "-g", "-fPIC", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-DPLF_EMU", "-DLSD_BIG_BUCKET=5",   # tiny threshold: the emulated tests stress the speculative LSD path
+    flags = ["-std=c++17", "-O2", "-g", "-fPIC", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-DPLF_EMU", "-DLSD_BIG_BUCKET=5", "-DLSD_GIANT_BUCKET=7", "-DGC_MAXWARPS=4",   # tiny threshold: the emulated tests stress the speculative LSD path
              
              "-Wno-unknown-pragmas", "-Wno-unused-function", "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     procs, objs = [], []
