@@ -519,10 +519,6 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         PLF_LAUNCH(k_lsd_cid, dim3(plf_div_up(nkeys[k], 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2[k], nkeys[k], o->d_label[k],
                    (const float*)o->d_fa[k], o->d_cs[k], (size_t)o->sp[k] * o->sh[k], o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
-        // which seeds are worth growing ahead of their turn (k_lsd_grow_cta)
-        PLF_LAUNCH(k_lsd_likely, dim3(plf_div_up(nkeys[k], 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2[k], nkeys[k], (const int*)o->d_label[k],
-                   (const float*)o->d_fa[k], o->sp[k], o->sh[k], o->prec, o->d_likely[k], o->kbits[k]);
-        PLF_CHECK_LAUNCH(ctx);
         PLF_CUDA(ctx, cudaMemcpyAsync(o->h_pin + 64 * k + 8, o->d_cnt[k] + CNT_BCOUNT, LSD_NBUCKET * sizeof(int), cudaMemcpyDeviceToHost, st));
         PLF_CUDA(ctx, cudaMemcpyAsync(o->h_pin + 64 * k + 1, o->d_cnt[k] + CNT_NCOMP, sizeof(int), cudaMemcpyDeviceToHost, st));   // largest component
     }
@@ -564,10 +560,15 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
                 for (int b = gthr; b < LSD_NBUCKET; b++) ngiant += bc[b];
                 if (ngiant <= resident(4) || gthr + 2 >= LSD_NBUCKET) break;
             }
-            // Speculation buys latency with extra work and shared memory.  A launch with hundreds of giant components has enough
-            // independent chains to fill the GPU with one warp per component (measured: 752x480 x 512 frames per call is 40 % faster
-            // without it, 1080p x 128 frames per call 15-25 % faster with it), so it is used only below that.
-            if (ngiant > resident(4) || ngiant > 300) { ngiant = 0; gthr = LSD_NBUCKET; }
+            // Speculation buys latency with extra work and shared memory, so it is used where the longest chain of the launch
+            // (largest component x ~0.37 us per pixel with one warp) outweighs the launch's bandwidth-bound work (~34 ns per 1000
+            // scaled pixels per frame, from the round-2 profiles): a single frame always qualifies, 1080p x 128 frames per call does
+            // (ratio 4.3, measured 15-25 % faster with it), 752x480 x 512 frames per call does not (ratio 1.4-2.7, measured 20 % slower with it).
+            {
+                const double chain_us = 0.37 * (double)o->h_pin[64 * k + 1];
+                const double parallel_us = 3.4e-5 * (double)nframes * (double)sp * (double)sh;
+                if (ngiant > resident(4) || chain_us < 4.0 * parallel_us || getenv("PLF_GC_OFF")) { ngiant = 0; gthr = LSD_NBUCKET; }
+            }
 #ifndef PLF_EMU
             if (!o->d_gcdbg && getenv("PLF_GC_DEBUG")) { PLF_CUDA(ctx, cudaMalloc((void**)&o->d_gcdbg, 16 * 8)); PLF_CUDA(ctx, cudaMemset(o->d_gcdbg, 0, 16 * 8)); }
 #endif
@@ -577,6 +578,10 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
                 while (gc_warps > 2 && ngiant > resident(gc_warps)) gc_warps--;
                 if (getenv("PLF_GC_WARPS") && atoi(getenv("PLF_GC_WARPS")) < gc_warps) gc_warps = atoi(getenv("PLF_GC_WARPS"));   // diagnosis
                 if (gc_warps < 2) gc_warps = 2;
+                // which seeds are worth growing ahead of their turn
+                PLF_LAUNCH(k_lsd_likely, dim3(plf_div_up(nkeys[k], 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2[k], nkeys[k], (const int*)o->d_label[k],
+                           (const float*)o->d_fa[k], o->sp[k], o->sh[k], o->prec, o->d_likely[k], o->kbits[k]);
+                PLF_CHECK_LAUNCH(ctx);
                 PLF_SMEM_OPTIN(ctx, k_lsd_grow_cta);
                 PLF_LAUNCH(k_lsd_grow_cta, dim3(ngiant), dim3(32 * gc_warps), (size_t)gc_warps * (wg_maxc / 8), st,
                            (const unsigned long long*)o->d_keys2[k], (const int2*)o->d_comp[k], (const int*)(o->d_cnt[k] + CNT_BCOUNT),
