@@ -645,41 +645,59 @@ def measure_matching(S, torch, dist, args, rank, world, dev, barrier, maxr, size
     from spl_slam_b200 import sharded
     NQ = 10000
     ctx_m = S.Context(dev)
+    comm = sharded.Comm(ctx_m)          # C-ABI communicator (plf_comm_*): NCCL all-gather + merge queued by libplf.so
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     gq = torch.Generator(device="cuda"); gq.manual_seed(1234)
     dq = torch.randint(0, 256, (NQ, 32), dtype=torch.uint8, device="cuda", generator=gq)
     out = []
     popc_peak = ctx_m.popc_peak()
-    for NT in sizes:
-        # the SAME global train set on every world size: generated in fixed chunks of 1e5 rows seeded by the chunk number
-        tb, te = sharded.train_shard(NT, rank, world)
-        CH = 100000
+    CH = 100000
+
+    def train_rows(lo, hi):
+        """Rows [lo, hi) of the global train set: fixed chunks of 1e5 rows seeded by the chunk number, so every world size
+        (and the unsharded check) sees the SAME set."""
         parts = []
-        for c in range(tb // CH, (te + CH - 1) // CH):
+        for c in range(lo // CH, (hi + CH - 1) // CH):
             g = torch.Generator(device="cuda"); g.manual_seed(4321 + c)
             blk = torch.randint(0, 256, (CH, 32), dtype=torch.uint8, device="cuda", generator=g)
-            lo, hi = max(tb, c * CH), min(te, (c + 1) * CH)
-            parts.append(blk[lo - c * CH:hi - c * CH])
-        dt = torch.cat(parts) if parts else torch.empty((0, 32), dtype=torch.uint8, device="cuda")
+            parts.append(blk[max(lo, c * CH) - c * CH:min(hi, (c + 1) * CH) - c * CH])
+        return torch.cat(parts) if parts else torch.empty((0, 32), dtype=torch.uint8, device="cuda")
+
+    for NT in sizes:
+        tb, te = sharded.train_shard(NT, rank, world)
+        dt = train_rows(tb, te)
         for _ in range(2):
-            idx, dst = sharded.knn2_sharded(ctx_m, dq, dt, tb)
+            idx, dst, m12, nm = comm.match_nnr(dq, dt, tb, 0.75)
+        ctx_m.synchronize()
         barrier()
         reps = []
         for _ in range(5 if NT >= 10 ** 7 else 7):
             flush.zero_(); torch.cuda.synchronize()
             ctx_m.timer_start()
-            idx, dst = sharded.knn2_sharded(ctx_m, dq, dt, tb)       # local top-2 + NCCL all-gather + merge (world > 1)
-            m12, nm = sharded.nnr_from_knn2(ctx_m, idx, dst, 0.75)
+            idx, dst, m12, nm = comm.match_nnr(dq, dt, tb, 0.75)       # local top-2 + ncclAllGather + merge + ratio test, one stream
             reps.append(ctx_m.timer_stop())
         barrier()
         ms = maxr(float(np.median(reps)))
+        verified = None
+        if world > 1 and NT <= 10 ** 6:
+            # the NCCL-merged table must equal the unsharded one: every rank searches the whole train set itself and compares
+            full = train_rows(0, NT)
+            ui = torch.empty((NQ, 2), dtype=torch.int32, device="cuda"); ud = torch.empty((NQ, 2), dtype=torch.int32, device="cuda")
+            ctx_m.check(ctx_m.lib.plf_hamming_knn2_device(ctx_m.h, dq.data_ptr(), NQ, full.data_ptr(), NT, 0, ui.data_ptr(), ud.data_ptr()))
+            ctx_m.synchronize()
+            assert torch.equal(ui, idx) and torch.equal(ud, dst), "sharded top-2 differs from the unsharded table at %d rows" % NT
+            verified = "equal to the unsharded table on every rank"
+            del full
         # checksum of the merged top-2 + matches: equal for every world size (same global train set), reported per N
         wq = (torch.arange(NQ, device="cuda", dtype=torch.int64) % 65521 + 1)
         csum = int(((idx.to(torch.int64) * 3 + dst.to(torch.int64)).sum(1) * wq).sum().item() + (m12.to(torch.int64) * wq).sum().item()) & 0xFFFFFFFFFFFF
-        ent = {"train_rows": NT, "ms": ms, "queries_per_s": NQ / (ms / 1e3), "pairs_per_s": NQ * NT / (ms / 1e3), "matches": nm, "checksum": csum,
+        ent = {"train_rows": NT, "ms": ms, "queries_per_s": NQ / (ms / 1e3), "pairs_per_s": NQ * NT / (ms / 1e3), "matches": int(nm.item()), "checksum": csum,
                "popc_frac": 8 * NQ * NT / (ms / 1e3) / world / popc_peak}
+        if verified:
+            ent["verified"] = verified
         out.append(ent)
-        del dt, parts
+        del dt
+    comm.close()
     ctx_m.close()
     return out, popc_peak
 

@@ -54,6 +54,7 @@ typedef struct plf_ctx plf_ctx;
 typedef struct plf_orb plf_orb;
 typedef struct plf_line plf_line;
 typedef struct plf_vocab plf_vocab;
+typedef struct plf_comm plf_comm;
 
 /* ---- context: one per host thread / GPU stream.  The reference calls its extractors and
  * matchNNR from concurrent std::threads (src/Frame.cc:116-119, :301-304;
@@ -201,6 +202,24 @@ plf_status plf_nnr_from_knn2_device(plf_ctx* ctx, const int32_t* dev_idx, const 
  * matches21[i2] == i1.  (The reference indexes matches_21[-1] when i2 == -1; defined here as "no match".) */
 plf_status plf_match_nnr_mutual(plf_ctx* ctx, const uint8_t* host_d1, int n1, const uint8_t* host_d2, int n2,
                                 float nnr, int32_t* host_matches12, int* nmatches);
+
+/* ---- multi-GPU matching (BASELINE config 5): one process per GPU, the TRAIN set row-sharded across the ranks
+ * (row j -> shard floor(j * world / nt)), queries replicated.  Replaces the same knnMatch / matchNNR calls as above when the
+ * train set is spread over the GPUs of a node.  A communicator wraps one NCCL communicator (bound at run time from
+ * libnccl.so.2): rank 0 calls plf_comm_unique_id and ships the 128 bytes to the other ranks by any means (MPI,
+ * torch.distributed, a file); every rank then calls plf_comm_create (collective).  plf_hamming_knn2_sharded_device =
+ * local top-2 with global indices + ONE ncclAllGather of 16 B per query per rank + merge by (distance, index), all queued
+ * on the context stream; the result (identical on every rank) equals the single-GPU table, ties included. */
+plf_status plf_comm_unique_id(uint8_t id[128]);
+plf_status plf_comm_create(plf_ctx* ctx, const uint8_t id[128], int rank, int world, plf_comm** out);
+void plf_comm_destroy(plf_comm* comm);
+int plf_comm_rank(const plf_comm* comm);
+int plf_comm_world(const plf_comm* comm);
+plf_status plf_hamming_knn2_sharded_device(plf_ctx* ctx, plf_comm* comm, const uint8_t* dev_q, int nq, const uint8_t* dev_t_local,
+                                           int64_t nt_local, int64_t train_index_base, int32_t* dev_idx, int32_t* dev_dist);
+plf_status plf_match_nnr_sharded_device(plf_ctx* ctx, plf_comm* comm, const uint8_t* dev_q, int nq, const uint8_t* dev_t_local,
+                                        int64_t nt_local, int64_t train_index_base, float nnr, int32_t* dev_idx, int32_t* dev_dist,
+                                        int32_t* dev_matches12, int32_t* dev_nmatches);
 
 /* Candidate-list matching: the data-parallel core of ORBmatcher::SearchForInitialization / SearchByProjection /
  * SearchByBoW and Linematcher::SearchForInitialization / SearchByProjection (src/ORBmatcher.cc:45-129, :406-521;

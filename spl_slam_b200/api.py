@@ -110,6 +110,13 @@ def load(path=None):
         "plf_hamming_knn2": (C.c_int, [vp, vp, C.c_int, vp, C.c_int64, i32p, i32p]),
         "plf_hamming_knn2_device": (C.c_int, [vp, vp, C.c_int, vp, C.c_int64, C.c_int64, vp, vp]),
         "plf_knn2_merge_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp]),
+        "plf_comm_unique_id": (C.c_int, [vp]),
+        "plf_comm_create": (C.c_int, [vp, vp, C.c_int, C.c_int, P(vp)]),
+        "plf_comm_destroy": (None, [vp]),
+        "plf_comm_rank": (C.c_int, [vp]),
+        "plf_comm_world": (C.c_int, [vp]),
+        "plf_hamming_knn2_sharded_device": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_int64, C.c_int64, vp, vp]),
+        "plf_match_nnr_sharded_device": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_int64, C.c_int64, C.c_float, vp, vp, vp, vp]),
         "plf_match_nnr": (C.c_int, [vp, vp, C.c_int, vp, C.c_int64, C.c_float, i32p, P(C.c_int)]),
         "plf_nnr_from_knn2_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_float, vp, vp]),
         "plf_popc_peak": (C.c_int, [vp, P(C.c_double)]),
