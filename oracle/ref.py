@@ -77,6 +77,9 @@ def lib(variant=""):
         L.ref_three_maxima.argtypes = [vp, C.c_int, vp]
         L.ref_set_heap_mode.argtypes = [C.c_int]
         L.ref_std_sort_desc.argtypes = [vp, C.c_int, vp]
+        L.ref_orb_search_for_initialization.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_int, vp]
+        L.ref_line_search_by_knn.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, C.c_float, vp]
+        L.ref_line_search_for_triangulation.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, vp]
         _LIBS[variant] = L
     return _LIBS[variant]
 
@@ -235,3 +238,40 @@ def std_sort_desc(keys, variant=""):
     p = np.zeros(max(len(k), 1), np.int32)
     lib(variant).ref_std_sort_desc(_p(k), len(k), _p(p))
     return p[:len(k)]
+
+
+def orb_search_for_initialization(k1, d1, k2, d2, bounds, prev, window, nnratio, check_ori, variant=""):
+    """The reference's ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:406-521) on mock Frames -> (nmatches, matches12, prev)."""
+    L = lib(variant)
+    k1 = np.ascontiguousarray(k1, KEYPOINT_DTYPE); k2 = np.ascontiguousarray(k2, KEYPOINT_DTYPE)
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    b = np.ascontiguousarray(bounds, np.float32); pv = np.ascontiguousarray(prev, np.float32).copy()
+    m = np.full(max(len(k1), 1), -1, np.int32)
+    n = _check(L.ref_orb_search_for_initialization(_p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2), _p(b), _p(pv), window, nnratio, int(check_ori), _p(m)), L) if True else 0
+    return n, m[:len(k1)], pv
+
+
+def line_search_by_knn(dkf, df, ml_state, ml_len, f_linelen, nnr, checklen, lengtherr, variant=""):
+    """The reference's Linematcher::SearchByKNN (src/Linematcher.cc:437-517) -> (return value, per frame line: key-frame line index or -1)."""
+    L = lib(variant)
+    dkf = np.ascontiguousarray(dkf, np.uint8); df = np.ascontiguousarray(df, np.uint8)
+    st = np.ascontiguousarray(ml_state, np.uint8); ln = np.ascontiguousarray(ml_len, np.float32); fl = np.ascontiguousarray(f_linelen, np.float32)
+    out = np.full(max(len(df), 1), -1, np.int32)
+    r = L.ref_line_search_by_knn(_p(dkf), len(dkf), _p(df), len(df), _p(st), _p(ln), _p(fl), nnr, int(checklen), lengtherr, _p(out))
+    if r == -1000:
+        raise RuntimeError("reference threw: %s" % L.ref_last_error().decode())
+    return r, out[:len(df)]
+
+
+def line_search_for_triangulation(d1, d2, has1, has2, mid1, mid2, scale, sigma2, cam, pose, F12, nnr, variant=""):
+    """The reference's Linematcher::SearchForTriangulation (src/Linematcher.cc:804-879) -> matched pairs (n x 2)."""
+    L = lib(variant)
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    h1 = np.ascontiguousarray(has1, np.uint8); h2 = np.ascontiguousarray(has2, np.uint8)
+    m1 = np.ascontiguousarray(mid1, KEYPOINT_DTYPE); m2 = np.ascontiguousarray(mid2, KEYPOINT_DTYPE)
+    sc = np.ascontiguousarray(scale, np.float32); sg = np.ascontiguousarray(sigma2, np.float32)
+    cm = np.ascontiguousarray(cam, np.float32); ps = np.ascontiguousarray(pose, np.float32); f = np.ascontiguousarray(F12, np.float32)
+    pairs = np.zeros((max(len(d1), 1), 2), np.int32)
+    n = _check(L.ref_line_search_for_triangulation(_p(d1), len(d1), _p(d2), len(d2), _p(h1), _p(h2), _p(m1), _p(m2), _p(sc), _p(sg), len(sc),
+                                                   _p(cm), _p(ps), _p(f), nnr, _p(pairs)), L)
+    return pairs[:n].copy()

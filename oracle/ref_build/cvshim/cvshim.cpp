@@ -118,6 +118,38 @@ double Mat::dot(const Mat& m) const
     return r;
 }
 
+/* core/src/matmul: for the small float matrices SPL-SLAM multiplies (3x3 by 3x1) OpenCV's gemm takes its unrolled path:
+ * every output element is the float sum a0*b0 + a1*b1 + a2*b2 taken left to right */
+Mat operator*(const Mat& a, const Mat& b)
+{
+    CV_Assert(a.type() == b.type() && (a.type() == CV_32FC1 || a.type() == CV_64FC1) && a.cols == b.rows);
+    Mat r(a.rows, b.cols, a.type());
+    for (int i = 0; i < a.rows; i++)
+        for (int j = 0; j < b.cols; j++) {
+            if (a.type() == CV_32FC1) {
+                float t = 0;
+                for (int k = 0; k < a.cols; k++) { float p = a.at<float>(i, k) * b.at<float>(k, j); t = k ? t + p : p; }
+                r.at<float>(i, j) = t;
+            } else {
+                double t = 0;
+                for (int k = 0; k < a.cols; k++) { double p = a.at<double>(i, k) * b.at<double>(k, j); t = k ? t + p : p; }
+                r.at<double>(i, j) = t;
+            }
+        }
+    return r;
+}
+Mat operator+(const Mat& a, const Mat& b)
+{
+    CV_Assert(a.type() == b.type() && (a.type() == CV_32FC1 || a.type() == CV_64FC1) && a.rows == b.rows && a.cols == b.cols);
+    Mat r(a.rows, a.cols, a.type());
+    for (int i = 0; i < a.rows; i++)
+        for (int j = 0; j < a.cols; j++) {
+            if (a.type() == CV_32FC1) r.at<float>(i, j) = a.at<float>(i, j) + b.at<float>(i, j);
+            else r.at<double>(i, j) = a.at<double>(i, j) + b.at<double>(i, j);
+        }
+    return r;
+}
+
 /* ------------------------------------------------------------------------------------------------ OutputArray */
 void _OutputArray::create(int r, int c, int t) const
 {

@@ -256,6 +256,7 @@ public:
 
     Mat operator()(const Rect& r) const { Mat m(*this); m.data = data + (size_t)r.y * step.p + (size_t)r.x * elemSize(); m.rows = r.height; m.cols = r.width; return m; }
     Mat rowRange(int a, int b) const { return (*this)(Rect(0, a, cols, b - a)); }
+    Mat row(int y) const { return rowRange(y, y + 1); }
     Mat colRange(int a, int b) const { return (*this)(Rect(a, 0, b - a, rows)); }
 
     bool empty() const { return data == 0 || rows == 0 || cols == 0; }
@@ -285,6 +286,9 @@ private:
     void unref() { if (refcount && --*refcount == 0) free(refcount); refcount = 0; }
     int* refcount = 0;
 };
+
+Mat operator*(const Mat& a, const Mat& b);   // CV_32F / CV_64F matrix product
+Mat operator+(const Mat& a, const Mat& b);
 
 template <typename T> class Mat_ : public Mat {
 public:

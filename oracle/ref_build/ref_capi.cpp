@@ -341,6 +341,94 @@ void ref_three_maxima(const int* sizes, int L, int* ind)
     ind[0] = a; ind[1] = b; ind[2] = c;
 }
 
+/* ---- the reference's matcher entry points on mock SLAM objects (tests/shim/mock_slam.hpp) ---- */
+static void fill_frame_points(PL_SLAM::Frame& F, const orc_keypoint* k, const uint8_t* d, int n, const float* bounds)
+{
+    F.mvKeysUn.resize(n);
+    if (n) memcpy(F.mvKeysUn.data(), k, n * sizeof(cv::KeyPoint));
+    F.mDescriptors = cv::Mat(n, 32, CV_8UC1, (void*)d);
+    F.SetBoundsAndAssign(bounds[0], bounds[1], bounds[2], bounds[3]);
+}
+/* ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:406-521); prev = n1 x 2 floats (in / out) */
+int ref_orb_search_for_initialization(const orc_keypoint* k1, const uint8_t* d1, int n1, const orc_keypoint* k2, const uint8_t* d2, int n2,
+                                      const float* bounds, float* prev, int window, float nnratio, int check_ori, int32_t* matches12)
+{
+    return guarded([&]() {
+        PL_SLAM::Frame F1, F2;
+        fill_frame_points(F1, k1, d1, n1, bounds);
+        fill_frame_points(F2, k2, d2, n2, bounds);
+        std::vector<cv::Point2f> pm(n1);
+        for (int i = 0; i < n1; i++) pm[i] = cv::Point2f(prev[2 * i], prev[2 * i + 1]);
+        std::vector<int> m;
+        PL_SLAM::ORBmatcher om(nnratio, check_ori != 0);
+        int n = om.SearchForInitialization(F1, F2, pm, m, window);
+        for (int i = 0; i < n1; i++) { matches12[i] = m[i]; prev[2 * i] = pm[i].x; prev[2 * i + 1] = pm[i].y; }
+        return n;
+    });
+}
+/* Linematcher::SearchByKNN (src/Linematcher.cc:437-517).  ml_state per key-frame line: 0 no MapLine, 1 good, 2 bad;
+ * out_ml[i2] = index of the key-frame line whose MapLine was assigned to frame line i2, or -1 */
+int ref_line_search_by_knn(const uint8_t* dkf, int nkf, const uint8_t* df, int nf, const uint8_t* ml_state, const float* ml_len,
+                           const float* f_linelen, float nnr, int checklen, float lengtherr, int32_t* out_ml)
+{
+    return guarded([&]() {
+        std::vector<PL_SLAM::MapLine> mls(nkf);
+        PL_SLAM::KeyFrame kf;
+        PL_SLAM::Frame F;
+        kf.mDescriptorLines = cv::Mat(nkf, 32, CV_8UC1, (void*)dkf);
+        kf.mvpMapLines.resize(nkf);
+        for (int i = 0; i < nkf; i++) {
+            mls[i].mbBad = ml_state[i] == 2; mls[i].mfLen = ml_len[i];
+            kf.mvpMapLines[i] = ml_state[i] ? &mls[i] : (PL_SLAM::MapLine*)NULL;
+        }
+        F.NL = nf;
+        F.mDescriptorLines = cv::Mat(nf, 32, CV_8UC1, (void*)df);
+        F.mvLinesUn.resize(nf);
+        for (int i = 0; i < nf; i++) F.mvLinesUn[i].lineLength = f_linelen[i];
+        std::vector<PL_SLAM::MapLine*> out;
+        PL_SLAM::Linematcher lm(nnr, true, checklen != 0, lengtherr);
+        int n = lm.SearchByKNN(&kf, F, out);
+        for (int i = 0; i < nf; i++) out_ml[i] = out[i] ? (int)(out[i] - mls.data()) : -1;
+        return n;
+    });
+}
+/* Linematcher::SearchForTriangulation (src/Linematcher.cc:804-879).  cam = fx, fy, cx, cy of key frame 2; pose = Ow1[3], R2w[9],
+ * t2w[3]; pairs = up to n1 (i1, i2); returns the number of pairs (the reference's own return value is decremented on
+ * out-of-bounds reads and is not reported) */
+int ref_line_search_for_triangulation(const uint8_t* d1, int n1, const uint8_t* d2, int n2, const uint8_t* has_ml1, const uint8_t* has_ml2,
+                                      const orc_keypoint* mid1, const orc_keypoint* mid2, const float* scale, const float* sigma2, int nlev,
+                                      const float* cam, const float* pose, const float* F12, float nnr, int32_t* pairs)
+{
+    return guarded([&]() {
+        PL_SLAM::MapLine dummy;
+        PL_SLAM::KeyFrame k1, k2;
+        k1.mDescriptorLines = cv::Mat(n1, 32, CV_8UC1, (void*)d1);
+        k2.mDescriptorLines = cv::Mat(n2, 32, CV_8UC1, (void*)d2);
+        k1.mvpMapLines.resize(n1); k2.mvpMapLines.resize(n2);
+        for (int i = 0; i < n1; i++) k1.mvpMapLines[i] = has_ml1[i] ? &dummy : (PL_SLAM::MapLine*)NULL;
+        for (int i = 0; i < n2; i++) k2.mvpMapLines[i] = has_ml2[i] ? &dummy : (PL_SLAM::MapLine*)NULL;
+        k1.mvMidPointsUn.resize(n1); k2.mvMidPointsUn.resize(n2);
+        if (n1) memcpy(k1.mvMidPointsUn.data(), mid1, n1 * sizeof(cv::KeyPoint));
+        if (n2) memcpy(k2.mvMidPointsUn.data(), mid2, n2 * sizeof(cv::KeyPoint));
+        for (PL_SLAM::KeyFrame* k : {&k1, &k2}) {
+            k->mvScaleFactorsLines.assign(scale, scale + nlev);
+            k->mvLevelSigma2Lines.assign(sigma2, sigma2 + nlev);
+            k->fx = cam[0]; k->fy = cam[1]; k->cx = cam[2]; k->cy = cam[3];
+        }
+        float ow[3], r[9], t[3], f[9];
+        memcpy(ow, pose, 12); memcpy(r, pose + 3, 36); memcpy(t, pose + 12, 12); memcpy(f, F12, 36);
+        k1.mOw = cv::Mat(3, 1, CV_32FC1, ow).clone();
+        k2.mRcw = cv::Mat(3, 3, CV_32FC1, r).clone();
+        k2.mtcw = cv::Mat(3, 1, CV_32FC1, t).clone();
+        cv::Mat Fm = cv::Mat(3, 3, CV_32FC1, f).clone();
+        std::vector<std::pair<size_t, size_t> > vp;
+        PL_SLAM::Linematcher lm(nnr, true, true, 0.1f);
+        lm.SearchForTriangulation(&k1, &k2, Fm, vp);
+        for (size_t i = 0; i < vp.size(); i++) { pairs[2 * i] = (int)vp[i].first; pairs[2 * i + 1] = (int)vp[i].second; }
+        return (int)vp.size();
+    });
+}
+
 } // extern "C"
 
 /* cv::BFMatcher model for matchNNR: Hamming, k = 2, ordering (distance, trainIdx) -- orc_knn2 */
