@@ -35,7 +35,16 @@ def test_orb_configs(S, oracle, gpu_ctx, w, h, nf, seed):
             assert np.array_equal(ex.debug_blurred(l), ox.level_blurred(l))
         xs, ys, rr = ex.debug_raw_keys(l)
         oxs, oys, orr = ox.level_raw(l)
-        assert sorted(zip(xs.tolist(), ys.tolist(), rr.tolist())) == sorted(zip(oxs.tolist(), oys.tolist(), orr.tolist()))
+        # the reference appends cell by cell (rows, then columns) and row-major inside a cell (ORBextractor.cc:783-830); the kernel
+        # appends in arrival order and carries that order as an explicit key, so: put the kernel's list into the reference's order
+        # and compare the two SEQUENCES (not sets)
+        lh, lw = ox.level_image(l).shape
+        width, height = lw - 32, lh - 32
+        ncols, nrows = width // 30, height // 30
+        wcell, hcell = -(-width // ncols), -(-height // nrows)
+        key = lambda x, y: ((y - 3) // hcell, (x - 3) // wcell, y, x)
+        got = sorted(zip(xs.tolist(), ys.tolist(), rr.tolist()), key=lambda t: key(t[0], t[1]))
+        assert got == list(zip(oxs.tolist(), oys.tolist(), orr.tolist())), "raw FAST list of level %d" % l
 
 
 def test_orb_batch_equals_single_and_stereo_pair(S, oracle, gpu_ctx):
@@ -454,3 +463,31 @@ def test_error_conventions(S, oracle, gpu_ctx):
         m.candidates_top2(d[:2], d[:5], [np.array([5], np.int32), np.zeros(0, np.int32)])
     with pytest.raises(S.PlfError):
         S.features_in_area(gpu_ctx, k, S.GridParams(0, 48, 0, 0, 1, 1), k["x"], k["y"], np.ones(len(k), np.float32))
+
+
+def test_descriptor_distance_batch(S, oracle, gpu_ctx):
+    """plf_descriptor_distance (ORBmatcher / Linematcher::DescriptorDistance for n pairs) on the device."""
+    import ctypes as C
+    rng = np.random.default_rng(9)
+    for n, hi in ((1, 256), (1000, 256), (4097, 4)):
+        a = rng.integers(0, hi, (n, 32), dtype=np.uint8); b = rng.integers(0, hi, (n, 32), dtype=np.uint8)
+        out = np.empty(n, np.int32)
+        gpu_ctx.check(gpu_ctx.lib.plf_descriptor_distance(gpu_ctx.h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p)))
+        want = np.unpackbits(a ^ b, axis=1).sum(1).astype(np.int32)
+        assert np.array_equal(out, want)
+        for i in range(0, n, max(1, n // 7)):
+            assert int(out[i]) == oracle.descriptor_distance(a[i], b[i])
+
+
+def test_vocab_load_text(S, oracle, gpu_ctx, tmp_path):
+    """plf_vocab_load_text (ORBVocabulary::loadFromTextFile, ORBvoc.txt format) + the tree descent on the device."""
+    voc = oracle.synth_vocabulary(6, 3, 77)
+    parent, desc, weight, leaf = voc
+    from test_emu_parity import _write_vocab_text
+    path = str(tmp_path / "voc.txt")
+    _write_vocab_text(path, 6, 3, voc)
+    v = S.ORBVocabulary(gpu_ctx, path=path)
+    feats = np.random.default_rng(5).integers(0, 256, (500, 32), dtype=np.uint8)
+    w, wt, nd = v.transform_features(feats, 2)
+    ow, owt, ond = oracle.bow_transform(voc, 3, feats, 2)
+    assert np.array_equal(w, ow) and np.array_equal(wt, owt) and np.array_equal(nd, ond)
