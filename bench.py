@@ -46,7 +46,7 @@ CONFIGS = {
     "c3": dict(W=1241, H=376, stereo=True, frames=512, sub=256, orb=dict(ORB_TUM, nfeatures=2000),
                line=dict(LSD_TUM, nfeatures=800, min_line_length=0.02 * 376),
                workload="KITTI-style stereo 1241x376 pairs, 2000 ORB + LSD/LBD 800 lines per image, stereo point matching + L<->R line matchNNR"),
-    "c4": dict(W=1920, H=1080, stereo=False, frames=1024, sub=128, orb=dict(ORB_TUM, nfeatures=2000),
+    "c4": dict(W=1920, H=1080, stereo=False, frames=1024, sub=512, orb=dict(ORB_TUM, nfeatures=2000),
                line=dict(LSD_TUM, nfeatures=800, min_line_length=0.02 * 1080),
                workload="batched sequence extraction: 1920x1080 frames, 2000 ORB (8 lv x1.2, FAST 20/7) + LSD/LBD 800 lines (TUM LSD options), frame-sharded"),
 }

@@ -102,8 +102,8 @@ void orc_fit_line_l2(const int32_t* pts, int count, float* line)
     x /= w; y /= w; x2 /= w; y2 /= w; xy /= w;
     double dx2 = x2 - x * x, dy2 = y2 - y * y, dxy = xy - x * y;
     float t = (float)atan2(2 * dxy, dx2 - dy2) / 2;
-    line[0] = (float)cos(t);
-    line[1] = (float)sin(t);
+    line[0] = cosf(t); /* cv2 4.13 evaluates cos / sin of the float angle in single precision (pinned: tests/test_oracle_vs_cv2.py) */
+    line[1] = sinf(t);
     line[2] = (float)x;
     line[3] = (float)y;
 }

@@ -61,6 +61,7 @@ struct plf_line {
     void* d_cubtmp[LINE_MAX_OCT];
     size_t cubtmp_bytes[LINE_MAX_OCT];
     size_t keycap[LINE_MAX_OCT];
+    int key_div;                            // seed-key capacity = scaled pixels / key_div (batches start at 4; halved on overflow, then the call is retried)
     size_t maskwords[LINE_MAX_OCT];
     int regcap;
     cudaStream_t st2;                      // stream of octave 1 (octave 0 uses the context stream)
@@ -262,6 +263,11 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         tabCount += (size_t)o->sw[k] + o->sh[k];
     }
     const size_t F = (size_t)nframes;
+    // Seed keys, region points and component records exist only for pixels with a defined gradient (5-10 % of an image, 20 % on
+    // busy ones): batches reserve a quarter of the pixel count (28 of the 49 bytes per scaled pixel are these arrays), which is
+    // what lets 256 1080p frames share a workspace; an image set that needs more makes the call re-prepare with twice the room.
+    if (o->key_div < 1) o->key_div = nframes >= 8 ? 4 : 1;
+    if (nframes < 8) o->key_div = 1;
     o->regcap = nframes * LINE_REGCAP_PER_FRAME;
     if (!o->st2) {
 #ifndef PLF_EMU
@@ -281,7 +287,7 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
     auto need = [&](size_t count, size_t elt) { bytes += plf_align_up(count * elt, 256); };
     for (int k = 0; k < noct; k++) {
         const size_t px = (size_t)o->ow[k] * o->oh[k], spx = (size_t)o->sp[k] * o->sh[k];
-        o->keycap[k] = F * spx;
+        o->keycap[k] = F * spx / (size_t)o->key_div + 4096;
         o->maskwords[k] = F * (spx / 32 + (size_t)o->sh[k] + 64);
         need(F * px, 1); need(F * px, 1); need(F * px, 2); need(F * px, 2);      // octave, LBD image, dx, dy
         need(F * px, 1); need(F * spx, 1);                                            // tmp, scaled
@@ -421,6 +427,7 @@ static std::mutex g_lsd_prephase[64];   // one per device: contexts of different
 // The octaves are independent until the line selection: each has its own workspace and (when there are two) its own
 // stream, the host walks both through the same phases, so the two region-growing chains run side by side.
 // With profiling on, everything stays on the context stream (the per-kernel event times must not overlap).
+#define PLF_RETRY_INTERNAL ((plf_status)1000)   // never leaves this file
 static plf_status lsd_detect_batch(plf_line* o, int nframes)
 {
     plf_ctx* ctx = o->ctx;
@@ -504,7 +511,14 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         cudaStream_t st = stk[k];
         PLF_CUDA(ctx, cudaStreamSynchronize(st));
         nkeys[k] = o->h_pin[64 * k];
-        if (nkeys[k] > (int)o->keycap[k]) return plf_fail(ctx, PLF_ERR_CAPACITY, "LSD key buffer overflow");
+        if (nkeys[k] > (int)o->keycap[k]) {
+            // more defined pixels than the workspace reserves: finish what is queued, then let the caller re-prepare and retry
+            for (int j = 0; j < noct; j++) cudaStreamSynchronize(stk[j]);
+            if (o->key_div <= 1) return plf_fail(ctx, PLF_ERR_CAPACITY, "LSD key buffer overflow");
+            o->key_div /= 2;
+            o->ws_frames = 0;
+            return PLF_RETRY_INTERNAL;
+        }
         if (nkeys[k] <= 0) continue;
         int fbits = 1;
         while ((1 << fbits) < nframes) fbits++;
@@ -729,11 +743,15 @@ extern "C" plf_status plf_line_extract_batch_device(plf_line* o, const uint8_t* 
     if (!dev_imgs || nframes < 1 || w <= 0 || h <= 0 || stride < (size_t)w || !dev_kl || !dev_desc || !dev_n_out || cap < 1)
         return plf_fail(ctx, PLF_ERR_INVALID, "plf_line_extract_batch_device: bad arguments");
     PLF_CUDA(ctx, cudaSetDevice(ctx->device));
-    plf_status st = line_prepare(o, w, h, nframes);
-    if (st) return st;
-    st = upload_images(o, dev_imgs, nframes, w, h, stride, frame_stride, true);
-    if (st) return st;
-    return line_extract_device_impl(o, nframes, dev_kl, dev_mid, dev_desc, cap, dev_n_out);
+    plf_status st;
+    do {
+        st = line_prepare(o, w, h, nframes);
+        if (st) return st;
+        st = upload_images(o, dev_imgs, nframes, w, h, stride, frame_stride, true);
+        if (st) return st;
+        st = line_extract_device_impl(o, nframes, dev_kl, dev_mid, dev_desc, cap, dev_n_out);
+    } while (st == PLF_RETRY_INTERNAL);
+    return st;
 }
 
 static plf_status check_counts(plf_ctx* ctx, const int32_t* n_out, int nframes)
@@ -769,13 +787,16 @@ extern "C" plf_status plf_line_extract_batch(plf_line* o, const uint8_t* host_im
     }
     if (stride < (size_t)w || !host_kl || !host_desc || cap < 1) return plf_fail(ctx, PLF_ERR_INVALID, "plf_line_extract_batch: bad arguments");
     PLF_CUDA(ctx, cudaSetDevice(ctx->device));
-    plf_status st = line_prepare(o, w, h, nframes);
-    if (st) return st;
-    st = line_out_staging(o, nframes, cap);
-    if (st) return st;
-    st = upload_images(o, host_imgs, nframes, w, h, stride, frame_stride, false);
-    if (st) return st;
-    st = line_extract_device_impl(o, nframes, o->d_okl, o->d_omid, o->d_odesc, cap, o->d_onout);
+    plf_status st;
+    do {
+        st = line_prepare(o, w, h, nframes);
+        if (st) return st;
+        st = line_out_staging(o, nframes, cap);
+        if (st) return st;
+        st = upload_images(o, host_imgs, nframes, w, h, stride, frame_stride, false);
+        if (st) return st;
+        st = line_extract_device_impl(o, nframes, o->d_okl, o->d_omid, o->d_odesc, cap, o->d_onout);
+    } while (st == PLF_RETRY_INTERNAL);
     if (st) return st;
     cudaStream_t s = ctx->stream;
     PLF_CUDA(ctx, cudaMemcpyAsync(host_kl, o->d_okl, (size_t)nframes * cap * sizeof(plf_keyline), cudaMemcpyDeviceToHost, s));

@@ -491,3 +491,18 @@ def test_vocab_load_text(S, oracle, gpu_ctx, tmp_path):
     w, wt, nd = v.transform_features(feats, 2)
     ow, owt, ond = oracle.bow_transform(voc, 3, feats, 2)
     assert np.array_equal(w, ow) and np.array_equal(wt, owt) and np.array_equal(nd, ond)
+
+
+def test_line_batch_key_workspace_retry(S, oracle, gpu_ctx):
+    """Batches reserve seed-key room for a quarter of the pixels; frames where far more pixels have a defined gradient (noise)
+    make the call re-prepare with more room and run again -- the results must not depend on it."""
+    rng = np.random.default_rng(12)
+    imgs = np.stack([oracle.gauss_blur(rng.integers(0, 256, (120, 160), dtype=np.uint8), 3, 0.8) for _ in range(6)] +
+                    [oracle.synth_image(160, 120, 40 + i) for i in range(4)])
+    le = S.Lineextractor(60, 2, 0, 1.1, 0.6, 2.2, 12.5, 1.0, 0.6, 1024, 0.0, ctx=gpu_ctx)
+    prm = oracle.line_params(60, 2, 0, 1.1, 0.6, 2.2, 12.5, 1.0, 0.6, 1024, 0.0)
+    for rep in range(2):       # the second call runs in the enlarged workspace
+        K, M, D = le.extract_batch(imgs)
+        for b in range(len(imgs)):
+            oK, oM, oD = oracle.line_extract(prm, imgs[b])
+            assert len(K[b]) == len(oK) and np.array_equal(K[b].view(np.uint8), oK.view(np.uint8)) and np.array_equal(D[b], oD)
