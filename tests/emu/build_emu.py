@@ -21,6 +21,8 @@ def build_emu(force=False):
     flags = ["-std=c++17", "-O2", "-g", "-fPIC", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-DPLF_EMU", "-DLSD_BIG_BUCKET=5", "-DLSD_GIANT_BUCKET=7", "-DGC_MAXWARPS=4",   # tiny threshold: the emulated tests stress the speculative LSD path
              
              "-Wno-unknown-pragmas", "-Wno-unused-function", "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    extra = os.environ.get("PLF_EMU_EXTRA_FLAGS", "").split()   # e.g. -fsanitize=address (profiles/emu_asan.sh)
+    flags = flags + extra
     procs, objs = [], []
     for s in srcs + [os.path.join(HERE, "cuda_emu.cc")]:
         o = os.path.join(objdir, os.path.basename(s) + ".o")
@@ -31,7 +33,7 @@ def build_emu(force=False):
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError("emu compile failed for %s:\n%s" % (s, out))
-    subprocess.check_call(["g++", "-shared", "-pthread", "-o", LIB] + objs)
+    subprocess.check_call(["g++", "-shared", "-pthread"] + extra + ["-o", LIB] + objs)
     return LIB
 
 
