@@ -180,6 +180,31 @@ plf_status plf_lbd_compute(plf_line* le, const uint8_t* host_img, int w, int h, 
  * (src/ORBmatcher.cc:1656-1672, src/Linematcher.cc:50-66), cv::BFMatcher(NORM_HAMMING).knnMatch(k=2)
  * as used by Linematcher::matchNNR (src/Linematcher.cc:520-541) and the mutual-consistency step of
  * Linematcher::SearchByKNN / SearchForTriangulation (:454-471, :825-839).  Descriptors are n x 32 bytes. ---- */
+/* ---- FLD line extractor: replaces PL_SLAM::Lineextractor's FLD branch (System.usingLsdFeature: 0): the FLD constructor
+ * (include/Lineextractor.h:55-57, src/Lineextractor.cc:69-110), ComputeFldWithLbd (:242-336), ComputePyramid /
+ * detectFldWithPyramid / detect (:413-460) and the detector itself (lineDetection, getPointChain, extractSegments,
+ * incidentPoint, additionalOperationsOnSegment, :546-905) over cv::Canny and cv::fitLine; descriptors by the same LBD path as
+ * the LSD branch.  do_merge (off in every shipped config) and Canny apertures other than 3 are rejected at create. ---- */
+typedef struct {
+    int nfeatures;             /* Lineextractor.nFeatures */
+    int nlevels;               /* Lineextractor.nLevels (pyrDown pyramid) */
+    double scale;              /* feature-split factor and the (reference's) octave -> image coordinate factor */
+    int length_threshold;      /* Lineextractor.threshold_length */
+    float distance_threshold;  /* Lineextractor.threshold_dist */
+    double canny_th1, canny_th2;
+    int canny_aperture_size;   /* must be 3 */
+    int do_merge;              /* must be 0 */
+} plf_fld_params;
+typedef struct plf_fld plf_fld;
+plf_status plf_fld_create(plf_ctx* ctx, const plf_fld_params* p, plf_fld** out);
+void plf_fld_destroy(plf_fld* fld);
+plf_status plf_fld_features_per_level(const plf_fld* fld, int32_t* per_level);
+/* Lineextractor::detect (single level): n x 4 floats (x1, y1, x2, y2) in detection order */
+plf_status plf_fld_detect(plf_fld* fld, const uint8_t* host_img, int w, int h, size_t stride, float* host_lines, int cap, int* n_out);
+/* ComputeFldWithLbd: KeyLines (68 B), mid-point KeyPoints, N x 32 LBD descriptors */
+plf_status plf_fld_extract(plf_fld* fld, const uint8_t* host_img, int w, int h, size_t stride, plf_keyline* host_kl,
+                           plf_keypoint* host_mid, uint8_t* host_desc, int cap, int* n_out);
+
 /* pairwise distances dist[i] = Hamming(a[i], b[i]) */
 plf_status plf_descriptor_distance(plf_ctx* ctx, const uint8_t* host_a, const uint8_t* host_b, int n, int32_t* host_dist);
 /* knnMatch(k=2): idx/dist are nq x 2; ascending distance, ties -> lowest train index; -1 where the

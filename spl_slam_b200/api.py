@@ -59,6 +59,12 @@ class LineParams(C.Structure):
                 ("n_bins", C.c_int), ("min_line_length", C.c_double)]
 
 
+class FldParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("nlevels", C.c_int), ("scale", C.c_double), ("length_threshold", C.c_int),
+                ("distance_threshold", C.c_float), ("canny_th1", C.c_double), ("canny_th2", C.c_double),
+                ("canny_aperture_size", C.c_int), ("do_merge", C.c_int)]
+
+
 _libs = {}
 
 
@@ -110,6 +116,11 @@ def load(path=None):
         "plf_hamming_knn2": (C.c_int, [vp, vp, C.c_int, vp, C.c_int64, i32p, i32p]),
         "plf_hamming_knn2_device": (C.c_int, [vp, vp, C.c_int, vp, C.c_int64, C.c_int64, vp, vp]),
         "plf_knn2_merge_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp]),
+        "plf_fld_create": (C.c_int, [vp, P(FldParams), P(vp)]),
+        "plf_fld_destroy": (None, [vp]),
+        "plf_fld_features_per_level": (C.c_int, [vp, i32p]),
+        "plf_fld_detect": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, P(C.c_int)]),
+        "plf_fld_extract": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_size_t, vp, vp, vp, C.c_int, P(C.c_int)]),
         "plf_comm_unique_id": (C.c_int, [vp]),
         "plf_comm_create": (C.c_int, [vp, vp, C.c_int, C.c_int, P(vp)]),
         "plf_comm_destroy": (None, [vp]),
@@ -457,6 +468,58 @@ class Lineextractor:
         if getattr(self, "h", None):
             if getattr(self.ctx, "h", None):
                 self.lib.plf_line_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FldLineextractor:
+    """Mirror of PL_SLAM::Lineextractor built with its FLD constructor (include/Lineextractor.h:55-57; System.usingLsdFeature: 0)."""
+
+    def __init__(self, nfeatures=240, nlevels=1, scale=1.05, length_threshold=10, distance_threshold=1.414213562, canny_th1=50.0,
+                 canny_th2=100.0, canny_aperture_size=3, do_merge=False, busingLSD=False, ctx=None, device=0, lib=None):
+        self.ctx = ctx or Context(device, lib)
+        self.lib = self.ctx.lib
+        self.prm = FldParams(nfeatures, nlevels, scale, length_threshold, distance_threshold, canny_th1, canny_th2, canny_aperture_size,
+                             1 if do_merge else 0)
+        h = C.c_void_p()
+        self.ctx.check(self.lib.plf_fld_create(self.ctx.h, C.byref(self.prm), C.byref(h)))
+        self.h = h
+        self.nfeatures, self.nlevels, self.busingLSD = nfeatures, nlevels, False
+        self.ctx._adopt(self)
+
+    def features_per_level(self):
+        per = np.zeros(self.nlevels, np.int32)
+        self.ctx.check(self.lib.plf_fld_features_per_level(self.h, _p(per)))
+        return per
+
+    def detect(self, image, cap=1 << 14):
+        """Lineextractor::detect(image, lines): n x 4 floats."""
+        img = _as_image(image)
+        lines = np.zeros((cap, 4), np.float32)
+        n = C.c_int()
+        self.ctx.check(self.lib.plf_fld_detect(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(lines), cap, C.byref(n)))
+        return lines[:n.value].copy()
+
+    def ComputeFldWithLbd(self, image):
+        """ComputeFldWithLbd(image, keyLines, keypoints, descriptors) (src/Lineextractor.cc:242-336)."""
+        img = _as_image(image)
+        if img is None:
+            return np.zeros(0, KEYLINE_DTYPE), np.zeros(0, KEYPOINT_DTYPE), np.zeros((0, 32), np.uint8)
+        cap = self.nfeatures * 2 + 16
+        kl = np.zeros(cap, KEYLINE_DTYPE); mid = np.zeros(cap, KEYPOINT_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int()
+        self.ctx.check(self.lib.plf_fld_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kl), _p(mid), _p(desc), cap, C.byref(n)))
+        return kl[:n.value].copy(), mid[:n.value].copy(), desc[:n.value].copy()
+
+    def close(self):
+        if getattr(self, "h", None):
+            if getattr(self.ctx, "h", None):
+                self.lib.plf_fld_destroy(self.h)
             self.h = None
 
     def __del__(self):

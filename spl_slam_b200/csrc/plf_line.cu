@@ -879,3 +879,4 @@ extern "C" plf_status plf_lbd_compute(plf_line* o, const uint8_t* host_img, int 
     return PLF_OK;
 }
 
+#include "plf_fld_impl.cuh"

@@ -1251,3 +1251,5 @@ k_lbd(const plf_keyline* __restrict__ kl, const int* __restrict__ nlines, int ca
     }
     if (fdesc) for (int i = tid; i < 72; i += 64) fdesc[((size_t)f * cap + li) * 72 + i] = dv[i];
 }
+
+#include "plf_fld_kernels.cuh"
