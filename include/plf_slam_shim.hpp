@@ -124,9 +124,8 @@ public:
     Lineextractor(int nfeatures = 240, int nlevels = 3, int refine = 0, double scale = 1.05, double sigma_scale = 0.6,
                   double quant = 2.0, double ang_th = 22.5, double log_eps = 1.0, double density_th = 0.7, int n_bins = 1024,
                   double min_line_length = 32.0, bool busingLSD = true, int device = 0)
-        : busingLSD(busingLSD), ctx_(device), le_(nullptr), nlevels(nlevels), scale(scale)
+        : busingLSD(busingLSD), ctx_(device), le_(nullptr), fld_(nullptr), nlevels(nlevels), scale(scale)
     {
-        if (!busingLSD) throw std::runtime_error("plf: the FLD branch is not part of the GPU hot path");
         plf_line_params p = {nfeatures, nlevels, refine, scale, sigma_scale, quant, ang_th, log_eps, density_th, n_bins, min_line_length};
         ctx_.check(plf_line_create(ctx_.get(), &p, &le_));
         mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels);
@@ -134,13 +133,50 @@ public:
         plf_line_tables(le_, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(), mvInvLevelSigma2.data(), nullptr);
         cap_ = plf_line_max_keylines(le_);
     }
-    ~Lineextractor() { plf_line_destroy(le_); }
+    // FLD-LBD constructor (include/Lineextractor.h:55-57, src/Lineextractor.cc:69-110)
+    Lineextractor(int _nfeatures, int _nlevels, double _scale, int _length_threshold, float _distance_threshold, double _canny_th1,
+                  double _canny_th2, int _canny_aperture_size, bool _do_merge, bool _busingLSD = false, int device = 0)
+        : busingLSD(_busingLSD), ctx_(device), le_(nullptr), fld_(nullptr), nlevels(_nlevels), scale(_scale)
+    {
+        // CV_Assert(_length_threshold > 0 && _distance_threshold > 0 && _canny_th1 > 0 && _canny_th2 > 0 && _canny_aperture_size > 0)
+        if (!(_length_threshold > 0 && _distance_threshold > 0 && _canny_th1 > 0 && _canny_th2 > 0 && _canny_aperture_size > 0))
+            throw std::runtime_error("Lineextractor: FLD parameters must be positive");
+        plf_fld_params p = {_nfeatures, _nlevels, _scale, _length_threshold, _distance_threshold, _canny_th1, _canny_th2, _canny_aperture_size,
+                            _do_merge ? 1 : 0};
+        ctx_.check(plf_fld_create(ctx_.get(), &p, &fld_));
+        cap_ = 2 * _nfeatures + 16;
+        mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels);
+        mvLevelSigma2.resize(nlevels); mvInvLevelSigma2.resize(nlevels);
+        mvScaleFactor[0] = 1.0f; mvLevelSigma2[0] = 1.0f;
+        for (int i = 1; i < nlevels; i++) { mvScaleFactor[i] = mvScaleFactor[i - 1] * scale; mvLevelSigma2[i] = mvScaleFactor[i] * mvScaleFactor[i]; }
+        for (int i = 0; i < nlevels; i++) { mvInvScaleFactor[i] = 1.0f / mvScaleFactor[i]; mvInvLevelSigma2[i] = 1.0f / mvLevelSigma2[i]; }
+    }
+    ~Lineextractor() { plf_line_destroy(le_); plf_fld_destroy(fld_); }
+
+    // src/Lineextractor.cc:242-336: replaces keyLines, appends to keypoints, overwrites descriptors
+    void ComputeFldWithLbd(cv::Mat& image, std::vector<KeyLine>& keyLines, std::vector<cv::KeyPoint>& keypoints, cv::Mat& descriptors)
+    {
+        if (image.empty()) return;
+        if (!fld_) throw std::runtime_error("Lineextractor: built with the LSD constructor");
+        std::vector<KeyLine> kl(cap_);
+        std::vector<cv::KeyPoint> mid(cap_);
+        std::vector<unsigned char> desc((size_t)cap_ * 32);
+        int n = 0;
+        ctx_.check(plf_fld_extract(fld_, image.data, image.cols, image.rows, image.step, (plf_keyline*)kl.data(), (plf_keypoint*)mid.data(),
+                                   desc.data(), cap_, &n));
+        keyLines.assign(kl.begin(), kl.begin() + n);
+        keypoints.insert(keypoints.end(), mid.begin(), mid.begin() + n);
+        if (n == 0) return;
+        descriptors.create(n, 32, CV_8UC1);
+        for (int i = 0; i < n; i++) std::memcpy(descriptors.ptr(i), &desc[(size_t)i * 32], 32);
+    }
 
     // src/Lineextractor.cc:112-212: appends to keyLines / keypoints, overwrites descriptors
     void ComputeLsdWithLbd(const cv::Mat& image, std::vector<KeyLine>& keyLines, std::vector<cv::KeyPoint>& keypoints,
                            cv::Mat& descriptors)
     {
         if (image.empty()) return;                                                       // :115-116
+        if (!le_) throw std::runtime_error("Lineextractor: built with the FLD constructor");
         if (image.depth() != 0 || image.channels() != 1) throw std::runtime_error("Error, depth image!= 0");   // LSDDetector_custom.cpp:236-237
         std::vector<KeyLine> kl(cap_);
         std::vector<cv::KeyPoint> mid(cap_);
@@ -169,6 +205,7 @@ public:
 protected:
     PlfContext ctx_;
     plf_line* le_;
+    plf_fld* fld_;
     int nlevels;
     double scale;
     int cap_;

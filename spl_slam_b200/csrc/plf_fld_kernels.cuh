@@ -180,52 +180,66 @@ k_fld_chains(uint8_t* __restrict__ edge, const uint8_t* __restrict__ img, int w,
     int nout = 0;
     const unsigned FULL = 0xffffffffu;
     for (int r = 0; r < h; r++) {
-        for (int c0 = 0; c0 < w; c0 += 32) {
-            const int c = c0 + lane;
-            unsigned m = __ballot_sync(FULL, c < w && E[(size_t)r * w + c] != 0);
+        for (int c0 = 0; c0 < w; c0 += 128) {
+            // 128 pixels per step: four bytes per lane, requested together
+            unsigned nz = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int c = c0 + 4 * lane + j;
+                if (c < w && E[(size_t)r * w + c] != 0) nz |= 1u << j;
+            }
+            unsigned m = __ballot_sync(FULL, nz != 0);
             while (m) {
-                const int cc = c0 + __ffs((int)m) - 1;
-                m &= m - 1;
-                if (lane == 0 && E[(size_t)r * w + cc] != 0) {
-                    // ---- a seed: follow the chain (lineDetection :760-775, getPointChain :689-740)
-                    int np = 0;
+                const int sl = __ffs((int)m) - 1;
+                const unsigned snz = __shfl_sync(FULL, nz, sl);
+                const int cc = c0 + 4 * sl + (__ffs((int)snz) - 1);
+                int np = 0;
+                {
+                    // ---- a seed: follow the chain (lineDetection :760-775, getPointChain :689-740).  The eight neighbours of the
+                    // current point are fetched by eight lanes at once; the choice among them is the reference's
                     int px = cc, py = r;
-                    points[np++] = px | (py << 16);
-                    E[(size_t)py * w + px] = 0;
+                    if (lane == 0) { points[np] = px | (py << 16); E[(size_t)py * w + px] = 0; }
+                    np++;
+                    __syncwarp();
                     float direction = 0.0f;
                     int step = 0;
+                    const int di = lane & 7;
+                    // indices[8][2] = {1,1},{1,0},{1,-1},{0,-1},{-1,-1},{-1,0},{-1,1},{0,1}  (row offset, column offset)
+                    const int drow = di < 3 ? 1 : (di == 3 || di == 7) ? 0 : -1;
+                    const int dcol = (di == 0 || di == 6 || di == 7) ? 1 : (di == 1 || di == 5) ? 0 : -1;
                     for (;;) {
-                        const int ind[8][2] = {{1, 1}, {1, 0}, {1, -1}, {0, -1}, {-1, -1}, {-1, 0}, {-1, 1}, {0, 1}};
-                        float min_dir_diff = 7.0f;
-                        int cpx = 0, cpy = 0, cdir = 0;
-                        bool found = false;
-                        for (int i = 0; i < 8; i++) {
-                            const int ci = px + ind[i][1], ri = py + ind[i][0];
-                            if (ri < 0 || ri == h || ci < 0 || ci == w) continue;
-                            if (E[(size_t)ri * w + ci] == 0) continue;
-                            if (step == 0) {
-                                cpx = ci; cpy = ri;
-                                direction = i > 4 ? (float)(i - 8) : (float)i;
-                                found = true;
-                                break;
-                            }
-                            const float curr_dir = i > 4 ? (float)(i - 8) : (float)i;
+                        const int ci = px + dcol, ri = py + drow;
+                        const bool on = lane < 8 && !(ri < 0 || ri == h || ci < 0 || ci == w) && E[(size_t)ri * w + ci] != 0;
+                        const unsigned nb = __ballot_sync(FULL, on);
+                        if (!nb) break;
+                        int pick;
+                        if (step == 0) {
+                            pick = __ffs((int)nb) - 1;                         // the first neighbour in table order
+                            direction = pick > 4 ? (float)(pick - 8) : (float)pick;
+                        } else {
+                            const float curr_dir = di > 4 ? (float)(di - 8) : (float)di;
                             float dir_diff = fabsf(curr_dir - direction);
                             dir_diff = dir_diff > 4.0f ? 8.0f - dir_diff : dir_diff;
-                            if (dir_diff <= min_dir_diff) { min_dir_diff = dir_diff; cpx = ci; cpy = ri; cdir = i > 4 ? i - 8 : i; }
+                            float best = on ? dir_diff : 100.0f;
+#pragma unroll
+                            for (int o = 4; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(FULL, best, o));
+                            best = __shfl_sync(FULL, best, 0);                  // lanes 8..31 reduced over idle lanes: take the real one
+                            // `dir_diff <= min_dir_diff` in table order: the LAST neighbour with the smallest difference wins
+                            const unsigned eq = __ballot_sync(FULL, on && dir_diff == best) & 0xffu;
+                            if (!(best < 2.0f)) break;
+                            pick = 31 - __clz((int)eq);
+                            const int cdir = pick > 4 ? pick - 8 : pick;
+                            direction = (direction * (float)step + (float)cdir) / (float)(step + 1);
                         }
-                        if (step > 0) {
-                            if (min_dir_diff < 2.0f) {
-                                direction = (direction * (float)step + (float)cdir) / (float)(step + 1);
-                                found = true;
-                            } else found = false;
-                        }
-                        if (!found) break;
-                        px = cpx; py = cpy;
-                        points[np++] = px | (py << 16);
+                        px = __shfl_sync(FULL, ci, pick);
+                        py = __shfl_sync(FULL, ri, pick);
+                        if (lane == 0) { points[np] = px | (py << 16); E[(size_t)py * w + px] = 0; }
+                        np++;
                         step++;
-                        E[(size_t)py * w + px] = 0;
+                        __syncwarp();
                     }
+                }
+                if (lane == 0) {
                     if (np >= threshold_length + 1) {
                         // ---- extractSegments (:614-687) on this chain, then the per-segment checks of lineDetection (:789-805)
                         const int total = np;
@@ -309,8 +323,14 @@ k_fld_chains(uint8_t* __restrict__ edge, const uint8_t* __restrict__ img, int w,
                     }
                 }
                 __syncwarp();
-                // pixels right of cc in this word may have been erased by the chain: refresh the mask
-                m &= __ballot_sync(FULL, c < w && E[(size_t)r * w + c] != 0);
+                // pixels of this 128-pixel group may have been erased by the chain (the seed itself has been): look again
+                nz = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int c = c0 + 4 * lane + j;
+                    if (c < w && E[(size_t)r * w + c] != 0) nz |= 1u << j;
+                }
+                m = __ballot_sync(FULL, nz != 0);
             }
         }
     }

@@ -43,6 +43,13 @@ int main(int argc, char** argv)
     orbR(imR, mask, kpsR, descR);
     std::vector<float> uRight, depth;
     PL_SLAM::ComputeStereoMatches(orb, orbR, kps, desc, kpsR, descR, 0.11f, 0.11f * 435.2f, uRight, depth);
+    // FLD branch: the second constructor and ComputeFldWithLbd
+    PL_SLAM::Lineextractor fe(240, 1, 1.05, 15, 1.732f, 50.0, 100.0, 3, false, false);
+    std::vector<PL_SLAM::KeyLine> fkl;
+    std::vector<cv::KeyPoint> fmid;
+    cv::Mat fld_desc;
+    fe.ComputeFldWithLbd(im, fkl, fmid, fld_desc);
+    if (fkl.empty() || fkl.size() != fmid.size() || fld_desc.rows != (int)fkl.size()) return 5;
     FILE* o = fopen(argv[4], "wb");
     int hdr[8] = {(int)kps.size(), (int)kl.size(), nm, d01, (int)k2.size(), orb.GetLevels(), orb.mvImagePyramid[1].cols, orb.mvImagePyramid[1].rows};
     fwrite(hdr, sizeof(int), 8, o);
