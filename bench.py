@@ -310,7 +310,7 @@ class Extraction:
         osub = args.orb_sub or min(self.BO, 256)
         self.OSUB = osub if self.BO % osub == 0 else self.BO
         from concurrent.futures import ThreadPoolExecutor
-        self.pool = ThreadPoolExecutor(NL + NO)
+        self.pool = ThreadPoolExecutor(NL + NO + 1)
         self.d_img = [torch.from_numpy(f).cuda() for f in sets]
         self.d_kps = torch.empty((B, capk, 28), dtype=torch.uint8, device="cuda"); self.d_desc = torch.empty((B, capk, 32), dtype=torch.uint8, device="cuda")
         self.d_nk = torch.empty(B, dtype=torch.int32, device="cuda")
@@ -385,51 +385,68 @@ class Extraction:
         self.h_ld = torch.empty((B, capl, 32), dtype=torch.uint8).pin_memory()
         self.n_k = np.zeros(B, np.int32); self.n_l = np.zeros(B, np.int32)
 
-    def e2e_orb(self, i, k):
+    def e2e_orb(self, i, k, dimg):
         W, H = self.W, self.H
-        img = self.h_img[k % self.nsets]
         for j in range(i * self.BO, (i + 1) * self.BO, self.OSUB):
             s = slice(j, j + self.OSUB)
-            self.ctx_os[i].check(self.lib.plf_orb_extract_batch(self.orbs[i].h, img[s].data_ptr(), self.OSUB, W, H, W, W * H, self.h_kps[s].data_ptr(),
-                                                                self.h_desc[s].data_ptr(), self.capk, self.n_k[s].ctypes.data))
+            self.ctx_os[i].check(self.lib.plf_orb_extract_batch_from_device(self.orbs[i].h, dimg[s].data_ptr(), self.OSUB, W, H, W, W * H,
+                                                                            self.h_kps[s].data_ptr(), self.h_desc[s].data_ptr(), self.capk, self.n_k[s].ctypes.data))
 
-    def e2e_line(self, i, k):
+    def e2e_line(self, i, k, dimg):
         W, H = self.W, self.H
-        img = self.h_img[k % self.nsets]
         for j in range(i * self.BL, (i + 1) * self.BL, self.SUB):
             s = slice(j, j + self.SUB)
-            self.ctx_ls[i].check(self.lib.plf_line_extract_batch(self.les[i].h, img[s].data_ptr(), self.SUB, W, H, W, W * H, self.h_kl[s].data_ptr(),
-                                                                 self.h_mid[s].data_ptr(), self.h_ld[s].data_ptr(), self.capl, self.n_l[s].ctypes.data))
+            self.ctx_ls[i].check(self.lib.plf_line_extract_batch_from_device(self.les[i].h, dimg[s].data_ptr(), self.SUB, W, H, W, W * H,
+                                                                             self.h_kl[s].data_ptr(), self.h_mid[s].data_ptr(), self.h_ld[s].data_ptr(),
+                                                                             self.capl, self.n_l[s].ctypes.data))
 
     def run_e2e(self, nsteps):
-        """The same through the host-buffer C-ABI calls: every call uploads its images from pinned host memory and
-        downloads its results (H2D + D2H inside the timed region); one host thread per extractor instance, the
-        reference's ORB thread and line thread (Frame.cc:301-304)."""
-        self.torch.cuda.synchronize()
+        """The same from HOST buffers through the C ABI: every step's images go from pinned host memory to the device ONCE
+        (plf_upload on an uploader context, one step ahead, two staging buffers); the ORB and line extractor instances -- one
+        host thread each, the reference's ORB thread and line thread (Frame.cc:301-304) -- wait for the upload on their own
+        streams (plf_ctx_wait) and return their results to host memory (plf_*_extract_batch_from_device: H2D once + D2H of
+        every result inside the timed region)."""
+        torch = self.torch
+        if not hasattr(self, "d_stage"):
+            self.d_stage = [torch.empty((self.B, self.H, self.W), dtype=torch.uint8, device="cuda") for _ in range(2)]
+            self.ctx_up = self.S.Context(self.dev)
+        torch.cuda.synchronize()
+        nbytes = self.B * self.W * self.H
+        ncons = self.NO + self.NL
+        free = [threading.Semaphore(1), threading.Semaphore(1)]
+        uploaded = [threading.Event() for _ in range(nsteps)]
+        left = [ncons] * nsteps
+        lock = threading.Lock()
         t0 = time.perf_counter()
-        gates = [threading.Semaphore(1) for _ in range(self.NO)]   # step 0 is free to start
 
-        def orb_steps(i):
+        def uploader():
             for k in range(nsteps):
-                gates[i].acquire()     # paced by the first line instance: ORB and line work of a step stay interleaved
-                self.e2e_orb(i, k)
+                free[k % 2].acquire()
+                self.ctx_up.check(self.lib.plf_upload(self.ctx_up.h, self.d_stage[k % 2].data_ptr(), self.h_img[k % self.nsets].data_ptr(), nbytes))
+                uploaded[k].set()
 
-        def line_steps(i):
+        def consumer(kind, i):
+            ctx = self.ctx_os[i] if kind == "orb" else self.ctx_ls[i]
             for k in range(nsteps):
-                if i == 0 and k + 1 < nsteps:
-                    for g_ in gates:
-                        g_.release()   # ORB instances may start step k + 1 (they run one step ahead, as in run_device)
-                self.e2e_line(i, k)
+                uploaded[k].wait()
+                ctx.wait(self.ctx_up)                      # this stream waits for the upload (device-side dependency, no host sync)
+                (self.e2e_orb if kind == "orb" else self.e2e_line)(i, k, self.d_stage[k % 2])
+                with lock:
+                    left[k] -= 1
+                    last = left[k] == 0
+                if last:
+                    free[k % 2].release()
 
-        futs = [self.pool.submit(orb_steps, i) for i in range(self.NO)] + [self.pool.submit(line_steps, i) for i in range(self.NL)]
+        futs = [self.pool.submit(uploader)] + [self.pool.submit(consumer, "orb", i) for i in range(self.NO)] + \
+               [self.pool.submit(consumer, "line", i) for i in range(self.NL)]
         for f in futs:
             f.result()
-        self.torch.cuda.synchronize()
+        torch.cuda.synchronize()
         return (time.perf_counter() - t0) * 1e3
 
     def e2e_bytes(self):
         B = self.B
-        return 2 * B * self.W * self.H, B * (self.capk * 60 + 4 + self.capl * (68 + 28 + 32) + 4)
+        return B * self.W * self.H, B * (self.capk * 60 + 4 + self.capl * (68 + 28 + 32) + 4)     # every frame is uploaded once
 
     def check_outputs(self):
         nk = self.d_nk.cpu().numpy(); nl = self.d_nl.cpu().numpy()

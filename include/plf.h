@@ -84,6 +84,14 @@ plf_status plf_profile_report(plf_ctx* ctx, char* buf, size_t bufsize);
  * last plf_timer_start of `ref` (same device); call before plf_profile_report */
 plf_status plf_profile_timeline(plf_ctx* ctx, plf_ctx* ref, char* buf, size_t bufsize);
 
+/* One upload for several consumers: the reference hands the same image to its ORB thread and its line thread
+ * (src/Frame.cc:301-304).  plf_upload queues the host -> device copy on `ctx`'s stream (asynchronous for pinned memory);
+ * a consumer context then calls plf_ctx_wait(consumer, ctx) and one of the *_from_device entry points below (device images,
+ * host results).  plf_device_malloc / plf_device_free are for hosts that do not link the CUDA runtime themselves. */
+plf_status plf_upload(plf_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);
+plf_status plf_device_malloc(plf_ctx* ctx, size_t bytes, void** out);
+void plf_device_free(plf_ctx* ctx, void* dev_ptr);
+
 /* ---- ORB extractor: replaces PL_SLAM::ORBextractor
  * (include/ORBextractor.h:45-113, src/ORBextractor.cc:410-470, :1043-1132) ---- */
 typedef struct {
@@ -115,6 +123,9 @@ plf_status plf_orb_extract_batch(plf_orb* orb, const uint8_t* host_imgs, int nfr
                                  int32_t* n_out);
 /* Same, inputs and outputs resident in device memory (no copies; asynchronous on the context stream;
  * dev_n_out is an int32[nframes] device array). */
+/* images already on the device (plf_upload), results to host buffers; dev_imgs must stay valid until the call returns */
+plf_status plf_orb_extract_batch_from_device(plf_orb* orb, const uint8_t* dev_imgs, int nframes, int w, int h, size_t stride,
+                                             size_t frame_stride, plf_keypoint* host_kps, uint8_t* host_desc, int cap, int32_t* n_out);
 plf_status plf_orb_extract_batch_device(plf_orb* orb, const uint8_t* dev_imgs, int nframes, int w, int h,
                                         size_t stride, size_t frame_stride, plf_keypoint* dev_kps,
                                         uint8_t* dev_desc, int cap, int32_t* dev_n_out);
@@ -165,6 +176,9 @@ plf_status plf_line_extract(plf_line* le, const uint8_t* host_img, int w, int h,
 plf_status plf_line_extract_batch(plf_line* le, const uint8_t* host_imgs, int nframes, int w, int h, size_t stride,
                                   size_t frame_stride, plf_keyline* host_kl, plf_keypoint* host_mid,
                                   uint8_t* host_desc, int cap, int32_t* n_out);
+plf_status plf_line_extract_batch_from_device(plf_line* le, const uint8_t* dev_imgs, int nframes, int w, int h, size_t stride,
+                                              size_t frame_stride, plf_keyline* host_kl, plf_keypoint* host_mid, uint8_t* host_desc,
+                                              int cap, int32_t* n_out);
 plf_status plf_line_extract_batch_device(plf_line* le, const uint8_t* dev_imgs, int nframes, int w, int h,
                                          size_t stride, size_t frame_stride, plf_keyline* dev_kl,
                                          plf_keypoint* dev_mid, uint8_t* dev_desc, int cap, int32_t* dev_n_out);

@@ -116,6 +116,11 @@ def load(path=None):
         "plf_hamming_knn2": (C.c_int, [vp, vp, C.c_int, vp, C.c_int64, i32p, i32p]),
         "plf_hamming_knn2_device": (C.c_int, [vp, vp, C.c_int, vp, C.c_int64, C.c_int64, vp, vp]),
         "plf_knn2_merge_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp]),
+        "plf_upload": (C.c_int, [vp, vp, vp, C.c_size_t]),
+        "plf_device_malloc": (C.c_int, [vp, C.c_size_t, P(vp)]),
+        "plf_device_free": (None, [vp, vp]),
+        "plf_orb_extract_batch_from_device": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, vp, vp, C.c_int, vp]),
+        "plf_line_extract_batch_from_device": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, vp, vp, vp, C.c_int, vp]),
         "plf_fld_create": (C.c_int, [vp, P(FldParams), P(vp)]),
         "plf_fld_destroy": (None, [vp]),
         "plf_fld_features_per_level": (C.c_int, [vp, i32p]),

@@ -35,11 +35,14 @@ extern "C" plf_status plf_ctx_create_prio(int device, int priority, plf_ctx** ou
 
 extern "C" plf_status plf_ctx_create(int device, plf_ctx** out) { return plf_ctx_create_prio(device, 0, out); }
 
+static void plf_prof_free(plf_ctx* c);
+
 extern "C" void plf_ctx_destroy(plf_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    plf_prof_free(c);
     if (c->scratch) cudaFree(c->scratch);
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaEventDestroy(c->ev0);
@@ -119,6 +122,17 @@ struct plf_prof_state {
     long count[PLF_PROF_NAMES];
     int nnames;
 };
+
+// the profiling state and the events it created lazily
+static void plf_prof_free(plf_ctx* c)
+{
+    if (!c->prof) return;
+#ifndef PLF_EMU
+    for (int i = 0; i < c->prof->created; i++) { cudaEventDestroy(c->prof->ev[i][0]); cudaEventDestroy(c->prof->ev[i][1]); }
+#endif
+    free(c->prof);
+    c->prof = nullptr;
+}
 
 #ifndef PLF_EMU
 void plf_prof_begin(plf_ctx* c, const char* name)
@@ -221,9 +235,37 @@ extern "C" plf_status plf_ctx_wait(plf_ctx* c, plf_ctx* other)
 {
     if (!c || !other) return PLF_ERR_INVALID;
     cudaEvent_t e;
-    PLF_CUDA(c, cudaEventCreate(&e));
-    PLF_CUDA(c, cudaEventRecord(e, other->stream));
-    PLF_CUDA(c, cudaStreamWaitEvent(c->stream, e, 0));
-    PLF_CUDA(c, cudaEventDestroy(e));
+    PLF_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaError_t r = cudaEventRecord(e, other->stream);
+    if (r == cudaSuccess) r = cudaStreamWaitEvent(c->stream, e, 0);
+    cudaEventDestroy(e);      // released once the wait has been consumed; also on the error path
+    PLF_CUDA(c, r);
     return PLF_OK;
+}
+
+// One upload for several consumers (ORB and line extractor of a frame, src/Frame.cc:301-304): the images go to the device once,
+// on this context's stream, in 16 MB pieces so that transfers queued by other contexts can slip in between; the consumers
+// make their streams wait for it with plf_ctx_wait(consumer, this) and call the *_from_device entry points.
+extern "C" plf_status plf_upload(plf_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes)
+{
+    if (!ctx || !dev_dst || !host_src) return plf_fail(ctx, PLF_ERR_INVALID, "plf_upload: bad arguments");
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t piece = (size_t)16 << 20;
+    for (size_t off = 0; off < bytes; off += piece)
+        PLF_CUDA(ctx, cudaMemcpyAsync((char*)dev_dst + off, (const char*)host_src + off, bytes - off < piece ? bytes - off : piece,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    return PLF_OK;
+}
+extern "C" plf_status plf_device_malloc(plf_ctx* ctx, size_t bytes, void** out)
+{
+    if (!ctx || !out) return PLF_ERR_INVALID;
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    PLF_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 1));
+    return PLF_OK;
+}
+extern "C" void plf_device_free(plf_ctx* ctx, void* p)
+{
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(p);
 }

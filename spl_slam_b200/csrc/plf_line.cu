@@ -774,9 +774,9 @@ static plf_status check_regions(plf_line* o)
     return PLF_OK;
 }
 
-extern "C" plf_status plf_line_extract_batch(plf_line* o, const uint8_t* host_imgs, int nframes, int w, int h, size_t stride,
-                                             size_t frame_stride, plf_keyline* host_kl, plf_keypoint* host_mid, uint8_t* host_desc,
-                                             int cap, int32_t* n_out)
+static plf_status line_extract_to_host(plf_line* o, const uint8_t* host_imgs, bool device_src, int nframes, int w, int h, size_t stride,
+                                       size_t frame_stride, plf_keyline* host_kl, plf_keypoint* host_mid, uint8_t* host_desc, int cap,
+                                       int32_t* n_out)
 {
     if (!o) return PLF_ERR_INVALID;
     plf_ctx* ctx = o->ctx;
@@ -793,7 +793,7 @@ extern "C" plf_status plf_line_extract_batch(plf_line* o, const uint8_t* host_im
         if (st) return st;
         st = line_out_staging(o, nframes, cap);
         if (st) return st;
-        st = upload_images(o, host_imgs, nframes, w, h, stride, frame_stride, false);
+        st = upload_images(o, host_imgs, nframes, w, h, stride, frame_stride, device_src);
         if (st) return st;
         st = line_extract_device_impl(o, nframes, o->d_okl, o->d_omid, o->d_odesc, cap, o->d_onout);
     } while (st == PLF_RETRY_INTERNAL);
@@ -807,6 +807,20 @@ extern "C" plf_status plf_line_extract_batch(plf_line* o, const uint8_t* host_im
     st = check_regions(o);
     if (st) return st;
     return check_counts(ctx, n_out, nframes);
+}
+
+extern "C" plf_status plf_line_extract_batch(plf_line* o, const uint8_t* host_imgs, int nframes, int w, int h, size_t stride,
+                                             size_t frame_stride, plf_keyline* host_kl, plf_keypoint* host_mid, uint8_t* host_desc,
+                                             int cap, int32_t* n_out)
+{
+    return line_extract_to_host(o, host_imgs, false, nframes, w, h, stride, frame_stride, host_kl, host_mid, host_desc, cap, n_out);
+}
+
+extern "C" plf_status plf_line_extract_batch_from_device(plf_line* o, const uint8_t* dev_imgs, int nframes, int w, int h, size_t stride,
+                                                         size_t frame_stride, plf_keyline* host_kl, plf_keypoint* host_mid,
+                                                         uint8_t* host_desc, int cap, int32_t* n_out)
+{
+    return line_extract_to_host(o, dev_imgs, true, nframes, w, h, stride, frame_stride, host_kl, host_mid, host_desc, cap, n_out);
 }
 
 extern "C" plf_status plf_line_extract(plf_line* o, const uint8_t* host_img, int w, int h, size_t stride, plf_keyline* host_kl,

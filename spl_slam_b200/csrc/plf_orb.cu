@@ -294,9 +294,8 @@ static plf_status orb_out_staging(plf_orb* o, int nframes, int cap)
     return PLF_OK;
 }
 
-extern "C" plf_status plf_orb_extract_batch(plf_orb* o, const uint8_t* host_imgs, int nframes, int w, int h, size_t stride,
-                                            size_t frame_stride, plf_keypoint* host_kps, uint8_t* host_desc, int cap,
-                                            int32_t* n_out)
+static plf_status orb_extract_to_host(plf_orb* o, const uint8_t* host_imgs, bool device_src, int nframes, int w, int h, size_t stride,
+                                      size_t frame_stride, plf_keypoint* host_kps, uint8_t* host_desc, int cap, int32_t* n_out)
 {
     if (!o) return PLF_ERR_INVALID;
     plf_ctx* ctx = o->ctx;
@@ -318,6 +317,11 @@ extern "C" plf_status plf_orb_extract_batch(plf_orb* o, const uint8_t* host_imgs
     // is ONE DMA transfer; other widths keep the 64-byte aligned pitch (the kernels' 32-bit fast paths need it).  The
     // level-0 buffer was sized for the aligned pitch, which is at least as large.
     const size_t p0 = (w & 3) ? (size_t)L0.pitch : (size_t)w;
+    if (device_src) {
+        // the images are on the device already (uploaded once for several extractors: plf_upload): level 0 is the caller's buffer
+        st = orb_run(o, host_imgs, stride, frame_stride, nframes, o->d_kps, o->d_desc, cap, o->d_nout);
+        if (st) return st;
+    } else {
     if (stride == p0 && frame_stride == p0 * h) {
         // in pieces of 16 MB, so that transfers queued by other (higher-priority) contexts can slip in between
         const size_t total = (size_t)nframes * frame_stride, piece = (size_t)16 << 20;
@@ -330,6 +334,7 @@ extern "C" plf_status plf_orb_extract_batch(plf_orb* o, const uint8_t* host_imgs
     }
     st = orb_run(o, o->lvl_own[0], p0, p0 * h, nframes, o->d_kps, o->d_desc, cap, o->d_nout);
     if (st) return st;
+    }
     void* pin;   // the counts go through pinned staging (a copy into pageable memory stalls the other contexts' host threads)
     st = plf_ctx_pinned(ctx, (size_t)nframes * sizeof(int), &pin);
     if (st) return st;
@@ -343,6 +348,20 @@ extern "C" plf_status plf_orb_extract_batch(plf_orb* o, const uint8_t* host_imgs
         if (n_out[f] == -2) return plf_fail(ctx, PLF_ERR_CAPACITY, "frame %d: output capacity %d too small (use plf_orb_max_keypoints)", f, cap);
     }
     return PLF_OK;
+}
+
+extern "C" plf_status plf_orb_extract_batch(plf_orb* o, const uint8_t* host_imgs, int nframes, int w, int h, size_t stride,
+                                            size_t frame_stride, plf_keypoint* host_kps, uint8_t* host_desc, int cap,
+                                            int32_t* n_out)
+{
+    return orb_extract_to_host(o, host_imgs, false, nframes, w, h, stride, frame_stride, host_kps, host_desc, cap, n_out);
+}
+
+extern "C" plf_status plf_orb_extract_batch_from_device(plf_orb* o, const uint8_t* dev_imgs, int nframes, int w, int h, size_t stride,
+                                                        size_t frame_stride, plf_keypoint* host_kps, uint8_t* host_desc, int cap,
+                                                        int32_t* n_out)
+{
+    return orb_extract_to_host(o, dev_imgs, true, nframes, w, h, stride, frame_stride, host_kps, host_desc, cap, n_out);
 }
 
 extern "C" plf_status plf_orb_extract(plf_orb* o, const uint8_t* host_img, int w, int h, size_t stride, plf_keypoint* host_kps,
