@@ -847,8 +847,9 @@ def main():
             if os.path.exists(tp):
                 try:
                     tj = json.load(open(tp))
-                    if tj.get("kernel") == name_k:
-                        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("note")
+                    if tj.get("kernel") == name_k:      # per-frame DRAM bytes of the capture x the frames of one launch here
+                        traffic = tj.get("dram_bytes_per_frame", 0) * B / nl_ * (2 if name_k.startswith("k_lsd") else 1)
+                        traffic_src = tj.get("note")
                 except Exception:
                     pass
             roof = {"bound": "hbm", "kernel": name_k, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,

@@ -22,7 +22,7 @@ for row in r[1:]:
     cnt[name] += 1
 total = sum(tot.values())
 with open(out, "w") as f:
-    f.write("# ncu launch list summary (round 1, final kernels)\n\nCommand: `%s`\n" % cmd)
+    f.write("# ncu launch list summary\n\nCommand: `%s`\n" % cmd)
     f.write("(per-launch times are cold-cache and serialised under ncu: compare SHARES, not absolutes; raw list: `%s`)\n\n" % src.split("/")[-1])
     f.write("| kernel | launches | total ms | share |\n|---|---|---|---|\n")
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
