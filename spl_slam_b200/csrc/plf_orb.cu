@@ -1,6 +1,7 @@
 // plf_orb.cu -- host driver of the ORB path: replaces PL_SLAM::ORBextractor
 // (include/ORBextractor.h:45-113, src/ORBextractor.cc:410-470, :765-853, :1043-1132).
 #include "plf_orb_kernels.cuh"
+#include "plf_orb_tma.cuh"
 #include <math.h>
 #include <vector>
 
@@ -258,8 +259,20 @@ static plf_status orb_run(plf_orb* o, const uint8_t* lvl0, size_t stride0, size_
     PLF_CHECK_LAUNCH(ctx);
     PLF_LAUNCH(k_octree, dim3(g.nlevels, nframes), dim3(OCT_T), o->oct_smem, st, g, P, o->oct_cap);
     PLF_CHECK_LAUNCH(ctx);
-    PLF_LAUNCH(k_describe, dim3(plf_div_up(cap, 8), nframes), dim3(256), 0, st, g, P, d_kps, d_desc, cap, d_nout);
-    PLF_CHECK_LAUNCH(ctx);
+#ifndef PLF_EMU
+    // the two patches of every keypoint staged in shared memory by TMA tile loads; k_describe (direct gathers) when a caller-owned
+    // level 0 is not 16-byte aligned or the driver does not offer cuTensorMapEncodeTiled
+    static const bool no_tma = getenv("PLF_NO_TMA") != nullptr;
+    OrbTensorMaps tm;
+    if (!no_tma && orb_make_tensor_maps(g, P, nframes, &tm)) {
+        PLF_LAUNCH(k_describe_tma, dim3(plf_div_up(cap, 8), nframes), dim3(256), 0, st, g, P, tm, d_kps, d_desc, cap, d_nout);
+        PLF_CHECK_LAUNCH(ctx);
+    } else
+#endif
+    {
+        PLF_LAUNCH(k_describe, dim3(plf_div_up(cap, 8), nframes), dim3(256), 0, st, g, P, d_kps, d_desc, cap, d_nout);
+        PLF_CHECK_LAUNCH(ctx);
+    }
     o->last_frames = nframes;
     return PLF_OK;
 }
