@@ -277,6 +277,9 @@ def c5_config(world, nt):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+STAGGER_MS = float(os.environ.get("PLF_BENCH_STAGGER_MS", "0"))
+
+
 class Extraction:
     """One configuration's extraction workload on this rank's GPU: device-resident and end-to-end runs."""
 
@@ -352,6 +355,8 @@ class Extraction:
                                                                         self.d_mid[s].data_ptr(), self.d_ld[s].data_ptr(), self.capl, self.d_nl[s].data_ptr()))
 
     def _line_steps(self, i, nsteps, with_orb):
+        if STAGGER_MS and i:
+            time.sleep(i * STAGGER_MS * 1e-3)    # contexts out of phase: one grows regions (latency chain) while the other streams
         for k in range(nsteps):
             if with_orb and i == 0 and k + 1 < nsteps:
                 self.dev_orb(k + 1)      # ORB launches of step k + 1 (low-priority streams): filler for the gaps the line path leaves

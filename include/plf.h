@@ -122,7 +122,13 @@ plf_status plf_orb_extract_batch(plf_orb* orb, const uint8_t* host_imgs, int nfr
                                  size_t frame_stride, plf_keypoint* host_kps, uint8_t* host_desc, int cap,
                                  int32_t* n_out);
 /* Same, inputs and outputs resident in device memory (no copies; asynchronous on the context stream;
- * dev_n_out is an int32[nframes] device array). */
+ * dev_n_out is an int32[nframes] device array).  The call cannot return a capacity error for work that is still queued, so
+ * the *_device entry points report it per frame in dev_n_out[f] < 0 (the host-buffer entry points turn the same codes into
+ * PLF_ERR_CAPACITY): ORB  -1 = a level's raw FAST list overflowed, -2 = more than cap keypoints;
+ * lines -1 = more than the per-octave detection capacity, -2 = more than cap keylines, -3 = the LSD region buffer of an
+ * octave overflowed somewhere in this batch (regions were dropped: no frame of the batch is valid).
+ * dev_imgs must stay alive and unchanged until plf_stereo_match* / plf_orb_pyramid_level for this batch have run: level 0 of
+ * the pyramid IS the caller's buffer (it is not copied). */
 /* images already on the device (plf_upload), results to host buffers; dev_imgs must stay valid until the call returns */
 plf_status plf_orb_extract_batch_from_device(plf_orb* orb, const uint8_t* dev_imgs, int nframes, int w, int h, size_t stride,
                                              size_t frame_stride, plf_keypoint* host_kps, uint8_t* host_desc, int cap, int32_t* n_out);

@@ -38,6 +38,9 @@ struct plf_ctx {
     // small reusable device scratch (grown on demand)
     void* scratch;
     size_t scratch_bytes;
+    // second region for the device copies of host-buffer arguments (the kernels' own temporaries live in `scratch`)
+    void* ioscratch;
+    size_t ioscratch_bytes;
     // pinned host staging (grown on demand)
     void* pinned;
     size_t pinned_bytes;
@@ -111,6 +114,7 @@ static inline cudaError_t plf_smem_optin(const void* kernel, int device)
     } while (0)
 
 plf_status plf_ctx_scratch(plf_ctx* ctx, size_t bytes, void** out);
+plf_status plf_ctx_ioscratch(plf_ctx* ctx, size_t bytes, void** out);
 plf_status plf_ctx_pinned(plf_ctx* ctx, size_t bytes, void** out);
 
 static inline size_t plf_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -44,6 +44,7 @@ extern "C" void plf_ctx_destroy(plf_ctx* c)
     cudaStreamSynchronize(c->stream);
     plf_prof_free(c);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->ioscratch) cudaFree(c->ioscratch);
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -92,6 +93,21 @@ plf_status plf_ctx_scratch(plf_ctx* c, size_t bytes, void** out)
         c->scratch_bytes = want;
     }
     *out = c->scratch;
+    return PLF_OK;
+}
+
+plf_status plf_ctx_ioscratch(plf_ctx* c, size_t bytes, void** out)
+{
+    if (bytes > c->ioscratch_bytes) {
+        PLF_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->ioscratch) cudaFree(c->ioscratch);
+        c->ioscratch = nullptr;
+        c->ioscratch_bytes = 0;
+        size_t want = plf_align_up(bytes + bytes / 4, 1 << 20);
+        PLF_CUDA(c, cudaMalloc(&c->ioscratch, want));
+        c->ioscratch_bytes = want;
+    }
+    *out = c->ioscratch;
     return PLF_OK;
 }
 

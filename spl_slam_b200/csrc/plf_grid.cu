@@ -190,9 +190,10 @@ extern "C" plf_status plf_grid_candidates(plf_ctx* ctx, const plf_keypoint* host
     const size_t kb = plf_align_up((size_t)cap * sizeof(plf_keypoint), 256), lb = plf_align_up((size_t)cap * sizeof(plf_keyline), 256);
     const size_t ib = plf_align_up((size_t)cap * 4, 256), cb = plf_align_up((size_t)(ncell + 1) * 4, 256), qb = plf_align_up((size_t)(nq + 1) * 4, 256);
     const size_t ob = plf_align_up((size_t)(cand_cap > 0 ? cand_cap : 1) * 4, 256);
-    uint8_t* base = nullptr;
-    PLF_CUDA(ctx, cudaMalloc((void**)&base, kb + lb + 2 * ib + cb + 256 + 6 * qb + ob));
-    uint8_t* p = base;
+    void* io = nullptr;
+    st = plf_ctx_ioscratch(ctx, kb + lb + 2 * ib + cb + 256 + 6 * qb + ob, &io);     // no cudaMalloc / cudaFree per call
+    if (st) return st;
+    uint8_t* p = (uint8_t*)io;
     plf_keypoint* dk = (plf_keypoint*)p; p += kb;
     plf_keyline* dl = (plf_keyline*)p; p += lb;
     int* items = (int*)p; p += ib;
@@ -230,7 +231,6 @@ extern "C" plf_status plf_grid_candidates(plf_ctx* ctx, const plf_keypoint* host
     } else {
         cudaStreamSynchronize(s);
     }
-    cudaFree(base);
     return st;
 }
 

@@ -654,7 +654,7 @@ static plf_status line_select(plf_line* o, int nframes, bool select, plf_keyline
     const int noct = o->prm.nlevels;
     PLF_LAUNCH(k_line_select, dim3(nframes), dim3(SEL_T), SEL_SMEM_BYTES(LINE_DETCAP), ctx->stream, (const plf_keyline*)o->d_det,
                (const int*)o->d_detcount, LINE_DETCAP, noct, select ? 1 : 0, o->per_level[0], noct > 1 ? o->per_level[1] : 0, d_kl, d_mid,
-               cap, d_nout);
+               cap, d_nout, (const int*)(o->d_cnt[0] + CNT_ERR), noct > 1 ? (const int*)(o->d_cnt[1] + CNT_ERR) : (const int*)nullptr);
     PLF_CHECK_LAUNCH(ctx);
     return PLF_OK;
 }
@@ -759,6 +759,7 @@ static plf_status check_counts(plf_ctx* ctx, const int32_t* n_out, int nframes)
     for (int f = 0; f < nframes; f++) {
         if (n_out[f] == -1) return plf_fail(ctx, PLF_ERR_CAPACITY, "frame %d: more than %d lines detected in one octave", f, LINE_DETCAP);
         if (n_out[f] == -2) return plf_fail(ctx, PLF_ERR_CAPACITY, "frame %d: keyline output capacity too small", f);
+        if (n_out[f] == -3) return plf_fail(ctx, PLF_ERR_CAPACITY, "LSD region buffer overflow (more than %d regions in one frame)", LINE_REGCAP_PER_FRAME);
     }
     return PLF_OK;
 }

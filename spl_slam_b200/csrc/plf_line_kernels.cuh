@@ -1045,7 +1045,7 @@ k_lsd_keylines(const unsigned long long* __restrict__ linekey, const int* __rest
 __global__ void __launch_bounds__(SEL_T)
 k_line_select(const plf_keyline* __restrict__ det, const int* __restrict__ detcount, int detcap, int noct,
               int select, int quota0, int quota1, plf_keyline* __restrict__ out_kl, plf_keypoint* __restrict__ out_mid,
-              int cap, int* __restrict__ n_out)
+              int cap, int* __restrict__ n_out, const int* __restrict__ regerr0, const int* __restrict__ regerr1)
 {
     __shared__ int s_pos[2][2];   // [octave]: {valid count, kept count}
     __shared__ int s_err, s_tie;
@@ -1116,7 +1116,12 @@ k_line_select(const plf_keyline* __restrict__ det, const int* __restrict__ detco
         outbase += keep;
         __syncthreads();
     }
-    if (tid == 0) n_out[f] = s_err ? -s_err : outbase;
+    // -1: more than detcap lines in one octave, -2: output capacity, -3: the LSD region buffer of an octave overflowed somewhere in
+    // this batch (sticky per call: regions were dropped, so no frame of the batch is trustworthy)
+    if (tid == 0) {
+        const bool regerr = (regerr0 && *regerr0) || (regerr1 && *regerr1);
+        n_out[f] = regerr ? -3 : (s_err ? -s_err : outbase);
+    }
 }
 
 // ---------------- LBD (binary_descriptor_custom.cpp:1026-1372 + :645-667) ----------------

@@ -228,11 +228,12 @@ struct match_bufs {
     int *idx, *dist, *m12, *m21, *nm;
 };
 
-static plf_status upload_desc(plf_ctx* ctx, uint8_t** dev, const uint8_t* host, size_t rows)
+// device copies of host-buffer arguments come out of the context's I/O scratch (no cudaMalloc / cudaFree per call: both
+// synchronise the whole device and would stall the other contexts' streams; matchNNR is a per-frame-pair call in SLAM)
+static inline size_t desc_bytes(size_t rows) { return plf_align_up(rows ? rows * 32 : 32, 256); }
+static plf_status upload_desc(plf_ctx* ctx, uint8_t* dev, const uint8_t* host, size_t rows)
 {
-    *dev = nullptr;
-    PLF_CUDA(ctx, cudaMalloc((void**)dev, rows ? rows * 32 : 32));
-    if (rows) PLF_CUDA(ctx, cudaMemcpyAsync(*dev, host, rows * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (rows) PLF_CUDA(ctx, cudaMemcpyAsync(dev, host, rows * 32, cudaMemcpyHostToDevice, ctx->stream));
     return PLF_OK;
 }
 
@@ -243,11 +244,13 @@ extern "C" plf_status plf_hamming_knn2(plf_ctx* ctx, const uint8_t* hq, int nq, 
         return plf_fail(ctx, PLF_ERR_INVALID, "plf_hamming_knn2: bad arguments");
     if (nq == 0) return PLF_OK;
     PLF_CUDA(ctx, cudaSetDevice(ctx->device));
-    uint8_t *dq = nullptr, *dt = nullptr;
-    int* dout = nullptr;
-    plf_status st = upload_desc(ctx, &dq, hq, (size_t)nq);
-    if (!st) st = upload_desc(ctx, &dt, ht, (size_t)nt);
-    if (!st && cudaMalloc((void**)&dout, (size_t)nq * 4 * sizeof(int)) != cudaSuccess) st = plf_fail(ctx, PLF_ERR_CUDA, "cudaMalloc failed");
+    void* io = nullptr;
+    plf_status st = plf_ctx_ioscratch(ctx, desc_bytes((size_t)nq) + desc_bytes((size_t)nt) + (size_t)nq * 4 * sizeof(int), &io);
+    if (st) return st;
+    uint8_t *dq = (uint8_t*)io, *dt = dq + desc_bytes((size_t)nq);
+    int* dout = (int*)(dt + desc_bytes((size_t)nt));
+    st = upload_desc(ctx, dq, hq, (size_t)nq);
+    if (!st) st = upload_desc(ctx, dt, ht, (size_t)nt);
     if (!st) st = knn2_device(ctx, dq, nq, dt, nt, 0, dout, dout + 2 * (size_t)nq);
     if (!st) {
         cudaError_t e = cudaMemcpyAsync(hidx, dout, (size_t)nq * 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
@@ -257,7 +260,6 @@ extern "C" plf_status plf_hamming_knn2(plf_ctx* ctx, const uint8_t* hq, int nq, 
     } else {
         cudaStreamSynchronize(ctx->stream);
     }
-    cudaFree(dq); cudaFree(dt); cudaFree(dout);
     return st;
 }
 
@@ -270,14 +272,16 @@ static plf_status match_nnr_impl(plf_ctx* ctx, const uint8_t* h1, int n1, const 
     if (n1 == 0) return PLF_OK;
     if (mutual && n2 > 0x7fffffff) return plf_fail(ctx, PLF_ERR_INVALID, "mutual matching needs n2 < 2^31");
     PLF_CUDA(ctx, cudaSetDevice(ctx->device));
-    uint8_t *d1 = nullptr, *d2 = nullptr;
-    int* w = nullptr;
     size_t nmax = (size_t)(n1 > n2 ? n1 : n2);
-    plf_status st = upload_desc(ctx, &d1, h1, (size_t)n1);
-    if (!st) st = upload_desc(ctx, &d2, h2, (size_t)n2);
     // layout: idx[2*nmax] dist[2*nmax] m12[n1] m21[n2] nm[2]
     size_t words = 4 * nmax + (size_t)n1 + (size_t)n2 + 2;
-    if (!st && cudaMalloc((void**)&w, words * sizeof(int)) != cudaSuccess) st = plf_fail(ctx, PLF_ERR_CUDA, "cudaMalloc failed");
+    void* io = nullptr;
+    plf_status st = plf_ctx_ioscratch(ctx, desc_bytes((size_t)n1) + desc_bytes((size_t)n2) + words * sizeof(int), &io);
+    if (st) return st;
+    uint8_t *d1 = (uint8_t*)io, *d2 = d1 + desc_bytes((size_t)n1);
+    int* w = (int*)(d2 + desc_bytes((size_t)n2));
+    st = upload_desc(ctx, d1, h1, (size_t)n1);
+    if (!st) st = upload_desc(ctx, d2, h2, (size_t)n2);
     int *idx = w, *dist = w + 2 * nmax, *m12 = w + 4 * nmax, *m21 = m12 + n1, *nm = m21 + n2;
     if (!st) st = knn2_device(ctx, d1, n1, d2, n2, 0, idx, dist);
     if (!st) st = plf_nnr_from_knn2_device(ctx, idx, dist, n1, nnr, m12, nm);
@@ -297,7 +301,6 @@ static plf_status match_nnr_impl(plf_ctx* ctx, const uint8_t* h1, int n1, const 
     } else {
         cudaStreamSynchronize(ctx->stream);
     }
-    cudaFree(d1); cudaFree(d2); cudaFree(w);
     return st;
 }
 
@@ -318,11 +321,13 @@ extern "C" plf_status plf_descriptor_distance(plf_ctx* ctx, const uint8_t* ha, c
     if (!ctx || n < 0 || (n > 0 && (!ha || !hb || !hd))) return plf_fail(ctx, PLF_ERR_INVALID, "plf_descriptor_distance: bad arguments");
     if (n == 0) return PLF_OK;
     PLF_CUDA(ctx, cudaSetDevice(ctx->device));
-    uint8_t *da = nullptr, *db = nullptr;
-    int* dd = nullptr;
-    plf_status st = upload_desc(ctx, &da, ha, (size_t)n);
-    if (!st) st = upload_desc(ctx, &db, hb, (size_t)n);
-    if (!st && cudaMalloc((void**)&dd, (size_t)n * sizeof(int)) != cudaSuccess) st = plf_fail(ctx, PLF_ERR_CUDA, "cudaMalloc failed");
+    void* io = nullptr;
+    plf_status st = plf_ctx_ioscratch(ctx, 2 * desc_bytes((size_t)n) + (size_t)n * sizeof(int), &io);
+    if (st) return st;
+    uint8_t *da = (uint8_t*)io, *db = da + desc_bytes((size_t)n);
+    int* dd = (int*)(db + desc_bytes((size_t)n));
+    st = upload_desc(ctx, da, ha, (size_t)n);
+    if (!st) st = upload_desc(ctx, db, hb, (size_t)n);
     if (!st) {
         PLF_LAUNCH(pair_distance_kernel, dim3(plf_div_up(n, 128)), dim3(128), 0, ctx->stream, (const uint4*)da, (const uint4*)db, n, dd);
         ctx->launches++;
@@ -330,7 +335,6 @@ extern "C" plf_status plf_descriptor_distance(plf_ctx* ctx, const uint8_t* ha, c
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) st = plf_fail(ctx, PLF_ERR_CUDA, "distance copy failed: %s", cudaGetErrorString(e));
     }
-    cudaFree(da); cudaFree(db); cudaFree(dd);
     return st;
 }
 
