@@ -6,21 +6,7 @@
 #include <vector>
 #include <algorithm>
 #include <mutex>
-#ifndef PLF_EMU
-#include <cub/device/device_radix_sort.cuh>   // library radix sort (a plain sort, like cuBLAS for a plain GEMM)
-#include <cub/device/device_scan.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
-struct PopcOp {
-    __host__ __device__ int operator()(unsigned v) const
-    {
-#ifdef __CUDA_ARCH__
-        return __popc(v);
-#else
-        return __builtin_popcount(v);
-#endif
-    }
-};
-#endif
+#include "plf_sort.cuh"      // the scan and the radix sort of the LSD pre-phase (own kernels)
 
 #define LINE_MAX_OCT 2
 #define LINE_DETCAP 4096       // detected lines per (frame, octave) before the response quota
@@ -44,7 +30,7 @@ struct plf_line {
     uint8_t* d_base;
     uint8_t *d_oct[LINE_MAX_OCT];                              // octave images (pitch == width)
     uint8_t *d_lbdimg[LINE_MAX_OCT];
-    short *d_dx[LINE_MAX_OCT], *d_dy[LINE_MAX_OCT];
+    short2* d_dxy[LINE_MAX_OCT];            // Sobel (dx, dy) of the LBD octave images, interleaved
     // LSD workspace, one set per octave: the octaves of a batch are independent until the line selection, so they run
     // on two streams and their region-growing chains overlap
     uint8_t *d_tmp[LINE_MAX_OCT], *d_scaled[LINE_MAX_OCT];
@@ -58,8 +44,8 @@ struct plf_line {
     unsigned long long *d_keys[LINE_MAX_OCT], *d_keys2[LINE_MAX_OCT], *d_linekey[LINE_MAX_OCT];
     LsdRegion* d_regions[LINE_MAX_OCT];
     float4* d_lines[LINE_MAX_OCT];
-    void* d_cubtmp[LINE_MAX_OCT];
-    size_t cubtmp_bytes[LINE_MAX_OCT];
+    int *d_sctile[LINE_MAX_OCT], *d_rshist[LINE_MAX_OCT], *d_rstile[LINE_MAX_OCT], *d_rsbase[LINE_MAX_OCT];   // scan tile sums; radix: (tile, digit) table, frame of tile, first tile of frame
+    size_t rs_tilecap[LINE_MAX_OCT];
     size_t keycap[LINE_MAX_OCT];
     int key_div;                            // seed-key capacity = scaled pixels / key_div (batches start at 4; halved on overflow, then the call is retried)
     size_t maskwords[LINE_MAX_OCT];
@@ -175,7 +161,6 @@ static void line_free_ws(plf_line* o)
 {
     if (o->d_base) cudaFree(o->d_base);
     if (o->d_tabs) cudaFree(o->d_tabs);
-    for (int k = 0; k < LINE_MAX_OCT; k++) { if (o->d_cubtmp[k]) cudaFree(o->d_cubtmp[k]); o->d_cubtmp[k] = nullptr; }
     o->d_base = nullptr; o->d_tabs = nullptr;
     o->ws_w = o->ws_h = o->ws_frames = 0;
 }
@@ -289,7 +274,7 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         const size_t px = (size_t)o->ow[k] * o->oh[k], spx = (size_t)o->sp[k] * o->sh[k];
         o->keycap[k] = F * spx / (size_t)o->key_div + 4096;
         o->maskwords[k] = F * (spx / 32 + (size_t)o->sh[k] + 64);
-        need(F * px, 1); need(F * px, 1); need(F * px, 2); need(F * px, 2);      // octave, LBD image, dx, dy
+        need(F * px, 1); need(F * px, 1); need(F * px, 4);      // octave, LBD image, (dx, dy)
         need(F * px, 1); need(F * spx, 1);                                            // tmp, scaled
         need(F * spx, 4); need(F * spx, 4); need(F * spx, 4); need(F * spx, 8);   // q, label, fa, cs
         need(o->keycap[k], 8); need(o->keycap[k], 8); need(o->keycap[k], 4); need(o->keycap[k], 8);    // keys, keys2, regpts, comp
@@ -298,6 +283,8 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         need(CNT_MAXQ + 2 * F, 4);
         need(o->maskwords[k], 4); need(o->maskwords[k] + 64, 4); need(F, 8);   // mask, offsets, bin coefficients
         need(o->keycap[k], 1); need((size_t)o->gc_grid * GC_BUF * GC_RMAX, sizeof(int2));   // likely flags, speculation scratch
+        o->rs_tilecap[k] = o->keycap[k] / RS_TILE + F + 1;
+        need(o->maskwords[k] / SC_TILE + 2, 4); need(o->rs_tilecap[k] * 256, 4); need(o->rs_tilecap[k], 4); need(F + 1, 4);   // scan / sort tables
     }
     need(F * noct * LINE_DETCAP, sizeof(plf_keyline));
     need(F * noct, 4);
@@ -308,8 +295,7 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         const size_t px = (size_t)o->ow[k] * o->oh[k], spx = (size_t)o->sp[k] * o->sh[k];
         o->d_oct[k] = carve<uint8_t>(p, F * px);
         o->d_lbdimg[k] = carve<uint8_t>(p, F * px);
-        o->d_dx[k] = carve<short>(p, F * px);
-        o->d_dy[k] = carve<short>(p, F * px);
+        o->d_dxy[k] = carve<short2>(p, F * px);
         o->d_tmp[k] = carve<uint8_t>(p, F * px);
         o->d_scaled[k] = carve<uint8_t>(p, F * spx);
         o->d_q[k] = carve<int>(p, F * spx);
@@ -329,6 +315,10 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         o->d_bincoef[k] = carve<double>(p, F);
         o->d_likely[k] = carve<unsigned char>(p, o->keycap[k]);
         o->d_gcscr[k] = carve<int2>(p, (size_t)o->gc_grid * GC_BUF * GC_RMAX);
+        o->d_sctile[k] = carve<int>(p, o->maskwords[k] / SC_TILE + 2);
+        o->d_rshist[k] = carve<int>(p, o->rs_tilecap[k] * 256);
+        o->d_rstile[k] = carve<int>(p, o->rs_tilecap[k]);
+        o->d_rsbase[k] = carve<int>(p, F + 1);
     }
     o->d_det = carve<plf_keyline>(p, F * noct * LINE_DETCAP);
     o->d_detcount = carve<int>(p, F * noct);
@@ -343,38 +333,36 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
         }
         PLF_CUDA(ctx, cudaMemcpy(o->d_tabs, tabs.data(), tabCount * sizeof(int2), cudaMemcpyHostToDevice));
     }
-#ifndef PLF_EMU
-    for (int k = 0; k < noct; k++) {
-        size_t t1 = 0, t3 = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, t1, o->d_keys[k], o->d_keys2[k], (int)o->keycap[k], 0, 64, ctx->stream);
-        cub::TransformInputIterator<int, PopcOp, const unsigned*> it(o->d_mask[k], PopcOp());
-        cub::DeviceScan::InclusiveSum(nullptr, t3, it, o->d_offs[k] + 1, (int)o->maskwords[k], ctx->stream);
-        o->cubtmp_bytes[k] = t1 > t3 ? t1 : t3;
-        PLF_CUDA(ctx, cudaMalloc(&o->d_cubtmp[k], o->cubtmp_bytes[k] + 256));
-    }
-#endif
     for (int k = 0; k < noct; k++) PLF_CUDA(ctx, cudaMemset(o->d_offs[k], 0, sizeof(int)));
     o->ws_w = w; o->ws_h = h; o->ws_frames = nframes;
     return PLF_OK;
 }
 
-// k_lsd_keys emits the keys in (frame, raster index) order, so a STABLE sort of the bits above the raster index
-// [begin_bit, end_bit) = (frame, root, bin) yields the fully sorted array with two radix passes fewer
-static plf_status sort_keys(plf_line* o, int k, int n, int begin_bit, int end_bit, cudaStream_t st)
+// k_lsd_keys emits the keys in (frame, raster index) order, so a STABLE sort of the (root, bin) bits above the raster index
+// inside every frame's own range yields the fully sorted array (plf_sort.cuh).  The result ends up in d_keys2[k] (the two
+// buffers trade places when the number of passes is even).
+static plf_status sort_keys(plf_line* o, int k, int n, int nframes, int wpf, cudaStream_t st)
 {
     plf_ctx* ctx = o->ctx;
-#ifdef PLF_EMU
-    std::stable_sort(o->d_keys[k], o->d_keys[k] + n, [begin_bit](unsigned long long a, unsigned long long b) { return (a >> begin_bit) < (b >> begin_bit); });
-    memcpy(o->d_keys2[k], o->d_keys[k], (size_t)n * 8);
-    for (int i = 1; i < n; i++)
-        if (o->d_keys2[k][i - 1] >= o->d_keys2[k][i]) return plf_fail(ctx, PLF_ERR_STATE, "LSD keys not in raster order before the sort");
-#else
-    size_t tb = o->cubtmp_bytes[k];
-    plf_prof_begin(ctx, "cub_radix_sort_keys");
-    cudaError_t e = cub::DeviceRadixSort::SortKeys(o->d_cubtmp[k], tb, o->d_keys[k], o->d_keys2[k], n, begin_bit, end_bit, st);
-    plf_prof_end(ctx);
-    PLF_CUDA(ctx, e);
-#endif
+    const int KB = o->kbits[k] & 0xff, BB = o->kbits[k] >> 8;
+    const int passes = (KB + BB + 7) / 8;
+    const int ntiles = n / RS_TILE + nframes;       // upper bound of the tiles in use (a frame's last tile may be partial)
+    PLF_LAUNCH(k_rs_frames, dim3(1), dim3(SC_T), 0, st, (const int*)o->d_offs[k], wpf, nframes, o->d_rsbase[k], o->d_rstile[k], (int)o->rs_tilecap[k]);
+    PLF_CHECK_LAUNCH(ctx);
+    unsigned long long *in = o->d_keys[k], *out = o->d_keys2[k];
+    for (int p = 0; p < passes; p++) {
+        const int shift = KB + 8 * p;
+        PLF_LAUNCH(k_rs_hist, dim3(ntiles), dim3(RS_T), 0, st, (const unsigned long long*)in, (const int*)o->d_offs[k], wpf, nframes, (const int*)o->d_rsbase[k],
+                   (const int*)o->d_rstile[k], shift, o->d_rshist[k]);
+        PLF_CHECK_LAUNCH(ctx);
+        PLF_LAUNCH(k_rs_offsets, dim3(nframes), dim3(256), 0, st, o->d_rshist[k], (const int*)o->d_offs[k], wpf, (const int*)o->d_rsbase[k]);
+        PLF_CHECK_LAUNCH(ctx);
+        PLF_LAUNCH(k_rs_scatter, dim3(ntiles), dim3(RS_T), 0, st, (const unsigned long long*)in, out, (const int*)o->d_offs[k], wpf, nframes,
+                   (const int*)o->d_rsbase[k], (const int*)o->d_rstile[k], shift, (const int*)o->d_rshist[k]);
+        PLF_CHECK_LAUNCH(ctx);
+        unsigned long long* t = in; in = out; out = t;
+    }
+    if (in != o->d_keys2[k]) { o->d_keys[k] = o->d_keys2[k]; o->d_keys2[k] = in; }      // `in` holds the sorted keys
     return PLF_OK;
 }
 
@@ -489,18 +477,15 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         PLF_CHECK_LAUNCH(ctx);
         // key positions: inclusive scan of the mask popcounts (d_offs[0] = 0 is set once per workspace)
         nwords[k] = nframes * sh * mw;
-#ifdef PLF_EMU
-        { int acc = 0; o->d_offs[k][0] = 0; for (int i = 0; i < nwords[k]; i++) { acc += __builtin_popcount(o->d_mask[k][i]); o->d_offs[k][i + 1] = acc; } }
-#else
         {
-            size_t tb = o->cubtmp_bytes[k];
-            cub::TransformInputIterator<int, PopcOp, const unsigned*> it(o->d_mask[k], PopcOp());
-            plf_prof_begin(ctx, "cub_scan_mask");
-            cudaError_t e = cub::DeviceScan::InclusiveSum(o->d_cubtmp[k], tb, it, o->d_offs[k] + 1, nwords[k], st);
-            plf_prof_end(ctx);
-            PLF_CUDA(ctx, e);
+            const int nt = plf_div_up(nwords[k], SC_TILE);
+            PLF_LAUNCH(k_scan_tile_sums, dim3(nt), dim3(SC_T), 0, st, (const unsigned*)o->d_mask[k], nwords[k], o->d_sctile[k]);
+            PLF_CHECK_LAUNCH(ctx);
+            PLF_LAUNCH(k_scan_top, dim3(1), dim3(SC_T), 0, st, o->d_sctile[k], nt);
+            PLF_CHECK_LAUNCH(ctx);
+            PLF_LAUNCH(k_scan_apply, dim3(nt), dim3(SC_T), 0, st, (const unsigned*)o->d_mask[k], nwords[k], (const int*)o->d_sctile[k], o->d_offs[k] + 1);
+            PLF_CHECK_LAUNCH(ctx);
         }
-#endif
         PLF_LAUNCH(k_lsd_keys, g2, b2, 0, st, o->d_label[k], (const int*)o->d_q[k], (const unsigned*)o->d_mask[k], mw, (const int*)o->d_offs[k],
                    (const double*)o->d_bincoef[k], sp, sh, o->prm.n_bins, o->d_keys[k], (int)o->keycap[k], o->kbits[k]);
         PLF_CHECK_LAUNCH(ctx);
@@ -520,9 +505,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             return PLF_RETRY_INTERNAL;
         }
         if (nkeys[k] <= 0) continue;
-        int fbits = 1;
-        while ((1 << fbits) < nframes) fbits++;
-        plf_status s = sort_keys(o, k, nkeys[k], o->kbits[k] & 0xff, o->keybits[k] + fbits > 64 ? 64 : o->keybits[k] + fbits, st);
+        plf_status s = sort_keys(o, k, nkeys[k], nframes, o->sh[k] * mwk[k], st);
         if (s) return s;
         for (int pass = 0; pass < 2; pass++) {
             PLF_LAUNCH(k_lsd_heads, dim3(plf_div_up(nkeys[k], 256)), dim3(256), 0, st, (const unsigned long long*)o->d_keys2[k], nkeys[k], o->d_comp[k],
@@ -606,7 +589,8 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             }
             PLF_SMEM_OPTIN(ctx, k_lsd_grow_warp);
             const int nmid = nbig - ngiant;
-            const int wg_ctas = plf_div_up(nmid, WG_WARPS) < 148 * 4 ? plf_div_up(nmid, WG_WARPS) : 148 * 4;
+            static const int wg_cap = getenv("PLF_WG_CTAS") ? atoi(getenv("PLF_WG_CTAS")) : 148 * 4;
+            const int wg_ctas = plf_div_up(nmid, WG_WARPS) < wg_cap ? plf_div_up(nmid, WG_WARPS) : wg_cap;
             if (nmid > 0) PLF_LAUNCH(k_lsd_grow_warp, dim3(wg_ctas), dim3(32 * WG_WARPS), wg_smem, st, (const unsigned long long*)o->d_keys2[k],
                        (const int2*)o->d_comp[k], (const int*)(o->d_cnt[k] + CNT_BCOUNT), (const float*)o->d_fa[k], (const float2*)o->d_cs[k],
                        (const int*)o->d_label[k], sp, sh, o->prec, o->min_reg[k], o->d_regpts[k], o->d_regions[k], o->d_cnt[k] + CNT_MAXQ + nframes, LINE_REGCAP_PER_FRAME, o->kbits[k], wg_maxc, gthr);
@@ -680,13 +664,15 @@ static plf_status lbd_batch(plf_line* o, int nframes, const plf_keyline* d_kl, c
         PLF_CHECK_LAUNCH(ctx);
         const int sbF = plf_strip_interior(ow, 4, 8);
         PLF_LAUNCH(k_sobel3, dim3(plf_div_up(sbF, 32) + 1, plf_div_up(oh, 4 * SB_ROWS), nframes), dim3(32, 4), 0, st, (const uint8_t*)o->d_lbdimg[k],
-                   (size_t)ow * oh, ow, ow, oh, o->d_dx[k], o->d_dy[k], (size_t)ow * oh, sbF, plf_div_up(sbF, 32));
+                   (size_t)ow * oh, ow, ow, oh, o->d_dxy[k], (size_t)ow * oh, sbF, plf_div_up(sbF, 32));
         PLF_CHECK_LAUNCH(ctx);
-        im.dx[k] = o->d_dx[k]; im.dy[k] = o->d_dy[k]; im.frame[k] = (size_t)ow * oh; im.w[k] = ow; im.h[k] = oh;
+        im.dxy[k] = o->d_dxy[k]; im.frame[k] = (size_t)ow * oh; im.w[k] = ow; im.h[k] = oh;
     }
     if (maxlines > 0) {
-        PLF_LAUNCH(k_lbd, dim3(maxlines, nframes), dim3(64), 0, st, d_kl, d_nlines, cap, im, o->lbd_coefs, d_desc, d_fdesc);
-        PLF_CHECK_LAUNCH(ctx);
+        {
+            PLF_LAUNCH(k_lbd, dim3(maxlines, nframes), dim3(64), 0, st, d_kl, d_nlines, cap, im, o->lbd_coefs, d_desc, d_fdesc);
+            PLF_CHECK_LAUNCH(ctx);
+        }
     }
     return PLF_OK;
 }

@@ -223,16 +223,15 @@ __device__ __forceinline__ void sobel_hrow(const uint8_t* __restrict__ rp, int x
 }
 __global__ void __launch_bounds__(128)
 k_sobel3(const uint8_t* __restrict__ src, size_t sframe, int spitch, int w, int h,
-         short* __restrict__ dx, short* __restrict__ dy, size_t dframe, int F, int ncx_int)
+         short2* __restrict__ dxy, size_t dframe, int F, int ncx_int)
 {
     const int strip = plf_strip_of(blockIdx.x, threadIdx.x, w, 1, F, ncx_int);
     const int x0 = 4 * strip, y0 = (blockIdx.y * 4 + threadIdx.y) * SB_ROWS;
     if (strip < 0 || x0 >= w || y0 >= h) return;
     const uint8_t* s = src + (size_t)blockIdx.z * sframe;
-    short* ox = dx + (size_t)blockIdx.z * dframe;
-    short* oy = dy + (size_t)blockIdx.z * dframe;
+    short2* oxy = dxy + (size_t)blockIdx.z * dframe;      // (dx, dy) interleaved: k_lbd fetches both with one 4-byte gather
     const bool fastx = ((((size_t)s) | (size_t)spitch) & 3) == 0 && x0 >= 4 && x0 + 8 <= w;
-    const bool fullw = (w & 3) == 0 && ((((size_t)ox) | ((size_t)oy)) & 7) == 0 && x0 + 4 <= w;
+    const bool fullw = (w & 3) == 0 && (((size_t)oxy) & 15) == 0 && x0 + 4 <= w;
     int D[3][4], S[3][4];
     sobel_hrow(s + (size_t)reflect_once(y0 - 1, h) * spitch, x0, w, fastx, D[0], S[0]);
     sobel_hrow(s + (size_t)y0 * spitch, x0, w, fastx, D[1], S[1]);
@@ -251,15 +250,14 @@ k_sobel3(const uint8_t* __restrict__ src, size_t sframe, int spitch, int w, int 
             if (y < yend) {
                 const size_t o = (size_t)y * w + x0;
                 if (fullw) {
-                    uint2 vx, vy;
-                    vx.x = (unsigned)(gx[0] & 0xffff) | ((unsigned)gx[1] << 16); vx.y = (unsigned)(gx[2] & 0xffff) | ((unsigned)gx[3] << 16);
-                    vy.x = (unsigned)(gy[0] & 0xffff) | ((unsigned)gy[1] << 16); vy.y = (unsigned)(gy[2] & 0xffff) | ((unsigned)gy[3] << 16);
-                    *(uint2*)(ox + o) = vx;
-                    *(uint2*)(oy + o) = vy;
+                    uint4 v;
+                    v.x = (unsigned)(gx[0] & 0xffff) | ((unsigned)gy[0] << 16); v.y = (unsigned)(gx[1] & 0xffff) | ((unsigned)gy[1] << 16);
+                    v.z = (unsigned)(gx[2] & 0xffff) | ((unsigned)gy[2] << 16); v.w = (unsigned)(gx[3] & 0xffff) | ((unsigned)gy[3] << 16);
+                    *(uint4*)(oxy + o) = v;
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        if (x0 + j < w) { ox[o + j] = (short)gx[j]; oy[o + j] = (short)gy[j]; }
+                        if (x0 + j < w) oxy[o + j] = make_short2((short)gx[j], (short)gy[j]);
                 }
             }
         }
@@ -1129,9 +1127,8 @@ k_line_select(const plf_keyline* __restrict__ det, const int* __restrict__ detco
 // (float sums in the reference's order), threads < 9 accumulate their band in row order, thread 0 does the
 // mean/std, normalisations and clamp; then 32 threads binarise.
 struct LbdImages {
-    const short* dx[2];
-    const short* dy[2];
-    size_t frame[2];   // elements per frame
+    const short2* dxy[2];   // (dx, dy) per pixel
+    size_t frame[2];   // pixels per frame
     int w[2], h[2];
 };
 struct LbdCoefs { float g[63]; float l[21]; };
@@ -1141,55 +1138,10 @@ __constant__ int c_lbd_comb[32][2] = {
     {2, 3}, {2, 4}, {2, 5}, {2, 6}, {2, 7}, {2, 8}, {3, 4}, {3, 5}, {3, 6}, {3, 7}, {3, 8},
     {4, 5}, {4, 6}, {4, 7}, {4, 8}, {5, 6}, {5, 7}, {5, 8}, {6, 7}, {6, 8}, {7, 8}};
 
-__global__ void __launch_bounds__(64, 16)
-k_lbd(const plf_keyline* __restrict__ kl, const int* __restrict__ nlines, int cap, LbdImages im, LbdCoefs cf,
-      uint8_t* __restrict__ desc, float* __restrict__ fdesc)
+// bands, mean / std, normalisations, clamp and the 32 comparison bytes from the 63 row sums (all 64 threads of the CTA call it)
+__device__ __forceinline__ void lbd_finish(const int tid, float (*rows)[4], float (*band)[8], float* dv, const LbdCoefs& cf,
+                                           uint8_t* __restrict__ desc, float* __restrict__ fdesc, const int f, const int cap, const int li)
 {
-    __shared__ float rows[63][4];
-    __shared__ float band[9][8];
-    __shared__ float dv[72];
-    const int f = blockIdx.y, li = blockIdx.x, tid = threadIdx.x;
-    int nl = nlines[f];
-    if (li >= nl) return;
-    const plf_keyline K = kl[(size_t)f * cap + li];
-    const int o = K.octave;
-    const int realWidth = im.w[o], imageWidth = realWidth - 1, imageHeight = im.h[o] - 1;
-    const short* pdx = im.dx[o] + (size_t)f * im.frame[o];
-    const short* pdy = im.dy[o] + (size_t)f * im.frame[o];
-    const short lengthOfLSP = (short)K.numOfPixels;
-    const short halfWidth = (short)((lengthOfLSP - 1) / 2);
-    const short halfHeight = 31;
-    const float midX = (float)(0.5 * (double)(K.sPointInOctaveX + K.ePointInOctaveX));
-    const float midY = (float)(0.5 * (double)(K.sPointInOctaveY + K.ePointInOctaveY));
-    const float dL0 = plf_libm::cosf_glibc(K.angle), dL1 = plf_libm::sinf_glibc(K.angle);   // cos(float) = cosf (:1130-1131)
-    const float dO0 = -dL1, dO1 = dL0;
-    if (tid < 63) {
-        float t0 = -dL0 * (float)halfWidth, t1 = dL1 * (float)halfHeight;
-        float sCorX0 = t0 + t1 + midX;
-        t0 = -dL1 * (float)halfWidth; t1 = dL0 * (float)halfHeight;
-        float sCorY0 = t0 - t1 + midY;
-        for (int hh = 0; hh < tid; hh++) { sCorX0 -= dL1; sCorY0 += dL0; }   // same repeated float updates as the row loop
-        float sCorX = sCorX0, sCorY = sCorY0;
-        float pgdL = 0, ngdL = 0, pgdO = 0, ngdO = 0;
-        for (int wID = 0; wID < lengthOfLSP; wID++) {
-            // round() of the reference (double, half away from zero) == roundf(): float -> double is exact and so is the rounding
-            short tc = (short)(int)roundf(sCorX);
-            const int xCor = tc < 0 ? 0 : (tc > imageWidth ? imageWidth : tc);
-            tc = (short)(int)roundf(sCorY);
-            const int yCor = tc < 0 ? 0 : (tc > imageHeight ? imageHeight : tc);
-            const float dxv = (float)pdx[yCor * realWidth + xCor], dyv = (float)pdy[yCor * realWidth + xCor];
-            float a0 = dxv * dL0, a1 = dyv * dL1;
-            const float gDL = a0 + a1;
-            a0 = dxv * dO0; a1 = dyv * dO1;
-            const float gDO = a0 + a1;
-            if (gDL > 0) pgdL += gDL; else ngdL -= gDL;
-            if (gDO > 0) pgdO += gDO; else ngdO -= gDO;
-            sCorX += dL0;
-            sCorY += dL1;
-        }
-        const float coef = cf.g[tid];
-        rows[tid][0] = coef * pgdL; rows[tid][1] = coef * ngdL; rows[tid][2] = coef * pgdO; rows[tid][3] = coef * ngdO;
-    }
     __syncthreads();
     if (tid < 9) {
         float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // pgdL, ngdL, pgdL2, ngdL2, pgdO, ngdO, pgdO2, ngdO2
@@ -1255,6 +1207,58 @@ k_lbd(const plf_keyline* __restrict__ kl, const int* __restrict__ nlines, int ca
         desc[((size_t)f * cap + li) * 32 + tid] = (uint8_t)r;
     }
     if (fdesc) for (int i = tid; i < 72; i += 64) fdesc[((size_t)f * cap + li) * 72 + i] = dv[i];
+}
+
+__global__ void __launch_bounds__(64, 16)
+k_lbd(const plf_keyline* __restrict__ kl, const int* __restrict__ nlines, int cap, LbdImages im, LbdCoefs cf,
+      uint8_t* __restrict__ desc, float* __restrict__ fdesc)
+{
+    __shared__ float rows[63][4];
+    __shared__ float band[9][8];
+    __shared__ float dv[72];
+    const int f = blockIdx.y, li = blockIdx.x, tid = threadIdx.x;
+    int nl = nlines[f];
+    if (li >= nl) return;
+    const plf_keyline K = kl[(size_t)f * cap + li];
+    const int o = K.octave;
+    const int realWidth = im.w[o], imageWidth = realWidth - 1, imageHeight = im.h[o] - 1;
+    const short2* pdxy = im.dxy[o] + (size_t)f * im.frame[o];
+    const short lengthOfLSP = (short)K.numOfPixels;
+    const short halfWidth = (short)((lengthOfLSP - 1) / 2);
+    const short halfHeight = 31;
+    const float midX = (float)(0.5 * (double)(K.sPointInOctaveX + K.ePointInOctaveX));
+    const float midY = (float)(0.5 * (double)(K.sPointInOctaveY + K.ePointInOctaveY));
+    const float dL0 = plf_libm::cosf_glibc(K.angle), dL1 = plf_libm::sinf_glibc(K.angle);   // cos(float) = cosf (:1130-1131)
+    const float dO0 = -dL1, dO1 = dL0;
+    if (tid < 63) {
+        float t0 = -dL0 * (float)halfWidth, t1 = dL1 * (float)halfHeight;
+        float sCorX0 = t0 + t1 + midX;
+        t0 = -dL1 * (float)halfWidth; t1 = dL0 * (float)halfHeight;
+        float sCorY0 = t0 - t1 + midY;
+        for (int hh = 0; hh < tid; hh++) { sCorX0 -= dL1; sCorY0 += dL0; }   // same repeated float updates as the row loop
+        float sCorX = sCorX0, sCorY = sCorY0;
+        float pgdL = 0, ngdL = 0, pgdO = 0, ngdO = 0;
+        for (int wID = 0; wID < lengthOfLSP; wID++) {
+            // round() of the reference (double, half away from zero) == roundf(): float -> double is exact and so is the rounding
+            short tc = (short)(int)roundf(sCorX);
+            const int xCor = tc < 0 ? 0 : (tc > imageWidth ? imageWidth : tc);
+            tc = (short)(int)roundf(sCorY);
+            const int yCor = tc < 0 ? 0 : (tc > imageHeight ? imageHeight : tc);
+            const short2 g2 = __ldg(&pdxy[yCor * realWidth + xCor]);
+            const float dxv = (float)g2.x, dyv = (float)g2.y;
+            float a0 = dxv * dL0, a1 = dyv * dL1;
+            const float gDL = a0 + a1;
+            a0 = dxv * dO0; a1 = dyv * dO1;
+            const float gDO = a0 + a1;
+            if (gDL > 0) pgdL += gDL; else ngdL -= gDL;
+            if (gDO > 0) pgdO += gDO; else ngdO -= gDO;
+            sCorX += dL0;
+            sCorY += dL1;
+        }
+        const float coef = cf.g[tid];
+        rows[tid][0] = coef * pgdL; rows[tid][1] = coef * ngdL; rows[tid][2] = coef * pgdO; rows[tid][3] = coef * ngdO;
+    }
+    lbd_finish(tid, rows, band, dv, cf, desc, fdesc, f, cap, li);
 }
 
 #include "plf_fld_kernels.cuh"

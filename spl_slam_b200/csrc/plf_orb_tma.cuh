@@ -12,7 +12,7 @@
 // another pitch takes k_describe).
 #pragma once
 #ifndef PLF_EMU
-#include <cuda.h>
+#include "plf_tma.cuh"
 
 struct OrbTensorMaps {
     CUtensorMap raw[ORB_MAX_LEVELS];
@@ -28,7 +28,6 @@ struct OrbTensorMaps {
 #define DT_BLR_OFF 1536                         // per warp: raw tile at 0, blurred tile at 1536 (both 128-byte aligned)
 #define DT_SLOT 4096
 
-__device__ __forceinline__ unsigned dt_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __global__ void __launch_bounds__(256)
 k_describe_tma(OrbGeom g, OrbPtrs p, const __grid_constant__ OrbTensorMaps tm, plf_keypoint* __restrict__ kps, uint8_t* __restrict__ desc,
@@ -58,15 +57,12 @@ k_describe_tma(OrbGeom g, OrbPtrs p, const __grid_constant__ OrbTensorMaps tm, p
     uint8_t* rawT = tiles[wl];
     uint8_t* blrT = tiles[wl] + DT_BLR_OFF;
     const int xr = (X - 15) & ~15, xb = (X - 19) & ~15;      // box origins; X >= 19 always (FAST starts 19 px inside)
-    const unsigned bar = dt_smem_u32(&bars[wl]);
+    const unsigned bar = plf_smem_u32(&bars[wl]);
     if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(DT_RAW_BYTES + DT_BLR_BYTES) : "memory");
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     ::"r"(dt_smem_u32(rawT)), "l"(&tm.raw[l]), "r"(bar), "r"(xr), "r"(Y - 15), "r"(f) : "memory");
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     ::"r"(dt_smem_u32(blrT)), "l"(&tm.blr[l]), "r"(bar), "r"(xb), "r"(Y - 19), "r"(f) : "memory");
+        plf_mbar_init(bar, 1);
+        plf_mbar_expect_tx(bar, DT_RAW_BYTES + DT_BLR_BYTES);
+        plf_tma_load_3d(plf_smem_u32(rawT), &tm.raw[l], bar, xr, Y - 15, f);
+        plf_tma_load_3d(plf_smem_u32(blrT), &tm.blr[l], bar, xb, Y - 19, f);
     }
     __syncwarp();
     // the lane's 16 point pairs (32 signed bytes) as two 16-byte loads, while the tiles are in flight
@@ -78,12 +74,7 @@ k_describe_tma(OrbGeom g, OrbPtrs p, const __grid_constant__ OrbTensorMaps tm, p
 #pragma unroll
         for (int i = 0; i < 32; i++) pat[i] = (signed char)((wds[i >> 2] >> (8 * (i & 3))) & 0xff);
     }
-    {
-        unsigned done = 0;
-        while (!done)
-            asm volatile("{ .reg .pred P1; mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2; selp.u32 %0, 1, 0, P1; }"
-                         : "=r"(done) : "r"(bar), "r"(0) : "memory");
-    }
+    plf_mbar_wait(bar, 0);
     // orientation on the un-blurred level: row v of the disc, columns -umax[v] .. umax[v]
     int m10 = 0, m01 = 0;
     if (lane < 31) {
@@ -133,42 +124,12 @@ k_describe_tma(OrbGeom g, OrbPtrs p, const __grid_constant__ OrbTensorMaps tm, p
 }
 
 // host: encode the per-level maps for this call (x, y, frame); false when a base or pitch is not 16-byte aligned
-typedef CUresult (*plf_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static plf_encode_tiled_fn plf_get_encode_tiled()
-{
-    static plf_encode_tiled_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = (plf_encode_tiled_fn)p;
-    }
-    return fn;
-}
 static bool orb_make_tensor_maps(const OrbGeom& g, const OrbPtrs& P, int nframes, OrbTensorMaps* tm)
 {
-    plf_encode_tiled_fn enc = plf_get_encode_tiled();
-    if (!enc) return false;
     for (int l = 0; l < g.nlevels; l++) {
         const OrbLevelGeom& L = g.lv[l];
-        for (int kind = 0; kind < 2; kind++) {
-            const void* base = kind ? (const void*)P.blr[l] : (const void*)P.lvl[l];
-            const size_t pitch = kind ? (size_t)L.pitch : (size_t)P.pitch[l];
-            const size_t fstride = kind ? L.frameBytes : P.frameStride[l];
-            if (((uintptr_t)base & 15) || (pitch & 15) || (fstride & 15)) return false;
-            const cuuint64_t dims[3] = {(cuuint64_t)L.w, (cuuint64_t)L.h, (cuuint64_t)nframes};
-            const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)fstride};
-            const cuuint32_t box[3] = {(cuuint32_t)(kind ? DT_BLR_W : DT_RAW_W), (cuuint32_t)(kind ? DT_BLR_H : DT_RAW_H), 1};
-            const cuuint32_t estr[3] = {1, 1, 1};
-            if (enc(kind ? &tm->blr[l] : &tm->raw[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-                return false;
-        }
+        if (!plf_tma_map_images(&tm->raw[l], P.lvl[l], 1, L.w, L.h, nframes, (size_t)P.pitch[l], P.frameStride[l], DT_RAW_W, DT_RAW_H)) return false;
+        if (!plf_tma_map_images(&tm->blr[l], P.blr[l], 1, L.w, L.h, nframes, (size_t)L.pitch, L.frameBytes, DT_BLR_W, DT_BLR_H)) return false;
     }
     return true;
 }

@@ -36,6 +36,8 @@ struct dim3 {
 };
 struct uchar4 { unsigned char x, y, z, w; };
 struct int2 { int x, y; };
+struct short2 { short x, y; };
+static inline short2 make_short2(short a, short b) { short2 r = {a, b}; return r; }
 struct uint2 { unsigned x, y; };
 struct int4 { int x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
