@@ -492,7 +492,9 @@ def algorithmic_bytes(cfg):
         "k_fast_cells": sumpx, "k_blur7": 2 * sumpx, "k_resize_linear": 2 * sumpx - 2 * px0 + (px0 - lv[-1][0] * lv[-1][1]),
         "k_gauss_strip<3>": 2 * p01, "k_gauss_strip<2>": 2 * px0, "k_resize_exact": p01 + spx,
         "k_pyrdown": 2 * (px0 + px0 // 4), "k_sobel3": 5 * p01,
-        "cub_radix_sort_keys": int(2 * 8 * 8 * dens * spx), "k_describe": 2 * 1024 * orb["nfeatures"], "k_lbd": 63 * 4 * 60 * line["nfeatures"],
+        # own radix sort: 4 passes over the 8-byte keys of the defined pixels (histogram reads them once, scatter reads and writes)
+        "k_rs_hist": int(4 * 8 * dens * spx), "k_rs_scatter": int(4 * 16 * dens * spx), "k_scan_apply": int(spx / 32 * 8), "k_scan_tile_sums": int(spx / 32 * 4),
+        "k_describe": 2 * 1024 * orb["nfeatures"], "k_describe_tma": (48 * 31 + 64 * 39 + 60) * orb["nfeatures"], "k_lbd": 63 * 4 * 60 * line["nfeatures"],
     }
     # B_orb + the per-octave line figures (LSD-pre, gradient, sort, grow, LBD-prep, LBD gathers)
     b_orb = px0 + sumpx + (sumpx - lv[-1][0] * lv[-1][1]) + sumpx + 2 * sumpx + 60 * orb["nfeatures"]

@@ -56,6 +56,10 @@ struct plf_line {
     int gc_grid;                            // speculator warps the scratch is sized for
     unsigned long long* d_gcdbg;            // PLF_GC_DEBUG=1: counters of k_lsd_grow_cta (diagnosis only)
     cudaEvent_t ev_img, ev_join;
+    // the three region-growing kernels of an octave (giant components, big components, the rest) work on disjoint components:
+    // they run side by side on the octave's stream and two helpers
+    cudaStream_t st_grow[LINE_MAX_OCT][2];
+    cudaEvent_t ev_fork[LINE_MAX_OCT], ev_grow[LINE_MAX_OCT][2];
     int* h_pin;                            // pinned host staging for the per-octave counters (64 ints each)
     int *d_detcount;
     int qthr;               // defined <=> gx^2 + gy^2 > qthr
@@ -174,6 +178,13 @@ extern "C" void plf_line_destroy(plf_line* o)
     if (o->st2) cudaStreamDestroy(o->st2);
     if (o->ev_img) cudaEventDestroy(o->ev_img);
     if (o->ev_join) cudaEventDestroy(o->ev_join);
+    for (int k = 0; k < LINE_MAX_OCT; k++) {
+        if (o->ev_fork[k]) cudaEventDestroy(o->ev_fork[k]);
+        for (int j = 0; j < 2; j++) {
+            if (o->ev_grow[k][j]) cudaEventDestroy(o->ev_grow[k][j]);
+            if (o->st_grow[k][j]) cudaStreamDestroy(o->st_grow[k][j]);
+        }
+    }
     if (o->h_pin) cudaFreeHost(o->h_pin);
     if (o->d_okl) cudaFree(o->d_okl);
     if (o->d_omid) cudaFree(o->d_omid);
@@ -265,6 +276,17 @@ static plf_status line_prepare(plf_line* o, int w, int h, int nframes)
 #endif
         PLF_CUDA(ctx, cudaEventCreate(&o->ev_img));
         PLF_CUDA(ctx, cudaEventCreate(&o->ev_join));
+        for (int k = 0; k < LINE_MAX_OCT; k++) {
+            PLF_CUDA(ctx, cudaEventCreateWithFlags(&o->ev_fork[k], cudaEventDisableTiming));
+            for (int j = 0; j < 2; j++) {
+                PLF_CUDA(ctx, cudaEventCreateWithFlags(&o->ev_grow[k][j], cudaEventDisableTiming));
+#ifndef PLF_EMU
+                PLF_CUDA(ctx, cudaStreamCreateWithPriority(&o->st_grow[k][j], cudaStreamNonBlocking, pr));
+#else
+                PLF_CUDA(ctx, cudaStreamCreateWithFlags(&o->st_grow[k][j], cudaStreamNonBlocking));
+#endif
+            }
+        }
         PLF_CUDA(ctx, cudaMallocHost((void**)&o->h_pin, LINE_MAX_OCT * 64 * sizeof(int)));
     }
     o->gc_grid = (int)((8 * F + 8) * (GC_MAXWARPS - 1) < 148 * 24 ? (8 * F + 8) * (GC_MAXWARPS - 1) : 148 * 24);   // most SPECULATOR WARPS of one k_lsd_grow_cta launch (its scratch is sized for them)
@@ -569,6 +591,15 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
 #ifndef PLF_EMU
             if (!o->d_gcdbg && getenv("PLF_GC_DEBUG")) { PLF_CUDA(ctx, cudaMalloc((void**)&o->d_gcdbg, 16 * 8)); PLF_CUDA(ctx, cudaMemset(o->d_gcdbg, 0, 16 * 8)); }
 #endif
+            // fork: the warp kernel and the thread kernel do not wait for the giant components' CTAs (disjoint components; regions
+            // are appended with atomics and ordered later by their keys).  With the per-launch profiler on everything stays on one stream.
+            const bool forked = !ctx->prof_on;
+            cudaStream_t st_w = forked ? o->st_grow[k][0] : st, st_t = forked ? o->st_grow[k][1] : st;
+            if (forked) {
+                PLF_CUDA(ctx, cudaEventRecord(o->ev_fork[k], st));
+                PLF_CUDA(ctx, cudaStreamWaitEvent(st_w, o->ev_fork[k], 0));
+                PLF_CUDA(ctx, cudaStreamWaitEvent(st_t, o->ev_fork[k], 0));
+            }
             if (ngiant > 0) {
                 int gc_warps = GC_SMEM_BUDGET / bm;
                 if (gc_warps > GC_MAXWARPS) gc_warps = GC_MAXWARPS;
@@ -589,16 +620,21 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
             }
             PLF_SMEM_OPTIN(ctx, k_lsd_grow_warp);
             const int nmid = nbig - ngiant;
-            static const int wg_cap = getenv("PLF_WG_CTAS") ? atoi(getenv("PLF_WG_CTAS")) : 148 * 4;
-            const int wg_ctas = plf_div_up(nmid, WG_WARPS) < wg_cap ? plf_div_up(nmid, WG_WARPS) : wg_cap;
-            if (nmid > 0) PLF_LAUNCH(k_lsd_grow_warp, dim3(wg_ctas), dim3(32 * WG_WARPS), wg_smem, st, (const unsigned long long*)o->d_keys2[k],
+            const int wg_ctas = plf_div_up(nmid, WG_WARPS) < 148 * 4 ? plf_div_up(nmid, WG_WARPS) : 148 * 4;
+            if (nmid > 0) PLF_LAUNCH(k_lsd_grow_warp, dim3(wg_ctas), dim3(32 * WG_WARPS), wg_smem, st_w, (const unsigned long long*)o->d_keys2[k],
                        (const int2*)o->d_comp[k], (const int*)(o->d_cnt[k] + CNT_BCOUNT), (const float*)o->d_fa[k], (const float2*)o->d_cs[k],
                        (const int*)o->d_label[k], sp, sh, o->prec, o->min_reg[k], o->d_regpts[k], o->d_regions[k], o->d_cnt[k] + CNT_MAXQ + nframes, LINE_REGCAP_PER_FRAME, o->kbits[k], wg_maxc, gthr);
             PLF_CHECK_LAUNCH(ctx);
-            PLF_LAUNCH(k_lsd_grow, dim3(148 * 4), dim3(128), 0, st, (const unsigned long long*)o->d_keys2[k], nkeys[k], (const int2*)o->d_comp[k],
+            PLF_LAUNCH(k_lsd_grow, dim3(148 * 4), dim3(128), 0, st_t, (const unsigned long long*)o->d_keys2[k], nkeys[k], (const int2*)o->d_comp[k],
                        (const int*)(o->d_cnt[k] + CNT_BCOUNT), o->d_cnt[k] + CNT_NEXT, o->d_fa[k], (const float2*)o->d_cs[k], sp, sh, o->prec,
                        o->min_reg[k], o->d_regpts[k], o->d_regions[k], o->d_cnt[k] + CNT_MAXQ + nframes, LINE_REGCAP_PER_FRAME, 1, wg_maxc, o->kbits[k]);
             PLF_CHECK_LAUNCH(ctx);
+            if (forked) {      // join before the rectangles
+                PLF_CUDA(ctx, cudaEventRecord(o->ev_grow[k][0], st_w));
+                PLF_CUDA(ctx, cudaEventRecord(o->ev_grow[k][1], st_t));
+                PLF_CUDA(ctx, cudaStreamWaitEvent(st, o->ev_grow[k][0], 0));
+                PLF_CUDA(ctx, cudaStreamWaitEvent(st, o->ev_grow[k][1], 0));
+            }
         }
         // enough CTAs per frame to fill the GPU for small batches
         int rsplit = plf_div_up(148 * 8, nframes);
