@@ -438,9 +438,22 @@ static std::mutex g_lsd_prephase[64];   // one per device: contexts of different
 // stream, the host walks both through the same phases, so the two region-growing chains run side by side.
 // With profiling on, everything stays on the context stream (the per-kernel event times must not overlap).
 #define PLF_RETRY_INTERNAL ((plf_status)1000)   // never leaves this file
+// host-side phase trace of a call (PLF_TRACE=1): microseconds since the start of lsd_detect_batch at each phase boundary
+#include <chrono>
+struct PhaseTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    PhaseTrace() : on(getenv("PLF_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what)
+    {
+        if (on) fprintf(stderr, "[trace] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
 static plf_status lsd_detect_batch(plf_line* o, int nframes)
 {
     plf_ctx* ctx = o->ctx;
+    PhaseTrace tr;
     const int noct = o->prm.nlevels;
     const double S = o->prm.scale;
     cudaStream_t st0 = ctx->stream;
@@ -450,6 +463,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
     // whatever is still queued on this stream (the image upload of a host-buffer call) finishes before the turn is
     // taken: the lock must not be held across a PCIe transfer
     PLF_CUDA(ctx, cudaStreamSynchronize(st0));
+    tr.mark("upload done");
     std::unique_lock<std::mutex> prephase(g_lsd_prephase[ctx->device & 63], std::defer_lock);
     if (!getenv("PLF_NO_PREPHASE_LOCK")) prephase.lock();
     // computeGaussianPyramid: pyrDown, no pre-blur (LSDDetector_custom.cpp:56-73)
@@ -514,9 +528,11 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         PLF_CUDA(ctx, cudaMemcpyAsync(o->h_pin + 64 * k, o->d_offs[k] + nwords[k], sizeof(int), cudaMemcpyDeviceToHost, st));   // pinned staging
     }
     // ---- phase 2: sort, component heads, sorted positions ----
+    tr.mark("phase 1 queued");
     for (int k = 0; k < noct; k++) {
         cudaStream_t st = stk[k];
         PLF_CUDA(ctx, cudaStreamSynchronize(st));
+        tr.mark("phase 1 done (octave)");
         nkeys[k] = o->h_pin[64 * k];
         if (nkeys[k] > (int)o->keycap[k]) {
             // more defined pixels than the workspace reserves: finish what is queued, then let the caller re-prepare and retry
@@ -541,8 +557,10 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         PLF_CUDA(ctx, cudaMemcpyAsync(o->h_pin + 64 * k + 8, o->d_cnt[k] + CNT_BCOUNT, LSD_NBUCKET * sizeof(int), cudaMemcpyDeviceToHost, st));
         PLF_CUDA(ctx, cudaMemcpyAsync(o->h_pin + 64 * k + 1, o->d_cnt[k] + CNT_NCOMP, sizeof(int), cudaMemcpyDeviceToHost, st));   // largest component
     }
+    tr.mark("phase 2 queued");
     for (int k = 0; k < noct; k++)
         if (nkeys[k] > 0) PLF_CUDA(ctx, cudaStreamSynchronize(stk[k]));
+    tr.mark("phase 2 done");
     if (prephase.owns_lock()) prephase.unlock();   // everything up to here has finished on the GPU; growing may overlap other contexts
     // ---- phase 3: region growing (the latency-bound chains of both octaves side by side), rectangles, keylines ----
     for (int k = 0; k < noct; k++) {
@@ -659,6 +677,8 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
                 nframes, hd[0], hd[1], hd[2], hd[3], hd[4], hd[5], hd[6], hd[7], hd[8]);
     }
 #endif
+    tr.mark("phase 3 queued");
+    if (tr.on) { for (int k = 0; k < noct; k++) cudaStreamSynchronize(stk[k]); tr.mark("phase 3 done (trace only sync)"); }
     // the selection / LBD that follow run on the context stream: join octave 1
     if (noct > 1 && stk[1] != st0) {
         PLF_CUDA(ctx, cudaEventRecord(o->ev_join, stk[1]));
