@@ -4,9 +4,7 @@
 // lists (CSR) that plf_hamming_candidates_device scans, in exactly the reference's order (cell column outer, cell row
 // inner, insertion order inside a cell), because the matchers' "first best wins" rule depends on it.
 #include "plf_common.cuh"
-#ifndef PLF_EMU
-#include <cub/device/device_scan.cuh>
-#endif
+#include "plf_sort.cuh"      // k_scan_top: single-CTA exclusive scan (the candidate offsets are a few thousand entries)
 
 // cell of a point; false when it falls outside the grid (undistorted coordinates may leave the image)
 __device__ __forceinline__ bool grid_pos(float x, float y, const plf_grid_params& g, int& cx, int& cy)
@@ -143,23 +141,16 @@ extern "C" plf_status plf_grid_query_device(plf_ctx* ctx, const plf_keypoint* de
     if (nq == 0) { PLF_CUDA(ctx, cudaMemsetAsync(dev_cand_off, 0, sizeof(int), s)); return PLF_OK; }
     // counts -> exclusive scan (nq + 1 entries) -> fill
     void* scr;
-    size_t tb = 0;
-#ifndef PLF_EMU
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int*)nullptr, (int*)nullptr, nq + 1, s);
-#endif
-    st = plf_ctx_scratch(ctx, (size_t)(nq + 1) * sizeof(int) + tb + 512, &scr);
+    st = plf_ctx_scratch(ctx, (size_t)(nq + 1) * sizeof(int) + 512, &scr);
     if (st) return st;
     int* counts = (int*)scr;
-    void* cubtmp = (char*)scr + plf_align_up((size_t)(nq + 1) * sizeof(int), 256);
     PLF_CUDA(ctx, cudaMemsetAsync(counts + nq, 0, sizeof(int), s));
     PLF_LAUNCH(k_grid_query, dim3(plf_div_up(nq, 128)), dim3(128), 0, s, dev_kps, *g, dev_cell_start, dev_cell_items, dev_qx, dev_qy, dev_qr,
                dev_qminl, dev_qmaxl, nq, counts, (const int*)nullptr, (int*)nullptr, 0, 0);
     PLF_CHECK_LAUNCH(ctx);
-#ifdef PLF_EMU
-    { int acc = 0; for (int i = 0; i <= nq; i++) { const int v = counts[i]; dev_cand_off[i] = acc; acc += v; } (void)cubtmp; }
-#else
-    PLF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(cubtmp, tb, (const int*)counts, dev_cand_off, nq + 1, s));
-#endif
+    PLF_CUDA(ctx, cudaMemcpyAsync(dev_cand_off, counts, (size_t)(nq + 1) * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    PLF_LAUNCH(k_scan_top, dim3(1), dim3(SC_T), 0, s, dev_cand_off, nq + 1);       // exclusive scan in place
+    PLF_CHECK_LAUNCH(ctx);
     void* pin;
     st = plf_ctx_pinned(ctx, 64, &pin);
     if (st) return st;

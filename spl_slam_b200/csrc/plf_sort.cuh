@@ -44,7 +44,7 @@ __device__ __forceinline__ int plf_block_exscan(int v, int* s_warp, int* total)
     return base + inc - v;
 }
 
-__global__ void __launch_bounds__(SC_T)
+static __global__ void __launch_bounds__(SC_T)
 k_scan_tile_sums(const unsigned* __restrict__ mask, int n, int* __restrict__ tsum)
 {
     __shared__ int s_warp[SC_T / 32];
@@ -61,7 +61,7 @@ k_scan_tile_sums(const unsigned* __restrict__ mask, int n, int* __restrict__ tsu
 }
 
 // one CTA: exclusive scan of the tile sums in place
-__global__ void __launch_bounds__(SC_T)
+static __global__ void __launch_bounds__(SC_T)
 k_scan_top(int* __restrict__ tsum, int ntiles)
 {
     __shared__ int s_warp[SC_T / 32];
@@ -82,7 +82,7 @@ k_scan_top(int* __restrict__ tsum, int ntiles)
 }
 
 // every thread owns SC_PER consecutive words of the tile
-__global__ void __launch_bounds__(SC_T)
+static __global__ void __launch_bounds__(SC_T)
 k_scan_apply(const unsigned* __restrict__ mask, int n, const int* __restrict__ tbase, int* __restrict__ out)
 {
     __shared__ int s_warp[SC_T / 32];
@@ -119,7 +119,7 @@ k_scan_apply(const unsigned* __restrict__ mask, int n, const int* __restrict__ t
 
 // per frame: number of tiles and their first index; tile_frame[t] = frame of tile t; tbase[nframes] = tiles in use
 // fo(f) = offs[f * wpf] (offs has the leading 0): first key of frame f.  One CTA.
-__global__ void __launch_bounds__(SC_T)
+static __global__ void __launch_bounds__(SC_T)
 k_rs_frames(const int* __restrict__ offs, int wpf, int nframes, int* __restrict__ tbase, int* __restrict__ tile_frame, int tile_cap)
 {
     __shared__ int s_warp[SC_T / 32];
@@ -175,7 +175,7 @@ __device__ __forceinline__ void rs_warp_count(const unsigned long long (&key)[RS
     }
 }
 
-__global__ void __launch_bounds__(RS_T)
+static __global__ void __launch_bounds__(RS_T)
 k_rs_hist(const unsigned long long* __restrict__ in, const int* __restrict__ offs, int wpf, int nframes, const int* __restrict__ tbase,
           const int* __restrict__ tile_frame, int shift, int* __restrict__ hist)
 {
@@ -202,7 +202,7 @@ k_rs_hist(const unsigned long long* __restrict__ in, const int* __restrict__ off
 
 // one CTA per frame, thread d = digit d: destination of (digit, tile) = frame start + keys of smaller digits + keys of this
 // digit in earlier tiles (in place: hist becomes the offset table)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_rs_offsets(int* __restrict__ hist, const int* __restrict__ offs, int wpf, const int* __restrict__ tbase)
 {
     __shared__ int s_warp[8];
@@ -219,7 +219,7 @@ k_rs_offsets(int* __restrict__ hist, const int* __restrict__ offs, int wpf, cons
     }
 }
 
-__global__ void __launch_bounds__(RS_T)
+static __global__ void __launch_bounds__(RS_T)
 k_rs_scatter(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, const int* __restrict__ offs, int wpf, int nframes,
              const int* __restrict__ tbase, const int* __restrict__ tile_frame, int shift, const int* __restrict__ toff)
 {
