@@ -424,9 +424,31 @@ class Extraction:
         lock = threading.Lock()
         t0 = time.perf_counter()
 
+        abort = threading.Event()
+
+        def guarded(fn):
+            # a failing worker must not leave the others waiting for it for ever (they would hold the rank at the next barrier
+            # until the NCCL watchdog fires): flag the abort, wake everybody, let the exception travel through the future
+            def run(*a):
+                try:
+                    fn(*a)
+                except BaseException:
+                    abort.set()
+                    for sem in free:
+                        sem.release()
+                    for ev in uploaded:
+                        ev.set()
+                    raise
+            return run
+
+        def check_abort():
+            if abort.is_set():
+                raise RuntimeError("another e2e worker failed")
+
         def uploader():
             for k in range(nsteps):
                 free[k % 2].acquire()
+                check_abort()
                 self.ctx_up.check(self.lib.plf_upload(self.ctx_up.h, self.d_stage[k % 2].data_ptr(), self.h_img[k % self.nsets].data_ptr(), nbytes))
                 uploaded[k].set()
 
@@ -434,6 +456,7 @@ class Extraction:
             ctx = self.ctx_os[i] if kind == "orb" else self.ctx_ls[i]
             for k in range(nsteps):
                 uploaded[k].wait()
+                check_abort()
                 ctx.wait(self.ctx_up)                      # this stream waits for the upload (device-side dependency, no host sync)
                 (self.e2e_orb if kind == "orb" else self.e2e_line)(i, k, self.d_stage[k % 2])
                 with lock:
@@ -442,10 +465,16 @@ class Extraction:
                 if last:
                     free[k % 2].release()
 
-        futs = [self.pool.submit(uploader)] + [self.pool.submit(consumer, "orb", i) for i in range(self.NO)] + \
-               [self.pool.submit(consumer, "line", i) for i in range(self.NL)]
+        futs = [self.pool.submit(guarded(uploader))] + [self.pool.submit(guarded(consumer), "orb", i) for i in range(self.NO)] + \
+               [self.pool.submit(guarded(consumer), "line", i) for i in range(self.NL)]
+        errs = []
         for f in futs:
-            f.result()
+            try:
+                f.result()
+            except BaseException as e:      # collect them all: the first one raised is the cause, the rest are "another worker failed"
+                errs.append(e)
+        if errs:
+            raise [e for e in errs if "another e2e worker failed" not in str(e)][0] if any("another e2e worker failed" not in str(e) for e in errs) else errs[0]
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) * 1e3
 
@@ -764,7 +793,9 @@ def main():
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank that dies must take the job down quickly, not after NCCL's default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=240))
 
     def barrier():
         torch.cuda.synchronize()

@@ -57,6 +57,7 @@ extern "C" const char* plf_last_error(const plf_ctx* c) { return c ? c->err : "n
 extern "C" plf_status plf_ctx_synchronize(plf_ctx* c)
 {
     if (!c) return PLF_ERR_INVALID;
+    PLF_CUDA(c, cudaSetDevice(c->device));
     PLF_CUDA(c, cudaStreamSynchronize(c->stream));
     return PLF_OK;
 }
@@ -66,6 +67,7 @@ extern "C" void* plf_ctx_stream(plf_ctx* c) { return c ? (void*)c->stream : null
 extern "C" plf_status plf_timer_start(plf_ctx* c)
 {
     if (!c) return PLF_ERR_INVALID;
+    PLF_CUDA(c, cudaSetDevice(c->device));
     PLF_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     return PLF_OK;
 }
@@ -73,6 +75,7 @@ extern "C" plf_status plf_timer_start(plf_ctx* c)
 extern "C" plf_status plf_timer_stop(plf_ctx* c, float* ms)
 {
     if (!c || !ms) return PLF_ERR_INVALID;
+    PLF_CUDA(c, cudaSetDevice(c->device));
     PLF_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     PLF_CUDA(c, cudaEventSynchronize(c->ev1));
     PLF_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
@@ -156,6 +159,7 @@ void plf_prof_begin(plf_ctx* c, const char* name)
     if (!c->prof_on || c->prof_n >= PLF_PROF_MAX) return;
     plf_prof_state* p = c->prof;
     if (c->prof_n >= p->created) {
+        cudaSetDevice(c->device);         // events are created on the current device
         cudaEventCreate(&p->ev[p->created][0]);
         cudaEventCreate(&p->ev[p->created][1]);
         p->created++;
@@ -250,6 +254,9 @@ extern "C" plf_status plf_profile_timeline(plf_ctx* c, plf_ctx* ref, char* buf, 
 extern "C" plf_status plf_ctx_wait(plf_ctx* c, plf_ctx* other)
 {
     if (!c || !other) return PLF_ERR_INVALID;
+    // the event must belong to the streams' device: a host thread that has never touched CUDA has device 0 current, which is the
+    // wrong one on every rank but the first (an event of another device fails with "invalid resource handle")
+    PLF_CUDA(c, cudaSetDevice(c->device));
     cudaEvent_t e;
     PLF_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     cudaError_t r = cudaEventRecord(e, other->stream);
