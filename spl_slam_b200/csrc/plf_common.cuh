@@ -38,6 +38,10 @@ struct plf_ctx {
     // small reusable device scratch (grown on demand)
     void* scratch;
     size_t scratch_bytes;
+    // host waits: spinning (lowest latency, the default) or sleep-and-poll.  Batch calls switch to sleeping:
+    // several ranks x several extractor threads spinning in cudaStreamSynchronize starve each other on the host cores
+    // (8 ranks x 5 threads on 32 cores: end-to-end throughput at 8 GPUs dropped to 0.80 of the device-resident figure)
+    int blocking;
     // second region for the device copies of host-buffer arguments (the kernels' own temporaries live in `scratch`)
     void* ioscratch;
     size_t ioscratch_bytes;
@@ -114,6 +118,7 @@ static inline cudaError_t plf_smem_optin(const void* kernel, int device)
     } while (0)
 
 plf_status plf_ctx_scratch(plf_ctx* ctx, size_t bytes, void** out);
+plf_status plf_sync(plf_ctx* ctx, cudaStream_t st);      // wait for a stream the way ctx->blocking says
 plf_status plf_ctx_ioscratch(plf_ctx* ctx, size_t bytes, void** out);
 plf_status plf_ctx_pinned(plf_ctx* ctx, size_t bytes, void** out);
 

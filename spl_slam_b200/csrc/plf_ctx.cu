@@ -1,5 +1,6 @@
 // plf_ctx.cu -- context, stream, timer and scratch management for libplf.so.
 #include "plf_common.cuh"
+#include <unistd.h>
 
 // priority: 0 = default, < 0 = lower than default (filler work), > 0 = higher (latency-critical work); mapped onto the
 // device's stream priority range
@@ -54,12 +55,31 @@ extern "C" void plf_ctx_destroy(plf_ctx* c)
 
 extern "C" const char* plf_last_error(const plf_ctx* c) { return c ? c->err : "null context"; }
 
+plf_status plf_sync(plf_ctx* c, cudaStream_t st)
+{
+#ifndef PLF_EMU
+    static const bool never_sleep = getenv("PLF_SPIN_SYNC") != nullptr;
+    if (c->blocking && !never_sleep) {
+        // sleep-and-poll: the waits of a batch call last milliseconds, 100 us of extra wake-up latency is noise, and the host
+        // core is free for the other ranks' threads meanwhile
+        for (;;) {
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q == cudaSuccess) return PLF_OK;
+            if (q != cudaErrorNotReady) return plf_fail(c, PLF_ERR_CUDA, "cudaStreamQuery failed: %s", cudaGetErrorString(q));
+            (void)cudaGetLastError();       // "not ready" must not be mistaken for a launch error by the next PLF_CHECK_LAUNCH
+            usleep(100);
+        }
+    }
+#endif
+    PLF_CUDA(c, cudaStreamSynchronize(st));
+    return PLF_OK;
+}
+
 extern "C" plf_status plf_ctx_synchronize(plf_ctx* c)
 {
     if (!c) return PLF_ERR_INVALID;
     PLF_CUDA(c, cudaSetDevice(c->device));
-    PLF_CUDA(c, cudaStreamSynchronize(c->stream));
-    return PLF_OK;
+    return plf_sync(c, c->stream);
 }
 
 extern "C" void* plf_ctx_stream(plf_ctx* c) { return c ? (void*)c->stream : nullptr; }

@@ -396,7 +396,7 @@ static plf_status read_ints(plf_ctx* ctx, const int* dev, int n, int* host)
     plf_status st = plf_ctx_pinned(ctx, (size_t)(n > 64 ? n : 64) * sizeof(int), &pin);
     if (st) return st;
     PLF_CUDA(ctx, cudaMemcpyAsync(pin, dev, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    { plf_status ss = plf_sync(ctx, ctx->stream); if (ss) return ss; }
     memcpy(host, pin, (size_t)n * sizeof(int));
     return PLF_OK;
 }
@@ -462,7 +462,8 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
     PLF_CUDA(ctx, cudaMemsetAsync(o->d_detcount, 0, (size_t)nframes * noct * sizeof(int), st0));
     // whatever is still queued on this stream (the image upload of a host-buffer call) finishes before the turn is
     // taken: the lock must not be held across a PCIe transfer
-    PLF_CUDA(ctx, cudaStreamSynchronize(st0));
+    ctx->blocking = nframes >= 32;      // batches sleep in their waits, single frames spin (latency)
+    { plf_status ss = plf_sync(ctx, st0); if (ss) return ss; }
     tr.mark("upload done");
     std::unique_lock<std::mutex> prephase(g_lsd_prephase[ctx->device & 63], std::defer_lock);
     if (!getenv("PLF_NO_PREPHASE_LOCK")) prephase.lock();
@@ -531,7 +532,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
     tr.mark("phase 1 queued");
     for (int k = 0; k < noct; k++) {
         cudaStream_t st = stk[k];
-        PLF_CUDA(ctx, cudaStreamSynchronize(st));
+        { plf_status ss = plf_sync(ctx, st); if (ss) return ss; }
         tr.mark("phase 1 done (octave)");
         nkeys[k] = o->h_pin[64 * k];
         if (nkeys[k] > (int)o->keycap[k]) {
@@ -559,7 +560,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
     }
     tr.mark("phase 2 queued");
     for (int k = 0; k < noct; k++)
-        if (nkeys[k] > 0) PLF_CUDA(ctx, cudaStreamSynchronize(stk[k]));
+        if (nkeys[k] > 0) { plf_status ss = plf_sync(ctx, stk[k]); if (ss) return ss; }
     tr.mark("phase 2 done");
     if (prephase.owns_lock()) prephase.unlock();   // everything up to here has finished on the GPU; growing may overlap other contexts
     // ---- phase 3: region growing (the latency-bound chains of both octaves side by side), rectangles, keylines ----

@@ -354,7 +354,8 @@ static plf_status orb_extract_to_host(plf_orb* o, const uint8_t* host_imgs, bool
     PLF_CUDA(ctx, cudaMemcpyAsync(pin, o->d_nout, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, s));
     PLF_CUDA(ctx, cudaMemcpyAsync(host_kps, o->d_kps, (size_t)nframes * cap * sizeof(plf_keypoint), cudaMemcpyDeviceToHost, s));
     PLF_CUDA(ctx, cudaMemcpyAsync(host_desc, o->d_desc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, s));
-    PLF_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->blocking = nframes >= 32;      // batches sleep in their waits, single frames spin (latency)
+    { plf_status ss = plf_sync(ctx, s); if (ss) return ss; }
     memcpy(n_out, pin, (size_t)nframes * sizeof(int));
     for (int f = 0; f < nframes; f++) {
         if (n_out[f] == -1) return plf_fail(ctx, PLF_ERR_CAPACITY, "frame %d: internal key/node list overflow", f);
