@@ -33,6 +33,9 @@
 #ifndef GC_BUF
 #define GC_BUF 4                            // scratch buffers (outstanding results) per speculator
 #endif
+#ifndef GC_CHUNK
+#define GC_CHUNK 8                          // seed positions a speculator claims at a time: consecutive likely seeds go to DIFFERENT warps,
+#endif                                      // so the regions the committer needs next are grown side by side, not one after the other
 #define GC_SLOTS ((GC_MAXWARPS - 1) * GC_BUF)
 #define GC_RMAX 2048                        // points per speculative region; larger regions are grown by the committer
 #define GC_SMEM_BUDGET (200 * 1024)
@@ -228,7 +231,7 @@ __device__ __forceinline__ int gc_grow(const int p, const int sc, const int star
 
 struct GcShared {
     int frontier;                 // seed position the committer is working on (positions before it are resolved)
-    int cursor;                   // next chunk of 32 seed positions nobody has scanned for speculation yet
+    int cursor;                   // next chunk of GC_CHUNK seed positions nobody has scanned for speculation yet
     int st[GC_SLOTS], pos[GC_SLOTS], n[GC_SLOTS];   // slot table: slot = (speculator - 1) * GC_BUF + buffer
     double ang[GC_SLOTS];
     int ring[GC_MAXWARPS][WG_RING];
@@ -397,12 +400,12 @@ k_lsd_grow_cta(const unsigned long long* __restrict__ keys, const int2* __restri
                 const int sl = (wid - 1) * GC_BUF + b;
                 if (!cand_mask) {
                     int cstart = 0;
-                    if (lane == 0) cstart = atomicAdd(&S.cursor, 32);
+                    if (lane == 0) cstart = atomicAdd(&S.cursor, GC_CHUNK);
                     cstart = __shfl_sync(FULL, cstart, 0);
                     if (cstart >= C) break;
                     chunk = cstart;
                     const int qq = chunk + lane;
-                    const bool ok = qq < C && likely[start + qq] && !((used[qq >> 5] >> (qq & 31)) & 1u);
+                    const bool ok = lane < GC_CHUNK && qq < C && likely[start + qq] && !((used[qq >> 5] >> (qq & 31)) & 1u);
                     cand_mask = __ballot_sync(FULL, ok);
                     if (!cand_mask) continue;
                 }
