@@ -1164,40 +1164,46 @@ __device__ __forceinline__ void lbd_finish(const int tid, float (*rows)[4], floa
             m = cc * (r2 * r2); s[6] += m;
             m = cc * (r3 * r3); s[7] += m;
         }
-        for (int k = 0; k < 8; k++) band[tid][k] = s[k];
+        // mean / standard deviation of this thread's band (:1262-1290): the same operations thread by thread instead of one
+        // thread walking the nine bands
+        const float invN = (tid == 0 || tid == 8) ? (float)(1.0 / 14.0) : (float)(1.0 / 21.0);
+        float temp, u, v;
+        temp = s[0] * invN; dv[tid * 8] = temp;
+        u = s[2] * invN; v = temp * temp; dv[tid * 8 + 4] = sqrtf(u - v);
+        temp = s[1] * invN; dv[tid * 8 + 1] = temp;
+        u = s[3] * invN; v = temp * temp; dv[tid * 8 + 5] = sqrtf(u - v);
+        temp = s[4] * invN; dv[tid * 8 + 2] = temp;
+        u = s[6] * invN; v = temp * temp; dv[tid * 8 + 6] = sqrtf(u - v);
+        temp = s[5] * invN; dv[tid * 8 + 3] = temp;
+        u = s[7] * invN; v = temp * temp; dv[tid * 8 + 7] = sqrtf(u - v);
     }
     __syncthreads();
+    // the three order-dependent float sums stay with one thread (the reference's order); the element-wise scalings and the
+    // clamp are spread over the CTA (same operation per element, so the same bits)
+    float* scale = &band[0][0];       // band[][] is dead from here: two floats of it carry the factors
     if (tid == 0) {
-        const float invN2 = (float)(1.0 / 14.0), invN3 = (float)(1.0 / 21.0);
-        for (int b = 0; b < 9; b++) {
-            const float invN = (b == 0 || b == 8) ? invN2 : invN3;
-            float temp, u, v;
-            temp = band[b][0] * invN; dv[b * 8] = temp;
-            u = band[b][2] * invN; v = temp * temp; dv[b * 8 + 4] = sqrtf(u - v);
-            temp = band[b][1] * invN; dv[b * 8 + 1] = temp;
-            u = band[b][3] * invN; v = temp * temp; dv[b * 8 + 5] = sqrtf(u - v);
-            temp = band[b][4] * invN; dv[b * 8 + 2] = temp;
-            u = band[b][6] * invN; v = temp * temp; dv[b * 8 + 6] = sqrtf(u - v);
-            temp = band[b][5] * invN; dv[b * 8 + 3] = temp;
-            u = band[b][7] * invN; v = temp * temp; dv[b * 8 + 7] = sqrtf(u - v);
-        }
         float tempM = 0, tempS = 0, m;
         for (int i = 0; i < 72; i += 8) {
             for (int k = 0; k < 4; k++) { m = dv[i + k] * dv[i + k]; tempM += m; }
             for (int k = 4; k < 8; k++) { m = dv[i + k] * dv[i + k]; tempS += m; }
         }
-        tempM = 1.0f / sqrtf(tempM);   // namespace cv: using std::sqrt -> sqrt(float); int / float (:1302-1303)
-        tempS = 1.0f / sqrtf(tempS);
-        for (int i = 0; i < 72; i += 8) {
-            for (int k = 0; k < 4; k++) dv[i + k] = dv[i + k] * tempM;
-            for (int k = 4; k < 8; k++) dv[i + k] = dv[i + k] * tempS;
-        }
-        for (int i = 0; i < 72; i++) if ((double)dv[i] > 0.4) dv[i] = (float)0.4;
-        float temp = 0;
-        for (int i = 0; i < 72; i++) { m = dv[i] * dv[i]; temp += m; }
-        temp = 1.0f / sqrtf(temp);
-        for (int i = 0; i < 72; i++) dv[i] = dv[i] * temp;
+        scale[0] = 1.0f / sqrtf(tempM);   // namespace cv: using std::sqrt -> sqrt(float); int / float (:1302-1303)
+        scale[1] = 1.0f / sqrtf(tempS);
     }
+    __syncthreads();
+    for (int i = tid; i < 72; i += 64) {
+        float x = dv[i] * ((i & 4) ? scale[1] : scale[0]);
+        if ((double)x > 0.4) x = (float)0.4;
+        dv[i] = x;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float temp = 0, m;
+        for (int i = 0; i < 72; i++) { m = dv[i] * dv[i]; temp += m; }
+        scale[2] = 1.0f / sqrtf(temp);
+    }
+    __syncthreads();
+    for (int i = tid; i < 72; i += 64) dv[i] = dv[i] * scale[2];
     __syncthreads();
     if (tid < 32 && desc) {
         const float* f1 = &dv[8 * c_lbd_comb[tid][0]];
