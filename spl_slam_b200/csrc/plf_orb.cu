@@ -252,9 +252,29 @@ static plf_status orb_run(plf_orb* o, const uint8_t* lvl0, size_t stride0, size_
     const int ftp = (fw + 3 + 3) & ~3;
     const int flcap = ((fw - 6) * (fh - 6) + 1) & ~1;   // work-list entries: one per interior pixel
     const size_t fsmem = (size_t)FAST_WARPS * (2 * ftp * fh + 2 * flcap);
-    PLF_SMEM_OPTIN(ctx, k_fast_cells);
-    PLF_LAUNCH(k_fast_cells, dim3(plf_div_up(g.totalCells, FAST_WARPS), nframes), dim3(32 * FAST_WARPS), fsmem, st, g, P, ftp, fh, flcap);
-    PLF_CHECK_LAUNCH(ctx);
+#ifndef PLF_EMU
+    static const bool no_tma = getenv("PLF_NO_TMA") != nullptr;
+    // cell windows by TMA box loads, double buffered per warp; k_fast_cells (register-staged loads) when a caller-owned level 0
+    // is not 16-byte aligned or the driver does not offer cuTensorMapEncodeTiled
+    const int ttp = (fw + 15 + 15) & ~15;                 // box width: the window plus the <= 15 columns before it
+    const int trows = (fh + 7) & ~7;                      // ttp * trows is a multiple of 128
+    const size_t tsmem = (size_t)FAST_WARPS * (3 * (size_t)ttp * trows + (((size_t)2 * flcap + 127) & ~(size_t)127));
+    OrbFastMaps fm;
+    static const bool want_fast_tma = getenv("PLF_FAST_TMA") != nullptr;      // opt-in until it has been through the GPU suite
+    bool fast_tma = want_fast_tma && !no_tma && ttp <= 256 && trows <= 256 && orb_make_fast_maps(g, P, nframes, ttp, trows, &fm);
+    if (fast_tma) {
+        const int cpw = 8;                                // cells per warp: long enough to hide the first load, short enough to balance
+        PLF_SMEM_OPTIN(ctx, k_fast_cells_tma);
+        PLF_LAUNCH(k_fast_cells_tma, dim3(plf_div_up(plf_div_up(g.totalCells, cpw), FAST_WARPS), nframes), dim3(32 * FAST_WARPS), tsmem, st, g, P, fm,
+                   ttp, trows, flcap, cpw);
+        PLF_CHECK_LAUNCH(ctx);
+    } else
+#endif
+    {
+        PLF_SMEM_OPTIN(ctx, k_fast_cells);
+        PLF_LAUNCH(k_fast_cells, dim3(plf_div_up(g.totalCells, FAST_WARPS), nframes), dim3(32 * FAST_WARPS), fsmem, st, g, P, ftp, fh, flcap);
+        PLF_CHECK_LAUNCH(ctx);
+    }
     PLF_LAUNCH(k_blur7, dim3(plf_div_up(g.totalBlurTiles, BLUR_WARPS), nframes), dim3(32 * BLUR_WARPS), 0, st, g, P);
     PLF_CHECK_LAUNCH(ctx);
     PLF_LAUNCH(k_octree, dim3(g.nlevels, nframes), dim3(OCT_T), o->oct_smem, st, g, P, o->oct_cap);
@@ -262,7 +282,6 @@ static plf_status orb_run(plf_orb* o, const uint8_t* lvl0, size_t stride0, size_
 #ifndef PLF_EMU
     // the two patches of every keypoint staged in shared memory by TMA tile loads; k_describe (direct gathers) when a caller-owned
     // level 0 is not 16-byte aligned or the driver does not offer cuTensorMapEncodeTiled
-    static const bool no_tma = getenv("PLF_NO_TMA") != nullptr;
     OrbTensorMaps tm;
     if (!no_tma && orb_make_tensor_maps(g, P, nframes, &tm)) {
         PLF_LAUNCH(k_describe_tma, dim3(plf_div_up(cap, 8), nframes), dim3(256), 0, st, g, P, tm, d_kps, d_desc, cap, d_nout);

@@ -177,48 +177,33 @@ __device__ __forceinline__ int fast_score(const uint8_t* c, int pitch, int sides
 // with an explicit order key that restates the reference's push_back order).
 // Dynamic shared memory per warp: pixel map and score map of `rows` x `tp` bytes (tp = window width + 3 alignment
 // bytes rounded up to a multiple of 4) and a 16-bit work list of `lcap` entries, sized from the largest cell.
-__global__ void __launch_bounds__(32 * FAST_WARPS)
-k_fast_cells(OrbGeom g, OrbPtrs p, int tp, int rows, int lcap)
+// geometry of one FAST cell of the fused (all levels) cell grid; ok = false for the cells the reference skips
+struct FastCell { int l, ci, cj, iniX, iniY, cw, ch; bool ok; };
+__device__ __forceinline__ FastCell fast_cell_geom(const OrbGeom& g, int cell)
 {
-    PLF_DYN_SMEM(smem);
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu, LT = (1u << lane) - 1u;
-    int cell = blockIdx.x * FAST_WARPS + wid, l = 0;
-    if (cell >= g.totalCells) return;
+    FastCell c;
+    int l = 0;
     while (l + 1 < g.nlevels && cell >= g.lv[l + 1].cellBase) l++;
     cell -= g.lv[l].cellBase;
     const OrbLevelGeom& L = g.lv[l];
-    const int ci = cell / L.nCols, cj = cell - ci * L.nCols;
+    c.l = l;
+    c.ci = cell / L.nCols; c.cj = cell - c.ci * L.nCols;
     const int maxBorderX = L.w - ORB_MINB, maxBorderY = L.h - ORB_MINB;
-    const int iniY = ORB_MINB + ci * L.hCell, iniX = ORB_MINB + cj * L.wCell;
-    if (iniY >= maxBorderY - 3 || iniX >= maxBorderX - 6) return;   // skip rules, :794, :803
-    const int maxY = min(iniY + L.hCell + 6, maxBorderY), maxX = min(iniX + L.wCell + 6, maxBorderX);
-    const int cw = maxX - iniX, ch = maxY - iniY;
-    if (cw < 7 || ch < 7) return;
-    const size_t per_warp = (size_t)2 * tp * rows + (size_t)2 * lcap;
-    uint8_t* tile = smem + (size_t)wid * per_warp;
-    uint8_t* best = tile + (size_t)tp * rows;
-    unsigned short* list = (unsigned short*)(best + (size_t)tp * rows);
-    const int spitch = p.pitch[l];
-    const uint8_t* src = p.lvl[l] + (size_t)blockIdx.y * p.frameStride[l] + (size_t)iniY * spitch + iniX;
-    // window -> shared memory; aligned buffers are read as 32-bit words (16 words x 2 rows per step)
-    const int off = (int)((size_t)src & 3);            // window column rx lives at map column rx + off
-    if (((size_t)spitch & 3) == 0) {
-        const unsigned* s4 = (const unsigned*)(src - off);
-        const int nW = (off + cw + 3) >> 2, wx = lane & 15;
-        for (int ry = lane >> 4; ry < ch; ry += 2)
-            if (wx < nW) {
-                ((unsigned*)tile)[ry * (tp >> 2) + wx] = s4[(size_t)ry * (spitch >> 2) + wx];
-                ((unsigned*)best)[ry * (tp >> 2) + wx] = 0u;
-            }
-    } else {
-        for (int ry = 0; ry < ch; ry++)
-            for (int rx = lane; rx < cw; rx += 32) {
-                tile[ry * tp + rx + off] = src[(size_t)ry * spitch + rx];
-                best[ry * tp + rx + off] = 0;
-            }
-    }
-    __syncwarp();
+    c.iniY = ORB_MINB + c.ci * L.hCell; c.iniX = ORB_MINB + c.cj * L.wCell;
+    c.ok = !(c.iniY >= maxBorderY - 3 || c.iniX >= maxBorderX - 6);   // skip rules, :794, :803
+    const int maxY = min(c.iniY + L.hCell + 6, maxBorderY), maxX = min(c.iniX + L.wCell + 6, maxBorderX);
+    c.cw = maxX - c.iniX; c.ch = maxY - c.iniY;
+    if (c.cw < 7 || c.ch < 7) c.ok = false;
+    return c;
+}
+
+// the two threshold passes over one cell window that sits in shared memory: `tile` = pixel map with row pitch tp (window column
+// rx at map column rx + off), `best` = score map of the same shape (all zero on entry), `list` = 16-bit work list
+__device__ __forceinline__ void fast_cell_passes(const OrbGeom& g, const OrbPtrs& p, const OrbLevelGeom& L, const int l, const int ci, const int cj,
+                                                 const int cw, const int ch, const int off, const int tp, uint8_t* tile, uint8_t* best,
+                                                 unsigned short* list, const int lane)
+{
+    const unsigned FULL = 0xffffffffu, LT = (1u << lane) - 1u;
     int* cnt = p.rawcount + (size_t)blockIdx.y * g.nlevels + l;
     unsigned* out = p.rawkeys + (size_t)blockIdx.y * g.rawPerFrame + L.rawOff;
     for (int pass = 0; pass < 2; pass++) {
@@ -313,6 +298,44 @@ k_fast_cells(OrbGeom g, OrbPtrs p, int tp, int rows, int lcap)
         if (found > 0) break;
         __syncwarp();
     }
+}
+
+__global__ void __launch_bounds__(32 * FAST_WARPS)
+k_fast_cells(OrbGeom g, OrbPtrs p, int tp, int rows, int lcap)
+{
+    PLF_DYN_SMEM(smem);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cell = blockIdx.x * FAST_WARPS + wid;
+    if (cell >= g.totalCells) return;
+    const FastCell C = fast_cell_geom(g, cell);
+    if (!C.ok) return;
+    const int l = C.l, ci = C.ci, cj = C.cj, iniX = C.iniX, iniY = C.iniY, cw = C.cw, ch = C.ch;
+    const OrbLevelGeom& L = g.lv[l];
+    const size_t per_warp = (size_t)2 * tp * rows + (size_t)2 * lcap;
+    uint8_t* tile = smem + (size_t)wid * per_warp;
+    uint8_t* best = tile + (size_t)tp * rows;
+    unsigned short* list = (unsigned short*)(best + (size_t)tp * rows);
+    const int spitch = p.pitch[l];
+    const uint8_t* src = p.lvl[l] + (size_t)blockIdx.y * p.frameStride[l] + (size_t)iniY * spitch + iniX;
+    // window -> shared memory; aligned buffers are read as 32-bit words (16 words x 2 rows per step)
+    const int off = (int)((size_t)src & 3);            // window column rx lives at map column rx + off
+    if (((size_t)spitch & 3) == 0) {
+        const unsigned* s4 = (const unsigned*)(src - off);
+        const int nW = (off + cw + 3) >> 2, wx = lane & 15;
+        for (int ry = lane >> 4; ry < ch; ry += 2)
+            if (wx < nW) {
+                ((unsigned*)tile)[ry * (tp >> 2) + wx] = s4[(size_t)ry * (spitch >> 2) + wx];
+                ((unsigned*)best)[ry * (tp >> 2) + wx] = 0u;
+            }
+    } else {
+        for (int ry = 0; ry < ch; ry++)
+            for (int rx = lane; rx < cw; rx += 32) {
+                tile[ry * tp + rx + off] = src[(size_t)ry * spitch + rx];
+                best[ry * tp + rx + off] = 0;
+            }
+    }
+    __syncwarp();
+    fast_cell_passes(g, p, L, l, ci, cj, cw, ch, off, tp, tile, best, list, lane);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -123,6 +123,75 @@ k_describe_tma(OrbGeom g, OrbPtrs p, const __grid_constant__ OrbTensorMaps tm, p
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// FAST with the cell windows fed by TMA.  k_fast_cells spends a third of its stall samples between the global loads of a cell
+// window and the shared-memory stores that stage it (one warp per cell: nothing else to do while the loads are in flight), and
+// a tenth of its instructions on that staging.  Here a warp walks `cpw` cells; lane 0 issues ONE cp.async.bulk.tensor.3d per
+// cell window (box tp x rows at a 16-byte aligned column, zero fill outside the level) into one of two buffers and the window of
+// the NEXT cell is already in flight while the warp runs the threshold passes on the current one (fast_cell_passes, shared with
+// k_fast_cells, which remains for level-0 buffers whose pitch is not a multiple of 16 bytes).  Consecutive cells go to
+// consecutive warps, so neighbouring windows (which overlap by 6 pixels) are fetched at about the same time and meet in L2.
+// Dynamic shared memory per warp: two pixel maps + score map (tp x rows each, tp a multiple of 16) + work list.
+struct OrbFastMaps { CUtensorMap m[ORB_MAX_LEVELS]; };
+
+__global__ void __launch_bounds__(32 * FAST_WARPS)
+k_fast_cells_tma(OrbGeom g, OrbPtrs p, const __grid_constant__ OrbFastMaps fm, int tp, int rows, int lcap, int cpw)
+{
+    extern __shared__ __align__(128) unsigned char smem_f[];
+    __shared__ __align__(8) unsigned long long bars[FAST_WARPS][2];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int map_bytes = tp * rows;                                     // a multiple of 128 (host)
+    const size_t per_warp = (size_t)3 * map_bytes + (((size_t)2 * lcap + 127) & ~(size_t)127);
+    uint8_t* buf0 = smem_f + (size_t)wid * per_warp;
+    uint8_t* best = buf0 + 2 * map_bytes;
+    unsigned short* list = (unsigned short*)(best + map_bytes);
+    const int nwarps = gridDim.x * FAST_WARPS, gw = blockIdx.x * FAST_WARPS + wid;
+    const int f = blockIdx.y;
+    const unsigned bar0 = plf_smem_u32(&bars[wid][0]), bar1 = plf_smem_u32(&bars[wid][1]);
+    if (lane == 0) { plf_mbar_init(bar0, 1); plf_mbar_init(bar1, 1); }
+    __syncwarp();
+    // cell k of this warp = gw + k * nwarps; buffer k & 1.  A skipped cell issues no load, so the phase of a buffer's barrier
+    // advances only with the loads actually issued into it: ph[b] = parity of the NEXT load's phase (warp-uniform registers)
+    FastCell cur, nxt;
+    cur.ok = false; nxt.ok = false;
+    unsigned ph0 = 0, ph1 = 0, cur_par = 0, nxt_par = 0;
+    int c = gw;
+    if (c < g.totalCells) {
+        cur = fast_cell_geom(g, c);
+        if (cur.ok) {
+            cur_par = ph0; ph0 ^= 1u;
+            if (lane == 0) {
+                plf_mbar_expect_tx(bar0, map_bytes);
+                plf_tma_load_3d(plf_smem_u32(buf0), &fm.m[cur.l], bar0, cur.iniX & ~15, cur.iniY, f);
+            }
+        }
+    }
+    for (int k = 0; k < cpw && c < g.totalCells; k++, c += nwarps) {
+        const int cn = c + nwarps;
+        nxt.ok = false;
+        __syncwarp();                    // every lane is done with the buffer the next load overwrites
+        if (k + 1 < cpw && cn < g.totalCells) {
+            nxt = fast_cell_geom(g, cn);
+            if (nxt.ok) {
+                const int nb = (k + 1) & 1;
+                if (nb) { nxt_par = ph1; ph1 ^= 1u; } else { nxt_par = ph0; ph0 ^= 1u; }
+                if (lane == 0) {
+                    const unsigned b = nb ? bar1 : bar0;
+                    plf_mbar_expect_tx(b, map_bytes);
+                    plf_tma_load_3d(plf_smem_u32(buf0 + nb * map_bytes), &fm.m[nxt.l], b, nxt.iniX & ~15, nxt.iniY, f);
+                }
+            }
+        }
+        if (cur.ok) {
+            for (int i = lane; i < (map_bytes >> 4); i += 32) ((uint4*)best)[i] = make_uint4(0u, 0u, 0u, 0u);
+            plf_mbar_wait((k & 1) ? bar1 : bar0, cur_par);
+            __syncwarp();
+            fast_cell_passes(g, p, g.lv[cur.l], cur.l, cur.ci, cur.cj, cur.cw, cur.ch, cur.iniX & 15, tp, buf0 + (k & 1) * map_bytes, best, list, lane);
+        }
+        cur = nxt; cur_par = nxt_par;
+    }
+}
+
 // host: encode the per-level maps for this call (x, y, frame); false when a base or pitch is not 16-byte aligned
 static bool orb_make_tensor_maps(const OrbGeom& g, const OrbPtrs& P, int nframes, OrbTensorMaps* tm)
 {
@@ -130,6 +199,15 @@ static bool orb_make_tensor_maps(const OrbGeom& g, const OrbPtrs& P, int nframes
         const OrbLevelGeom& L = g.lv[l];
         if (!plf_tma_map_images(&tm->raw[l], P.lvl[l], 1, L.w, L.h, nframes, (size_t)P.pitch[l], P.frameStride[l], DT_RAW_W, DT_RAW_H)) return false;
         if (!plf_tma_map_images(&tm->blr[l], P.blr[l], 1, L.w, L.h, nframes, (size_t)L.pitch, L.frameBytes, DT_BLR_W, DT_BLR_H)) return false;
+    }
+    return true;
+}
+// FAST window maps: one box shape (tp x rows) for every level
+static bool orb_make_fast_maps(const OrbGeom& g, const OrbPtrs& P, int nframes, int tp, int rows, OrbFastMaps* fm)
+{
+    for (int l = 0; l < g.nlevels; l++) {
+        const OrbLevelGeom& L = g.lv[l];
+        if (!plf_tma_map_images(&fm->m[l], P.lvl[l], 1, L.w, L.h, nframes, (size_t)P.pitch[l], P.frameStride[l], tp, rows)) return false;
     }
     return true;
 }

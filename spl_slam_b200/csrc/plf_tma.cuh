@@ -53,9 +53,12 @@ __device__ __forceinline__ void plf_mbar_expect_tx(unsigned bar, int bytes)
 __device__ __forceinline__ void plf_mbar_wait(unsigned bar, unsigned parity)
 {
     unsigned done = 0;
-    while (!done)
+    // a wait that cannot complete (wrong parity, wrong byte count, faulted copy) must become an error, not a hung GPU
+    for (unsigned spins = 0; !done; spins++) {
         asm volatile("{ .reg .pred P1; mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2; selp.u32 %0, 1, 0, P1; }"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spins > (1u << 22)) asm volatile("trap;");
+    }
 }
 // box at (x, y, z) of the map -> shared memory (128-byte aligned), completion counted in bytes on the barrier
 __device__ __forceinline__ void plf_tma_load_3d(unsigned dst, const CUtensorMap* tm, unsigned bar, int x, int y, int z)
