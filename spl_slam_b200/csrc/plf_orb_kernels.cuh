@@ -236,6 +236,7 @@ __device__ __forceinline__ void fast_cell_passes(const OrbGeom& g, const OrbPtrs
                     const unsigned gh = __vcmpgtu4(__vabsdiffu4(C, Lf), th4) | __vcmpgtu4(__vabsdiffu4(C, Rt), th4);
                     go = gv & gh & vmask;
                 }
+                if (!__any_sync(FULL, go != 0u)) continue;      // no survivor in these rows (flat areas): skip the compaction votes
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
                     const bool g1 = (go >> (8 * b)) & 1u;
