@@ -148,6 +148,14 @@ __host__ __device__ __forceinline__ float plf_fast_atan2(float y, float x)
     return a;
 }
 
+// REFLECT_101 for an index that is at most n - 1 beyond either end (every strip kernel: halo <= 8, rows >= 16 px): one
+// reflection, no loop -- the edge strips execute this 12 times per row and were a tenth of k_blur7's instructions with the loop
+__host__ __device__ __forceinline__ int plf_reflect101_near(int p, int n)
+{
+    p = p < 0 ? -p : p;
+    return p >= n ? 2 * (n - 1) - p : p;
+}
+
 __host__ __device__ __forceinline__ int plf_reflect101(int p, int n)
 {
     if (n == 1) return 0;
@@ -179,8 +187,13 @@ __device__ __forceinline__ void plf_blur_hrow(const uint8_t* __restrict__ rp, in
         w0 = p[0]; w1 = p[1]; w2 = p[2];
     } else {
         unsigned b[12];
+        if (w >= 16) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) b[i] = (i >= 4 - R && i < 8 + R) ? rp[plf_reflect101(x0 - 4 + i, w)] : 0u;
+            for (int i = 0; i < 12; i++) b[i] = (i >= 4 - R && i < 8 + R) ? rp[plf_reflect101_near(x0 - 4 + i, w)] : 0u;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 12; i++) b[i] = (i >= 4 - R && i < 8 + R) ? rp[plf_reflect101(x0 - 4 + i, w)] : 0u;
+        }
         w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
         w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
         w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);

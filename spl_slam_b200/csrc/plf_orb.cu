@@ -260,8 +260,7 @@ static plf_status orb_run(plf_orb* o, const uint8_t* lvl0, size_t stride0, size_
     const int trows = (fh + 7) & ~7;                      // ttp * trows is a multiple of 128
     const size_t tsmem = (size_t)FAST_WARPS * (3 * (size_t)ttp * trows + (((size_t)2 * flcap + 127) & ~(size_t)127));
     OrbFastMaps fm;
-    static const bool want_fast_tma = getenv("PLF_FAST_TMA") != nullptr;      // opt-in until it has been through the GPU suite
-    bool fast_tma = want_fast_tma && !no_tma && ttp <= 256 && trows <= 256 && orb_make_fast_maps(g, P, nframes, ttp, trows, &fm);
+    bool fast_tma = !no_tma && ttp <= 256 && trows <= 256 && orb_make_fast_maps(g, P, nframes, ttp, trows, &fm);
     if (fast_tma) {
         const int cpw = 8;                                // cells per warp: long enough to hide the first load, short enough to balance
         PLF_SMEM_OPTIN(ctx, k_fast_cells_tma);
