@@ -178,10 +178,10 @@ __host__ __device__ __forceinline__ int plf_reflect101(int p, int n)
 // ------------------------------------------------------------------------------------------------
 struct BlurTaps { int k[8]; };   // k[0..2R]
 
+// the 12 bytes x0-4 .. x0+7 of a row as three words (aligned fast path, or gathered with REFLECT_101)
 template <int R>
-__device__ __forceinline__ void plf_blur_hrow(const uint8_t* __restrict__ rp, int x0, int w, bool fastx, const int (&kc)[2 * R + 1], int (&out)[4])
+__device__ __forceinline__ void plf_blur_load3(const uint8_t* __restrict__ rp, int x0, int w, bool fastx, unsigned& w0, unsigned& w1, unsigned& w2)
 {
-    unsigned w0, w1, w2;
     if (fastx) {
         const unsigned* p = (const unsigned*)(rp + x0 - 4);
         w0 = p[0]; w1 = p[1]; w2 = p[2];
@@ -198,6 +198,12 @@ __device__ __forceinline__ void plf_blur_hrow(const uint8_t* __restrict__ rp, in
         w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
         w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
     }
+}
+
+// horizontal sums of the four pixels of a strip from the three words of its row
+template <int R>
+__device__ __forceinline__ void plf_blur_hsum(unsigned w0, unsigned w1, unsigned w2, const int (&kc)[2 * R + 1], int (&out)[4])
+{
     // q[i] = byte(i) | byte(i + 2) << 16, byte index relative to x0 - 4
     unsigned q[10];
     q[0] = __byte_perm(w0, 0u, 0x4240); q[1] = __byte_perm(w0, 0u, 0x4341);
@@ -213,6 +219,14 @@ __device__ __forceinline__ void plf_blur_hrow(const uint8_t* __restrict__ rp, in
     }
     out[0] = (int)(h02 & 0xffffu); out[2] = (int)(h02 >> 16);
     out[1] = (int)(h13 & 0xffffu); out[3] = (int)(h13 >> 16);
+}
+
+template <int R>
+__device__ __forceinline__ void plf_blur_hrow(const uint8_t* __restrict__ rp, int x0, int w, bool fastx, const int (&kc)[2 * R + 1], int (&out)[4])
+{
+    unsigned w0, w1, w2;
+    plf_blur_load3<R>(rp, x0, w, fastx, w0, w1, w2);
+    plf_blur_hsum<R>(w0, w1, w2, kc, out);
 }
 
 template <int R>
@@ -237,15 +251,20 @@ __device__ __forceinline__ void plf_blur_strip(const uint8_t* __restrict__ src, 
         plf_blur_hrow<R>(src + (size_t)yy * spitch, x0, w, fastx, kc, ring[t]);
     }
     const int yend = min(y0 + rows, h);
+    // the words of the NEXT input row are requested before the current row is worked on: the loads were what the kernel
+    // waited for at the first byte permute of every row (14 % of k_blur7's stall samples)
+    auto row_of = [&](int y) { int yy = min(y, h - 1) + R; return yy >= h ? 2 * (h - 1) - yy : yy; };
+    unsigned n0, n1, n2;
+    plf_blur_load3<R>(src + (size_t)row_of(y0) * spitch, x0, w, fastx, n0, n1, n2);
     // rows are processed K at a time so that the ring slots are compile-time; rows past the image bottom are
     // computed from clamped addresses and simply not stored (no branch around the loads)
     for (int yb = y0; yb < yend; yb += K) {
 #pragma unroll
         for (int s = 0; s < K; s++) {        // slot (s + K - 1) % K receives row y + R
             const int y = yb + s;
-            int yy = min(y, h - 1) + R;
-            yy = yy >= h ? 2 * (h - 1) - yy : yy;
-            plf_blur_hrow<R>(src + (size_t)yy * spitch, x0, w, fastx, kc, ring[(s + K - 1) % K]);
+            const unsigned c0 = n0, c1 = n1, c2 = n2;
+            plf_blur_load3<R>(src + (size_t)row_of(y + 1) * spitch, x0, w, fastx, n0, n1, n2);
+            plf_blur_hsum<R>(c0, c1, c2, kc, ring[(s + K - 1) % K]);
             unsigned o = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
