@@ -491,7 +491,7 @@ static plf_status lsd_detect_batch(plf_line* o, int nframes)
         size_t sframe = (size_t)ow * oh;
         if (S != 1) {
             { plf_status gs = gauss_batch(ctx, st, o->d_oct[k], o->d_tmp[k], ow, oh, nframes, o->lsd_gauss); if (gs) return gs; }
-            PLF_LAUNCH(k_resize_exact, dim3(plf_div_up(sw, 128), plf_div_up(sh, 8), nframes), dim3(32, 8), 0, st, (const uint8_t*)o->d_tmp[k],
+            PLF_LAUNCH(k_resize_exact, dim3(plf_div_up(sw, 128), plf_div_up(sh, 8 * RX_ROWS), nframes), dim3(32, 8), 0, st, (const uint8_t*)o->d_tmp[k],
                        (size_t)ow * oh, ow, ow, oh, o->d_scaled[k], (size_t)sp * sh, sp, sw, sh, o->xtab[k], o->ytab[k]);
             PLF_CHECK_LAUNCH(ctx);
             scaled = o->d_scaled[k]; spitch = sp; sframe = (size_t)sp * sh;

@@ -242,6 +242,7 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
     }
     return r;
 }
+static inline unsigned __dp2a_lo(unsigned a, unsigned b, unsigned c) { return c + (a & 0xffffu) * (b & 0xffu) + (a >> 16) * ((b >> 8) & 0xffu); }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh)
 {
     unsigned long long v = ((unsigned long long)hi << 32) | lo;
