@@ -80,6 +80,10 @@ static void orb_free_ws(plf_orb* o)
     if (o->d_tabs) cudaFree(o->d_tabs);
     o->d_levels = nullptr; o->d_lists = nullptr; o->d_tabs = nullptr;
     o->ws_w = o->ws_h = o->ws_frames = 0;
+    // nothing of the last batch can be read any more (plf_orb_pyramid_level / plf_stereo_match* check last_frames): a failed
+    // re-prepare must not leave them pointing into freed memory
+    o->last_frames = 0;
+    memset(&o->ptrs, 0, sizeof(o->ptrs));
 }
 
 extern "C" void plf_orb_destroy(plf_orb* o)
