@@ -326,6 +326,7 @@ k_lsd_grad(const uint8_t* __restrict__ img, size_t iframe, int ipitch, int w, in
            int* __restrict__ q, float* __restrict__ fa, int* __restrict__ label,
            unsigned* __restrict__ mask, int mw, int* __restrict__ maxq)
 {
+    __shared__ unsigned s_ang[4][256];                    // per warp: 128 packed (gx, gy) in, 128 angles out
     const int lane = threadIdx.x;
     const int x0 = (blockIdx.x * 32 + lane) * 4, y0 = (blockIdx.y * 4 + threadIdx.y) * GRAD_ROWS;
     const int f = blockIdx.z;
@@ -384,15 +385,47 @@ k_lsd_grad(const uint8_t* __restrict__ img, size_t iframe, int ipitch, int w, in
         m |= __shfl_xor_sync(FULL, m, 4);
         const int seg = blockIdx.x * 4 + (lane >> 3);
         if ((lane & 7) == 0 && seg < mw) mask[((size_t)f * h + y) * mw + seg] = m;
-        if (x0 < P) {
-            const size_t o = (size_t)f * P * h + (size_t)y * P + x0;
-            float4 ang = make_float4(LSD_NOTDEF, LSD_NOTDEF, LSD_NOTDEF, LSD_NOTDEF);
-            if (nib) {
+        // Level-line angles.  Defined pixels are ~7 % of an image, but almost every warp row has a few, so evaluating fastAtan2
+        // per pixel slot (j = 0 .. 3) ran the arctangent four times per row with one or two active lanes each.  Instead the
+        // defined pixels of the warp's row are compacted through shared memory ((j, lane) order by four ballots), the arctangent
+        // runs ONCE over the compacted list (<= 128 entries, typically ~9), and every lane picks its own results up again.
+        float4 ang = make_float4(LSD_NOTDEF, LSD_NOTDEF, LSD_NOTDEF, LSD_NOTDEF);
+        {
+            const unsigned LT = (1u << lane) - 1u;
+            unsigned bal[4];
+            int idx[4], total = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                bal[j] = __ballot_sync(FULL, (nib >> j) & 1u);
+                idx[j] = total + __popc(bal[j] & LT);
+                total += __popc(bal[j]);
+            }
+            if (total) {                                   // warp-uniform
+                unsigned* sin_ = s_ang[threadIdx.y];
+                float* sout = (float*)(s_ang[threadIdx.y] + 128);
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if ((nib >> j) & 1u) sin_[idx[j]] = ((unsigned)gx[j] & 0xffffu) | ((unsigned)gy[j] << 16);
+                __syncwarp();
+                for (int i = lane; i < total; i += 32) {
+                    const unsigned pk = sin_[i];
+                    const int ggx = (int)(short)(pk & 0xffffu), ggy = (int)(short)(pk >> 16);
+                    sout[i] = plf_fast_atan2((float)ggx, (float)(-ggy));
+                }
+                __syncwarp();
                 float* av = &ang.x;
 #pragma unroll
                 for (int j = 0; j < 4; j++)
+                    if ((nib >> j) & 1u) av[j] = sout[idx[j]];
+                __syncwarp();                              // the buffers are reused by the next row
+            }
+        }
+        if (x0 < P) {
+            const size_t o = (size_t)f * P * h + (size_t)y * P + x0;
+            if (nib) {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
                     if ((nib >> j) & 1u) {
-                        av[j] = plf_fast_atan2((float)gx[j], (float)(-gy[j]));
                         q[o + j] = qq[j];     // (cos / sin of the angle are filled in densely by k_lsd_cid after the sort)
                         // head of the run of defined pixels this pixel belongs to (inside its 32-px segment)
                         const int bit = 4 * (lane & 7) + j;
