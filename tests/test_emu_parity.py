@@ -93,7 +93,7 @@ def test_emu_octree_standalone(S, oracle, emu_lib):
         assert np.array_equal(ref, got), (W, H, n, N)
 
 
-@pytest.mark.parametrize("w,h,nf,sc,seed", [(160, 120, 40, 1.1, 0), (240, 160, 20, 1.1, 3)])
+@pytest.mark.parametrize("w,h,nf,sc,seed", [(128, 96, 40, 1.1, 0), (192, 128, 20, 1.1, 3)])
 def test_emu_lines(S, oracle, emu_lib, w, h, nf, sc, seed):
     ctx = S.Context(0, emu_lib)
     le = S.Lineextractor(nf, 2, 0, sc, 0.6, 2.2, 12.5, 1.0, 0.6, 1024, 0.0, ctx=ctx)
@@ -126,7 +126,7 @@ def test_emu_lines_batch_with_flat_frame(S, oracle, emu_lib):
     ctx = S.Context(0, emu_lib)
     le = S.Lineextractor(40, 2, 0, 1.1, 0.6, 2.2, 12.5, 1.0, 0.6, 1024, 0.0, ctx=ctx)
     prm = oracle.line_params(40, 2, 0, 1.1, 0.6, 2.2, 12.5, 1.0, 0.6, 1024, 0.0)
-    imgs = np.stack([oracle.synth_image(160, 120, 5), np.full((120, 160), 90, np.uint8), oracle.synth_image(160, 120, 6)])
+    imgs = np.stack([oracle.synth_image(128, 96, 5), np.full((96, 128), 90, np.uint8), oracle.synth_image(128, 96, 6)])
     Ks, Ms, Ds = le.extract_batch(imgs)
     for b in range(3):
         oK, oM, oD = oracle.line_extract(prm, imgs[b])
