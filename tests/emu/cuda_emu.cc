@@ -45,7 +45,7 @@ WarpState* g_warps = new WarpState[MAXT / 32];
 
 struct Pool {
     std::mutex m;
-    std::condition_variable cv_start, cv_done;
+    std::condition_variable cv_warp[1024 / 32], cv_done;      // launches wake only the warps they use
     std::vector<pthread_t> threads;
     unsigned long long epoch = 0;
     int nthreads_active = 0, ndone = 0;
@@ -65,7 +65,7 @@ void* worker(void* arg)
     for (;;) {
         {
             std::unique_lock<std::mutex> lk(g_pool.m);
-            g_pool.cv_start.wait(lk, [&] { return g_pool.epoch != seen; });
+            g_pool.cv_warp[id / 32].wait(lk, [&] { return g_pool.epoch != seen; });
             seen = g_pool.epoch;
             if (id >= g_pool.nthreads_active) continue;
         }
@@ -130,7 +130,7 @@ void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>&
                     g_pool.dyn = dyn.data();
                     g_pool.nthreads_active = nt; g_pool.ndone = 0;
                     g_pool.epoch++;
-                    g_pool.cv_start.notify_all();
+                    for (int w = 0; w * 32 < nt; w++) g_pool.cv_warp[w].notify_all();
                     g_pool.cv_done.wait(lk, [&] { return g_pool.ndone == nt; });
                 }
             }

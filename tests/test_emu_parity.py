@@ -145,9 +145,9 @@ def _stereo_pair(oracle, w, h, seed, shift):
 
 def test_emu_stereo_match(S, oracle, emu_lib):
     ctx = S.Context(0, emu_lib)
-    left, right = _stereo_pair(oracle, 320, 240, 3, 9)
-    exL = S.ORBextractor(400, 1.2, 4, 20, 7, ctx=ctx); exR = S.ORBextractor(400, 1.2, 4, 20, 7, ctx=ctx)
-    oxL = oracle.ORBextractor(400, 1.2, 4, 20, 7); oxR = oracle.ORBextractor(400, 1.2, 4, 20, 7)
+    left, right = _stereo_pair(oracle, 256, 192, 3, 9)
+    exL = S.ORBextractor(300, 1.2, 4, 20, 7, ctx=ctx); exR = S.ORBextractor(300, 1.2, 4, 20, 7, ctx=ctx)
+    oxL = oracle.ORBextractor(300, 1.2, 4, 20, 7); oxR = oracle.ORBextractor(300, 1.2, 4, 20, 7)
     kL, dL = exL(left); kR, dR = exR(right)
     okL, odL = oxL(left); okR, odR = oxR(right)
     assert np.array_equal(kL.view(np.uint8), okL.view(np.uint8)) and np.array_equal(kR.view(np.uint8), okR.view(np.uint8))
