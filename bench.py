@@ -518,7 +518,7 @@ def algorithmic_bytes(cfg):
         "k_lsd_grad": int((1 + 4 + 1 / 8 + dens * 8) * spx), "k_ccl_merge": int((1 / 8 + dens * 8) * spx),
         "k_lsd_keys": int((1 / 8 + dens * 16) * spx), "k_lsd_cid": int(dens * (8 + 4 + 4 + 8) * spx),
         "k_lsd_rect": int(dens * 2 * (4 + 4) * spx),
-        "k_fast_cells": sumpx, "k_blur7": 2 * sumpx, "k_resize_linear": 2 * sumpx - 2 * px0 + (px0 - lv[-1][0] * lv[-1][1]),
+        "k_fast_cells": sumpx, "k_fast_cells_tma": sumpx, "k_blur7": 2 * sumpx, "k_resize_linear": 2 * sumpx - 2 * px0 + (px0 - lv[-1][0] * lv[-1][1]),
         "k_gauss_strip<3>": 2 * p01, "k_gauss_strip<2>": 2 * px0, "k_resize_exact": p01 + spx,
         "k_pyrdown": 2 * (px0 + px0 // 4), "k_sobel3": 5 * p01,
         # own radix sort: 4 passes over the 8-byte keys of the defined pixels (histogram reads them once, scatter reads and writes)
