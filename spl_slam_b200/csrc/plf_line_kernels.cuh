@@ -160,13 +160,8 @@ __device__ __forceinline__ void row_words3(const uint8_t* __restrict__ rp, int x
         w0 = p[0]; w1 = p[1]; w2 = p[2];
     } else {
         unsigned b[12];
-        if (w >= 16) {
 #pragma unroll
-            for (int i = 0; i < 12; i++) b[i] = rp[plf_reflect101_near(x0 - 4 + i, w)];
-        } else {
-#pragma unroll
-            for (int i = 0; i < 12; i++) b[i] = rp[plf_reflect101(x0 - 4 + i, w)];
-        }
+        for (int i = 0; i < 12; i++) b[i] = rp[plf_reflect101(x0 - 4 + i, w)];
         w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
         w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
         w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
@@ -192,13 +187,8 @@ __device__ __forceinline__ void pyrdown_hrow(const uint8_t* __restrict__ rp, int
 #pragma unroll
         for (int i = 0; i < 16; i++) b[i] = (ww[i >> 2] >> (8 * (i & 3))) & 0xffu;
     } else {
-        if (w >= 16) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) b[i] = (i >= 2 && i <= 12) ? rp[plf_reflect101_near(sx0 - 4 + i, w)] : 0u;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; i++) b[i] = (i >= 2 && i <= 12) ? rp[plf_reflect101(sx0 - 4 + i, w)] : 0u;
-        }
+        for (int i = 0; i < 16; i++) b[i] = (i >= 2 && i <= 12) ? rp[plf_reflect101(sx0 - 4 + i, w)] : 0u;
     }
 #pragma unroll
     for (int j = 0; j < 4; j++)   // source column 2 * (x0 + j) is byte 4 + 2j
