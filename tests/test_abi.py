@@ -52,3 +52,16 @@ def test_product_does_not_import_oracle():
                 assert "oracle" not in src.replace("the oracle", "").replace("oracle's", "").replace("like the oracle", "") \
                     or f.endswith((".cu", ".cuh")), f
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_product_kernels_use_no_library_kernels():
+    """The hot path is hand-written: no CUB / Thrust / cuBLAS / cuDNN / CUTLASS header or call anywhere in the product sources
+    (the scan and the radix sort of the LSD pre-phase are spl_slam_b200/csrc/plf_sort.cuh)."""
+    import re
+    bad = re.compile(r"#\s*include\s*<\s*(cub|thrust|cublas|cudnn|cutlass|cute)[/_.]|\b(cub|thrust)::|cublas[A-Z]\w*\(")
+    for f in sorted(os.listdir(os.path.join(ROOT, "spl_slam_b200", "csrc"))):
+        if f.endswith((".cu", ".cuh")):
+            src = open(os.path.join(ROOT, "spl_slam_b200", "csrc", f)).read()
+            code = "\n".join(l.split("//")[0] for l in src.splitlines())       # comments may name what was replaced
+            m = bad.search(code)
+            assert m is None, "%s: %s" % (f, m.group(0) if m else "")
