@@ -506,3 +506,26 @@ def test_line_batch_key_workspace_retry(S, oracle, gpu_ctx):
         for b in range(len(imgs)):
             oK, oM, oD = oracle.line_extract(prm, imgs[b])
             assert len(K[b]) == len(oK) and np.array_equal(K[b].view(np.uint8), oK.view(np.uint8)) and np.array_equal(D[b], oD)
+
+
+def test_orb_register_staged_kernels_without_tma():
+    """k_fast_cells / k_describe (the kernels taken when a caller's level-0 pitch is not a multiple of 16 bytes, or with
+    PLF_NO_TMA=1) give the same keypoints and descriptors as the TMA-fed ones: the variable is read once per process, so the
+    comparison runs in a child process."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "import spl_slam_b200 as S\n"
+        "from oracle import oracle as O\n"
+        "O.build(); ctx = S.Context(0)\n"
+        "for (w, h, nf, seed) in ((752, 480, 1200, 1), (640, 480, 1000, 0)):\n"
+        "    img = O.synth_image(w, h, seed)\n"
+        "    k, d = S.ORBextractor(nf, 1.2, 8, 20, 7, ctx=ctx)(img)\n"
+        "    ok, od = O.ORBextractor(nf, 1.2, 8, 20, 7)(img)\n"
+        "    assert len(k) == len(ok) and np.array_equal(k.view(np.uint8), ok.view(np.uint8)) and np.array_equal(d, od)\n"
+        "rep = ctx.profile_report() if hasattr(ctx, 'profile_report') else {}\n"
+        "print('ok')\n" % root)
+    env = dict(os.environ, PLF_NO_TMA="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
