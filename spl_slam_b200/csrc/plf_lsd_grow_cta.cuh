@@ -344,16 +344,44 @@ k_lsd_grow_cta(const unsigned long long* __restrict__ keys, const int2* __restri
                             const int* sxy = (const int*)(cta_scr + (size_t)slot * GC_RMAX);   // [GC_RMAX] xy, then [GC_RMAX] component index
                             const int* scc = sxy + GC_RMAX;
                             bool bad = false;
-                            for (int i = lane; i < n; i += 32) {
-                                const int cc = scc[i];
-                                bad |= ((used[cc >> 5] >> (cc & 31)) & 1u) != 0;
-                            }
-                            if (!__any_sync(FULL, bad)) {
+                            if (n <= 128) {
+                                // the usual case: the region's points and component indices are fetched ONCE (both loads in flight
+                                // together), validated from registers and written from registers -- one round trip to the scratch
+                                // instead of a validation pass followed by a copy pass
+                                int rcc[4], rxy[4];
+#pragma unroll
+                                for (int t = 0; t < 4; t++) {
+                                    const int i = lane + 32 * t;
+                                    rcc[t] = i < n ? scc[i] : -1;
+                                    rxy[t] = i < n ? sxy[i] : 0;
+                                }
+#pragma unroll
+                                for (int t = 0; t < 4; t++)
+                                    if (rcc[t] >= 0) bad |= ((used[rcc[t] >> 5] >> (rcc[t] & 31)) & 1u) != 0;
+                                bad = __any_sync(FULL, bad);
+                                if (!bad) {
+#pragma unroll
+                                    for (int t = 0; t < 4; t++)
+                                        if (rcc[t] >= 0) {
+                                            regpts[arena + lane + 32 * t] = rxy[t];
+                                            atomicOr(&used[rcc[t] >> 5], 1u << (rcc[t] & 31));
+                                        }
+                                }
+                            } else {
                                 for (int i = lane; i < n; i += 32) {
                                     const int cc = scc[i];
-                                    regpts[arena + i] = sxy[i];
-                                    atomicOr(&used[cc >> 5], 1u << (cc & 31));
+                                    bad |= ((used[cc >> 5] >> (cc & 31)) & 1u) != 0;
                                 }
+                                bad = __any_sync(FULL, bad);
+                                if (!bad) {
+                                    for (int i = lane; i < n; i += 32) {
+                                        const int cc = scc[i];
+                                        regpts[arena + i] = sxy[i];
+                                        atomicOr(&used[cc >> 5], 1u << (cc & 31));
+                                    }
+                                }
+                            }
+                            if (!bad) {
                                 nreg = n;
                                 reg_angle = S.ang[slot];
                                 d_ok++; d_okpx += n;
